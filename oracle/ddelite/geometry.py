@@ -1,0 +1,376 @@
+"""Geometry samplers/filters restated from DeepXDE semantics.
+
+Only the shapes the BASELINE configs and their neighbours use: Interval, TimeDomain,
+Hypercube/Rectangle/Cuboid, Disk, GeometryXTime.  'pseudo' sampling is
+np.random.random (the global legacy RNG, which the resamplers depend on:
+/root/reference/AI4XDE/algorithm/RAD.py:25).  Quasi-random names ('Hammersley', ...)
+come from scikit-optimize in DeepXDE; skopt is absent here, so they use a plain
+van-der-Corput/Hammersley construction (same distribution, not the same points).
+"""
+import itertools
+
+import numpy as np
+
+from . import config
+
+
+def _primes(n):
+    out, c = [], 2
+    while len(out) < n:
+        if all(c % p for p in out):
+            out.append(c)
+        c += 1
+    return out
+
+
+def _van_der_corput(n, base, start=1):
+    seq = np.zeros(n)
+    for idx in range(n):
+        k, f, v = idx + start, 1.0 / base, 0.0
+        while k > 0:
+            v += f * (k % base)
+            k //= base
+            f /= base
+        seq[idx] = v
+    return seq
+
+
+def sample(n_samples, dimension, sampler="pseudo"):
+    if sampler == "pseudo":
+        return np.random.random(size=(n_samples, dimension)).astype(config.real(np))
+    if sampler in ("LHS", "Halton", "Hammersley", "Sobol"):
+        cols = []
+        primes = _primes(dimension)
+        if sampler == "Hammersley" and dimension > 1:
+            cols.append((np.arange(n_samples) + 0.5) / n_samples)
+            primes = primes[: dimension - 1]
+        for p in primes:
+            cols.append(_van_der_corput(n_samples, p))
+        return np.stack(cols, axis=1).astype(config.real(np))
+    raise ValueError("f{sampler} sampling is not available.")
+
+
+class Geometry:
+    def __init__(self, dim, bbox, diam):
+        self.dim = dim
+        self.bbox = bbox
+        self.diam = min(diam, np.linalg.norm(bbox[1] - bbox[0]))
+        self.idstr = type(self).__name__
+
+    def uniform_points(self, n, boundary=True):
+        return self.random_points(n)
+
+    def uniform_boundary_points(self, n):
+        return self.random_boundary_points(n)
+
+    def periodic_point(self, x, component):
+        raise NotImplementedError
+
+
+class Interval(Geometry):
+    def __init__(self, l, r):
+        super().__init__(1, (np.array([l]), np.array([r])), r - l)
+        self.l, self.r = l, r
+
+    def inside(self, x):
+        return np.logical_and(self.l <= x, x <= self.r).flatten()
+
+    def on_boundary(self, x):
+        return np.any(np.isclose(x, [self.l, self.r]), axis=-1)
+
+    def boundary_normal(self, x):
+        return -np.isclose(x, self.l).astype(config.real(np)) + np.isclose(x, self.r).astype(
+            config.real(np)
+        )
+
+    def uniform_points(self, n, boundary=True):
+        if boundary:
+            return np.linspace(self.l, self.r, num=n, dtype=config.real(np))[:, None]
+        return np.linspace(self.l, self.r, num=n + 1, endpoint=False, dtype=config.real(np))[
+            1:, None
+        ]
+
+    def random_points(self, n, random="pseudo"):
+        x = sample(n, 1, random)
+        return (self.diam * x + self.l).astype(config.real(np))
+
+    def uniform_boundary_points(self, n):
+        if n == 1:
+            return np.array([[self.l]]).astype(config.real(np))
+        xl = np.full((n // 2, 1), self.l).astype(config.real(np))
+        xr = np.full((n - n // 2, 1), self.r).astype(config.real(np))
+        return np.vstack((xl, xr))
+
+    def random_boundary_points(self, n, random="pseudo"):
+        if n == 2:
+            return np.array([[self.l], [self.r]]).astype(config.real(np))
+        return np.random.choice([self.l, self.r], n)[:, None].astype(config.real(np))
+
+    def periodic_point(self, x, component=0):
+        tmp = np.copy(x)
+        tmp[np.isclose(x, self.l)] = self.r
+        tmp[np.isclose(x, self.r)] = self.l
+        return tmp
+
+
+class TimeDomain(Interval):
+    def __init__(self, t0, t1):
+        super().__init__(t0, t1)
+        self.t0, self.t1 = t0, t1
+
+    def on_initial(self, t):
+        return np.isclose(t, self.t0).flatten()
+
+
+class Hypercube(Geometry):
+    def __init__(self, xmin, xmax):
+        if len(xmin) != len(xmax):
+            raise ValueError("Dimensions of xmin and xmax do not match.")
+        self.xmin = np.array(xmin, dtype=config.real(np))
+        self.xmax = np.array(xmax, dtype=config.real(np))
+        if np.any(self.xmin >= self.xmax):
+            raise ValueError("xmin >= xmax")
+        self.side_length = self.xmax - self.xmin
+        super().__init__(len(xmin), (self.xmin, self.xmax), np.linalg.norm(self.side_length))
+        self.volume = np.prod(self.side_length)
+
+    def inside(self, x):
+        return np.logical_and(np.all(x >= self.xmin, axis=-1), np.all(x <= self.xmax, axis=-1))
+
+    def on_boundary(self, x):
+        _on = np.logical_or(
+            np.any(np.isclose(x, self.xmin), axis=-1), np.any(np.isclose(x, self.xmax), axis=-1)
+        )
+        return np.logical_and(self.inside(x), _on)
+
+    def boundary_normal(self, x):
+        _n = -np.isclose(x, self.xmin).astype(config.real(np)) + np.isclose(x, self.xmax)
+        idx = np.count_nonzero(_n, axis=-1) > 1
+        if np.any(idx):
+            l = np.linalg.norm(_n[idx], axis=-1, keepdims=True)
+            _n[idx] /= l
+        return _n
+
+    def uniform_points(self, n, boundary=True):
+        dx = (self.volume / n) ** (1 / self.dim)
+        xi = []
+        for i in range(self.dim):
+            ni = int(np.ceil(self.side_length[i] / dx))
+            if boundary:
+                xi.append(np.linspace(self.xmin[i], self.xmax[i], num=ni, dtype=config.real(np)))
+            else:
+                xi.append(
+                    np.linspace(
+                        self.xmin[i], self.xmax[i], num=ni + 1, endpoint=False, dtype=config.real(np)
+                    )[1:]
+                )
+        return np.array(list(itertools.product(*xi)))
+
+    def random_points(self, n, random="pseudo"):
+        x = sample(n, self.dim, random)
+        return (self.xmax - self.xmin) * x + self.xmin
+
+    def random_boundary_points(self, n, random="pseudo"):
+        x = sample(n, self.dim, random)
+        rand_dim = np.random.randint(self.dim, size=n)
+        x[np.arange(n), rand_dim] = np.round(x[np.arange(n), rand_dim])
+        return (self.xmax - self.xmin) * x + self.xmin
+
+    def periodic_point(self, x, component):
+        y = np.copy(x)
+        _on_xmin = np.isclose(y[:, component], self.xmin[component])
+        _on_xmax = np.isclose(y[:, component], self.xmax[component])
+        y[:, component][_on_xmin] = self.xmax[component]
+        y[:, component][_on_xmax] = self.xmin[component]
+        return y
+
+
+class Rectangle(Hypercube):
+    def __init__(self, xmin, xmax):
+        super().__init__(xmin, xmax)
+        self.perimeter = 2 * np.sum(self.xmax - self.xmin)
+        self.area = np.prod(self.xmax - self.xmin)
+
+    def uniform_boundary_points(self, n):
+        nx, ny = np.ceil(n / self.perimeter * (self.xmax - self.xmin)).astype(int)
+        xbot = np.hstack(
+            (
+                np.linspace(self.xmin[0], self.xmax[0], num=nx, endpoint=False)[:, None],
+                np.full([nx, 1], self.xmin[1]),
+            )
+        )
+        yrig = np.hstack(
+            (
+                np.full([ny, 1], self.xmax[0]),
+                np.linspace(self.xmin[1], self.xmax[1], num=ny, endpoint=False)[:, None],
+            )
+        )
+        xtop = np.hstack(
+            (
+                np.linspace(self.xmin[0], self.xmax[0], num=nx + 1)[1:, None],
+                np.full([nx, 1], self.xmax[1]),
+            )
+        )
+        ylef = np.hstack(
+            (
+                np.full([ny, 1], self.xmin[0]),
+                np.linspace(self.xmin[1], self.xmax[1], num=ny + 1)[1:, None],
+            )
+        )
+        return np.vstack((xbot, yrig, xtop, ylef)).astype(config.real(np))
+
+    def random_boundary_points(self, n, random="pseudo"):
+        l1 = self.xmax[0] - self.xmin[0]
+        l2 = l1 + self.xmax[1] - self.xmin[1]
+        l3 = l2 + l1
+        u = np.ravel(sample(n + 2, 1, random))
+        u = u[np.logical_not(np.isclose(u, l1 / self.perimeter))]
+        u = u[np.logical_not(np.isclose(u, l3 / self.perimeter))]
+        u = u[:n]
+        u *= self.perimeter
+        x = []
+        for l in u:
+            if l < l1:
+                x.append([self.xmin[0] + l, self.xmin[1]])
+            elif l < l2:
+                x.append([self.xmax[0], self.xmin[1] + l - l1])
+            elif l < l3:
+                x.append([self.xmax[0] - l + l2, self.xmax[1]])
+            else:
+                x.append([self.xmin[0], self.xmax[1] - l + l3])
+        return np.vstack(x).astype(config.real(np))
+
+
+class Cuboid(Hypercube):
+    pass
+
+
+class Disk(Geometry):
+    def __init__(self, center, radius):
+        self.center = np.array(center, dtype=config.real(np))
+        self.radius = radius
+        super().__init__(2, (self.center - radius, self.center + radius), 2 * radius)
+        self._r2 = radius**2
+
+    def inside(self, x):
+        return np.linalg.norm(x - self.center, axis=-1) <= self.radius
+
+    def on_boundary(self, x):
+        return np.isclose(np.linalg.norm(x - self.center, axis=-1), self.radius)
+
+    def boundary_normal(self, x):
+        _n = x - self.center
+        l = np.linalg.norm(_n, axis=-1, keepdims=True)
+        _n = _n / l * np.isclose(l, self.radius)
+        return _n
+
+    def random_points(self, n, random="pseudo"):
+        rng = sample(n, 2, random)
+        r, theta = rng[:, 0], 2 * np.pi * rng[:, 1]
+        x, y = np.cos(theta), np.sin(theta)
+        return (self.radius * (np.sqrt(r) * np.vstack((x, y))).T + self.center).astype(
+            config.real(np)
+        )
+
+    def uniform_boundary_points(self, n):
+        theta = np.linspace(0, 2 * np.pi, num=n, endpoint=False)
+        X = np.vstack((np.cos(theta), np.sin(theta))).T
+        return (self.radius * X + self.center).astype(config.real(np))
+
+    def random_boundary_points(self, n, random="pseudo"):
+        u = sample(n, 1, random)
+        theta = 2 * np.pi * u
+        X = np.hstack((np.cos(theta), np.sin(theta)))
+        return (self.radius * X + self.center).astype(config.real(np))
+
+
+class GeometryXTime:
+    def __init__(self, geometry, timedomain):
+        self.geometry = geometry
+        self.timedomain = timedomain
+        self.dim = geometry.dim + timedomain.dim
+
+    def on_boundary(self, x):
+        return self.geometry.on_boundary(x[:, :-1])
+
+    def on_initial(self, x):
+        return self.timedomain.on_initial(x[:, -1:])
+
+    def boundary_normal(self, x):
+        _n = self.geometry.boundary_normal(x[:, :-1])
+        return np.hstack([_n, np.zeros((len(_n), 1))])
+
+    def uniform_points(self, n, boundary=True):
+        nx = int(
+            np.ceil(
+                (n * np.prod(self.geometry.bbox[1] - self.geometry.bbox[0]) / self.timedomain.diam)
+                ** 0.5
+            )
+        )
+        nt = int(np.ceil(n / nx))
+        x = self.geometry.uniform_points(nx, boundary=boundary)
+        nx = len(x)
+        if boundary:
+            t = self.timedomain.uniform_points(nt, boundary=True)
+        else:
+            t = np.linspace(
+                self.timedomain.t1, self.timedomain.t0, num=nt, endpoint=False, dtype=config.real(np)
+            )[:, None]
+        xt = []
+        for ti in t:
+            xt.append(np.hstack((x, np.full([nx, 1], ti[0]))))
+        return np.vstack(xt)
+
+    def random_points(self, n, random="pseudo"):
+        if isinstance(self.geometry, Interval):
+            geom = Hypercube(
+                [self.geometry.l, self.timedomain.t0], [self.geometry.r, self.timedomain.t1]
+            )
+            return geom.random_points(n, random=random)
+        if isinstance(self.geometry, Hypercube):
+            geom = Hypercube(
+                np.append(self.geometry.xmin, self.timedomain.t0),
+                np.append(self.geometry.xmax, self.timedomain.t1),
+            )
+            return geom.random_points(n, random=random)
+        x = self.geometry.random_points(n, random=random)
+        t = self.timedomain.random_points(n, random=random)
+        t = np.random.permutation(t)
+        return np.hstack((x, t))
+
+    def uniform_boundary_points(self, n):
+        if self.geometry.dim == 1:
+            nx = 2
+        else:
+            s = 2 * sum(map(lambda l: l[0] * l[1], itertools.combinations(self.geometry.bbox[1] - self.geometry.bbox[0], 2)))
+            nx = int((n * s / self.timedomain.diam) ** 0.5)
+        nt = int(np.ceil(n / nx))
+        x = self.geometry.uniform_boundary_points(nx)
+        nx = len(x)
+        t = np.linspace(
+            self.timedomain.t1, self.timedomain.t0, num=nt, endpoint=False, dtype=config.real(np)
+        )
+        xt = []
+        for ti in t:
+            xt.append(np.hstack((x, np.full([nx, 1], ti))))
+        return np.vstack(xt)
+
+    def random_boundary_points(self, n, random="pseudo"):
+        x = self.geometry.random_boundary_points(n, random=random)
+        t = self.timedomain.random_points(n, random=random)
+        t = np.random.permutation(t)
+        return np.hstack((x, t))
+
+    def uniform_initial_points(self, n):
+        x = self.geometry.uniform_points(n, True)
+        t = self.timedomain.t0
+        return np.hstack((x, np.full([len(x), 1], t, dtype=config.real(np))))
+
+    def random_initial_points(self, n, random="pseudo"):
+        x = self.geometry.random_points(n, random=random)
+        t = self.timedomain.t0
+        return np.hstack((x, np.full([n, 1], t, dtype=config.real(np))))
+
+    def periodic_point(self, x, component):
+        xp = self.geometry.periodic_point(x[:, :-1], component)
+        return np.hstack([xp, x[:, -1:]])

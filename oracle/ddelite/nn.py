@@ -1,0 +1,98 @@
+"""dde.nn.FNN restated: torch.nn.Linear stack, Glorot init,
+zero bias, optional feature/output transforms applied inside forward()."""
+import torch
+
+from . import config
+
+_ACT = {
+    "tanh": torch.tanh,
+    "sin": torch.sin,
+    "sigmoid": torch.sigmoid,
+    "relu": torch.relu,
+    "elu": torch.nn.functional.elu,
+    "selu": torch.nn.functional.selu,
+    "silu": torch.nn.functional.silu,
+    "swish": torch.nn.functional.silu,
+    "gelu": torch.nn.functional.gelu,
+    "linear": lambda x: x,
+    None: lambda x: x,
+}
+
+_INIT = {
+    "Glorot normal": torch.nn.init.xavier_normal_,
+    "Glorot uniform": torch.nn.init.xavier_uniform_,
+    "He normal": torch.nn.init.kaiming_normal_,
+    "He uniform": torch.nn.init.kaiming_uniform_,
+    "zeros": torch.nn.init.zeros_,
+}
+
+
+def get_activation(identifier):
+    if callable(identifier):
+        return identifier
+    return _ACT[identifier]
+
+
+def get_initializer(identifier):
+    return _INIT[identifier]
+
+
+class NN(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.regularizer = None
+        self._auxiliary_vars = None
+        self._input_transform = None
+        self._output_transform = None
+
+    @property
+    def auxiliary_vars(self):
+        return self._auxiliary_vars
+
+    @auxiliary_vars.setter
+    def auxiliary_vars(self, value):
+        self._auxiliary_vars = value
+
+    def apply_feature_transform(self, transform):
+        self._input_transform = transform
+
+    def apply_output_transform(self, transform):
+        self._output_transform = transform
+
+    def num_trainable_parameters(self):
+        return sum(v.numel() for v in self.parameters() if v.requires_grad)
+
+
+class FNN(NN):
+    def __init__(self, layer_sizes, activation, kernel_initializer):
+        super().__init__()
+        if isinstance(activation, list):
+            if not (len(layer_sizes) - 1) == len(activation):
+                raise ValueError("Total number of activation functions do not match with sum of hidden layers and output layer!")
+            self.activation = list(map(get_activation, activation))
+        else:
+            self.activation = get_activation(activation)
+        initializer = get_initializer(kernel_initializer)
+        initializer_zero = get_initializer("zeros")
+        self.linears = torch.nn.ModuleList()
+        for i in range(1, len(layer_sizes)):
+            self.linears.append(
+                torch.nn.Linear(layer_sizes[i - 1], layer_sizes[i], dtype=config.real(torch))
+            )
+            initializer(self.linears[-1].weight)
+            initializer_zero(self.linears[-1].bias)
+
+    def forward(self, inputs):
+        x = inputs
+        if self._input_transform is not None:
+            x = self._input_transform(x)
+        for j, linear in enumerate(self.linears[:-1]):
+            x = (
+                self.activation[j](linear(x))
+                if isinstance(self.activation, list)
+                else self.activation(linear(x))
+            )
+        x = self.linears[-1](x)
+        if self._output_transform is not None:
+            x = self._output_transform(inputs, x)
+        return x
