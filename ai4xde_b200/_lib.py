@@ -1,0 +1,287 @@
+"""ctypes binding of libai4xde_b200.so (C ABI declared in include/ai4xde_b200.h).
+
+There is no CPU fallback: every compute entry point raises if the shared library is missing
+or if it is handed anything but CUDA tensors.  torch is used here only for device memory and
+the current stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libai4xde_b200.so")
+
+MAX_LINEAR, MAX_FIRST, MAX_SECOND = 16, 4, 10
+ACT = {"tanh": 0, "sin": 1, "sigmoid": 2}
+ENGINE = {"auto": 0, "fp32": 1, "tf32": 2, "tf32x3": 3}
+
+
+class NetDesc(C.Structure):
+    _fields_ = [
+        ("n_linear", C.c_int32),
+        ("widths", C.c_int32 * (MAX_LINEAR + 1)),
+        ("activation", C.c_int32),
+        ("n_nets", C.c_int32),
+    ]
+
+
+class JetDesc(C.Structure):
+    _fields_ = [
+        ("n1", C.c_int32),
+        ("dir1", C.c_int32 * MAX_FIRST),
+        ("n2", C.c_int32),
+        ("pa", C.c_int32 * MAX_SECOND),
+        ("pb", C.c_int32 * MAX_SECOND),
+    ]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "ax_version": (C.c_int, []),
+    "ax_last_error": (C.c_char_p, []),
+    "ax_launch_count": (C.c_int64, []),
+    "ax_param_count": (C.c_int64, [C.POINTER(NetDesc)]),
+    "ax_jet_supported": (C.c_int, [C.POINTER(JetDesc)]),
+    "ax_engine_supported": (C.c_int, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int]),
+    "ax_stash_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64, C.c_int]),
+    "ax_forward_ws_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64]),
+    "ax_backward_ws_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64]),
+    "ax_jet_mlp_forward": (
+        C.c_int,
+        [C.POINTER(NetDesc), C.POINTER(JetDesc), _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_int, _P,
+         C.c_size_t, C.c_int, _P],
+    ),
+    "ax_jet_mlp_backward": (
+        C.c_int,
+        [C.POINTER(NetDesc), C.POINTER(JetDesc), _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P,
+         C.c_size_t, C.c_int, _P],
+    ),
+    "ax_resample_ws_bytes": (C.c_size_t, [C.c_int64]),
+    "ax_pairwise_sum_f32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "ax_pairwise_sum_f64": (C.c_int, [_P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "ax_rad_probabilities": (
+        C.c_int,
+        [_P, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_double, _P, _P, C.c_size_t, _P],
+    ),
+    "ax_choice_round": (
+        C.c_int,
+        [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, _P, C.c_size_t, _P],
+    ),
+    "ax_r3_retain": (
+        C.c_int,
+        [_P, C.c_int32, C.c_int64, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P,
+         _P, _P, _P, C.c_size_t, _P],
+    ),
+    "ax_gather_points": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen the in-tree library; raise loudly if it is not there (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m ai4xde_b200.build` "
+            "(ai4xde_b200 has no CPU or PyTorch fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().ax_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise NativeLibraryError(f"{what} failed: {last_error()}")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeLibraryError(
+                "ai4xde_b200 kernels need CUDA tensors (sm_100a); there is no CPU path"
+            )
+
+
+def make_net_desc(widths, activation, n_nets=1):
+    if len(widths) - 1 > MAX_LINEAR or len(widths) < 3:
+        raise ValueError(f"layer_size {widths}: need 1..{MAX_LINEAR - 1} hidden layers")
+    if activation not in ACT:
+        raise NotImplementedError(
+            f"activation {activation!r} is not in the fused path (tanh, sin, sigmoid are)"
+        )
+    d = NetDesc()
+    d.n_linear = len(widths) - 1
+    for i, w in enumerate(widths):
+        d.widths[i] = int(w)
+    d.activation = ACT[activation]
+    d.n_nets = int(n_nets)
+    return d
+
+
+def make_jet_desc(dirs, pairs):
+    """dirs: input coordinate of each first-order stream; pairs: (a, b) indices into dirs."""
+    d = JetDesc()
+    d.n1 = len(dirs)
+    for i, v in enumerate(dirs):
+        d.dir1[i] = int(v)
+    d.n2 = len(pairs)
+    for q, (a, b) in enumerate(pairs):
+        d.pa[q], d.pb[q] = int(a), int(b)
+    return d
+
+
+def param_count(net):
+    return int(load().ax_param_count(C.byref(net)))
+
+
+def jet_supported(jet):
+    return bool(load().ax_jet_supported(C.byref(jet)))
+
+
+def engine_supported(net, jet, engine):
+    return bool(load().ax_engine_supported(C.byref(net), C.byref(jet), ENGINE[engine]))
+
+
+def launch_count():
+    return int(load().ax_launch_count())
+
+
+def pad32(n):
+    return max(32, (int(n) + 31) // 32 * 32)
+
+
+def _bytes_buf(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def jet_forward(net, jet, params, x_soa, n, keep_all, engine="auto"):
+    """params [K, P] f32, x_soa [d, ldn] f32 -> (jets [K, S, C, ldn], stash)."""
+    lib = load()
+    _need_cuda(params, x_soa)
+    ldn = x_soa.shape[1]
+    S = 1 + jet.n1 + jet.n2
+    C_out = net.widths[net.n_linear]
+    dev = x_soa.device
+    jets = torch.empty((net.n_nets, S, C_out, ldn), dtype=torch.float32, device=dev)
+    stash = _bytes_buf(lib.ax_stash_bytes(C.byref(net), C.byref(jet), ldn, int(keep_all)), dev)
+    wsb = lib.ax_forward_ws_bytes(C.byref(net), C.byref(jet), ldn)
+    ws = _bytes_buf(wsb, dev)
+    rc = lib.ax_jet_mlp_forward(
+        C.byref(net), C.byref(jet), _ptr(params), _ptr(x_soa), int(n), int(ldn), _ptr(jets),
+        _ptr(stash), int(keep_all), _ptr(ws), int(wsb), ENGINE[engine], _stream()
+    )
+    _check(rc, "ax_jet_mlp_forward")
+    return jets, stash
+
+
+def jet_backward(net, jet, params, x_soa, n, jets_bar, stash, engine="auto"):
+    """-> grad [K, P] f32 of sum(jets * jets_bar) w.r.t. params."""
+    lib = load()
+    _need_cuda(params, x_soa, jets_bar, stash)
+    ldn = x_soa.shape[1]
+    dev = x_soa.device
+    grad = torch.empty_like(params)
+    wsb = lib.ax_backward_ws_bytes(C.byref(net), C.byref(jet), ldn)
+    ws = _bytes_buf(wsb, dev)
+    rc = lib.ax_jet_mlp_backward(
+        C.byref(net), C.byref(jet), _ptr(params), _ptr(x_soa), int(n), int(ldn), _ptr(jets_bar),
+        _ptr(stash), _ptr(grad), _ptr(ws), int(wsb), ENGINE[engine], _stream()
+    )
+    _check(rc, "ax_jet_mlp_backward")
+    return grad
+
+
+# ---- resampling ---------------------------------------------------------------------------
+def resample_ws(n, device):
+    nbytes = load().ax_resample_ws_bytes(int(n))
+    return _bytes_buf(nbytes, device), int(nbytes)
+
+
+def pairwise_sum(a):
+    """NumPy-order pairwise sum of a 1-D float32/float64 CUDA tensor -> 0-d tensor."""
+    lib = load()
+    _need_cuda(a)
+    a = a.contiguous()
+    out = torch.empty((1,), dtype=a.dtype, device=a.device)
+    ws, wsb = resample_ws(a.numel(), a.device)
+    fn = lib.ax_pairwise_sum_f32 if a.dtype == torch.float32 else lib.ax_pairwise_sum_f64
+    _check(fn(_ptr(a), a.numel(), _ptr(out), _ptr(ws), wsb, _stream()), "ax_pairwise_sum")
+    return out[0]
+
+
+def rad_probabilities(res, n, k, c):
+    """res [n_res, ldr] f32 residuals -> p [n] f64 (RAD.py:29-32 rounding order)."""
+    lib = load()
+    _need_cuda(res)
+    p = torch.empty((n,), dtype=torch.float64, device=res.device)
+    ws, wsb = resample_ws(n, res.device)
+    rc = lib.ax_rad_probabilities(_ptr(res), res.shape[0], res.shape[1], int(n), float(k), float(c),
+                                  _ptr(p), _ptr(ws), wsb, _stream())
+    _check(rc, "ax_rad_probabilities")
+    return p
+
+
+def choice_round(p, u, found, n_found, n_found_out, ws, wsb):
+    lib = load()
+    _need_cuda(p, u, found, n_found_out)
+    rc = lib.ax_choice_round(_ptr(p), p.numel(), _ptr(u), u.numel(), _ptr(found), int(n_found),
+                             _ptr(n_found_out), _ptr(ws), wsb, _stream())
+    _check(rc, "ax_choice_round")
+
+
+def r3_retain(res, x_soa, n, place_at_end=True):
+    """res [n_res, ldr] f32, x_soa [d, ldn] -> (x_out [d, ldn], n_keep (device i64), thr, res_sum)."""
+    lib = load()
+    _need_cuda(res, x_soa)
+    dev = x_soa.device
+    d, ldn = x_soa.shape
+    x_out = torch.empty_like(x_soa)
+    n_keep = torch.zeros((1,), dtype=torch.int64, device=dev)
+    thr = torch.zeros((1,), dtype=torch.float32, device=dev)
+    res_sum = torch.empty((n,), dtype=torch.float32, device=dev)
+    ws, wsb = resample_ws(n, dev)
+    rc = lib.ax_r3_retain(_ptr(res), res.shape[0], res.shape[1], _ptr(x_soa), d, int(n), ldn,
+                          _ptr(x_out), ldn, int(bool(place_at_end)), _ptr(n_keep), _ptr(thr),
+                          _ptr(res_sum), _ptr(ws), wsb, _stream())
+    _check(rc, "ax_r3_retain")
+    return x_out, n_keep, thr, res_sum
+
+
+def gather_points(x_soa, idx):
+    lib = load()
+    _need_cuda(x_soa, idx)
+    d, ldn = x_soa.shape
+    m = idx.numel()
+    out = torch.zeros((d, pad32(m)), dtype=torch.float32, device=x_soa.device)
+    _check(lib.ax_gather_points(_ptr(x_soa), d, ldn, _ptr(idx), m, _ptr(out), out.shape[1], _stream()),
+           "ax_gather_points")
+    return out

@@ -1,0 +1,251 @@
+// abi.cu -- extern "C" boundary of libai4xde_b200.so (see include/ai4xde_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_engine.cuh"
+
+namespace ax {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int make_geom(const ax_net_desc *net, NetGeom *g) {
+  if (!net || net->n_linear < 2 || net->n_linear > AX_MAX_LINEAR) {
+    set_error("net: n_linear must be in [2, %d] (at least one hidden layer)", AX_MAX_LINEAR);
+    return 1;
+  }
+  if (net->n_nets < 1) {
+    set_error("net: n_nets must be >= 1");
+    return 1;
+  }
+  if (net->activation < AX_ACT_TANH || net->activation > AX_ACT_SIGMOID) {
+    set_error("net: unknown activation %d", net->activation);
+    return 1;
+  }
+  g->n_linear = net->n_linear;
+  g->L = net->n_linear - 1;
+  g->Hmax = 0;
+  int64_t off = 0;
+  for (int l = 0; l <= net->n_linear; ++l) {
+    if (net->widths[l] < 1) {
+      set_error("net: widths[%d] = %d", l, net->widths[l]);
+      return 1;
+    }
+    g->widths[l] = net->widths[l];
+    if (l >= 1 && l < net->n_linear && net->widths[l] > g->Hmax) g->Hmax = net->widths[l];
+  }
+  if (net->widths[0] > 8) {
+    set_error("net: d_in = %d > 8 not supported", net->widths[0]);
+    return 1;
+  }
+  for (int l = 0; l < net->n_linear; ++l) {
+    g->w_off[l] = off;
+    off += (int64_t)net->widths[l] * net->widths[l + 1];
+    g->b_off[l] = off;
+    off += net->widths[l + 1];
+  }
+  g->P = off;
+  return 0;
+}
+
+template <class P>
+static bool pattern_equals(const ax_jet_desc *jet) {
+  if (jet->n1 != P::N1 || jet->n2 != P::N2) return false;
+  for (int q = 0; q < P::N2; ++q)
+    if (jet->pa[q] != P::pa(q) || jet->pb[q] != P::pb(q)) return false;
+  return true;
+}
+
+int match_pattern(const ax_jet_desc *jet) {
+  if (!jet || jet->n1 < 0 || jet->n1 > AX_MAX_FIRST || jet->n2 < 0 || jet->n2 > AX_MAX_SECOND) return -1;
+#define AX_MATCH(ID, PAT) \
+  if (pattern_equals<PAT>(jet)) return ID;
+  AX_FOR_EACH_PATTERN(AX_MATCH)
+#undef AX_MATCH
+  return -1;
+}
+
+static int check_jet(const ax_net_desc *net, const ax_jet_desc *jet) {
+  const int id = match_pattern(jet);
+  if (id < 0) {
+    set_error("jet: (n1=%d, n2=%d) is not one of the compiled stream patterns", jet ? jet->n1 : -1,
+              jet ? jet->n2 : -1);
+    return -1;
+  }
+  for (int j = 0; j < jet->n1; ++j)
+    if (jet->dir1[j] < 0 || jet->dir1[j] >= net->widths[0]) {
+      set_error("jet: dir1[%d] = %d out of range for d_in = %d", j, jet->dir1[j], net->widths[0]);
+      return -1;
+    }
+  return id;
+}
+
+size_t simt_backward_ws_bytes(const NetGeom &g, int S, int64_t ldn, int n_nets) {
+  size_t gb = (size_t)2 * n_nets * S * g.Hmax * ldn;
+  size_t part = 0;
+  for (int l = 0; l <= g.L; ++l) {
+    const int Hout = g.widths[l + 1], Hin = g.widths[l];
+    const int64_t tiles = (int64_t)((Hout + 63) / 64) * ((Hin + 63) / 64) * n_nets;
+    const int64_t nsplit = (4 * 148 + tiles - 1) / tiles;
+    const size_t cnt = (size_t)n_nets * nsplit * ((size_t)Hout * Hin + Hout);
+    if (cnt > part) part = cnt;
+  }
+  return (gb + part) * sizeof(float);
+}
+
+__global__ void k_reduce_partials(const float *__restrict__ partial, int64_t partial_net_stride,
+                                  int64_t partial_split_stride, int nsplit, int64_t count,
+                                  float *__restrict__ grad, int64_t p_stride, int64_t off) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int net = blockIdx.y;
+  if (j >= count) return;
+  const float *p = partial + net * partial_net_stride + j;
+  float s = 0.0f;
+  for (int k = 0; k < nsplit; ++k) s += p[(int64_t)k * partial_split_stride];
+  grad[net * p_stride + off + j] = s;
+}
+
+static int jet_S(const ax_jet_desc *jet) { return 1 + jet->n1 + jet->n2; }
+
+}  // namespace ax
+
+using namespace ax;
+
+extern "C" {
+
+int ax_version(void) { return 100; }
+const char *ax_last_error(void) { return g_err; }
+int64_t ax_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int64_t ax_param_count(const ax_net_desc *net) {
+  NetGeom g;
+  if (make_geom(net, &g)) return -1;
+  return g.P;
+}
+
+int ax_jet_supported(const ax_jet_desc *jet) { return match_pattern(jet) >= 0 ? 1 : 0; }
+
+int ax_engine_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  if (match_pattern(jet) < 0) return 0;
+  if (engine == AX_ENGINE_FP32) return 1;
+  if (engine == AX_ENGINE_TF32 || engine == AX_ENGINE_TF32X3) return tc_supported(g, net, jet, engine) ? 1 : 0;
+  return engine == AX_ENGINE_AUTO ? 1 : 0;
+}
+
+size_t ax_stash_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  const int slots = keep_all ? g.L : (g.L < 2 ? g.L : 2);
+  return (size_t)net->n_nets * slots * jet_S(jet) * g.Hmax * ldn * sizeof(float);
+}
+
+size_t ax_forward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  return tc_forward_ws_bytes(g, net, jet, ldn);
+}
+
+size_t ax_backward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  size_t a = simt_backward_ws_bytes(g, jet_S(jet), ldn, net->n_nets);
+  size_t b = tc_backward_ws_bytes(g, net, jet, ldn);
+  return a > b ? a : b;
+}
+
+static int resolve_engine(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
+  if (engine == AX_ENGINE_AUTO) return tc_supported(g, net, jet, AX_ENGINE_TF32) ? AX_ENGINE_TF32 : AX_ENGINE_FP32;
+  return engine;
+}
+
+int ax_jet_mlp_forward(const ax_net_desc *net, const ax_jet_desc *jet, const float *params,
+                       const float *x_soa, int64_t n, int64_t ldn, float *jets, float *stash,
+                       int keep_all_layers, void *ws, size_t ws_bytes, int engine, void *stream) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 1;
+  const int id = check_jet(net, jet);
+  if (id < 0) return 1;
+  if (n <= 0) return 0;
+  if (ldn < n || (ldn % 32) != 0) {
+    set_error("ldn = %lld must be a multiple of 32 and >= n = %lld", (long long)ldn, (long long)n);
+    return 1;
+  }
+  if (!params || !x_soa || !jets || !stash) {
+    set_error("null device pointer");
+    return 1;
+  }
+  FwdArgs a{net, jet, params, x_soa, n, ldn, jets, stash, keep_all_layers, ws, ws_bytes, (cudaStream_t)stream};
+  engine = resolve_engine(g, net, jet, engine);
+  if (engine == AX_ENGINE_TF32 || engine == AX_ENGINE_TF32X3) {
+    if (!tc_supported(g, net, jet, engine)) {
+      set_error("tensor-core engine does not support this net/jet (hidden widths must be equal and a multiple of 64)");
+      return 1;
+    }
+    return tc_forward(g, a, engine);
+  }
+  switch (id) {
+#define AX_CASE(ID, PAT) \
+  case ID:               \
+    return simt_forward<PAT>(a);
+    AX_FOR_EACH_PATTERN(AX_CASE)
+#undef AX_CASE
+  }
+  set_error("unreachable pattern id %d", id);
+  return 1;
+}
+
+int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const float *params,
+                        const float *x_soa, int64_t n, int64_t ldn, const float *jets_bar,
+                        const float *stash, float *grad_params, void *ws, size_t ws_bytes,
+                        int engine, void *stream) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 1;
+  const int id = check_jet(net, jet);
+  if (id < 0) return 1;
+  if (ldn < n || (ldn % 32) != 0) {
+    set_error("ldn = %lld must be a multiple of 32 and >= n = %lld", (long long)ldn, (long long)n);
+    return 1;
+  }
+  if (!params || !x_soa || !jets_bar || !stash || !grad_params || !ws) {
+    set_error("null device pointer");
+    return 1;
+  }
+  if (n <= 0) {
+    AX_CUDA_OK(cudaMemsetAsync(grad_params, 0, sizeof(float) * g.P * net->n_nets, (cudaStream_t)stream));
+    return 0;
+  }
+  BwdArgs a{net, jet, params, x_soa, n, ldn, jets_bar, stash, grad_params, ws, ws_bytes, (cudaStream_t)stream};
+  engine = resolve_engine(g, net, jet, engine);
+  if (engine == AX_ENGINE_TF32 || engine == AX_ENGINE_TF32X3) {
+    if (!tc_supported(g, net, jet, engine)) {
+      set_error("tensor-core engine does not support this net/jet");
+      return 1;
+    }
+    return tc_backward(g, a, engine);
+  }
+  switch (id) {
+#define AX_CASE(ID, PAT) \
+  case ID:               \
+    return simt_backward<PAT>(a);
+    AX_FOR_EACH_PATTERN(AX_CASE)
+#undef AX_CASE
+  }
+  set_error("unreachable pattern id %d", id);
+  return 1;
+}
+
+}  // extern "C"

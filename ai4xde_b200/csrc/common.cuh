@@ -1,0 +1,191 @@
+// common.cuh -- shared definitions for the jet-MLP kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ai4xde_b200.h"
+
+namespace ax {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define AX_CUDA_OK(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ax::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+#define AX_LAUNCH_OK()                                                                \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ax::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                                       \
+    }                                                                                 \
+    ax::count_launch();                                                               \
+  } while (0)
+
+// ---- compile-time stream patterns -------------------------------------------------------
+// Stream s=0 is the value; s=1..N1 first-order; s=1+N1+q second-order stream q that
+// differentiates along first-order streams pa(q) and pb(q) (4 bits each, packed).
+template <int N1_, int N2_, unsigned long long PA_, unsigned long long PB_>
+struct Pattern {
+  static constexpr int N1 = N1_;
+  static constexpr int N2 = N2_;
+  static constexpr int S = 1 + N1_ + N2_;
+  __host__ __device__ static constexpr int pa(int q) { return (int)((PA_ >> (4 * q)) & 15ull); }
+  __host__ __device__ static constexpr int pb(int q) { return (int)((PB_ >> (4 * q)) & 15ull); }
+};
+
+// The compiled family.  Any request is served by the smallest superset (host side).
+using P_V = Pattern<0, 0, 0x0ull, 0x0ull>;          // {0}
+using P_1 = Pattern<1, 0, 0x0ull, 0x0ull>;          // {0,a}
+using P_1_D = Pattern<1, 1, 0x0ull, 0x0ull>;        // {0,a,aa}
+using P_2 = Pattern<2, 0, 0x0ull, 0x0ull>;          // {0,a,b}
+using P_2_A = Pattern<2, 1, 0x0ull, 0x0ull>;        // {0,a,b,aa}
+using P_2_D = Pattern<2, 2, 0x10ull, 0x10ull>;      // {0,a,b,aa,bb}
+using P_2_F = Pattern<2, 3, 0x100ull, 0x110ull>;    // {0,a,b,aa,ab,bb}
+using P_3 = Pattern<3, 0, 0x0ull, 0x0ull>;          // {0,a,b,c}
+using P_3_D = Pattern<3, 3, 0x210ull, 0x210ull>;    // + aa,bb,cc
+using P_3_F = Pattern<3, 6, 0x211000ull, 0x221210ull>;  // aa,ab,ac,bb,bc,cc
+using P_4 = Pattern<4, 0, 0x0ull, 0x0ull>;
+using P_4_D = Pattern<4, 4, 0x3210ull, 0x3210ull>;
+using P_4_F = Pattern<4, 10, 0x3221110000ull, 0x3323213210ull>;
+
+#define AX_FOR_EACH_PATTERN(X) \
+  X(0, P_V) X(1, P_1) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F) X(7, P_3) \
+  X(8, P_3_D) X(9, P_3_F) X(10, P_4) X(11, P_4_D) X(12, P_4_F)
+constexpr int kNumPatterns = 13;
+
+// returns pattern id or -1
+int match_pattern(const ax_jet_desc *jet);
+
+// ---- activation derivatives -------------------------------------------------------------
+struct ActD {
+  float a, s1, s2, s3;
+};
+
+// full-accuracy tanh for the FP32 engine (libdevice tanhf: ~1 ulp)
+__device__ __forceinline__ float act_value(int act, float z) {
+  if (act == AX_ACT_TANH) return tanhf(z);
+  if (act == AX_ACT_SIN) return sinf(z);
+  return 1.0f / (1.0f + expf(-z));
+}
+
+// what slot 0 of the stash holds for this activation, given the pre-activation z
+__device__ __forceinline__ float stash_slot0(int act, float z) {
+  if (act == AX_ACT_SIN) return z;
+  return act_value(act, z);
+}
+
+// derivatives of the activation from stash slot 0
+template <bool NEED3>
+__device__ __forceinline__ ActD act_from_stash(int act, float v) {
+  ActD d;
+  if (act == AX_ACT_TANH) {
+    d.a = v;
+    d.s1 = fmaf(-v, v, 1.0f);
+    d.s2 = -2.0f * v * d.s1;
+    d.s3 = NEED3 ? -2.0f * d.s1 * fmaf(-3.0f * v, v, 1.0f) : 0.0f;
+  } else if (act == AX_ACT_SIN) {
+    float s, c;
+    sincosf(v, &s, &c);
+    d.a = s;
+    d.s1 = c;
+    d.s2 = -s;
+    d.s3 = -c;
+  } else {
+    d.a = v;
+    d.s1 = v * (1.0f - v);
+    d.s2 = d.s1 * (1.0f - 2.0f * v);
+    d.s3 = NEED3 ? d.s1 * fmaf(6.0f * v, v - 1.0f, 1.0f) : 0.0f;
+  }
+  return d;
+}
+
+// Taylor-mode push through the activation: z[S] pre-activation streams -> st[S] stash
+// streams (slot 0 replaced) ; A[S] post-activation streams via jet_reconstruct.
+template <class P>
+__device__ __forceinline__ void jet_reconstruct(int act, const float (&st)[P::S], float (&A)[P::S]) {
+  ActD d = act_from_stash<false>(act, st[0]);
+  A[0] = d.a;
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) A[1 + j] = d.s1 * st[1 + j];
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q)
+    A[1 + P::N1 + q] = fmaf(d.s2 * st[1 + P::pa(q)], st[1 + P::pb(q)], d.s1 * st[1 + P::N1 + q]);
+}
+
+// reverse of jet_reconstruct: given stash streams and adjoints of A, adjoints of z
+template <class P>
+__device__ __forceinline__ void jet_adjoint(int act, const float (&st)[P::S], const float (&ab)[P::S],
+                                            float (&zb)[P::S]) {
+  ActD d = act_from_stash<true>(act, st[0]);
+  float z0b = d.s1 * ab[0];
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) {
+    zb[1 + j] = d.s1 * ab[1 + j];
+    z0b = fmaf(d.s2 * st[1 + j], ab[1 + j], z0b);
+  }
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q) {
+    const float za = st[1 + P::pa(q)], zc = st[1 + P::pb(q)], zq = st[1 + P::N1 + q];
+    const float aq = ab[1 + P::N1 + q];
+    zb[1 + P::N1 + q] = d.s1 * aq;
+    zb[1 + P::pa(q)] = fmaf(d.s2 * zc, aq, zb[1 + P::pa(q)]);
+    zb[1 + P::pb(q)] = fmaf(d.s2 * za, aq, zb[1 + P::pb(q)]);
+    z0b = fmaf(fmaf(d.s3 * za, zc, d.s2 * zq), aq, z0b);
+  }
+  zb[0] = z0b;
+}
+
+// ---- host-side launch geometry shared by the engines ------------------------------------
+struct NetGeom {
+  int n_linear;
+  int L;  // hidden layers
+  int widths[AX_MAX_LINEAR + 1];
+  int Hmax;
+  int64_t P;                         // params per net
+  int64_t w_off[AX_MAX_LINEAR];      // offset of W_l in the flat parameter vector
+  int64_t b_off[AX_MAX_LINEAR];
+};
+int make_geom(const ax_net_desc *net, NetGeom *g);
+
+// engine entry points (one per pattern, defined in simt_*.cu)
+struct FwdArgs {
+  const ax_net_desc *net;
+  const ax_jet_desc *jet;
+  const float *params, *x;
+  int64_t n, ldn;
+  float *jets, *stash;
+  int keep_all;
+  void *ws;
+  size_t ws_bytes;
+  cudaStream_t stream;
+};
+struct BwdArgs {
+  const ax_net_desc *net;
+  const ax_jet_desc *jet;
+  const float *params, *x;
+  int64_t n, ldn;
+  const float *jets_bar, *stash;
+  float *grad;
+  void *ws;
+  size_t ws_bytes;
+  cudaStream_t stream;
+};
+
+template <class P>
+int simt_forward(const FwdArgs &a);
+template <class P>
+int simt_backward(const BwdArgs &a);
+
+size_t simt_backward_ws_bytes(const NetGeom &g, int S, int64_t ldn, int n_nets);
+
+}  // namespace ax

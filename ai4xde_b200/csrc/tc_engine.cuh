@@ -1,0 +1,11 @@
+// tc_engine.cuh -- tcgen05 (TF32) engine entry points; see tc_engine.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ax {
+bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine);
+size_t tc_forward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
+size_t tc_backward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
+int tc_forward(const NetGeom &g, const FwdArgs &a, int engine);
+int tc_backward(const NetGeom &g, const BwdArgs &a, int engine);
+}  // namespace ax

@@ -1,0 +1,64 @@
+"""Numeric policy of the fused path.
+
+The reference flips DeepXDE to float64 at import (/root/reference/AI4XDE/solver/PDESolver.py:6).
+The fused kernels compute in float32 (TF32 on the tensor-core engine) by contract, so
+`set_default_float("float64")` is accepted for source compatibility, keeps host-side NumPy point
+sets in float64 (the resamplers' RNG stream and index selection depend on that), and leaves
+device tensors in float32 -- said once, loudly."""
+import warnings
+
+import numpy as np
+import torch
+
+_state = {"host": np.float32, "warned": False, "engine": "auto"}
+
+
+def real(package):
+    if package is np:
+        return _state["host"]
+    if package is torch:
+        return torch.float32
+    raise ValueError(package)
+
+
+def set_default_float(value):
+    if value == "float64":
+        _state["host"] = np.float64
+        if not _state["warned"]:
+            warnings.warn(
+                "ai4xde_b200: float64 requested; host point sets stay float64, the fused B200 path "
+                "computes in float32/TF32 (master weights float32).",
+                stacklevel=2,
+            )
+            _state["warned"] = True
+    elif value == "float32":
+        _state["host"] = np.float32
+    else:
+        raise ValueError(f"{value} not supported")
+
+
+def default_float():
+    return "float64" if _state["host"] is np.float64 else "float32"
+
+
+def set_engine(name):
+    """'auto' | 'fp32' | 'tf32' | 'tf32x3' -- arithmetic engine of the jet kernels."""
+    if name not in ("auto", "fp32", "tf32", "tf32x3"):
+        raise ValueError(name)
+    _state["engine"] = name
+
+
+def engine():
+    return _state["engine"]
+
+
+def device():
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+
+def set_random_seed(seed):
+    import random
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)

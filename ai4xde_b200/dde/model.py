@@ -1,0 +1,418 @@
+"""dde.Model of the fused path: compile / train / predict with the seams the reference patches
+(`outputs_losses_train`, `outputs_losses_test`, `train_step`; see
+/root/reference/AI4XDE/algorithm/FBPINN.py:143-194) -- SURVEY.md 8a rows M1/M2, 8b.
+
+What changes against DeepXDE: the collocation set lives on the device (re-uploaded only when the
+host arrays change), the network evaluation inside every closure is the fused jet kernel sequence,
+the derivative-stream set is discovered once by a kernel-free dry run of the case's own
+`pde`/BC code, and the data-parallel gradient exchange (if torch.distributed is initialised) is one
+all-reduce of the flat gradient.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .. import jet
+from . import config, gradients as grad, losses as losses_module, metrics as metrics_module
+from . import optimizers, utils
+from .callbacks import CallbackList
+
+
+class TrainState:
+    def __init__(self):
+        self.epoch = self.step = 0
+        self.X_train = self.y_train = self.train_aux_vars = None
+        self.X_test = self.y_test = self.test_aux_vars = None
+        self.y_pred_train = self.loss_train = self.loss_test = None
+        self.y_pred_test = self.y_std_test = self.metrics_test = None
+        self.best_step = 0
+        self.best_loss_train = self.best_loss_test = np.inf
+        self.best_y = self.best_ystd = self.best_metrics = None
+
+    def set_data_train(self, X_train, y_train, train_aux_vars=None):
+        self.X_train, self.y_train, self.train_aux_vars = X_train, y_train, train_aux_vars
+
+    def set_data_test(self, X_test, y_test, test_aux_vars=None):
+        self.X_test, self.y_test, self.test_aux_vars = X_test, y_test, test_aux_vars
+
+    def update_best(self):
+        if self.best_loss_train > np.sum(self.loss_train):
+            self.best_step = self.step
+            self.best_loss_train = np.sum(self.loss_train)
+            self.best_loss_test = np.sum(self.loss_test)
+            self.best_y, self.best_ystd = self.y_pred_test, self.y_std_test
+            self.best_metrics = self.metrics_test
+
+    def disregard_best(self):
+        self.best_loss_train = np.inf
+
+
+class LossHistory:
+    def __init__(self):
+        self.steps, self.loss_train, self.loss_test, self.metrics_test = [], [], [], []
+
+    def append(self, step, loss_train, loss_test, metrics_test):
+        self.steps.append(step)
+        self.loss_train.append(loss_train)
+        self.loss_test.append(self.loss_test[-1] if loss_test is None else loss_test)
+        self.metrics_test.append(self.metrics_test[-1] if metrics_test is None else metrics_test)
+
+
+class _DeviceBatch:
+    """Device-resident mirror of one host point array: AoS tensor for the case's `pde` code,
+    SoA copy for the kernels."""
+
+    __slots__ = ("host", "aos", "soa")
+
+    def __init__(self, host):
+        self.host = host
+        dev = config.device()
+        if torch.is_tensor(host):
+            t = host.to(device=dev, dtype=torch.float32, non_blocking=True)
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(host, dtype=np.float32)).to(dev, non_blocking=True)
+        self.aos = t
+        self.soa = jet.to_soa(t)
+
+
+class Model:
+    verbose = int(os.environ.get("AI4XDE_B200_VERBOSE", "0"))
+
+    def __init__(self, data, net):
+        self.data, self.net = data, net
+        self.opt_name = None
+        self.batch_size = None
+        self.callbacks = None
+        self.metrics = None
+        self.external_trainable_variables = []
+        self.train_state = TrainState()
+        self.losshistory = LossHistory()
+        self.stop_training = False
+        self.opt = self.lr_scheduler = None
+        self.loss_weights = None
+        self.outputs = self.outputs_losses_train = self.outputs_losses_test = self.train_step = None
+        self._batches = []      # small LRU of _DeviceBatch
+        self._specs = {}        # stream sets by use
+        self._weights_dev = None
+
+    # ---- device mirror -----------------------------------------------------------------------
+    def device_batch(self, inputs):
+        for b in self._batches:
+            if b.host is inputs:
+                return b
+        b = _DeviceBatch(inputs)
+        self._batches.append(b)
+        if len(self._batches) > 4:
+            self._batches.pop(0)
+        return b
+
+    def drop_device_batches(self):
+        self._batches.clear()
+
+    # ---- stream-set discovery ----------------------------------------------------------------
+    def _n_out(self):
+        return self.net.layer_sizes[-1]
+
+    def spec_for_losses(self, batch, targets, loss_fn, losses_fn):
+        key = ("losses", id(self.data), id(self.data.pde), len(self.data.bcs))
+        spec = self._specs.get(key)
+        if spec is None:
+            x = batch.aos.detach().requires_grad_()
+
+            def fn(xx, y):
+                if self.net._output_transform is not None:
+                    y = self.net._output_transform(xx, y)
+                out = losses_fn(targets, y, loss_fn, xx, self)
+                grad.clear()
+                return out
+
+            spec = jet.probe_streams(x, self._n_out(), fn)
+            self._specs[key] = spec
+            if Model.verbose:
+                print(f"[ai4xde_b200] streams for training losses: {spec}")
+        return spec
+
+    def spec_for_operator(self, batch, operator):
+        key = ("operator", id(operator))
+        hit = self._specs.get(key)
+        if hit is not None and hit[0] is operator:
+            return hit[1]
+        x = batch.aos.detach().requires_grad_()
+
+        def fn(xx, y):
+            if self.net._output_transform is not None:
+                y = self.net._output_transform(xx, y)
+            out = self._call_operator(operator, xx, y)
+            grad.clear()
+            return out
+
+        spec = jet.probe_streams(x, self._n_out(), fn)
+        self._specs[key] = (operator, spec)
+        if Model.verbose:
+            print(f"[ai4xde_b200] streams for operator {getattr(operator, '__name__', operator)}: {spec}")
+        return spec
+
+    def _call_operator(self, operator, x, y):
+        nargs = utils.get_num_args(operator)
+        if nargs == 2:
+            return operator(x, y)
+        if nargs == 3:
+            return operator(x, y, self.net.auxiliary_vars)
+        raise ValueError("operator must take 2 or 3 arguments")
+
+    # ---- compile -----------------------------------------------------------------------------
+    def compile(self, optimizer, lr=None, loss="MSE", metrics=None, decay=None, loss_weights=None,
+                external_trainable_variables=None):
+        self.opt_name = optimizer
+        loss_fn = losses_module.get(loss)
+        self.loss_weights = loss_weights
+        self._weights_dev = None
+        if external_trainable_variables is None:
+            self.external_trainable_variables = []
+        else:
+            if not isinstance(external_trainable_variables, list):
+                external_trainable_variables = [external_trainable_variables]
+            self.external_trainable_variables = external_trainable_variables
+
+        def outputs(training, inputs):
+            self.net.train(mode=training)
+            batch = self.device_batch(inputs)
+            with torch.no_grad():
+                with self.net.jet_scope(jet.JetSpec.value_only(), batch.soa, param_grad=False):
+                    return self.net(batch.aos)
+
+        def outputs_losses(training, inputs, targets, auxiliary_vars, losses_fn, param_grad=True):
+            self.net.auxiliary_vars = None
+            if auxiliary_vars is not None:
+                self.net.auxiliary_vars = torch.as_tensor(auxiliary_vars, dtype=torch.float32, device=config.device())
+            self.net.train(mode=training)
+            batch = self.device_batch(inputs)
+            if targets is not None:
+                targets = torch.as_tensor(targets, dtype=torch.float32, device=config.device())
+            spec = self.spec_for_losses(batch, targets, loss_fn, losses_fn)
+            x = batch.aos.detach().requires_grad_()
+            with self.net.jet_scope(spec, batch.soa, param_grad=param_grad):
+                outputs_ = self.net(x)
+            losses = losses_fn(targets, outputs_, loss_fn, x, self)
+            if not isinstance(losses, list):
+                losses = [losses]
+            losses = torch.stack(losses)
+            if self.loss_weights is not None:
+                if self._weights_dev is None:
+                    self._weights_dev = torch.as_tensor(self.loss_weights, dtype=torch.float32, device=losses.device)
+                losses = losses * self._weights_dev
+            grad.clear()
+            return outputs_, losses
+
+        def outputs_losses_train(inputs, targets, auxiliary_vars):
+            return outputs_losses(True, inputs, targets, auxiliary_vars, self.data.losses_train)
+
+        def outputs_losses_test(inputs, targets, auxiliary_vars):
+            return outputs_losses(False, inputs, targets, auxiliary_vars, self.data.losses_test)
+
+        trainable = list(self.net.parameters()) + self.external_trainable_variables
+        self.opt, self.lr_scheduler = optimizers.get(trainable, self.opt_name, learning_rate=lr, decay=decay)
+
+        def train_step(inputs, targets, auxiliary_vars):
+            def closure():
+                losses = outputs_losses_train(inputs, targets, auxiliary_vars)[1]
+                total_loss = torch.sum(losses)
+                self.opt.zero_grad()
+                total_loss.backward()
+                _allreduce_grads(trainable)
+                return total_loss
+
+            self.opt.step(closure)
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step()
+
+        self.outputs = outputs
+        self._outputs_losses_eval = lambda training, i, t, a: outputs_losses(
+            training, i, t, a, self.data.losses_train if training else self.data.losses_test, param_grad=False)
+        self.outputs_losses_train = outputs_losses_train
+        self.outputs_losses_test = outputs_losses_test
+        self.train_step = train_step
+        self.metrics = [metrics_module.get(m) for m in (metrics or [])]
+
+    # ---- training ----------------------------------------------------------------------------
+    def _outputs(self, training, inputs):
+        return utils.to_numpy(self.outputs(training, inputs))
+
+    def _outputs_losses(self, training, inputs, targets, auxiliary_vars):
+        # evaluation only (no parameter gradient wanted): skip the per-layer stash unless the
+        # user replaced the closures (FBPINN-style patching), in which case call theirs.
+        fn = self.outputs_losses_train if training else self.outputs_losses_test
+        own = getattr(fn, "__qualname__", "").startswith("Model.compile")
+        outs = self._outputs_losses_eval(training, inputs, targets, auxiliary_vars) if own else fn(
+            inputs, targets, auxiliary_vars)
+        return utils.to_numpy(outs[0]), utils.to_numpy(outs[1])
+
+    def _train_step(self, inputs, targets, auxiliary_vars):
+        self.train_step(inputs, targets, auxiliary_vars)
+
+    def train(self, iterations=None, batch_size=None, display_every=1000, disregard_previous_best=False,
+              callbacks=None, model_restore_path=None, model_save_path=None, epochs=None):
+        if iterations is None and epochs is not None:
+            iterations = epochs
+        self.batch_size = batch_size
+        self.callbacks = CallbackList(callbacks=callbacks)
+        self.callbacks.set_model(self)
+        if disregard_previous_best:
+            self.train_state.disregard_best()
+        if model_restore_path is not None:
+            self.restore(model_restore_path)
+        self.stop_training = False
+        self.train_state.set_data_train(*self.data.train_next_batch(self.batch_size))
+        self.train_state.set_data_test(*self.data.test())
+        self._test()
+        self.callbacks.on_train_begin()
+        if optimizers.is_external_optimizer(self.opt_name):
+            self._train_lbfgs()
+        else:
+            if iterations is None:
+                raise ValueError("No iterations for {}.".format(self.opt_name))
+            self._train_sgd(iterations, display_every)
+        self.callbacks.on_train_end()
+        if model_save_path is not None:
+            self.save(model_save_path)
+        return self.losshistory, self.train_state
+
+    def _train_sgd(self, iterations, display_every):
+        ts = self.train_state
+        for i in range(iterations):
+            self.callbacks.on_epoch_begin()
+            self.callbacks.on_batch_begin()
+            ts.set_data_train(*self.data.train_next_batch(self.batch_size))
+            self._train_step(ts.X_train, ts.y_train, ts.train_aux_vars)
+            ts.epoch += 1
+            ts.step += 1
+            if ts.step % display_every == 0 or i + 1 == iterations:
+                self._test()
+            self.callbacks.on_batch_end()
+            self.callbacks.on_epoch_end()
+            if self.stop_training:
+                break
+
+    def _train_lbfgs(self):
+        ts = self.train_state
+        prev = 0
+        while prev < optimizers.LBFGS_options["maxiter"]:
+            self.callbacks.on_epoch_begin()
+            self.callbacks.on_batch_begin()
+            ts.set_data_train(*self.data.train_next_batch(self.batch_size))
+            self._train_step(ts.X_train, ts.y_train, ts.train_aux_vars)
+            n_iter = self.opt.state_dict()["state"][0]["n_iter"]
+            if prev == n_iter:
+                break
+            ts.epoch += n_iter - prev
+            ts.step += n_iter - prev
+            prev = n_iter
+            self._test()
+            self.callbacks.on_batch_end()
+            self.callbacks.on_epoch_end()
+            if self.stop_training:
+                break
+
+    def _test(self):
+        ts = self.train_state
+        ts.y_pred_train, ts.loss_train = self._outputs_losses(True, ts.X_train, ts.y_train, ts.train_aux_vars)
+        ts.y_pred_test, ts.loss_test = self._outputs_losses(False, ts.X_test, ts.y_test, ts.test_aux_vars)
+        if isinstance(ts.y_test, (list, tuple)):
+            ts.metrics_test = [m(ts.y_test[i], ts.y_pred_test[i]) for m in self.metrics for i in range(len(ts.y_test))]
+        else:
+            ts.metrics_test = [m(ts.y_test, ts.y_pred_test) for m in self.metrics]
+        ts.update_best()
+        self.losshistory.append(ts.step, ts.loss_train, ts.loss_test, ts.metrics_test)
+        if np.isnan(ts.loss_train).any() or np.isnan(ts.loss_test).any():
+            self.stop_training = True
+        if Model.verbose:
+            print(ts.step, utils.list_to_str(ts.loss_train), utils.list_to_str(ts.loss_test),
+                  utils.list_to_str(ts.metrics_test), flush=True)
+
+    # ---- inference ---------------------------------------------------------------------------
+    def predict(self, x, operator=None, callbacks=None):
+        if isinstance(x, tuple):
+            raise NotImplementedError("tuple inputs are outside the fused path")
+        x = np.asarray(x, dtype=config.real(np))
+        cbs = CallbackList(callbacks=callbacks)
+        cbs.set_model(self)
+        cbs.on_predict_begin()
+        if operator is None:
+            y = self._outputs(False, x)
+        else:
+            y = utils.to_numpy(self.predict_on_device(x, operator))
+        cbs.on_predict_end()
+        return y
+
+    def predict_on_device(self, x, operator):
+        """`operator(x, net(x))` evaluated with forward-only jets; returns device tensor(s)."""
+        self.net.eval()
+        batch = self.device_batch(x)
+        spec = self.spec_for_operator(batch, operator)
+        xt = batch.aos.detach().requires_grad_()
+        with self.net.jet_scope(spec, batch.soa, param_grad=False):
+            outputs = self.net(xt)
+        y = self._call_operator(operator, xt, outputs)
+        grad.clear()
+        if isinstance(y, (list, tuple)):
+            return [t.detach() for t in y]
+        return y.detach()
+
+    # ---- persistence -------------------------------------------------------------------------
+    def state_dict(self):
+        return self.net.state_dict()
+
+    def save(self, save_path, protocol="backend", verbose=0):
+        save_path = f"{save_path}-{self.train_state.epoch}.pt"
+        torch.save({"model_state_dict": self.net.state_dict(),
+                    "optimizer_state_dict": self.opt.state_dict()}, save_path)
+        return save_path
+
+    def restore(self, save_path, device=None, verbose=0):
+        ckpt = torch.load(save_path, map_location=device or config.device())
+        self.net.load_state_dict(ckpt["model_state_dict"])
+        self.opt.load_state_dict(ckpt["optimizer_state_dict"])
+
+
+def _allreduce_grads(params):
+    """Data-parallel exchange: one all-reduce (mean) of the flattened gradient, NCCL over NVLink
+    when the process group is up.  No-op for a single process."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off : off + n].view_as(g))
+        off += n
+
+
+def saveplot(loss_history, train_state, issave=True, isplot=True, loss_fname="loss.dat",
+             train_fname="train.dat", test_fname="test.dat", output_dir=None):
+    """dde.saveplot as used at /root/reference/AI4XDE/solver/PDESolver.py:31 (issave only;
+    plotting is out of scope and matplotlib is not required)."""
+    output_dir = output_dir or os.getcwd()
+    os.makedirs(output_dir, exist_ok=True)
+    if not issave:
+        return
+    steps = np.array(loss_history.steps)[:, None]
+    cols = [steps, np.array(loss_history.loss_train).reshape(len(steps), -1),
+            np.array(loss_history.loss_test).reshape(len(steps), -1)]
+    m = np.array(loss_history.metrics_test).reshape(len(steps), -1)
+    if m.size:
+        cols.append(m)
+    np.savetxt(os.path.join(output_dir, loss_fname), np.hstack(cols), header="step, loss_train, loss_test, metrics_test")
+    if train_state.X_train is not None and train_state.y_pred_train is not None:
+        np.savetxt(os.path.join(output_dir, train_fname),
+                   np.hstack((train_state.X_train, np.asarray(train_state.y_pred_train))), header="x, y_pred")
+    if train_state.X_test is not None and train_state.best_y is not None:
+        np.savetxt(os.path.join(output_dir, test_fname),
+                   np.hstack((train_state.X_test, np.asarray(train_state.best_y))), header="x, y_pred")

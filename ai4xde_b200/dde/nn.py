@@ -1,0 +1,206 @@
+"""dde.nn.FNN of the fused path (SURVEY.md 8a row N1, 8b `net.forward` seam).
+
+Same constructor, parameter names (`linears.{i}.weight/bias`, torch.nn.Linear layout), Glorot
+initialisers, `apply_feature_transform` / `apply_output_transform`, `.train()/.eval()`,
+`.auxiliary_vars`, `.regularizer` as DeepXDE's PyTorch FNN that
+/root/reference/AI4XDE/cases/PDECases.py:38-42 constructs -- but `forward` runs ONE fused
+Taylor-mode kernel sequence (ai4xde_b200/csrc) that returns the value and every derivative stream
+the case asks for, instead of a Linear/tanh module chain to be differentiated by autograd.
+All master weights live in one flat float32 device buffer; the nn.Linear parameters are views.
+"""
+import contextlib
+
+import torch
+
+from .. import _lib, jet
+from . import config, gradients as grad
+
+_INIT = {
+    "Glorot normal": torch.nn.init.xavier_normal_,
+    "Glorot uniform": torch.nn.init.xavier_uniform_,
+    "He normal": torch.nn.init.kaiming_normal_,
+    "He uniform": torch.nn.init.kaiming_uniform_,
+    "zeros": torch.nn.init.zeros_,
+}
+
+
+class _JetScope:
+    __slots__ = ("spec", "x_soa", "param_grad", "probe_streams")
+
+    def __init__(self, spec=None, x_soa=None, param_grad=True, probe_streams=None):
+        self.spec, self.x_soa, self.param_grad, self.probe_streams = spec, x_soa, param_grad, probe_streams
+
+
+class _FusedForward(torch.autograd.Function):
+    """Routes the flat-buffer gradient of jet.JetMLP back to the per-layer nn.Parameters."""
+
+    @staticmethod
+    def forward(ctx, net, x_soa, n, spec, engine, need_backward, *params):
+        flat = net.flat_params()
+        jets, stash = _lib.jet_forward(net.net_desc, spec.desc, flat, x_soa, n,
+                                       keep_all=need_backward, engine=engine)
+        ctx.net, ctx.spec, ctx.engine, ctx.n = net, spec, engine, n
+        ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = x_soa, stash, bool(need_backward), flat
+        ctx.shapes = [p.shape for p in params]
+        return tuple(jets[0, s, :, :n].t() for s in range(spec.S))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        if not ctx.kept:
+            raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
+        net, spec, n = ctx.net, ctx.spec, ctx.n
+        ldn = ctx.x_soa.shape[1]
+        c_out = net.layer_sizes[-1]
+        jets_bar = torch.zeros((1, spec.S, c_out, ldn), dtype=torch.float32, device=ctx.flat.device)
+        for s, g in enumerate(gouts):
+            if g is not None:
+                jets_bar[0, s, :, :n] = g.t()
+        g_flat = _lib.jet_backward(net.net_desc, spec.desc, ctx.flat, ctx.x_soa, n, jets_bar, ctx.stash,
+                                   engine=ctx.engine)[0]
+        ctx.stash = None
+        outs, off = [], 0
+        for shp in ctx.shapes:
+            cnt = 1
+            for d in shp:
+                cnt *= d
+            outs.append(g_flat[off : off + cnt].view(shp))
+            off += cnt
+        return (None, None, None, None, None, None) + tuple(outs)
+
+
+class NN(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.regularizer = None
+        self._auxiliary_vars = None
+        self._input_transform = None
+        self._output_transform = None
+
+    @property
+    def auxiliary_vars(self):
+        return self._auxiliary_vars
+
+    @auxiliary_vars.setter
+    def auxiliary_vars(self, value):
+        self._auxiliary_vars = value
+
+    def apply_feature_transform(self, transform):
+        self._input_transform = transform
+
+    def apply_output_transform(self, transform):
+        self._output_transform = transform
+
+    def num_trainable_parameters(self):
+        return sum(v.numel() for v in self.parameters() if v.requires_grad)
+
+
+class FNN(NN):
+    def __init__(self, layer_sizes, activation, kernel_initializer):
+        super().__init__()
+        if isinstance(activation, (list, tuple)):
+            if len(set(activation)) != 1:
+                raise NotImplementedError("per-layer activations are not in the fused path")
+            activation = activation[0]
+        if not isinstance(activation, str):
+            raise NotImplementedError("callable activations are not in the fused path (tanh, sin, sigmoid are)")
+        self.layer_sizes = [int(w) for w in layer_sizes]
+        self.activation_name = activation
+        self.net_desc = _lib.make_net_desc(self.layer_sizes, activation)
+        init = _INIT[kernel_initializer]
+        self.linears = torch.nn.ModuleList()
+        for i in range(1, len(self.layer_sizes)):
+            lin = torch.nn.Linear(self.layer_sizes[i - 1], self.layer_sizes[i], dtype=torch.float32)
+            init(lin.weight)
+            torch.nn.init.zeros_(lin.bias)
+            self.linears.append(lin)
+        self._flat = None
+        self._scope = _JetScope()
+        self._pack(config.device())
+
+    # ---- flat master buffer ----------------------------------------------------------------
+    def _param_list(self):
+        out = []
+        for lin in self.linears:
+            out += [lin.weight, lin.bias]
+        return out
+
+    def _pack(self, device):
+        ps = self._param_list()
+        flat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=device)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            flat[off : off + n] = p.detach().reshape(-1).to(device=device, dtype=torch.float32)
+            p.data = flat[off : off + n].view(p.shape)
+            off += n
+        self._flat = flat
+
+    def flat_params(self):
+        """[1, P] view of the master buffer (re-packed if someone moved the parameters)."""
+        ps = self._param_list()
+        base, off, ok = self._flat.data_ptr(), 0, True
+        for p in ps:
+            if p.data_ptr() != base + 4 * off or p.dtype != torch.float32 or p.device != self._flat.device:
+                ok = False
+                break
+            off += p.numel()
+        if not ok:
+            self._pack(ps[0].device if ps[0].device.type == "cuda" else config.device())
+        return self._flat.view(1, -1)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._flat = torch.empty(0)
+        self._pack(self._param_list()[0].device)
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.flat_params()
+        return out
+
+    # ---- evaluation ------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def jet_scope(self, spec=None, x_soa=None, param_grad=True, probe_streams=None):
+        prev = self._scope
+        self._scope = _JetScope(spec, x_soa, param_grad, probe_streams)
+        try:
+            yield
+        finally:
+            self._scope = prev
+
+    def forward(self, inputs):
+        if self._input_transform is not None:
+            raise NotImplementedError(
+                "feature transforms are not in the fused jet path yet (the kernels differentiate "
+                "w.r.t. the raw network inputs)"
+            )
+        sc = self._scope
+        x = inputs
+        if sc.probe_streams is not None:
+            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+        else:
+            wants_jets = x.requires_grad and torch.is_grad_enabled()
+            if not wants_jets:
+                spec = jet.JetSpec.value_only()
+            elif sc.spec is not None:
+                spec = sc.spec
+            else:
+                spec = jet.JetSpec.full(x.shape[1])
+            x_soa = sc.x_soa if sc.x_soa is not None and sc.x_soa.shape[1] >= x.shape[0] else jet.to_soa(x)
+            params = self._param_list()
+            need_bwd = bool(sc.param_grad and torch.is_grad_enabled() and any(p.requires_grad for p in params))
+            streams = _FusedForward.apply(self, x_soa, x.shape[0], spec, config.engine(), need_bwd, *params)
+            if wants_jets:
+                y = jet.make_leaf(x, spec, streams)
+                grad.register(y, jet.JetOutput(x, spec, streams))
+            else:
+                y = streams[0]
+        if self._output_transform is not None:
+            y = self._output_transform(inputs, y)
+        return y
+
+
+def get_supported_activations():
+    return sorted(_lib.ACT)

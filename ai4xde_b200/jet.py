@@ -1,0 +1,279 @@
+"""Jet streams on the host side: stream-set selection, the autograd bridge to the fused
+kernels, and the "function with known derivatives" leaves that let torch.autograd differentiate
+through arbitrary output transforms / residual algebra down to the kernel's Taylor-mode jets.
+
+Replaces, for the network part, DeepXDE's Jacobian/Hessian autograd passes requested by every
+`pde(x, y)` closure (e.g. /root/reference/AI4XDE/cases/PDECases.py:1087-1094) -- SURVEY.md
+section 8a rows G1/G2/N1.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+
+class JetSpec:
+    """Which derivative streams the kernels carry.
+
+    dirs  : input coordinate of first-order stream j            (stream index 1 + j)
+    pairs : (a, b) indices into dirs of second-order stream q   (stream index 1 + n1 + q)
+    Always one of the compiled patterns (ai4xde_b200/csrc/common.cuh); requests are widened to
+    the smallest compiled superset.
+    """
+
+    def __init__(self, dirs, pairs):
+        self.dirs = tuple(int(d) for d in dirs)
+        self.pairs = tuple((int(a), int(b)) for a, b in pairs)
+        self.n1, self.n2 = len(self.dirs), len(self.pairs)
+        self.S = 1 + self.n1 + self.n2
+        self.first_of_dim = {d: j for j, d in enumerate(self.dirs)}
+        self.second_of_dims = {}
+        for q, (a, b) in enumerate(self.pairs):
+            da, db = self.dirs[a], self.dirs[b]
+            self.second_of_dims[(da, db)] = q
+            self.second_of_dims[(db, da)] = q
+        self.desc = _lib.make_jet_desc(self.dirs, self.pairs)
+
+    def key(self):
+        return (self.dirs, self.pairs)
+
+    def __repr__(self):
+        return f"JetSpec(dirs={self.dirs}, pairs={self.pairs})"
+
+    @staticmethod
+    def value_only():
+        return JetSpec((), ())
+
+    @staticmethod
+    def full(d_in):
+        if d_in > _lib.MAX_FIRST:
+            raise NotImplementedError(
+                f"second-order jets w.r.t. {d_in} inputs exceed the compiled patterns (max {_lib.MAX_FIRST})"
+            )
+        dirs = list(range(d_in))
+        pairs = [(a, b) for a in range(d_in) for b in range(a, d_in)]
+        return JetSpec(dirs, pairs)
+
+    @staticmethod
+    def covering(need1, need2):
+        """Smallest compiled pattern covering first-order dims `need1` and second-order dim
+        pairs `need2` (iterables of ints / of (j, k))."""
+        need2 = {tuple(sorted(p)) for p in need2}
+        dims = sorted(set(need1) | {d for p in need2 for d in p})
+        n1 = len(dims)
+        if n1 > _lib.MAX_FIRST:
+            raise NotImplementedError(
+                f"derivatives w.r.t. {n1} different inputs exceed the compiled patterns (max {_lib.MAX_FIRST})"
+            )
+        if not need2:
+            return JetSpec(dims, [])
+        diag_only = all(j == k for j, k in need2)
+        if diag_only and n1 == 1:
+            return JetSpec(dims, [(0, 0)])
+        if diag_only and n1 == 2 and len(need2) == 1:
+            (j, _), = need2
+            other = [d for d in dims if d != j]
+            return JetSpec([j] + other, [(0, 0)])
+        if diag_only:
+            return JetSpec(dims, [(a, a) for a in range(n1)])
+        return JetSpec(dims, [(a, b) for a in range(n1) for b in range(a, n1)])
+
+
+def to_soa(x):
+    """(n, d) -> zero-padded [d, ldn] float32 (the kernels' point layout)."""
+    n, d = x.shape
+    ldn = _lib.pad32(n)
+    out = torch.zeros((d, ldn), dtype=torch.float32, device=x.device)
+    out[:, :n] = x.detach().t()
+    return out
+
+
+class JetMLP(Function):
+    """params -> S jet streams, each (K, n, C); backward = fused reverse pass."""
+
+    @staticmethod
+    def forward(ctx, flat_params, x_soa, n, net_desc, spec, engine, need_backward):
+        jets, stash = _lib.jet_forward(net_desc, spec.desc, flat_params, x_soa, n,
+                                       keep_all=need_backward, engine=engine)
+        ctx.net_desc, ctx.spec, ctx.engine, ctx.n = net_desc, spec, engine, n
+        ctx.x_soa, ctx.stash, ctx.kept = x_soa, stash, bool(need_backward)
+        ctx.save_for_backward(flat_params)
+        # jets: [K, S, C, ldn] -> per-stream (K, n, C) strided views
+        return tuple(jets[:, s, :, :n].transpose(1, 2) for s in range(spec.S))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gouts):
+        if not ctx.kept:
+            raise RuntimeError("JetMLP: backward requested but the forward ran without a stash")
+        (flat_params,) = ctx.saved_tensors
+        net, spec, n = ctx.net_desc, ctx.spec, ctx.n
+        ldn = ctx.x_soa.shape[1]
+        C_out = net.widths[net.n_linear]
+        jets_bar = torch.zeros((net.n_nets, spec.S, C_out, ldn), dtype=torch.float32,
+                               device=flat_params.device)
+        for s, g in enumerate(gouts):
+            if g is not None:
+                jets_bar[:, s, :, :n] = g.transpose(1, 2)
+        grad = _lib.jet_backward(net, spec.desc, flat_params, ctx.x_soa, n, jets_bar, ctx.stash,
+                                 engine=ctx.engine)
+        ctx.stash = None
+        return grad, None, None, None, None, None, None
+
+
+# ---- functions with known derivatives -------------------------------------------------------
+class _Leaf2(Function):
+    """Second-order stream as a function of x; differentiating it again is third order."""
+
+    @staticmethod
+    def forward(ctx, x, h):
+        return h.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.needs_input_grad[0] and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "third- and higher-order derivatives of the network are not in the fused jet "
+                "kernels (second order is the compiled maximum)"
+            )
+        return None, g
+
+
+class _Leaf1(Function):
+    """First-order stream j as a function of x: d/dx_k = second-order stream (j, k)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, j, fj, *seconds):
+        ctx.spec, ctx.j = spec, j
+        ctx.save_for_backward(x, *seconds)
+        return fj.clone()
+
+    @staticmethod
+    def backward(ctx, gd):
+        x, *seconds = ctx.saved_tensors
+        spec, j = ctx.spec, ctx.j
+        gx = None
+        if ctx.needs_input_grad[0]:
+            cols = []
+            dj = spec.dirs[j]
+            for dim in range(x.shape[1]):
+                q = spec.second_of_dims.get((dj, dim))
+                if q is None:
+                    cols.append(torch.zeros_like(gd[:, 0]))
+                    continue
+                h = seconds[q]
+                if torch.is_grad_enabled():
+                    h = _Leaf2.apply(x, h)
+                cols.append((gd * h).sum(dim=1))
+            gx = torch.stack(cols, dim=1)
+        return (gx, None, None, gd) + (None,) * len(seconds)
+
+
+class _Leaf0(Function):
+    """Network output as a function of x whose x-derivatives are the kernel's jets."""
+
+    @staticmethod
+    def forward(ctx, x, spec, value, *streams):
+        ctx.spec = spec
+        ctx.save_for_backward(x, *streams)
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, *streams = ctx.saved_tensors
+        spec = ctx.spec
+        gx = None
+        if ctx.needs_input_grad[0]:
+            cols = []
+            for dim in range(x.shape[1]):
+                j = spec.first_of_dim.get(dim)
+                if j is None:
+                    cols.append(torch.zeros_like(gy[:, 0]))
+                    continue
+                fj = streams[j]
+                if torch.is_grad_enabled():
+                    fj = _Leaf1.apply(x, spec, j, fj, *streams[spec.n1:])
+                cols.append((gy * fj).sum(dim=1))
+            gx = torch.stack(cols, dim=1)
+        return (gx, None, gy) + (None,) * len(streams)
+
+
+class JetOutput:
+    """Record kept per network evaluation so dde.grad.jacobian/hessian can read the streams
+    directly when asked about the raw network output (no output transform in between)."""
+
+    __slots__ = ("x", "spec", "streams")
+
+    def __init__(self, x, spec, streams):
+        self.x, self.spec, self.streams = x, spec, streams
+
+    def first(self, comp, dim):
+        j = self.spec.first_of_dim.get(dim)
+        if j is None:
+            return None
+        return self.streams[1 + j][:, comp : comp + 1]
+
+    def first_all(self, comp):
+        """(n, d_in) Jacobian row of component `comp`, or None if a column is not carried."""
+        cols = []
+        for dim in range(self.x.shape[1]):
+            c = self.first(comp, dim)
+            if c is None:
+                return None
+            cols.append(c)
+        return torch.cat(cols, dim=1)
+
+    def second(self, comp, dim_i, dim_j):
+        q = self.spec.second_of_dims.get((dim_i, dim_j))
+        if q is None:
+            return None
+        return self.streams[1 + self.spec.n1 + q][:, comp : comp + 1]
+
+
+def make_leaf(x, spec, streams):
+    """streams: S tensors (n, C). Returns y (n, C) differentiable w.r.t. x via the streams."""
+    return _Leaf0.apply(x, spec, streams[0], *streams[1:])
+
+
+def probe_streams(x, n_out, fn):
+    """Find which derivative streams `fn(x, y)` really uses.
+
+    fn receives the input tensor and a stand-in network output whose value / first / second
+    derivative streams are independent random tensors, and must return the tensors that the
+    training loss (or the predict operator) is built from.  A stream is needed iff the result
+    has a non-zero gradient w.r.t. it.  Returns JetSpec.covering(...).  No kernel is involved.
+    """
+    n, d = x.shape
+    if d > _lib.MAX_FIRST:
+        # cannot even express the full second-order set; probe first order only
+        raise NotImplementedError(f"probe for d_in={d} > {_lib.MAX_FIRST} inputs")
+    full = JetSpec.full(d)
+    gen = torch.Generator(device=x.device)
+    gen.manual_seed(1234)
+    mk = lambda: torch.randn((n, n_out), dtype=x.dtype, device=x.device, generator=gen).requires_grad_()
+    streams = [mk() for _ in range(full.S)]
+    with torch.enable_grad():
+        y = make_leaf(x, full, streams)
+        outs = fn(x, y)
+        if not isinstance(outs, (list, tuple)):
+            outs = [outs]
+        total = None
+        for o in outs:
+            if o is None or not torch.is_tensor(o) or not o.requires_grad:
+                continue
+            t = (o.to(x.dtype) ** 2).sum()
+            total = t if total is None else total + t
+        if total is None:
+            return JetSpec.value_only()
+        grads = torch.autograd.grad(total, streams[1:], allow_unused=True)
+    need1, need2 = [], []
+    for j in range(full.n1):
+        g = grads[j]
+        if g is not None and bool((g != 0).any()):
+            need1.append(full.dirs[j])
+    for q, (a, b) in enumerate(full.pairs):
+        g = grads[full.n1 + q]
+        if g is not None and bool((g != 0).any()):
+            need2.append((full.dirs[a], full.dirs[b]))
+    return JetSpec.covering(need1, need2)

@@ -1,0 +1,152 @@
+/*
+ * ai4xde_b200.h -- C ABI of the B200-native PINN residual hot path.
+ *
+ * The reference (AI4XDE, pure Python on DeepXDE/PyTorch) has no FFI; the seams this
+ * library replaces are Python attribute look-ups.  Every entry
+ * point below names the reference call it stands in for (paths relative to
+ * /root/reference/).  Conventions: plain pointers and sizes only; every pointer is a
+ * DEVICE pointer unless its name starts with h_; the caller owns every buffer; nothing
+ * is allocated behind the caller's back (query ax_*_bytes first); work is enqueued on
+ * `stream` (a cudaStream_t passed as void*) and the call returns without synchronising
+ * unless stated; return value 0 = ok, non-zero = error with text in ax_last_error().
+ *
+ * Layouts (all float32 unless stated, `ldn` = padded point count, multiple of 32):
+ *   x_soa    [d_in][ldn]                     collocation points, structure-of-arrays
+ *   params   [n_nets][P]                     per net: W0 (out,in) row-major, b0, W1, b1 ...
+ *                                            == torch.nn.Linear order (dde.nn.FNN)
+ *   jets     [n_nets][S][d_out][ldn]         stream 0 = value, 1..n1 = first order,
+ *                                            n1+1.. = second order (ax_jet_desc order)
+ *   stash    [n_nets][L][S][H_max][ldn]      per hidden layer: slot 0 = activation value
+ *                                            (tanh/sigmoid) or pre-activation (sin);
+ *                                            slots 1.. = pre-activation derivative streams
+ */
+#ifndef AI4XDE_B200_H
+#define AI4XDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AX_MAX_LINEAR 16
+#define AX_MAX_FIRST 4
+#define AX_MAX_SECOND 10
+
+enum { AX_ACT_TANH = 0, AX_ACT_SIN = 1, AX_ACT_SIGMOID = 2 };
+/* arithmetic engines: FP32 FMA (any width) or tcgen05 tensor cores (hidden width multiple of 64) */
+enum { AX_ENGINE_AUTO = 0, AX_ENGINE_FP32 = 1, AX_ENGINE_TF32 = 2, AX_ENGINE_TF32X3 = 3 };
+
+/* dde.nn.FNN(layer_size, activation, initializer): cases/PDECases.py:38-42 */
+typedef struct ax_net_desc {
+  int32_t n_linear;                  /* number of Linear layers (hidden layers + 1) */
+  int32_t widths[AX_MAX_LINEAR + 1]; /* widths[0]=d_in ... widths[n_linear]=d_out */
+  int32_t activation;                /* AX_ACT_* */
+  int32_t n_nets;                    /* K nets evaluated on the same points (FBPINN) */
+} ax_net_desc;
+
+/* which derivatives the case's pde()/BCs ask of dde.grad.jacobian / hessian */
+typedef struct ax_jet_desc {
+  int32_t n1;                  /* first-order streams */
+  int32_t dir1[AX_MAX_FIRST];  /* input coordinate differentiated by first-order stream j */
+  int32_t n2;                  /* second-order streams */
+  int32_t pa[AX_MAX_SECOND];   /* stream q is d2/d(dir1[pa[q]]) d(dir1[pb[q]]), pa<=pb */
+  int32_t pb[AX_MAX_SECOND];
+} ax_jet_desc;
+
+int ax_version(void);
+const char *ax_last_error(void);
+
+/* parameters per net, == sum(p.numel() for p in net.parameters()) */
+int64_t ax_param_count(const ax_net_desc *net);
+/* 1 if (n1, pa, pb) is one of the compiled stream patterns, else 0 */
+int ax_jet_supported(const ax_jet_desc *jet);
+/* 1 if the tensor-core engine can run this net (sm_100a tcgen05 path), else 0 */
+int ax_engine_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engine);
+
+size_t ax_stash_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all_layers);
+size_t ax_forward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
+size_t ax_backward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
+
+/*
+ * Fused Taylor-mode forward of the tanh/sin MLP: value + requested derivative streams.
+ * Replaces  outputs = net(inputs)  together with every later
+ * dde.grad.jacobian(outputs, inputs, i, j) / dde.grad.hessian(outputs, inputs, component, i, j)
+ * of the case's pde (e.g. cases/PDECases.py:1087-1094) -- [DeepXDE] Jacobian/Hessian via
+ * torch.autograd.grad(create_graph=True).
+ * keep_all_layers=1 keeps every hidden layer in `stash` for ax_jet_mlp_backward;
+ * 0 ping-pongs two layers (forward-only probes: model.predict(X, operator=pde),
+ * algorithm/RAD.py:26, R3Sampling.py:78).
+ */
+int ax_jet_mlp_forward(const ax_net_desc *net, const ax_jet_desc *jet, const float *params,
+                       const float *x_soa, int64_t n, int64_t ldn, float *jets, float *stash,
+                       int keep_all_layers, void *ws, size_t ws_bytes, int engine, void *stream);
+
+/*
+ * Matching reverse pass: parameter gradient of  sum(jets * jets_bar).
+ * Replaces the part of  total_loss.backward()  (algorithm/FBPINN.py:178-184 shows the
+ * DeepXDE closure) that runs through the network and its double-backward graph.
+ * grad_params [n_nets][P] is OVERWRITTEN (deterministic two-level reduction).
+ */
+int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const float *params,
+                        const float *x_soa, int64_t n, int64_t ldn, const float *jets_bar,
+                        const float *stash, float *grad_params, void *ws, size_t ws_bytes,
+                        int engine, void *stream);
+
+/* ---- residual-driven resampling, device resident ------------------------------------- */
+
+/* scratch for the resampling entry points below (covers all of them for n elements) */
+size_t ax_resample_ws_bytes(int64_t n);
+
+/*
+ * NumPy-order sums.  ax_pairwise_sum_* reproduces np.add.reduce / ndarray.mean()'s pairwise
+ * rounding order bit for bit (the order behind algorithm/RAD.py:31 `.mean()` and
+ * R3Sampling.py:91 `np.mean(res)`); result written to out[0] (device).
+ */
+int ax_pairwise_sum_f32(const float *a, int64_t n, float *out, void *ws, size_t ws_bytes, void *stream);
+int ax_pairwise_sum_f64(const double *a, int64_t n, double *out, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * RAD / RAR_D probability (algorithm/RAD.py:26-32, RAR_D.py:24-28):
+ *   Y = sum_r |res_r| (float64);  e = Y^k / mean(Y^k) + c;  p = e / sum(e)
+ * res: [n_res][ldr] float32 residuals, p_out: [n] float64.  mean is NumPy-pairwise, sum(e) is
+ * the sequential left-to-right float64 sum of Python's builtin sum (RAD.py:32).
+ */
+int ax_rad_probabilities(const float *res, int32_t n_res, int64_t ldr, int64_t n, double k, double c,
+                         double *p_out, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * One round of the legacy numpy.random.choice(n, size, replace=False, p=p) loop body
+ * (algorithm/RAD.py:33-38): zero p at `found[0:n_found]`, cdf = cumsum(p) (sequential
+ * float64, as NumPy), cdf /= cdf[-1], new = searchsorted(cdf, u, 'right'), keep first
+ * occurrences in draw order.  u: [n_draw] float64 uniforms from the caller's RNG stream
+ * (np.random.random_sample in parity mode).  Appends to found[n_found...] and writes the new
+ * total to n_found_out[0] (device int64).  p is modified in place (zeroing), as in NumPy.
+ */
+int ax_choice_round(double *p, int64_t n, const double *u, int64_t n_draw, int64_t *found,
+                    int64_t n_found, int64_t *n_found_out, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * R3 retain step (algorithm/R3Sampling.py:77-93): res = sum_r |res_r|; thr = mean(res)
+ * (NumPy pairwise order, float32); keep = res > thr; x_out[:, 0:n_keep] = x[:, keep]
+ * compacted in order (at columns [n-n_keep, n) when place_at_end, leaving [0, n-n_keep) for the
+ * refill, i.e. train_x_all = [new ; retained], R3Sampling.py:95-98).  x, x_out: [d][ldn] SoA.
+ * n_keep_out[0] (device int64), thr_out[0], res_sum_out [n].
+ */
+int ax_r3_retain(const float *res, int32_t n_res, int64_t ldr, const float *x_soa, int32_t d,
+                 int64_t n, int64_t ldn, float *x_out, int64_t ldn_out, int32_t place_at_end,
+                 int64_t *n_keep_out, float *thr_out, float *res_sum_out, void *ws, size_t ws_bytes,
+                 void *stream);
+
+/* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
+int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
+                     float *x_out, int64_t ldn_out, void *stream);
+
+/* kernels launched by this library since load (the bench's gpu_launches counter) */
+int64_t ax_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AI4XDE_B200_H */

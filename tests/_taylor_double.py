@@ -1,0 +1,97 @@
+"""Plain-PyTorch Taylor-mode stand-in for the two kernel entry points (test double).
+
+Same signatures as ai4xde_b200._lib.jet_forward / jet_backward, same tensor layouts, computed
+with ordinary torch ops (any device, any float dtype).  Two uses, both in tests only:
+  * `not gpu` tests monkey-patch it under the product's host code to exercise the boundary
+    (stream discovery, grad interception, losses, Model loops, resamplers' host logic) on CPU;
+  * `gpu` tests use it as the plain-PyTorch reference of the fused op.
+It is never imported by the product package.
+"""
+import torch
+
+
+def _act(name, z):
+    if name == 0:
+        a = torch.tanh(z)
+        s1 = 1 - a * a
+        s2 = -2 * a * s1
+    elif name == 1:
+        a = torch.sin(z)
+        s1 = torch.cos(z)
+        s2 = -a
+    else:
+        a = torch.sigmoid(z)
+        s1 = a * (1 - a)
+        s2 = s1 * (1 - 2 * a)
+    return a, s1, s2
+
+
+def _unpack(net, flat):
+    ws, off = [], 0
+    for l in range(net.n_linear):
+        i, o = net.widths[l], net.widths[l + 1]
+        W = flat[off : off + i * o].view(o, i)
+        off += i * o
+        b = flat[off : off + o]
+        off += o
+        ws.append((W, b))
+    return ws
+
+
+def taylor_streams(net, jet, flat, x):
+    """flat: [P] params, x: (n, d) -> list of S tensors (n, C)."""
+    n1, n2 = jet.n1, jet.n2
+    dirs = [jet.dir1[j] for j in range(n1)]
+    pairs = [(jet.pa[q], jet.pb[q]) for q in range(n2)]
+    layers = _unpack(net, flat)
+    W, b = layers[0]
+    z = [x @ W.t() + b]
+    z += [W[:, d].unsqueeze(0).expand(x.shape[0], -1) for d in dirs]
+    z += [torch.zeros_like(z[0]) for _ in pairs]
+    for W, b in layers[1:]:
+        a, s1, s2 = _act(net.activation, z[0])
+        A = [a] + [s1 * z[1 + j] for j in range(n1)]
+        A += [s2 * z[1 + pa] * z[1 + pb] + s1 * z[1 + n1 + q] for q, (pa, pb) in enumerate(pairs)]
+        z = [A[0] @ W.t() + b] + [As @ W.t() for As in A[1:]]
+    return z
+
+
+def jet_forward(net, jet, params, x_soa, n, keep_all, engine="auto"):
+    K = net.n_nets
+    S = 1 + jet.n1 + jet.n2
+    C = net.widths[net.n_linear]
+    ldn = x_soa.shape[1]
+    x = x_soa[:, :n].t()
+    jets = torch.zeros((K, S, C, ldn), dtype=params.dtype, device=params.device)
+    with torch.no_grad():
+        for k in range(K):
+            st = taylor_streams(net, jet, params[k], x)
+            for s in range(S):
+                jets[k, s, :, :n] = st[s].t()
+    return jets, torch.zeros(1)
+
+
+def jet_backward(net, jet, params, x_soa, n, jets_bar, stash, engine="auto"):
+    K = net.n_nets
+    S = 1 + jet.n1 + jet.n2
+    x = x_soa[:, :n].t()
+    grads = []
+    for k in range(K):
+        p = params[k].detach().clone().requires_grad_()
+        with torch.enable_grad():
+            st = taylor_streams(net, jet, p, x)
+            tot = sum((st[s].t() * jets_bar[k, s, :, :n]).sum() for s in range(S))
+            (g,) = torch.autograd.grad(tot, p)
+        grads.append(g)
+    return torch.stack(grads)
+
+
+def install(monkeypatch=None):
+    """Route the product's kernel calls to this double (CPU host-logic tests only)."""
+    from ai4xde_b200 import _lib
+
+    if monkeypatch is not None:
+        monkeypatch.setattr(_lib, "jet_forward", jet_forward)
+        monkeypatch.setattr(_lib, "jet_backward", jet_backward)
+    else:
+        _lib.jet_forward, _lib.jet_backward = jet_forward, jet_backward

@@ -1,0 +1,93 @@
+"""Shared helper of the parity tests, smoke() and the bench: build one BASELINE config on the
+oracle (CPU, float64) and on the product (fused path) with IDENTICAL points and weights, and
+compare residuals, per-term losses and the flat parameter gradient."""
+import numpy as np
+import torch
+
+
+def build_product(cfg, odata, onet, soft=True):
+    """Product-side twin of oracle.cases.build(cfg): same points (as anchors), same weights."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    ls = [l.in_features for l in onet.linears] + [onet.linears[-1].out_features]
+    n_all = len(odata.train_x_all)
+    if cfg == "cfg1":
+        case = pc.Burgers(NumDomain=0, layer_size=ls, soft_constraints=True)
+        gt = case.geomtime
+        data = dde.data.TimePDE(gt, case.pde, case.data.bcs, num_domain=0, anchors=odata.train_x_all,
+                                train_distribution="pseudo")
+    elif cfg == "cfg2":
+        case = pc.AllenCahn(NumDomain=0, layer_size=ls)
+        data = dde.data.TimePDE(case.geomtime, case.pde, [], num_domain=0, anchors=odata.train_x_all,
+                                train_distribution="pseudo")
+    elif cfg == "cfg3":
+        case = pc.NS_Flow_in_LidDriven_Cavity(NumDomain=1, layer_size=ls, train_distribution="pseudo")
+        data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=odata.train_x_all,
+                            train_distribution="pseudo")
+    elif cfg == "cfg4":
+        case = pc.Helmholtz(NumDomain=1, layer_size=ls, activation="tanh", honor_num_domain=True)
+        data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=odata.train_x_all,
+                            train_distribution="pseudo", solution=case.sol)
+    elif cfg == "cfg5":
+        case = pc.Poisson_1D_Fourier_Net(NumDomain=1, layer_size=ls)
+        data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=odata.train_x_all,
+                            train_distribution="pseudo", solution=case.sol)
+    else:
+        raise KeyError(cfg)
+    assert len(data.train_x_all) == n_all
+    case.data = data
+    case.net.load_state_dict({k: v.detach().float() for k, v in onet.state_dict().items()})
+    return case
+
+
+def product_vs_oracle(cfg, n_domain, engine="fp32", seed=0, oracle_dtype="float64"):
+    from oracle import cases as oc, ddelite
+    import ai4xde_b200.dde as dde
+
+    prev = ddelite.config.default_float()
+    ddelite.config.set_default_float(oracle_dtype)
+    try:
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        odata, onet, _ = oc.build(cfg, n_domain)
+        lw = oc.LOSS_WEIGHTS.get(cfg)
+        ref = oc.train_step_outputs(odata, onet, lw)
+    finally:
+        ddelite.config.set_default_float(prev)
+        torch.set_default_dtype(torch.float32)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dde.config.set_default_float("float64")  # host point sets as in the reference; device math is f32
+    case = build_product(cfg, odata, onet)
+    dde.config.set_engine(engine)
+    try:
+        model = dde.Model(case.data, case.net)
+        model.compile("adam", lr=1e-3, loss_weights=lw)
+        assert np.array_equal(case.data.train_x.astype(np.float64), odata.train_x.astype(np.float64))
+        res = model.predict_on_device(case.data.train_x, case.pde)
+        res = list(res) if isinstance(res, (list, tuple)) else [res]
+        outs, losses = model.outputs_losses_train(case.data.train_x, None, None)
+        case.net.zero_grad()
+        losses.sum().backward()
+        g = torch.cat([p.grad.reshape(-1) for p in case.net.parameters()]).double().cpu().numpy()
+    finally:
+        dde.config.set_engine("auto")
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+    res_rel = max(rel(r.double().cpu().numpy(), rr) for r, rr in zip(res, ref["residuals"]))
+    return {
+        "loss_rel": rel(losses.detach().double().cpu().numpy(), ref["losses"]),
+        "grad_rel": rel(g, ref["grad"]),
+        "res_rel": res_rel,
+        "out_rel": rel(outs.detach().double().cpu().numpy(), ref["outputs"]),
+        "n_rows": len(case.data.train_x),
+        "losses": losses.detach().cpu().numpy(),
+        "ref_losses": ref["losses"],
+        "model": model,
+        "case": case,
+    }

@@ -1,0 +1,149 @@
+"""GPU parity of the C-ABI kernels (called through ai4xde_b200._lib) against the plain-PyTorch
+Taylor-mode double in float64 and against NumPy for the resampling entry points."""
+import numpy as np
+import pytest
+import torch
+
+import _taylor_double as td
+from ai4xde_b200 import _lib
+from ai4xde_b200.jet import JetSpec, to_soa
+
+pytestmark = pytest.mark.gpu
+
+SPECS = {
+    "v": ((), ()),
+    "1": ((0,), ()),
+    "1d": ((0,), ((0, 0),)),
+    "2": ((0, 1), ()),
+    "2a": ((1, 0), ((0, 0),)),
+    "2d": ((0, 1), ((0, 0), (1, 1))),
+    "2f": ((0, 1), ((0, 0), (0, 1), (1, 1))),
+    "3d": ((0, 1, 2), ((0, 0), (1, 1), (2, 2))),
+    "3f": ((0, 1, 2), ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))),
+    "4f": ((0, 1, 2, 3), tuple((a, b) for a in range(4) for b in range(a, 4))),
+}
+
+CASES = [
+    # widths, activation, spec, n, n_nets
+    ([2, 20, 20, 20, 1], "tanh", "2a", 3020, 1),
+    ([2, 64, 64, 64, 64, 1], "tanh", "2a", 1000, 1),
+    ([2, 128, 128, 3], "tanh", "2d", 777, 1),
+    ([2, 256, 256, 256, 1], "tanh", "2d", 515, 1),
+    ([2, 150, 150, 1], "sin", "2d", 300, 1),
+    ([1, 64, 64, 64, 1], "tanh", "1d", 2048, 4),
+    ([2, 50, 50, 50, 50, 3], "tanh", "2f", 333, 1),
+    ([3, 33, 17, 2], "sigmoid", "3d", 100, 1),
+    ([3, 40, 40, 2], "tanh", "3f", 65, 1),
+    ([4, 50, 50, 4], "tanh", "4f", 130, 1),
+    ([2, 32, 32, 1], "tanh", "v", 1, 1),
+    ([1, 20, 20, 1], "tanh", "1", 31, 2),
+    ([2, 20, 20, 1], "tanh", "2", 33, 1),
+]
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("widths,act,spec,n,k", CASES)
+def test_jet_forward_backward_fp32(widths, act, spec, n, k):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7)
+    dirs, pairs = SPECS[spec]
+    js = JetSpec(dirs, pairs)
+    net = _lib.make_net_desc(widths, act, n_nets=k)
+    P = _lib.param_count(net)
+    params = (torch.randn((k, P), generator=g) * 0.3).to(dev)
+    x = (torch.rand((n, widths[0]), generator=g) * 2 - 1).to(dev)
+    x_soa = to_soa(x)
+    jets, stash = _lib.jet_forward(net, js.desc, params, x_soa, n, keep_all=True, engine="fp32")
+    ref, _ = td.jet_forward(net, js.desc, params.double(), x_soa.double(), n, True)
+    assert _rel(jets[..., :n].double(), ref[..., :n]) < 1e-5
+    # forward-only (ping-pong stash) must agree bit for bit with the stash-everything run
+    jets2, _ = _lib.jet_forward(net, js.desc, params, x_soa, n, keep_all=False, engine="fp32")
+    assert torch.equal(jets2[..., :n], jets[..., :n])
+    jets_bar = torch.randn(jets.shape, generator=g).to(dev)
+    jets_bar[..., n:] = 0
+    grad = _lib.jet_backward(net, js.desc, params, x_soa, n, jets_bar, stash, engine="fp32")
+    gref = td.jet_backward(net, js.desc, params.double(), x_soa.double(), n, jets_bar.double(), None)
+    assert _rel(grad.double(), gref) < 2e-5
+    # deterministic reduction: a second run gives the same bits
+    grad2 = _lib.jet_backward(net, js.desc, params, x_soa, n, jets_bar, stash, engine="fp32")
+    assert torch.equal(grad, grad2)
+
+
+def test_unsupported_requests_fail_loudly():
+    net = _lib.make_net_desc([2, 8, 1], "tanh")
+    bad = _lib.make_jet_desc((0, 1), ((1, 1),))  # not a compiled pattern
+    assert not _lib.jet_supported(bad)
+    dev = torch.device("cuda:0")
+    with pytest.raises(_lib.NativeLibraryError):
+        _lib.jet_forward(net, bad, torch.zeros((1, 33), device=dev), torch.zeros((2, 32), device=dev), 4, True)
+    with pytest.raises(_lib.NativeLibraryError):
+        _lib.jet_forward(net, JetSpec((0,), ()).desc, torch.zeros((1, 33)), torch.zeros((2, 32)), 4, True)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 128, 129, 1000, 4097, 100000, 2**20 + 80])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_pairwise_sum_matches_numpy(n, dtype):
+    rng = np.random.RandomState(n)
+    a = rng.rand(n).astype(np.float32 if dtype == torch.float32 else np.float64)
+    got = _lib.pairwise_sum(torch.as_tensor(a).cuda()).item()
+    want = np.add.reduce(a)
+    assert got == want
+
+
+@pytest.mark.parametrize("n,m,k,c,nres", [(20000, 2000, 1, 1, 1), (100000, 10000, 1, 1, 1),
+                                          (100000, 20, 2, 0, 1), (1000, 999, 1, 1, 1), (5000, 500, 1, 1, 3)])
+def test_rad_selection_bit_exact(n, m, k, c, nres):
+    from oracle import sampling
+
+    rng = np.random.RandomState(3)
+    res = (rng.randn(nres, n, 1) * np.exp(rng.randn(nres, n, 1))).astype(np.float32)
+    X = rng.rand(n, 2)
+    np.random.seed(11)
+    residual = res[0] if nres == 1 else [r for r in res]
+    ids_ref, _ = sampling.rad_select(X, residual, m, k=k, c=c)
+    p_ref = sampling.rad_probabilities(
+        np.abs(res[0]).astype(np.float64) if nres == 1 else np.sum(np.abs(res).astype(np.float64), axis=0), k, c)
+
+    dev = torch.device("cuda:0")
+    ldr = _lib.pad32(n)
+    r = torch.zeros((nres, ldr), dtype=torch.float32, device=dev)
+    r[:, :n] = torch.as_tensor(res[:, :, 0]).to(dev)
+    p = _lib.rad_probabilities(r, n, k, c)
+    assert np.array_equal(p.cpu().numpy(), p_ref)
+    np.random.seed(11)
+    found = torch.zeros((m,), dtype=torch.int64, device=dev)
+    n_found_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+    ws, wsb = _lib.resample_ws(n, dev)
+    n_found = 0
+    while n_found < m:
+        u = torch.as_tensor(np.random.random_sample(m - n_found)).to(dev)
+        _lib.choice_round(p, u, found, n_found, n_found_dev, ws, wsb)
+        n_found = int(n_found_dev.item())
+    assert np.array_equal(found.cpu().numpy(), ids_ref)
+
+
+@pytest.mark.parametrize("n,nres", [(1000, 1), (100000, 1), (2**20 + 80, 1), (4097, 3)])
+def test_r3_retain_bit_exact(n, nres):
+    from oracle import sampling
+
+    rng = np.random.RandomState(5)
+    res = (rng.randn(nres, n, 1) * np.exp(rng.randn(nres, n, 1))).astype(np.float32)
+    X = rng.rand(n, 2).astype(np.float32)
+    rs = sampling.r3_residual(res[0] if nres == 1 else res)
+    thr, keep, Xr = sampling.r3_select(X, rs)
+
+    dev = torch.device("cuda:0")
+    ldn = _lib.pad32(n)
+    r = torch.zeros((nres, ldn), dtype=torch.float32, device=dev)
+    r[:, :n] = torch.as_tensor(res[:, :, 0]).to(dev)
+    x_soa = to_soa(torch.as_tensor(X).to(dev))
+    x_out, n_keep, thr_d, res_sum = _lib.r3_retain(r, x_soa, n, place_at_end=True)
+    nk = int(n_keep.item())
+    assert thr_d.item() == thr
+    assert np.array_equal(res_sum.cpu().numpy(), rs.astype(np.float32))
+    assert nk == int(keep.sum())
+    got = x_out[:, n - nk : n].t().cpu().numpy()
+    assert np.array_equal(got, Xr)
