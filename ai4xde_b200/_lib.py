@@ -41,6 +41,8 @@ _SIGNATURES = {
     "ax_version": (C.c_int, []),
     "ax_last_error": (C.c_char_p, []),
     "ax_launch_count": (C.c_int64, []),
+    "ax_timing_enable": (None, [C.c_int]),
+    "ax_timing_report": (C.c_int64, [C.c_char_p, C.c_int64]),
     "ax_param_count": (C.c_int64, [C.POINTER(NetDesc)]),
     "ax_jet_supported": (C.c_int, [C.POINTER(JetDesc)]),
     "ax_engine_supported": (C.c_int, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int]),
@@ -173,6 +175,21 @@ def engine_supported(net, jet, engine):
 
 def launch_count():
     return int(load().ax_launch_count())
+
+
+def timing_enable(on):
+    load().ax_timing_enable(int(bool(on)))
+
+
+def timing_report():
+    """{kernel: {launches, ms, flops, bytes}} for the launches since the last report."""
+    import json
+
+    lib = load()
+    need = lib.ax_timing_report(None, 0)
+    buf = C.create_string_buffer(int(need) + 4096)
+    lib.ax_timing_report(buf, len(buf))
+    return json.loads(buf.value.decode())
 
 
 def pad32(n):

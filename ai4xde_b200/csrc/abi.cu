@@ -3,6 +3,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "simt_kernels.cuh"
@@ -20,6 +24,34 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-kernel timing ------------------------------------------------------------------
+struct TimedRec {
+  const char *name;
+  cudaEvent_t beg, end;
+  double flops, bytes;
+};
+static bool g_timing = false;
+static std::vector<TimedRec> g_recs;
+static std::mutex g_timing_mu;
+
+KernelTimer::KernelTimer(const char *name, cudaStream_t st, double flops, double bytes) : slot(-1), stream(st) {
+  if (!g_timing) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  TimedRec r;
+  r.name = name;
+  r.flops = flops;
+  r.bytes = bytes;
+  if (cudaEventCreate(&r.beg) != cudaSuccess || cudaEventCreate(&r.end) != cudaSuccess) return;
+  cudaEventRecord(r.beg, st);
+  g_recs.push_back(r);
+  slot = (int)g_recs.size() - 1;
+}
+KernelTimer::~KernelTimer() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  cudaEventRecord(g_recs[slot].end, stream);
+}
 
 int make_geom(const ax_net_desc *net, NetGeom *g) {
   if (!net || net->n_linear < 2 || net->n_linear > AX_MAX_LINEAR) {
@@ -128,6 +160,53 @@ extern "C" {
 int ax_version(void) { return 100; }
 const char *ax_last_error(void) { return g_err; }
 int64_t ax_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void ax_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing = on != 0;
+}
+
+// Synchronises the device, aggregates the recorded launches by kernel name into a JSON object
+// {"name": {"launches": n, "ms": total, "flops": total, "bytes": total}, ...}, clears the records.
+// Returns the number of bytes needed (including the terminator); writes at most `cap` bytes.
+int64_t ax_timing_report(char *buf, int64_t cap) {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  struct Agg {
+    long long n = 0;
+    double ms = 0, flops = 0, bytes = 0;
+  };
+  std::map<std::string, Agg> agg;
+  for (auto &r : g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.beg, r.end) == cudaSuccess) {
+      Agg &a = agg[r.name];
+      a.n += 1;
+      a.ms += ms;
+      a.flops += r.flops;
+      a.bytes += r.bytes;
+    }
+    cudaEventDestroy(r.beg);
+    cudaEventDestroy(r.end);
+  }
+  g_recs.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto &kv : agg) {
+    char line[512];
+    snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  if (buf && cap > 0) {
+    const int64_t m = (int64_t)out.size() < cap - 1 ? (int64_t)out.size() : cap - 1;
+    memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
 
 int64_t ax_param_count(const ax_net_desc *net) {
   NetGeom g;

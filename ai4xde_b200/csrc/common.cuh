@@ -31,6 +31,14 @@ void count_launch(int n = 1);
     ax::count_launch();                                                               \
   } while (0)
 
+// ---- optional per-kernel timing (CUDA events on the launching stream; bench.py reads it) ----
+struct KernelTimer {
+  KernelTimer(const char *name, cudaStream_t stream, double flops = 0.0, double bytes = 0.0);
+  ~KernelTimer();
+  int slot;
+  cudaStream_t stream;
+};
+
 // ---- compile-time stream patterns -------------------------------------------------------
 // Stream s=0 is the value; s=1..N1 first-order; s=1+N1+q second-order stream q that
 // differentiates along first-order streams pa(q) and pb(q) (4 bits each, packed).

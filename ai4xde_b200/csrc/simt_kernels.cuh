@@ -316,6 +316,9 @@ __global__ void k_reduce_partials(const float *__restrict__ partial, int64_t par
 template <class P, int MODE>
 static int launch_layer(const LayerArgs &la, int n_nets, cudaStream_t stream) {
   const int64_t ptiles = (la.n + 31) / 32;
+  KernelTimer timer(MODE == MODE_DGRAD ? "simt_layer_dgrad" : (MODE == MODE_FWD_ACT ? "simt_layer_fwd" : "simt_layer_out"),
+                    stream, 2.0 * P::S * la.Kdim * la.Ndim * (double)la.n * n_nets,
+                    4.0 * P::S * ((double)la.Kdim + la.Ndim * (MODE == MODE_DGRAD ? 2.0 : 1.0)) * (double)la.n * n_nets);
   if (P::S <= 6) {
     constexpr int UI = 8, NW = 8;
     dim3 grid((unsigned)ptiles, (unsigned)((la.Ndim + UI * NW - 1) / (UI * NW)), (unsigned)n_nets);
@@ -354,9 +357,13 @@ int simt_forward(const FwdArgs &a) {
   {
     dim3 grid((unsigned)((a.n + 255) / 256), (unsigned)((g.widths[1] + kFirstUnits - 1) / kFirstUnits),
               (unsigned)K);
-    k_first_layer<P><<<grid, 256, 0, a.stream>>>(a.params, g.P, g.w_off[0], g.b_off[0], a.x,
-                                                 g.widths[0], make_dirs(a.jet), g.widths[1], a.n,
-                                                 a.ldn, slot(0), stash_net_stride, act);
+    {
+      KernelTimer timer("simt_first_layer", a.stream, 2.0 * g.widths[0] * g.widths[1] * (double)a.n * K,
+                        4.0 * S * g.widths[1] * (double)a.n * K);
+      k_first_layer<P><<<grid, 256, 0, a.stream>>>(a.params, g.P, g.w_off[0], g.b_off[0], a.x,
+                                                   g.widths[0], make_dirs(a.jet), g.widths[1], a.n,
+                                                   a.ldn, slot(0), stash_net_stride, act);
+    }
     AX_LAUNCH_OK();
   }
   for (int l = 1; l < g.L; ++l) {
@@ -437,7 +444,11 @@ static int launch_wgrad(WgradArgs wa, int n_nets, float *grad, int64_t p_stride,
   wa.partial_net_stride = count * pl.nsplit;
   dim3 grid((unsigned)((wa.Hout + 63) / 64), (unsigned)((wa.Hin + 63) / 64),
             (unsigned)(pl.nsplit * n_nets));
-  k_wgrad<P, PC><<<grid, 256, smem, stream>>>(wa);
+  {
+    KernelTimer timer("simt_wgrad", stream, 2.0 * P::S * wa.Hout * wa.Hin * (double)wa.n * n_nets,
+                      4.0 * P::S * ((double)wa.Hout + wa.Hin) * (double)wa.n * n_nets);
+    k_wgrad<P, PC><<<grid, 256, smem, stream>>>(wa);
+  }
   AX_LAUNCH_OK();
   dim3 rg((unsigned)((count + 255) / 256), (unsigned)n_nets);
   k_reduce_partials<<<rg, 256, 0, stream>>>(wa.partial, wa.partial_net_stride,

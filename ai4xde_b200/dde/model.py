@@ -95,6 +95,7 @@ class Model:
         self._batches = []      # small LRU of _DeviceBatch
         self._specs = {}        # stream sets by use
         self._weights_dev = None
+        self.last_total_loss = None  # device scalar of the most recent closure evaluation
 
     # ---- device mirror -----------------------------------------------------------------------
     def device_batch(self, inputs):
@@ -221,6 +222,7 @@ class Model:
                 self.opt.zero_grad()
                 total_loss.backward()
                 _allreduce_grads(trainable)
+                self.last_total_loss = total_loss.detach()
                 return total_loss
 
             self.opt.step(closure)

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- train collocation points/sec (residual + backward) on the BASELINE cfg4 workload:
+Helmholtz 2-D, FNN 2-[256]x6-1 tanh, 2^20 collocation points per GPU (+80 boundary rows),
+loss_weights [1, 100], Adam 1e-3; weak scaling over 1/2/4/8 GPUs (one process per GPU,
+all-reduce of the flat gradient).
+
+One "step" = one optimiser step of dde.Model.train_step on one batch: fused jet forward, the
+case's own pde()/BC code, per-term MSE, fused backward, all-reduce (N>1), Adam.
+  value  : points/s with the batch already resident in HBM when the timed region starts
+  e2e    : same call fed HOST buffers (pinned) every step; host->device copy of the batch and
+           device->host read of the loss inside the timed region
+  roofline: dominant kernel class, algorithmic FLOPs / CUDA-event time (ax_timing_* hooks)
+  cpu_baseline: the oracle (reference restatement: ddelite + torch.autograd, float64) timed on
+           this box's host cores on a bounded sample (N=1, rank 0 only)
+`--impl reference` times that CPU path as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+H, L, S = 256, 6, 5
+P1 = 2 * H
+PREST = (L - 1) * H * H + H * 1
+F_FWD = 2 * (P1 + S * PREST)      # 3 280 384 FLOP / point   
+F_TRAIN = 3 * F_FWD               # 9 841 152 FLOP / point
+WORKLOAD = "cfg4: Helmholtz 2D, FNN 2-[256]x6-1 tanh, 2^20 pts/GPU + 80 bdry, loss_weights [1,100], Adam"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=2**20, help="collocation points per GPU")
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
+    ap.add_argument("--cpu-points", type=int, default=2**11, help="points per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(points, steps, warmup, threads_list=None):
+    """Time the oracle's train step (ddelite + autograd, float64 -- the reference default,
+    /root/reference/AI4XDE/solver/PDESolver.py:6) on host cores.  Returns best over thread counts."""
+    import numpy as np
+    import torch
+    from oracle import cases as oc, ddelite
+
+    cores = os.cpu_count() or 1
+    if threads_list is None:
+        threads_list = sorted({1, max(1, cores // 2), cores})
+    ddelite.config.set_default_float("float64")
+    best = None
+    try:
+        np.random.seed(0)
+        torch.manual_seed(0)
+        data, net, _ = oc.build("cfg4", points)
+        model = ddelite.Model(data, net)
+        model.compile("adam", lr=1e-3, loss_weights=oc.LOSS_WEIGHTS["cfg4"])
+        X = data.train_x
+        for th in threads_list:
+            torch.set_num_threads(th)
+            for _ in range(warmup):
+                model.train_step(X, None, None)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                model.train_step(X, None, None)
+            dt = (time.perf_counter() - t0) / steps
+            if best is None or dt < best[0]:
+                best = (dt, th)
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    dt, th = best
+    return {"value": points / dt, "unit": "points/s", "cores": th, "kind": "port",
+            "sample": f"oracle (ddelite+autograd, float64) train step on {points} pts of the cfg4 net, "
+                      f"{steps} steps after {warmup} warm-up, best of threads {threads_list} "
+                      f"(os.cpu_count()={cores})",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.cpu_points, max(1, args.steps), max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": "train collocation points/sec (residual+backward)",
+        "value": r["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_points_per_step": args.cpu_points},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import warnings
+    warnings.simplefilter("ignore")
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import _lib, cases
+
+    dde.config.set_engine(args.engine)
+    n = args.points
+    np.random.seed(1234 + rank)     # each rank owns its own 2^20 points (weak scaling)
+    torch.manual_seed(0)            # identical weights on every rank
+    case = cases.Helmholtz(NumDomain=n, layer_size=[2] + [H] * L + [1], activation="tanh",
+                           honor_num_domain=True)
+    model = dde.Model(case.data, case.net)
+    case.compile(model, "adam", lr=1e-3)
+    X = case.data.train_x                       # (80 bc rows + 80 + n, 2) host float64
+    rows = X.shape[0]
+    n_pts = case.data.train_x_all.shape[0]      # points counted by the metric (no BC duplicates)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        model.train_step(X, None, None)
+    barrier()
+    launches0 = _lib.launch_count()
+    _lib.timing_enable(True)
+    _lib.timing_report()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        model.train_step(X, None, None)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    kern = _lib.timing_report()
+    _lib.timing_enable(False)
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_step = ms / args.steps
+    value = world * n_pts * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, loss out, every step ----------------------------------
+    host = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).pin_memory()
+    views = [host.view_as(host) for _ in range(args.steps + args.warmup)]   # distinct objects -> no device cache hit
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    for i in range(args.warmup):
+        model.train_step(views[i], None, None)
+        loss_host.copy_(model.last_total_loss, non_blocking=False)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        model.train_step(views[args.warmup + i], None, None)
+        loss_host.copy_(model.last_total_loss, non_blocking=False)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * n_pts * args.steps / (e2e_ms * 1e-3)
+    final_loss = float(loss_host.item())
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense = half the bf16 rate)" if peaks \
+            else "fallback 1.4 PFLOP/s bf16 sustained / 2"
+        tf32_peak = bf16 / 2.0
+        dom = max(kern.items(), key=lambda kv: kv[1]["ms"]) if kern else None
+        roofline = None
+        if dom is not None:
+            name, k = dom
+            achieved = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
+            roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tf32_peak,
+                        "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+                        "peak_source": peak_src, "launches": k["launches"],
+                        "avg_ms_per_launch": k["ms"] / max(1, k["launches"]),
+                        "whole_step_frac": (world * n_pts * F_TRAIN / (ms_step * 1e-3) / 1e12) / (tf32_peak * world),
+                        "kernels": {kk: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                                         "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0}
+                                    for kk, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(args.cpu_points, 3, 1)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": "train collocation points/sec (residual+backward)", "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.engine == "fp32" else "tf32/f32-accumulate (f32 first/last layer)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_per_gpu": n_pts, "rows_per_step": rows, "engine": args.engine,
+                       "l2": "working set (per-layer jet stash, GBs) far exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}", "flop_per_point": F_TRAIN},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "final_loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

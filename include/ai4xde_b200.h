@@ -146,6 +146,15 @@ int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *
 /* kernels launched by this library since load (the bench's gpu_launches counter) */
 int64_t ax_launch_count(void);
 
+/*
+ * Per-kernel device timing for bench.py's roofline line: when enabled every kernel this library
+ * launches is bracketed by CUDA events on the launching stream.  ax_timing_report synchronises
+ * the device and writes a JSON object {"kernel": {"launches","ms","flops","bytes"}} (algorithmic
+ * flops / bytes as stated in DESIGN.md) into h_buf (host), returning the size needed.
+ */
+void ax_timing_enable(int on);
+int64_t ax_timing_report(char *h_buf, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif
