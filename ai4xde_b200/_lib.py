@@ -76,6 +76,7 @@ _SIGNATURES = {
          _P, _P, _P, C.c_size_t, _P],
     ),
     "ax_gather_points": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
+    "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
 }
 
 _lib = None
@@ -186,9 +187,10 @@ def timing_report():
     import json
 
     lib = load()
-    need = lib.ax_timing_report(None, 0)
-    buf = C.create_string_buffer(int(need) + 4096)
-    lib.ax_timing_report(buf, len(buf))
+    buf = C.create_string_buffer(1 << 16)  # one call: the report clears the records
+    need = lib.ax_timing_report(buf, len(buf))
+    if need > len(buf):
+        raise NativeLibraryError("timing report truncated")
     return json.loads(buf.value.decode())
 
 
@@ -291,6 +293,18 @@ def r3_retain(res, x_soa, n, place_at_end=True):
                           _ptr(res_sum), _ptr(ws), wsb, _stream())
     _check(rc, "ax_r3_retain")
     return x_out, n_keep, thr, res_sum
+
+
+def debug_tc_wgrad(zbar, a):
+    """zbar, a: [rows, H] f32 CUDA -> zbar^T a through the tcgen05 weight-gradient kernel."""
+    lib = load()
+    _need_cuda(zbar, a)
+    rows, H = zbar.shape
+    out = torch.empty((H, H), dtype=torch.float32, device=zbar.device)
+    ws = torch.empty((149 * H * H,), dtype=torch.float32, device=zbar.device)
+    _check(lib.ax_debug_tc_wgrad(_ptr(zbar), _ptr(a), rows, H, _ptr(out), _ptr(ws), _stream()),
+           "ax_debug_tc_wgrad")
+    return out
 
 
 def gather_points(x_soa, idx):

@@ -327,4 +327,11 @@ int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const fl
   return 1;
 }
 
+// testing hook (tests/test_gpu_tc.py): tensor-core weight-gradient GEMM on caller-provided matrices.
+// ws needs (SM count + 1) * H * H floats.
+int ax_debug_tc_wgrad(const float *zbar, const float *a, int64_t rows, int32_t H, float *out, float *ws,
+                      void *stream) {
+  return tc_debug_wgrad(zbar, a, rows, H, out, ws, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -1,17 +1,1089 @@
-// tc_engine.cu -- tcgen05 TF32 engine (placeholder until the tensor path lands: reports
-// "unsupported" so AX_ENGINE_AUTO resolves to the FP32 engine; explicit requests fail loudly).
+// tc_engine.cu -- tcgen05 (TF32, FP32 accumulate in TMEM) engine of the jet MLP for hidden widths
+// 64 / 128 / 256, sm_100a only.
+//
+// Data layout in HBM (this engine):   act[layer][(point, stream)][unit]   unit fastest, i.e. a
+// row-major matrix with one row per (point, stream) pair and H columns.  Each hidden layer is
+//        Z^T [unit_out][(p,s)]  =  W [unit_out][unit_in]  *  A^T [unit_in][(p,s)]
+// issued as tcgen05.mma with BOTH operands K-major (W is nn.Linear's (out,in) row-major; A rows
+// are contiguous in `unit`), so the accumulator has TMEM lane = output unit and TMEM column =
+// (point, stream): one epilogue thread owns ALL streams of a (unit, point) pair and applies the
+// activation jet / its adjoint with no cross-thread exchange, then writes 128-byte coalesced
+// rows (32 consecutive units of one (p,s) row per warp store).
+// The stash keeps POST-activation streams (a, a_j, a_jk): they are the next layer's and the
+// weight-gradient GEMM's operands as they lie, and tanh/sigmoid adjoints are division-free in
+// them (see jet_adjoint_A).  Weight gradient: dW[i][k] = sum_rows Zbar[row][i] * A[row][k] with
+// both operands MN-major (rows are the contraction), 256x256 FP32 accumulator = all of TMEM.
+//
+// Operands are staged by TMA (cp.async.bulk.tensor.3d, 128B swizzle) through an mbarrier ring;
+// one elected thread issues tcgen05.mma; four epilogue warps drain TMEM with tcgen05.ld.
+// Reference behaviour replaced: see simt_kernels.cuh (same math, FP32 engine).
+#include <cuda.h>
+
+#include "simt_kernels.cuh"
 #include "tc_engine.cuh"
 
 namespace ax {
-bool tc_supported(const NetGeom &, const ax_net_desc *, const ax_jet_desc *, int) { return false; }
-size_t tc_forward_ws_bytes(const NetGeom &, const ax_net_desc *, const ax_jet_desc *, int64_t) { return 0; }
-size_t tc_backward_ws_bytes(const NetGeom &, const ax_net_desc *, const ax_jet_desc *, int64_t) { return 0; }
-int tc_forward(const NetGeom &, const FwdArgs &, int) {
-  set_error("tensor-core engine not built");
+
+// =========================================================================================
+// device primitives
+// =========================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *r) {
+  uint32_t *u = reinterpret_cast<uint32_t *>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *r) {
+  uint32_t *u = reinterpret_cast<uint32_t *>(r);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+}
+// NC consecutive columns (NC multiple of 8) of this thread's TMEM lane into r[0..NC)
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float *r) {
+  static_assert(NC % 8 == 0, "column count must be a multiple of 8");
+#pragma unroll
+  for (int c = 0; c + 16 <= NC; c += 16) tmem_ld16(taddr + c, r + c);
+  if (NC % 16) tmem_ld8(taddr + (NC / 16) * 16, r + (NC / 16) * 16);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B)
+// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (the only layout tcgen05 accepts for
+// MN-major 32-bit operands)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor, kind::tf32, FP32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// =========================================================================================
+// pointwise jet math on POST-activation streams
+// =========================================================================================
+// tanh / sigmoid only (sin needs the pre-activation; the FP32 engine serves it).
+template <class P>
+__device__ __forceinline__ void jet_forward_A(int act, float (&z)[P::S], float (&A)[P::S]) {
+  float a, s1, s2;
+  if (act == AX_ACT_TANH) {
+    a = tanhf(z[0]);
+    s1 = fmaf(-a, a, 1.0f);
+    s2 = -2.0f * a * s1;
+  } else {
+    a = 1.0f / (1.0f + expf(-z[0]));
+    s1 = a * (1.0f - a);
+    s2 = s1 * (1.0f - 2.0f * a);
+  }
+  A[0] = a;
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) A[1 + j] = s1 * z[1 + j];
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q)
+    A[1 + P::N1 + q] = fmaf(s2 * z[1 + P::pa(q)], z[1 + P::pb(q)], s1 * z[1 + P::N1 + q]);
+}
+
+// Adjoint through the activation expressed in the stored POST-activation streams A:
+//   tanh:    da_j/dz0 = -2 a a_j,   da_q/dz_a = -2 a a_b,   da_q/dz0 = -2 (a_a a_b + a a_q)
+//   sigmoid: da_j/dz0 = (1-2a) a_j, da_q/dz_a = (1-2a) a_b, da_q/dz0 = (1-2a) a_q - 2 a_a a_b
+// (the 1/s1 factors of the z-stream form cancel exactly: no division, safe in saturation)
+template <class P>
+__device__ __forceinline__ void jet_adjoint_A(int act, const float (&A)[P::S], const float (&ab)[P::S],
+                                              float (&zb)[P::S]) {
+  const float a = A[0];
+  float s1, c1, c2;  // da_q/dz0 = c1 * a_q + c2 * a_a a_b ; first-order factor = c1
+  if (act == AX_ACT_TANH) {
+    s1 = fmaf(-a, a, 1.0f);
+    c1 = -2.0f * a;
+    c2 = -2.0f;
+  } else {
+    s1 = a * (1.0f - a);
+    c1 = 1.0f - 2.0f * a;
+    c2 = -2.0f;
+  }
+  float z0b = s1 * ab[0];
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) {
+    zb[1 + j] = s1 * ab[1 + j];
+    z0b = fmaf(c1 * A[1 + j], ab[1 + j], z0b);
+  }
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q) {
+    const float aa = A[1 + P::pa(q)], ac = A[1 + P::pb(q)], aq = A[1 + P::N1 + q];
+    const float g = ab[1 + P::N1 + q];
+    zb[1 + P::N1 + q] = s1 * g;
+    zb[1 + P::pa(q)] = fmaf(c1 * ac, g, zb[1 + P::pa(q)]);
+    zb[1 + P::pb(q)] = fmaf(c1 * aa, g, zb[1 + P::pb(q)]);
+    z0b = fmaf(fmaf(c2 * aa, ac, c1 * aq), g, z0b);
+  }
+  zb[0] = z0b;
+}
+
+// =========================================================================================
+// tile geometry
+// =========================================================================================
+template <int S>
+struct TileOf {
+  // points per tile: multiple of 16 with S*PT <= 256
+  static constexpr int PT = (256 / S) / 16 * 16;
+  static constexpr int N = S * PT;
+};
+
+constexpr int kTcThreads = 192;    // wgrad: warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int kGemmThreads = 320;  // layer GEMMs: warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
+
+struct GemmArgs {
+  const float *bias;      // fwd: bias of this layer [H]
+  const float *stash_in;  // dgrad: POST-activation streams of the destination layer [rows][H]
+  float *out;             // fwd: act of this layer; dgrad: zbar of the previous layer  [rows][H]
+  float *db_partial;      // dgrad: [grid][H] per-CTA sums of zbar_0 (bias gradient of the dest layer)
+  long long n;            // points
+  int num_tiles;
+  int act;
+};
+
+// -----------------------------------------------------------------------------------------
+// kernel A:  out^T[unit][(p,s)] = Wop[unit][:] . In[(p,s)][:]    (both K-major)
+//   MODE 0: forward  (epilogue: + bias, activation jet, store POST-activation streams)
+//   MODE 1: dgrad    (Wop = W^T; epilogue: adjoint with the stash, store zbar; bias-grad partials)
+// -----------------------------------------------------------------------------------------
+template <class P, int MODE, int H>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_in, GemmArgs g) {
+  constexpr int S = P::S;
+  constexpr int PT = TileOf<S>::PT, N = TileOf<S>::N;
+  constexpr int NH = (H + 127) / 128;  // accumulator halves (M = 128 each)
+  constexpr int HM = NH * 128;         // W rows staged (zero-filled past H by TMA)
+  constexpr int KB = H / 32;           // 128-byte K blocks
+  constexpr int W_BYTES = HM * 128, IN_BYTES = N * 128, STAGE_BYTES = W_BYTES + IN_BYTES;
+  constexpr int NSTAGE = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
+  constexpr int TMEM_COLS = NH == 2 ? 512 : 256;
+  constexpr uint32_t IDESC = make_idesc(N, 0, 0);
+  static_assert(NSTAGE >= 2, "pipeline needs two stages");
+  static_assert(N % 16 == 0 && N <= 256, "bad N");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = (uint64_t *)(smem + NSTAGE * STAGE_BYTES);
+  uint64_t *empty = full + NSTAGE;
+  uint64_t *tmem_full = empty + NSTAGE;
+  uint64_t *tmem_empty = tmem_full + 1;
+  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kEpiWarps);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int row0 = tile * N;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t *sw = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_3d(&map_w, &full[stage], sw, 0, 0, kb);
+          tma_load_3d(&map_in, &full[stage], sw + W_BYTES, 0, row0, kb);
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty, tphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sw = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sin = sw + W_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t db = make_desc(sin + ks * 32, 16, 1024);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const uint64_t da = make_desc(sw + h * (128 * 128) + ks * 32, 16, 1024);
+              umma_tf32(tmem_base + h * 256, da, db, IDESC, (kb | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tmem_full);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    // 8 warps: warp w may read TMEM lanes 32*(w%4)..; the two warps of a quarter alternate over the
+    // 8-point column groups.  The dgrad stash rows are software-prefetched one group ahead.
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    const int sub = (warp - 2) >> 2;  // 0 / 1: which of the quarter's two warps
+    constexpr int G8 = PT / 8;        // 8-point groups per tile and half
+    constexpr int ITEMS = NH * G8;
+    constexpr int MY_ITEMS = (ITEMS + 1) / 2;
+    uint32_t tphase = 0;
+    float dbsum[NH];
+    float bias[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      dbsum[h] = 0.0f;
+      const int o = h * 128 + q * 32 + lane;
+      bias[h] = (MODE == 0 && o < H) ? __ldg(g.bias + o) : 0.0f;
+    }
+    const float *__restrict__ stash_in = g.stash_in;
+    float *__restrict__ outp = g.out;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const long long p0 = (long long)tile * PT;
+      float st[MODE == 1 ? 8 * S : 1];
+      auto prefetch = [&](int item) {
+        if (MODE == 1) {
+          const int h = item / G8, grp = item - h * G8;
+          const int o = h * 128 + q * 32 + lane;
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            const long long p = p0 + grp * 8 + pp;
+            const bool ok = (o < H) && (p < g.n);
+#pragma unroll
+            for (int s = 0; s < S; ++s) st[pp * S + s] = ok ? __ldg(stash_in + (p * S + s) * H + o) : 0.0f;
+          }
+        }
+      };
+      if (sub < ITEMS) prefetch(sub);
+      mbar_wait(tmem_full, tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < MY_ITEMS; ++k) {
+        const int item = sub + 2 * k;
+        if (item >= ITEMS) break;
+        const int h = item / G8, grp = item - h * G8;
+        const int o = h * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + grp * 8 * S;
+        float r[8 * S];
+        tmem_ld_cols<8 * S>(taddr, r);
+        tmem_ld_wait();
+        if (item + 2 >= ITEMS) {
+          // this warp's last read of the accumulator: hand TMEM back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        float cur[MODE == 1 ? 8 * S : 1];
+        if (MODE == 1) {
+#pragma unroll
+          for (int i = 0; i < 8 * S; ++i) cur[i] = st[i];
+          if (item + 2 < ITEMS) prefetch(item + 2);
+        }
+        if (o < H) {
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            const long long p = p0 + grp * 8 + pp;
+            if (p < g.n) {
+              float z[S], w[S];
+#pragma unroll
+              for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
+              float *dst = outp + (p * S) * H + o;
+              if (MODE == 0) {
+                z[0] += bias[h];
+                jet_forward_A<P>(g.act, z, w);
+                dst[0] = w[0];
+#pragma unroll
+                for (int s = 1; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+              } else {
+                float a[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) a[s] = cur[pp * S + s];
+                jet_adjoint_A<P>(g.act, a, z, w);
+                dbsum[h] += w[0];
+#pragma unroll
+                for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+              }
+            }
+          }
+        }
+      }
+      tphase ^= 1;
+    }
+    if (MODE == 1) {
+      // two warps share each unit: combine through shared memory in a fixed order
+      float *red = reinterpret_cast<float *>(tmem_slot + 4);  // [2][NH][128]
+#pragma unroll
+      for (int h = 0; h < NH; ++h) red[(sub * NH + h) * 128 + q * 32 + lane] = dbsum[h];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (sub == 0) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const int o = h * 128 + q * 32 + lane;
+          if (o < H)
+            g.db_partial[(long long)blockIdx.x * H + o] =
+                red[(0 * NH + h) * 128 + q * 32 + lane] + red[(1 * NH + h) * 128 + q * 32 + lane];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// kernel B:  dW[i][k] = sum_rows Zbar[row][i] * A[row][k]      (both operands MN-major)
+// each CTA reduces its own row range into a 256-lane x H-column FP32 accumulator and writes a
+// partial; a deterministic second pass sums the partials.
+// -----------------------------------------------------------------------------------------
+struct WgArgs {
+  float *partial;  // [grid][H][H]
+  long long rows;  // n * S
+  long long rows_per_cta;  // multiple of 32
+};
+
+template <int H>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_a, WgArgs g) {
+  constexpr int NH = (H + 127) / 128;
+  constexpr int ZB = NH * 4;   // 32-unit blocks staged for the M operand (zero-filled past H)
+  constexpr int AB = H / 32;   // 32-unit blocks of the N operand
+  constexpr int Z_BYTES = ZB * 4096, A_BYTES = AB * 4096, STAGE_BYTES = Z_BYTES + A_BYTES;
+  constexpr int NSTAGE = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  constexpr int TMEM_COLS = NH == 2 ? 512 : 256;
+  constexpr uint32_t IDESC = make_idesc(H, 1, 1);
+  static_assert(NSTAGE >= 2, "pipeline needs two stages");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = (uint64_t *)(smem + NSTAGE * STAGE_BYTES);
+  uint64_t *empty = full + NSTAGE;
+  uint64_t *tmem_full = empty + NSTAGE;
+  uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long r_beg = (long long)blockIdx.x * g.rows_per_cta;
+  long long r_end = r_beg + g.rows_per_cta;
+  if (r_end > g.rows) r_end = g.rows;
+  const int chunks = r_beg < r_end ? (int)((r_end - r_beg + 31) / 32) : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *sz = smem + stage * STAGE_BYTES;
+        mbar_expect_tx(&full[stage], STAGE_BYTES);
+        tma_load_3d(&map_z, &full[stage], sz, 0, (int)(r_beg + (long long)c * 32), 0);
+        tma_load_3d(&map_a, &full[stage], sz + Z_BYTES, 0, (int)(r_beg + (long long)c * 32), 0);
+        if (++stage == NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sz = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sa = sz + Z_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          // MN-major, 32B-base swizzle: 128B along MN x 4 K-rows per atom; LBO = next 32-unit block,
+          // SBO = next group of 4 K-rows; one MMA (K = 8) spans two groups
+          const uint64_t db = make_desc(sa + ks * 1024, 4096, 512, 1);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            const uint64_t da = make_desc(sz + h * (4 * 4096) + ks * 1024, 4096, 512, 1);
+            umma_tf32(tmem_base + h * 256, da, db, IDESC, (c | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    float *part = g.partial + (long long)blockIdx.x * H * H;
+    if (chunks > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+      const int i = h * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        float r[32];
+        if (chunks > 0) {
+          tmem_ld16(taddr + c0, &r[0]);
+          tmem_ld16(taddr + c0 + 16, &r[16]);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = 0.0f;
+        }
+        if (i < H) {
+          float4 *dst = reinterpret_cast<float4 *>(part + (long long)i * H + c0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =========================================================================================
+// small FP32 kernels either side of the tensor-core layers (this engine's layout)
+// =========================================================================================
+// layer 0: POST-activation streams from x.   block = H threads (unit), 32 points per block
+template <class P>
+__global__ void k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float *__restrict__ x,
+                           int d_in, JetDirs dirs, int H, long long n, long long ldn, float *__restrict__ act0,
+                           int act) {
+  constexpr int S = P::S;
+  const int o = threadIdx.x;
+  if (o >= H) return;
+  float w[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) w[d] = d < d_in ? __ldg(W + (long long)o * d_in + d) : 0.0f;
+  const float bo = __ldg(b + o);
+  float wd[P::N1 > 0 ? P::N1 : 1];
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) wd[j] = __ldg(W + (long long)o * d_in + dirs.d[j]);
+  const long long p_beg = (long long)blockIdx.x * 32;
+  for (int pp = 0; pp < 32; ++pp) {
+    const long long p = p_beg + pp;
+    if (p >= n) break;
+    float z[S], A[S];
+    z[0] = bo;
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      if (d < d_in) z[0] = fmaf(w[d], __ldg(x + (long long)d * ldn + p), z[0]);
+#pragma unroll
+    for (int j = 0; j < P::N1; ++j) z[1 + j] = wd[j];
+#pragma unroll
+    for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
+    jet_forward_A<P>(act, z, A);
+    float *dst = act0 + (p * S) * H + o;
+    dst[0] = A[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) dst[(long long)s * H] = to_tf32(A[s]);
+  }
+}
+
+// output layer forward: jets[s][c][p] = sum_k Wout[c][k] A[(p,s)][k] (+ b_c for s = 0); warp per row
+__global__ void k_tc_last_fwd(const float *__restrict__ Wout, const float *__restrict__ bout,
+                              const float *__restrict__ actL, int H, int C, int S, long long n, long long ldn,
+                              float *__restrict__ jets) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp_global; row < n * S; row += nwarps) {
+    const long long p = row / S;
+    const int s = (int)(row - p * S);
+    const float *a = actL + row * H;
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.0f;
+      for (int k = lane; k < H; k += 32) acc = fmaf(__ldg(Wout + (long long)c * H + k), a[k], acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) jets[((long long)s * C + c) * ldn + p] = acc + (s == 0 ? __ldg(bout + c) : 0.0f);
+    }
+  }
+}
+
+// output layer backward: zbar_{L-1} from jets_bar; per-block partials of dWout, dbout, db_{L-1}
+// block = H threads (unit k), PB points per block.  partial layout per block: [C*H | C | H]
+template <class P>
+__global__ void k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar,
+                              const float *__restrict__ actL, int H, int C, long long n, long long ldn,
+                              int pts_per_block, float *__restrict__ gout, float *__restrict__ partial, int act) {
+  constexpr int S = P::S;
+  const int k = threadIdx.x;
+  if (k >= H) return;
+  float wc[4], dw[4], dbo[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    wc[c] = c < C ? __ldg(Wout + (long long)c * H + k) : 0.0f;
+    dw[c] = 0.0f;
+    dbo[c] = 0.0f;
+  }
+  float dbh = 0.0f;
+  const long long p_beg = (long long)blockIdx.x * pts_per_block;
+  for (int pp = 0; pp < pts_per_block; ++pp) {
+    const long long p = p_beg + pp;
+    if (p >= n) break;
+    float A[S], ab[S], zb[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      A[s] = actL[(p * S + s) * H + k];
+      float acc = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) {
+          const float ob = __ldg(jets_bar + ((long long)s * C + c) * ldn + p);
+          acc = fmaf(wc[c], ob, acc);
+          dw[c] = fmaf(ob, A[s], dw[c]);
+          if (s == 0) dbo[c] += ob;
+        }
+      ab[s] = acc;
+    }
+    jet_adjoint_A<P>(act, A, ab, zb);
+    dbh += zb[0];
+    float *dst = gout + (p * S) * H + k;
+#pragma unroll
+    for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(zb[s]);
+  }
+  float *part = partial + (long long)blockIdx.x * ((long long)C * H + C + H);
+  for (int c = 0; c < C; ++c) part[(long long)c * H + k] = dw[c];
+  if (k == 0)
+    for (int c = 0; c < C; ++c) part[(long long)C * H + c] = dbo[c];
+  part[(long long)C * H + C + k] = dbh;
+}
+
+// first layer backward: dW0[i][d] = sum_p zbar_0 x_d + sum_j [dir_j == d] zbar_j ; block = H threads
+template <class P>
+__global__ void k_tc_first_bwd(const float *__restrict__ g0, const float *__restrict__ x, int d_in, JetDirs dirs,
+                               int H, long long n, long long ldn, int pts_per_block,
+                               float *__restrict__ partial) {
+  constexpr int S = P::S;
+  const int i = threadIdx.x;
+  if (i >= H) return;
+  float acc[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) acc[d] = 0.0f;
+  const long long p_beg = (long long)blockIdx.x * pts_per_block;
+  for (int pp = 0; pp < pts_per_block; ++pp) {
+    const long long p = p_beg + pp;
+    if (p >= n) break;
+    const float *src = g0 + (p * S) * H + i;
+    const float z0 = src[0];
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      if (d < d_in) acc[d] = fmaf(z0, __ldg(x + (long long)d * ldn + p), acc[d]);
+#pragma unroll
+    for (int j = 0; j < P::N1; ++j) {
+      const float zj = src[(long long)(1 + j) * H];
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (d == dirs.d[j]) acc[d] += zj;
+    }
+  }
+  float *part = partial + (long long)blockIdx.x * ((long long)H * d_in);
+  for (int d = 0; d < d_in; ++d) part[(long long)i * d_in + d] = acc[d];
+}
+
+__global__ void k_tc_round_copy(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols,
+                                int transpose) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx - r * cols;
+  const float v = to_tf32(src[idx]);
+  if (transpose)
+    dst[(long long)c * rows + r] = v;
+  else
+    dst[idx] = v;
+}
+
+// out[off + j] = sum_b partial[b * stride + sub + j]
+__global__ void k_tc_reduce(const float *__restrict__ partial, long long stride, long long sub, int nblocks,
+                            long long count, float *__restrict__ out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  float s = 0.0f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * stride + sub + j];
+  out[j] = s;
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major [rows][cols] float matrix viewed as [cols/32][rows][32]; box = (32, box_rows, box_blocks)
+static int make_map(CUtensorMap *m, const float *base, long long rows, int cols, int box_rows, int box_blocks,
+                    bool atom32 = false) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return 1;
+  }
+  cuuint64_t gdim[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d box=(%d,%d)", (int)r, rows, cols, box_rows,
+              box_blocks);
+    return 1;
+  }
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <class P, int MODE, int H>
+static int launch_gemm(const float *wop, const float *in, const GemmArgs &ga, long long rows, cudaStream_t st) {
+  constexpr int S = P::S, N = TileOf<S>::N, NH = (H + 127) / 128, HM = NH * 128;
+  constexpr int STAGE_BYTES = (HM + N) * 128;
+  constexpr int NSTAGE = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
+  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256 + 2 * NH * 128 * sizeof(float);
+  CUtensorMap mw, mi;
+  if (make_map(&mw, wop, H, H, HM, 1)) return 1;
+  if (make_map(&mi, in, rows, H, N, 1)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<P, MODE, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int grid = ga.num_tiles < sm_count() ? ga.num_tiles : sm_count();
+  {
+    KernelTimer t(MODE == 0 ? "tc_gemm_fwd" : "tc_gemm_dgrad", st, 2.0 * S * H * (double)H * (double)ga.n,
+                  4.0 * S * H * (double)ga.n * (MODE == 0 ? 2.0 : 3.0));
+    k_tc_gemm<P, MODE, H><<<grid, kGemmThreads, smem, st>>>(mw, mi, ga);
+  }
+  AX_LAUNCH_OK();
+  return 0;
+}
+
+template <int H>
+static int launch_wgrad(const float *zbar, const float *a, long long rows, float *partial, int *grid_out,
+                        cudaStream_t st, int S) {
+  constexpr int NH = (H + 127) / 128, ZB = NH * 4, AB = H / 32;
+  constexpr int STAGE_BYTES = (ZB + AB) * 4096;
+  constexpr int NSTAGE = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256;
+  CUtensorMap mz, ma;
+  if (make_map(&mz, zbar, rows, H, 32, ZB, true)) return 1;
+  if (make_map(&ma, a, rows, H, 32, AB, true)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  int grid = sm_count();
+  long long per = (rows + grid - 1) / grid;
+  per = (per + 31) / 32 * 32;
+  if (per < 32) per = 32;
+  grid = (int)((rows + per - 1) / per);
+  WgArgs wa{partial, rows, per};
+  {
+    KernelTimer t("tc_gemm_wgrad", st, 2.0 * H * (double)H * (double)rows, 8.0 * H * (double)rows);
+    k_tc_wgrad<H><<<grid, kTcThreads, smem, st>>>(mz, ma, wa);
+  }
+  AX_LAUNCH_OK();
+  *grid_out = grid;
+  (void)S;
+  return 0;
+}
+
+static int reduce_to(const float *partial, long long stride, long long sub, int nblocks, long long count,
+                     float *out, cudaStream_t st) {
+  k_tc_reduce<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partial, stride, sub, nblocks, count, out);
+  AX_LAUNCH_OK();
+  return 0;
+}
+
+constexpr int kLastPts = 256;   // points per block of the output-layer backward
+constexpr int kFirstPts = 256;  // points per block of the first-layer backward
+
+static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id == 4 || id == 5 || id == 6; }
+
+bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
+  if (engine != AX_ENGINE_TF32) return false;
+  if (net->activation != AX_ACT_TANH && net->activation != AX_ACT_SIGMOID) return false;
+  if (g.L < 2) return false;
+  const int H = g.widths[1];
+  if (H != 64 && H != 128 && H != 256) return false;
+  for (int l = 1; l <= g.L; ++l)
+    if (g.widths[l] != H) return false;
+  if (g.widths[g.L + 1] > 4) return false;
+  return pattern_in_tc(match_pattern(jet));
+}
+
+struct BwdWs {
+  float *g[2];
+  float *wround;     // (L-1) x H x H : tf32-rounded W^T copies
+  float *partial;    // scratch for every partial reduction
+  size_t partial_floats;
+  size_t total_bytes;
+};
+
+static void plan_bwd_ws(const NetGeom &g, int S, long long ldn, BwdWs *w, void *base) {
+  const int H = g.widths[1], C = g.widths[g.L + 1], d_in = g.widths[0];
+  const size_t gfl = (size_t)ldn * S * H;
+  const size_t wr = (size_t)(g.L - 1) * H * H;
+  const size_t nb_last = (size_t)(ldn + kLastPts - 1) / kLastPts;
+  const size_t nb_first = (size_t)(ldn + kFirstPts - 1) / kFirstPts;
+  size_t pf = (size_t)(sm_count() + 1) * H * H;               // wgrad partials
+  size_t a = nb_last * ((size_t)C * H + C + H);               // last-layer partials
+  size_t b = nb_first * ((size_t)H * d_in);                   // first-layer partials
+  size_t c = (size_t)(sm_count() + 1) * H;                    // dgrad bias partials (kept separately)
+  if (a > pf) pf = a;
+  if (b > pf) pf = b;
+  float *p = (float *)base;
+  w->g[0] = p;
+  w->g[1] = p + gfl;
+  w->wround = p + 2 * gfl;
+  w->partial = w->wround + wr;
+  w->partial_floats = pf + c;
+  w->total_bytes = (2 * gfl + wr + pf + c) * sizeof(float);
+}
+
+size_t tc_forward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
+  if (!tc_supported(g, net, jet, AX_ENGINE_TF32)) return 0;
+  const int H = g.widths[1];
+  return (size_t)(g.L - 1) * H * H * sizeof(float) * net->n_nets;  // tf32-rounded weights
+}
+
+size_t tc_backward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
+  if (!tc_supported(g, net, jet, AX_ENGINE_TF32)) return 0;
+  BwdWs w;
+  plan_bwd_ws(g, 1 + jet->n1 + jet->n2, ldn, &w, nullptr);
+  return w.total_bytes;
+}
+
+template <class P, int H>
+static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
+  constexpr int S = P::S, PT = TileOf<S>::PT;
+  const int act = a.net->activation, C = g.widths[g.L + 1], d_in = g.widths[0];
+  const long long rows = a.n * S;
+  const size_t layer_fl = (size_t)a.ldn * S * H;
+  const int slots = a.keep_all ? g.L : 2;
+  const JetDirs dirs = make_dirs(a.jet);
+  const size_t need = (size_t)(g.L - 1) * H * H * sizeof(float) * a.net->n_nets;
+  if (a.ws_bytes < need || !a.ws) {
+    set_error("forward workspace too small: %zu < %zu", a.ws_bytes, need);
+    return 1;
+  }
+  for (int net = 0; net < a.net->n_nets; ++net) {
+    const float *prm = a.params + (long long)net * g.P;
+    float *stash = a.stash + (size_t)net * slots * layer_fl;
+    float *wr = (float *)a.ws + (size_t)net * (g.L - 1) * H * H;
+    float *jets = a.jets + (size_t)net * S * C * a.ldn;
+    auto slot = [&](int l) { return stash + (size_t)(a.keep_all ? l : (l & 1)) * layer_fl; };
+    for (int l = 1; l < g.L; ++l) {
+      k_tc_round_copy<<<(H * H + 255) / 256, 256, 0, a.stream>>>(prm + g.w_off[l], wr + (size_t)(l - 1) * H * H, H,
+                                                                H, 0);
+      AX_LAUNCH_OK();
+    }
+    {
+      KernelTimer t("tc_first_layer", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
+      k_tc_first<P><<<(unsigned)((a.n + 31) / 32), H, 0, a.stream>>>(prm + g.w_off[0], prm + g.b_off[0], a.x, d_in,
+                                                                    dirs, H, a.n, a.ldn, slot(0), act);
+    }
+    AX_LAUNCH_OK();
+    for (int l = 1; l < g.L; ++l) {
+      GemmArgs ga{};
+      ga.bias = prm + g.b_off[l];
+      ga.out = slot(l);
+      ga.n = a.n;
+      ga.num_tiles = (int)((a.n + PT - 1) / PT);
+      ga.act = act;
+      if (launch_gemm<P, 0, H>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream)) return 1;
+    }
+    {
+      KernelTimer t("tc_last_fwd", a.stream, 2.0 * S * H * C * (double)a.n, 4.0 * S * H * (double)a.n);
+      const int blocks = sm_count() * 8;
+      k_tc_last_fwd<<<blocks, 256, 0, a.stream>>>(prm + g.w_off[g.L], prm + g.b_off[g.L], slot(g.L - 1), H, C, S,
+                                                  a.n, a.ldn, jets);
+    }
+    AX_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <class P, int H>
+static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
+  constexpr int S = P::S, PT = TileOf<S>::PT;
+  const int act = a.net->activation, C = g.widths[g.L + 1], d_in = g.widths[0], L = g.L;
+  const long long rows = a.n * S;
+  const size_t layer_fl = (size_t)a.ldn * S * H;
+  const JetDirs dirs = make_dirs(a.jet);
+  BwdWs w;
+  plan_bwd_ws(g, S, a.ldn, &w, a.ws);
+  if (a.ws_bytes < w.total_bytes) {
+    set_error("backward workspace too small: %zu < %zu", a.ws_bytes, w.total_bytes);
+    return 1;
+  }
+  float *dbpart = w.partial + (w.partial_floats - (size_t)(sm_count() + 1) * H);
+  for (int net = 0; net < a.net->n_nets; ++net) {
+    const float *prm = a.params + (long long)net * g.P;
+    float *grad = a.grad + (long long)net * g.P;
+    const float *stash = a.stash + (size_t)net * L * layer_fl;
+    const float *jbar = a.jets_bar + (size_t)net * S * C * a.ldn;
+    auto slot = [&](int l) { return stash + (size_t)l * layer_fl; };
+    for (int l = 1; l < L; ++l) {
+      k_tc_round_copy<<<(H * H + 255) / 256, 256, 0, a.stream>>>(prm + g.w_off[l], w.wround + (size_t)(l - 1) * H * H,
+                                                                H, H, 1);
+      AX_LAUNCH_OK();
+    }
+    // output layer
+    int cur = 0;
+    {
+      const int nb = (int)((a.n + kLastPts - 1) / kLastPts);
+      {
+        KernelTimer t("tc_last_bwd", a.stream, 4.0 * S * H * C * (double)a.n, 8.0 * S * H * (double)a.n);
+        k_tc_last_bwd<P><<<nb, H, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn, kLastPts,
+                                                 w.g[cur], w.partial, act);
+      }
+      AX_LAUNCH_OK();
+      const long long stride = (long long)C * H + C + H;
+      if (reduce_to(w.partial, stride, 0, nb, (long long)C * H + C, grad + g.w_off[L], a.stream)) return 1;
+      if (reduce_to(w.partial, stride, (long long)C * H + C, nb, H, grad + g.b_off[L - 1], a.stream)) return 1;
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      // dW_l = zbar_l^T A_{l-1}
+      int wg_grid = 0;
+      if (launch_wgrad<H>(w.g[cur], slot(l - 1), rows, w.partial, &wg_grid, a.stream, S)) return 1;
+      if (reduce_to(w.partial, (long long)H * H, 0, wg_grid, (long long)H * H, grad + g.w_off[l], a.stream)) return 1;
+      // zbar_{l-1} = adjoint(W_l^T zbar_l)
+      GemmArgs ga{};
+      ga.stash_in = slot(l - 1);
+      ga.out = w.g[cur ^ 1];
+      ga.db_partial = dbpart;
+      ga.n = a.n;
+      ga.num_tiles = (int)((a.n + PT - 1) / PT);
+      ga.act = act;
+      if (launch_gemm<P, 1, H>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], ga, rows, a.stream)) return 1;
+      const int grid = ga.num_tiles < sm_count() ? ga.num_tiles : sm_count();
+      if (reduce_to(dbpart, H, 0, grid, H, grad + g.b_off[l - 1], a.stream)) return 1;
+      cur ^= 1;
+    }
+    {
+      const int nb = (int)((a.n + kFirstPts - 1) / kFirstPts);
+      {
+        KernelTimer t("tc_first_bwd", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
+        k_tc_first_bwd<P><<<nb, H, 0, a.stream>>>(w.g[cur], a.x, d_in, dirs, H, a.n, a.ldn, kFirstPts, w.partial);
+      }
+      AX_LAUNCH_OK();
+      if (reduce_to(w.partial, (long long)H * d_in, 0, nb, (long long)H * d_in, grad + g.w_off[0], a.stream)) return 1;
+    }
+  }
+  return 0;
+}
+
+// test hook: dW[H][H] = zbar[rows][H]^T a[rows][H] through the tensor-core weight-gradient path
+int tc_debug_wgrad(const float *zbar, const float *a, long long rows, int H, float *out, float *ws,
+                   cudaStream_t st) {
+  int grid = 0;
+  if (H == 64) {
+    if (launch_wgrad<64>(zbar, a, rows, ws, &grid, st, 1)) return 1;
+  } else if (H == 128) {
+    if (launch_wgrad<128>(zbar, a, rows, ws, &grid, st, 1)) return 1;
+  } else if (H == 256) {
+    if (launch_wgrad<256>(zbar, a, rows, ws, &grid, st, 1)) return 1;
+  } else {
+    set_error("H must be 64, 128 or 256");
+    return 1;
+  }
+  return reduce_to(ws, (long long)H * H, 0, grid, (long long)H * H, out, st);
+}
+
+#define AX_TC_PATTERNS(X) X(0, P_V) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F)
+
+int tc_forward(const NetGeom &g, const FwdArgs &a, int engine) {
+  const int id = match_pattern(a.jet), H = g.widths[1];
+  (void)engine;
+#define AX_TC_FWD(ID, PAT)                                   \
+  if (id == ID) {                                            \
+    if (H == 64) return tc_forward_impl<PAT, 64>(g, a);      \
+    if (H == 128) return tc_forward_impl<PAT, 128>(g, a);    \
+    return tc_forward_impl<PAT, 256>(g, a);                  \
+  }
+  AX_TC_PATTERNS(AX_TC_FWD)
+#undef AX_TC_FWD
+  set_error("tensor-core engine: stream pattern %d not compiled", id);
   return 1;
 }
-int tc_backward(const NetGeom &, const BwdArgs &, int) {
-  set_error("tensor-core engine not built");
+
+int tc_backward(const NetGeom &g, const BwdArgs &a, int engine) {
+  const int id = match_pattern(a.jet), H = g.widths[1];
+  (void)engine;
+#define AX_TC_BWD(ID, PAT)                                   \
+  if (id == ID) {                                            \
+    if (H == 64) return tc_backward_impl<PAT, 64>(g, a);     \
+    if (H == 128) return tc_backward_impl<PAT, 128>(g, a);   \
+    return tc_backward_impl<PAT, 256>(g, a);                 \
+  }
+  AX_TC_PATTERNS(AX_TC_BWD)
+#undef AX_TC_BWD
+  set_error("tensor-core engine: stream pattern %d not compiled", id);
   return 1;
 }
+
 }  // namespace ax

@@ -8,4 +8,5 @@ size_t tc_forward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_je
 size_t tc_backward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
 int tc_forward(const NetGeom &g, const FwdArgs &a, int engine);
 int tc_backward(const NetGeom &g, const BwdArgs &a, int engine);
+int tc_debug_wgrad(const float *zbar, const float *a, long long rows, int H, float *out, float *ws, cudaStream_t st);
 }  // namespace ax

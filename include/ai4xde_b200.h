@@ -155,6 +155,11 @@ int64_t ax_launch_count(void);
 void ax_timing_enable(int on);
 int64_t ax_timing_report(char *h_buf, int64_t cap);
 
+/* testing hook: dW[H][H] = zbar[rows][H]^T a[rows][H] on the tcgen05 weight-gradient path
+ * (H in {64,128,256}); ws: at least 149*H*H floats. */
+int ax_debug_tc_wgrad(const float *zbar, const float *a, int64_t rows, int32_t H, float *out, float *ws,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

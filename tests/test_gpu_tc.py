@@ -1,0 +1,112 @@
+"""GPU parity of the tcgen05 (TF32) engine.  Bounds are looser than the FP32 engine's 1e-5 and are
+STATED here: TF32 keeps 10 mantissa bits (operands rounded to nearest, FP32 accumulate), so with
+Glorot-scale weights the jets and gradients agree with the float64 Taylor-mode double to a few
+1e-3 relative (of the largest entry), growing with depth."""
+import numpy as np
+import pytest
+import torch
+
+import _taylor_double as td
+from ai4xde_b200 import _lib
+from ai4xde_b200.jet import JetSpec, to_soa
+from parity_util import product_vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+TF32_JET_TOL = 1e-2
+TF32_GRAD_TOL = 2e-2
+
+
+def _glorot_params(widths, gen, k=1):
+    chunks = []
+    for i, o in zip(widths[:-1], widths[1:]):
+        chunks.append(torch.randn((k, o * i), generator=gen) * (2.0 / (i + o)) ** 0.5)
+        chunks.append(torch.randn((k, o), generator=gen) * 0.1)
+    return torch.cat(chunks, dim=1)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("widths,act,spec,n", [
+    ([2, 128, 128, 1], "tanh", ((), ()), 300),
+    ([2, 128, 128, 1], "tanh", ((0, 1), ((0, 0), (1, 1))), 300),
+    ([2, 256, 256, 256, 1], "tanh", ((0, 1), ((0, 0), (1, 1))), 1000),
+    ([2, 64, 64, 64, 64, 1], "tanh", ((1, 0), ((0, 0),)), 10000),
+    ([1, 64, 64, 64, 1], "tanh", ((0,), ((0, 0),)), 2048),
+    ([2, 128, 128, 128, 128, 128, 3], "tanh", ((0, 1), ((0, 0), (1, 1))), 5001),
+    ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((0, 0), (1, 1))), 20000),
+    ([2, 128, 128, 128, 2], "sigmoid", ((0, 1), ((0, 0), (0, 1), (1, 1))), 777),
+    ([2, 64, 64, 1], "tanh", ((0, 1), ()), 95),
+])
+def test_tf32_engine_matches_double(widths, act, spec, n):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(11)
+    js = JetSpec(*spec)
+    net = _lib.make_net_desc(widths, act)
+    assert _lib.engine_supported(net, js.desc, "tf32")
+    params = _glorot_params(widths, gen).to(dev)
+    x = (torch.rand((n, widths[0]), generator=gen) * 2 - 1).to(dev)
+    xs = to_soa(x)
+    jets, stash = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=True, engine="tf32")
+    ref, _ = td.jet_forward(net, js.desc, params.double(), xs.double(), n, True)
+    for s in range(js.S):
+        assert _rel(jets[0, s, :, :n].double(), ref[0, s, :, :n]) < TF32_JET_TOL, f"stream {s}"
+    jets2, _ = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=False, engine="tf32")
+    assert torch.equal(jets2[..., :n], jets[..., :n])
+    jb = torch.randn(jets.shape, generator=gen).to(dev)
+    jb[..., n:] = 0
+    grad = _lib.jet_backward(net, js.desc, params, xs, n, jb, stash, engine="tf32")
+    gref = td.jet_backward(net, js.desc, params.double(), xs.double(), n, jb.double(), None)
+    off = 0
+    for i, o in zip(widths[:-1], widths[1:]):
+        for cnt in (i * o, o):
+            assert _rel(grad[0, off:off + cnt].double(), gref[0, off:off + cnt]) < TF32_GRAD_TOL, f"param block at {off}"
+            off += cnt
+    grad2 = _lib.jet_backward(net, js.desc, params, xs, n, jb, stash, engine="tf32")
+    assert torch.equal(grad, grad2)  # deterministic two-level reduction
+
+
+def test_tf32_engine_refuses_what_it_cannot_do():
+    net = _lib.make_net_desc([2, 150, 150, 1], "tanh")
+    js = JetSpec((0, 1), ((0, 0), (1, 1)))
+    assert not _lib.engine_supported(net, js.desc, "tf32")
+    dev = torch.device("cuda:0")
+    with pytest.raises(_lib.NativeLibraryError):
+        _lib.jet_forward(net, js.desc, torch.zeros((1, _lib.param_count(net)), device=dev),
+                         torch.zeros((2, 32), device=dev), 8, True, engine="tf32")
+    sin_net = _lib.make_net_desc([2, 128, 128, 1], "sin")
+    assert not _lib.engine_supported(sin_net, js.desc, "tf32")   # served by the FP32 engine
+
+
+@pytest.mark.parametrize("H", [64, 128, 256])
+def test_tc_wgrad_kernel(H):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(0)
+    for rows in (1, 31, 33, 1000, 50001):
+        z = torch.randn((rows, H), generator=gen).to(dev)
+        a = torch.randn((rows, H), generator=gen).to(dev)
+        out = _lib.debug_tc_wgrad(z, a)
+        ref = z.double().t() @ a.double()
+        assert _rel(out.double(), ref) < 3e-3
+
+
+# Product-level parity on the BASELINE configs whose nets the tensor-core engine serves.
+# Stated TF32 bounds (relative to the largest reference entry).
+TF32_CFG_TOL = {
+    "cfg2": dict(loss=2e-3, grad=1e-2, res=5e-3),
+    "cfg3": dict(loss=5e-3, grad=2e-2, res=1e-2),
+    "cfg4": dict(loss=5e-3, grad=2e-2, res=1e-2),
+    "cfg5": dict(loss=5e-3, grad=2e-2, res=1e-2),
+}
+
+
+@pytest.mark.parametrize("cfg,n", [("cfg2", 10000), ("cfg3", 4096), ("cfg4", 4096), ("cfg5", 4096)])
+def test_tf32_engine_matches_oracle(cfg, n):
+    r = product_vs_oracle(cfg, n, engine="tf32")
+    print(cfg, {k: v for k, v in r.items() if k.endswith("_rel")})
+    tol = TF32_CFG_TOL[cfg]
+    assert r["loss_rel"] < tol["loss"], r
+    assert r["grad_rel"] < tol["grad"], r
+    assert r["res_rel"] < tol["res"], r
