@@ -1,0 +1,12 @@
+"""Algorithms available on the fused path (mirror of AI4XDE.algorithm).  HPO, FI_PINN, CausalPINN
+and the skopt-based Uniform sampler are outside the hot-path scope."""
+from .pinn import PINN
+from .rad import RAD
+from .rar_d import RAR_D
+from .rar_g import RAR_G
+from .r3sampling import R3Sampling
+from .random_r import Random_R
+from .gpinn import gPINN
+from .fbpinn import FBPINN
+
+__all__ = ["PINN", "R3Sampling", "RAD", "Random_R", "RAR_D", "RAR_G", "gPINN", "FBPINN"]

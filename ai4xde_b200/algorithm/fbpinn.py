@@ -1,0 +1,185 @@
+"""FBPINN: finite-basis PINN on a 1-D domain decomposition
+(/root/reference/AI4XDE/algorithm/FBPINN.py:7-213).
+
+Same decomposition (uniform split, `overlap` * width on each side, clipped), same sigmoid window,
+same wiring (the window reaches the sub-net only when the parent case wires `output_transform`
+through the base `gen_net`; sub-cases are built with the parent's class defaults), same Gauss-Seidel
+schedule (each subdomain model in turn: Adam, then L-BFGS, only its own parameters stepped) and the
+same patched closures on every `dde.Model` (`outputs_losses_train/test`, `train_step`).
+
+What changes: the K subdomain nets share one [K, P] weight bank and `get_predict` evaluates ALL of
+them on the batch with ONE fused jet launch (`n_nets = K`); the reverse pass runs only for the net
+being trained."""
+import numpy as np
+import torch
+
+from .. import dde, jet
+from ..dde import backend as bkd
+from ..dde import gradients as grad
+from ..dde import config as dconfig
+from ..solver import PINNSolver
+
+
+class Domain_decomposition:
+    def __init__(self, PDECase, segment, overlap=0.1):
+        self.PDECase = PDECase
+        self.segment = segment
+        self.overlap = overlap
+        self.dim = PDECase.geomtime.dim
+        self.window_func_list = []
+        self.limits = []
+        self.pdeCase_list = [self.gen_pde(d) for d in self.domain_decomposition()]
+
+    def gen_pde(self, domain):
+        parent_cls = self.PDECase.__class__
+        window_func = self.get_window_func([domain.l, domain.r])
+        self.window_func_list.append(window_func)
+        self.limits.append((domain.l, domain.r))
+
+        class PDE(parent_cls):
+            def gen_geomtime(self):
+                return domain
+
+            def output_transform(self, x, y):
+                y_parent = super().output_transform(x, y)
+                if y_parent is not None:
+                    y = y_parent
+                return window_func(x) * y
+
+        return PDE()
+
+    def get_window_func(self, x_limit):
+        lo, hi = x_limit
+
+        def window_func(x):
+            return bkd.sigmoid(x - lo) * bkd.sigmoid(hi - x)
+
+        return window_func
+
+    def domain_decomposition(self):
+        geomtime = self.PDECase.geomtime
+        if isinstance(geomtime, dde.geometry.TimeDomain):
+            make = dde.geometry.TimeDomain
+        elif isinstance(geomtime, dde.geometry.Interval):
+            make = dde.geometry.Interval
+        else:
+            raise ValueError("Only support geomtime Interval")
+        lo, hi = geomtime.l, geomtime.r
+        edges = np.linspace(lo, hi, self.segment + 1)
+        out = []
+        for i in range(self.segment):
+            width = edges[i + 1] - edges[i]
+            out.append(make(max(edges[i] - self.overlap * width, lo), min(edges[i + 1] + self.overlap * width, hi)))
+        return out
+
+
+class FBPINN(PINNSolver):
+    def __init__(self, PDECase, segment, iter=10):
+        self.iter = iter
+        self.domains = Domain_decomposition(PDECase, segment)
+        super().__init__(name="FBPINN", PDECase=PDECase)
+        self.model_list = [dde.Model(pde.data, pde.net) for pde in self.domains.pdeCase_list]
+        self.bank = dde.nn.NetBank([m.net for m in self.model_list])
+        self._specs = {}
+
+    # ---- schedule (FBPINN.py:112-123) -------------------------------------------------------
+    def train_step(self, lr=1e-3, iterations=1000, callbacks=None, eval=True):
+        for pde, model in zip(self.domains.pdeCase_list, self.model_list):
+            self.compile(pde, model, "adam", lr=lr)
+            model.train(iterations=iterations, callbacks=callbacks)
+            self.compile(pde, model, "L-BFGS")
+            self.losshistory, self.train_state = model.train()
+            if eval:
+                self.eval()
+
+    def closure(self):
+        for _ in range(self.iter):
+            self.train_step()
+
+    # ---- sum over subdomain nets --------------------------------------------------------------
+    def _combine(self, x, y_all):
+        """sum_j T_j(x, N_j(x)) with T_j the sub-case's wired output transform (window * parent)."""
+        C = self.bank.layer_sizes[-1]
+        result = None
+        for j, model in enumerate(self.model_list):
+            y = y_all[:, j * C : (j + 1) * C]
+            tf = model.net._output_transform
+            if tf is not None:
+                y = tf(x, y)
+            result = y if result is None else result + y
+        return result
+
+    def get_predict(self, input, active=None, spec=None, x_soa=None, param_grad=True):
+        y_all = self.bank.forward_all(input, x_soa=x_soa, spec=spec, active=active, param_grad=param_grad)
+        return self._combine(input, y_all)
+
+    def _spec_for(self, model, batch, targets, loss_fn, losses_fn):
+        key = (id(model.data), id(model.data.pde))
+        if key not in self._specs:
+            x = batch.aos.detach().requires_grad_()
+            C, K = self.bank.layer_sizes[-1], self.bank.K
+
+            def fn(xx, y_all):
+                out = losses_fn(targets, self._combine(xx, y_all), loss_fn, xx, model)
+                grad.clear()
+                return out
+
+            self._specs[key] = jet.probe_streams(x, K * C, fn)
+        return self._specs[key]
+
+    # ---- per-model closures (FBPINN.py:125-194) ------------------------------------------------
+    def compile(self, pde, model, optimizer, lr=None, loss="MSE", metrics=None, decay=None,
+                loss_weights=None, external_trainable_variables=None):
+        loss_fn = dde.losses.get(loss)
+        k = self.model_list.index(model)
+        dev = dconfig.device()
+
+        def outputs_losses(training, inputs, targets, auxiliary_vars, losses_fn):
+            model.net.auxiliary_vars = auxiliary_vars
+            model.net.train(mode=training)
+            batch = model.device_batch(inputs)
+            if targets is not None:
+                targets = torch.as_tensor(targets, dtype=torch.float32, device=dev)
+            spec = self._spec_for(model, batch, targets, loss_fn, losses_fn)
+            x = batch.aos.detach().requires_grad_()
+            outputs_ = self.get_predict(x, active=[k], spec=spec, x_soa=batch.soa)
+            losses = losses_fn(targets, outputs_, loss_fn, x, model)
+            if not isinstance(losses, list):
+                losses = [losses]
+            losses = torch.stack(losses)
+            if loss_weights is not None:
+                losses = losses * torch.as_tensor(loss_weights, dtype=torch.float32, device=dev)
+            grad.clear()
+            return outputs_, losses
+
+        def outputs_losses_train(inputs, targets, auxiliary_vars):
+            return outputs_losses(True, inputs, targets, auxiliary_vars, model.data.losses_train)
+
+        def outputs_losses_test(inputs, targets, auxiliary_vars):
+            return outputs_losses(False, inputs, targets, auxiliary_vars, model.data.losses_test)
+
+        def train_step(inputs, targets, auxiliary_vars):
+            def closure():
+                losses = outputs_losses_train(inputs, targets, auxiliary_vars)[1]
+                total_loss = torch.sum(losses)
+                model.opt.zero_grad()
+                total_loss.backward()
+                model.last_total_loss = total_loss.detach()
+                return total_loss
+
+            model.opt.step(closure)
+            if model.lr_scheduler is not None:
+                model.lr_scheduler.step()
+
+        pde.compile(model, optimizer, lr, loss, decay)
+        model.outputs_losses_train = outputs_losses_train
+        model.outputs_losses_test = outputs_losses_test
+        model.train_step = train_step
+
+    def eval(self):
+        X, y = self.PDECase.get_testdata()
+        with torch.no_grad():
+            y_pred = bkd.to_numpy(self.get_predict(bkd.from_numpy(X), param_grad=False))
+        error = dde.metrics.l2_relative_error(y, y_pred)
+        print("L2 relative error:", error)
+        self.error.append(np.array(error))

@@ -1,0 +1,27 @@
+"""RAD: residual-based adaptive distribution (/root/reference/AI4XDE/algorithm/RAD.py:7-42).
+Candidate residuals, probabilities and the without-replacement draw run on the device
+(ai4xde_b200/resample.py); the candidate points and the uniforms come from NumPy's global legacy
+stream in the reference's order (candidates first, then one `random_sample` per retry round), so the
+selected set equals `np.random.choice(..., replace=False, p=...)` on the same residuals."""
+from .. import dde, resample
+from ..solver import PINNSolver
+
+
+class RAD(PINNSolver):
+    def __init__(self, PDECase, iter=100, k=1, c=1, warmup_iter=1000):
+        dde.optimizers.config.set_LBFGS_options(maxiter=1000)
+        super().__init__(name=f"RAD_k_{k}_c_{c}", PDECase=PDECase)
+        self.iter, self.k, self.c, self.warmup_iter = iter, k, c, warmup_iter
+
+    def resample(self):
+        case = self.PDECase
+        X = case.geomtime.random_points(case.NumDomain * 10)
+        ids = resample.rad_select(self.model, X, case.pde, case.NumDomain, k=self.k, c=self.c)
+        case.data.replace_with_anchors(X[ids])
+        return ids
+
+    def closure(self):
+        self.train_step(iterations=self.warmup_iter)
+        for _ in range(self.iter):
+            self.resample()
+            self.train_step(iterations=1000)

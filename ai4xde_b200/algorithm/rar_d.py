@@ -1,0 +1,26 @@
+"""RAR_D: residual-based adaptive refinement with distribution
+(/root/reference/AI4XDE/algorithm/RAR_D.py:7-37): 100 000 candidates per round, NumDomain // 100
+new anchors drawn with probability ~ |residual|^k / mean + c and ADDED to the training set."""
+from .. import dde, resample
+from ..solver import PINNSolver
+
+
+class RAR_D(PINNSolver):
+    def __init__(self, PDECase, iter=100, k=2, c=0):
+        dde.optimizers.config.set_LBFGS_options(maxiter=1000)
+        super().__init__(name=f"RAR_D_k_{k}_c_{c}", PDECase=PDECase)
+        self.iter, self.k, self.c = iter, k, c
+        self.num_candidates = 100000
+
+    def resample(self):
+        case = self.PDECase
+        X = case.geomtime.random_points(self.num_candidates)
+        ids = resample.rad_select(self.model, X, case.pde, case.NumDomain // 100, k=self.k, c=self.c)
+        case.data.add_anchors(X[ids])
+        return ids
+
+    def closure(self):
+        self.train_step()
+        for _ in range(self.iter):
+            self.resample()
+            self.train_step(iterations=1000)

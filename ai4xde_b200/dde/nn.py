@@ -136,6 +136,17 @@ class FNN(NN):
             off += n
         self._flat = flat
 
+    def adopt_storage(self, row):
+        """Move the master weights into `row` (a [P] float32 slice of a shared [K, P] bank) so that
+        K structurally identical nets can be evaluated by one fused launch (NetBank)."""
+        off = 0
+        for p in self._param_list():
+            n = p.numel()
+            row[off : off + n] = p.detach().reshape(-1).to(device=row.device, dtype=torch.float32)
+            p.data = row[off : off + n].view(p.shape)
+            off += n
+        self._flat = row
+
     def flat_params(self):
         """[1, P] view of the master buffer (re-packed if someone moved the parameters)."""
         ps = self._param_list()
@@ -199,6 +210,99 @@ class FNN(NN):
                 y = streams[0]
         if self._output_transform is not None:
             y = self._output_transform(inputs, y)
+        return y
+
+
+class _FusedBankForward(torch.autograd.Function):
+    """K nets, one launch.  Streams come back as (n, K*C); the reverse pass runs the fused backward
+    only for the `active` nets (FBPINN trains one subdomain net at a time,
+    /root/reference/AI4XDE/algorithm/FBPINN.py:112-119)."""
+
+    @staticmethod
+    def forward(ctx, bank, x_soa, n, spec, engine, need_backward, active, *params):
+        jets, stash = _lib.jet_forward(bank.net_desc, spec.desc, bank.flat, x_soa, n,
+                                       keep_all=need_backward, engine=engine)
+        ctx.bank, ctx.spec, ctx.engine, ctx.n, ctx.active = bank, spec, engine, n, tuple(active)
+        ctx.x_soa, ctx.stash, ctx.kept = x_soa, stash, bool(need_backward)
+        K, S, C = jets.shape[0], jets.shape[1], jets.shape[2]
+        return tuple(jets[:, s, :, :n].permute(2, 0, 1).reshape(n, K * C) for s in range(S))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        if not ctx.kept:
+            raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
+        bank, spec, n = ctx.bank, ctx.spec, ctx.n
+        K, C = bank.K, bank.layer_sizes[-1]
+        ldn = ctx.x_soa.shape[1]
+        jets_bar = torch.zeros((K, spec.S, C, ldn), dtype=torch.float32, device=bank.flat.device)
+        for s, g in enumerate(gouts):
+            if g is not None:
+                jets_bar[:, s, :, :n] = g.reshape(n, K, C).permute(1, 2, 0)
+        per_net_stash = ctx.stash.numel() // K
+        grads = []
+        for k in ctx.active:
+            g_flat = _lib.jet_backward(bank.single_desc, spec.desc, bank.flat[k : k + 1], ctx.x_soa, n,
+                                       jets_bar[k : k + 1], ctx.stash[k * per_net_stash : (k + 1) * per_net_stash],
+                                       engine=ctx.engine)[0]
+            off = 0
+            for shp in bank.shapes:
+                cnt = 1
+                for d in shp:
+                    cnt *= d
+                grads.append(g_flat[off : off + cnt].view(shp))
+                off += cnt
+        ctx.stash = None
+        return (None,) * 7 + tuple(grads)
+
+
+class NetBank:
+    """K structurally identical FNNs sharing one [K, P] master buffer, evaluated on the same points
+    by a single fused kernel sequence (`n_nets = K` in the C ABI)."""
+
+    def __init__(self, nets):
+        first = nets[0]
+        for n_ in nets:
+            if n_.layer_sizes != first.layer_sizes or n_.activation_name != first.activation_name:
+                raise ValueError("NetBank needs structurally identical nets")
+            if n_._input_transform is not None:
+                raise NotImplementedError("feature transforms are not in the fused jet path yet")
+        self.nets = list(nets)
+        self.K = len(nets)
+        self.layer_sizes = first.layer_sizes
+        self.net_desc = _lib.make_net_desc(first.layer_sizes, first.activation_name, n_nets=self.K)
+        self.single_desc = _lib.make_net_desc(first.layer_sizes, first.activation_name, n_nets=1)
+        P = _lib.param_count(self.single_desc) if False else sum(p.numel() for p in first._param_list())
+        self.flat = torch.empty((self.K, P), dtype=torch.float32, device=config.device())
+        for k, n_ in enumerate(self.nets):
+            n_.adopt_storage(self.flat[k])
+        self.shapes = [p.shape for p in first._param_list()]
+
+    def _check_storage(self):
+        base, P = self.flat.data_ptr(), self.flat.shape[1]
+        for k, n_ in enumerate(self.nets):
+            if n_._param_list()[0].data_ptr() != base + 4 * k * P:
+                n_.adopt_storage(self.flat[k])
+
+    def forward_all(self, x, x_soa=None, spec=None, active=None, param_grad=True):
+        """Raw outputs of all K nets on x as one (n, K*C) tensor whose x-derivatives are the
+        kernels' jet streams; parameter gradients flow to the `active` nets only."""
+        self._check_storage()
+        wants_jets = x.requires_grad and torch.is_grad_enabled()
+        if not wants_jets:
+            spec = jet.JetSpec.value_only()
+        elif spec is None:
+            spec = jet.JetSpec.full(x.shape[1])
+        if x_soa is None or x_soa.shape[1] < x.shape[0]:
+            x_soa = jet.to_soa(x)
+        active = list(range(self.K)) if active is None else list(active)
+        need_bwd = bool(param_grad and torch.is_grad_enabled() and active)
+        params = [p for k in active for p in self.nets[k]._param_list()]
+        streams = _FusedBankForward.apply(self, x_soa, x.shape[0], spec, config.engine(), need_bwd, active, *params)
+        if not wants_jets:
+            return streams[0]
+        y = jet.make_leaf(x, spec, streams)
+        grad.register(y, jet.JetOutput(x, spec, streams))
         return y
 
 

@@ -8,7 +8,6 @@ section 8a rows G1/G2/N1.
 """
 import torch
 from torch.autograd import Function
-from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -87,39 +86,6 @@ def to_soa(x):
     out = torch.zeros((d, ldn), dtype=torch.float32, device=x.device)
     out[:, :n] = x.detach().t()
     return out
-
-
-class JetMLP(Function):
-    """params -> S jet streams, each (K, n, C); backward = fused reverse pass."""
-
-    @staticmethod
-    def forward(ctx, flat_params, x_soa, n, net_desc, spec, engine, need_backward):
-        jets, stash = _lib.jet_forward(net_desc, spec.desc, flat_params, x_soa, n,
-                                       keep_all=need_backward, engine=engine)
-        ctx.net_desc, ctx.spec, ctx.engine, ctx.n = net_desc, spec, engine, n
-        ctx.x_soa, ctx.stash, ctx.kept = x_soa, stash, bool(need_backward)
-        ctx.save_for_backward(flat_params)
-        # jets: [K, S, C, ldn] -> per-stream (K, n, C) strided views
-        return tuple(jets[:, s, :, :n].transpose(1, 2) for s in range(spec.S))
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, *gouts):
-        if not ctx.kept:
-            raise RuntimeError("JetMLP: backward requested but the forward ran without a stash")
-        (flat_params,) = ctx.saved_tensors
-        net, spec, n = ctx.net_desc, ctx.spec, ctx.n
-        ldn = ctx.x_soa.shape[1]
-        C_out = net.widths[net.n_linear]
-        jets_bar = torch.zeros((net.n_nets, spec.S, C_out, ldn), dtype=torch.float32,
-                               device=flat_params.device)
-        for s, g in enumerate(gouts):
-            if g is not None:
-                jets_bar[:, s, :, :n] = g.transpose(1, 2)
-        grad = _lib.jet_backward(net, spec.desc, flat_params, ctx.x_soa, n, jets_bar, ctx.stash,
-                                 engine=ctx.engine)
-        ctx.stash = None
-        return grad, None, None, None, None, None, None
 
 
 # ---- functions with known derivatives -------------------------------------------------------
@@ -203,16 +169,22 @@ class JetOutput:
     """Record kept per network evaluation so dde.grad.jacobian/hessian can read the streams
     directly when asked about the raw network output (no output transform in between)."""
 
-    __slots__ = ("x", "spec", "streams")
+    __slots__ = ("x", "spec", "streams", "_first", "_second")
 
     def __init__(self, x, spec, streams):
         self.x, self.spec, self.streams = x, spec, streams
+        self._first, self._second = {}, {}
 
     def first(self, comp, dim):
+        """d y_comp / d x_dim as a tensor that is itself differentiable w.r.t. x (through the
+        second-order streams), so `jacobian(jacobian(y, x), x)` keeps working."""
         j = self.spec.first_of_dim.get(dim)
         if j is None:
             return None
-        return self.streams[1 + j][:, comp : comp + 1]
+        if j not in self._first:
+            n1 = self.spec.n1
+            self._first[j] = _Leaf1.apply(self.x, self.spec, j, self.streams[1 + j], *self.streams[1 + n1:])
+        return self._first[j][:, comp : comp + 1]
 
     def first_all(self, comp):
         """(n, d_in) Jacobian row of component `comp`, or None if a column is not carried."""
@@ -228,7 +200,9 @@ class JetOutput:
         q = self.spec.second_of_dims.get((dim_i, dim_j))
         if q is None:
             return None
-        return self.streams[1 + self.spec.n1 + q][:, comp : comp + 1]
+        if q not in self._second:
+            self._second[q] = _Leaf2.apply(self.x, self.streams[1 + self.spec.n1 + q])
+        return self._second[q][:, comp : comp + 1]
 
 
 def make_leaf(x, spec, streams):

@@ -1,0 +1,140 @@
+"""GPU: the algorithm mirrors on the fused path against the oracle's NumPy selections, on the same
+residuals (whatever the device computed) and the same NumPy random stream."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    warnings.simplefilter("ignore")
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float64")
+    return dde
+
+
+def test_rad_round_equals_numpy_choice_on_device_residuals():
+    dde = _setup()
+    from ai4xde_b200 import algorithm, cases
+    from oracle import sampling
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = cases.AllenCahn(NumDomain=2000, layer_size=[2] + [64] * 4 + [1])
+    solver = algorithm.RAD(case, iter=1, k=1, c=1)
+    case.compile(solver.model, "adam", lr=1e-3)
+    np.random.seed(21)
+    state = np.random.get_state()
+    ids = solver.resample()
+    # oracle: same candidates, the device's residuals, NumPy's own choice
+    np.random.set_state(state)
+    X = case.geomtime.random_points(case.NumDomain * 10)
+    res = solver.model.predict(X, operator=case.pde)
+    ids_ref, picked = sampling.rad_select(X, res, case.NumDomain, k=1, c=1)
+    assert np.array_equal(ids, ids_ref)
+    assert np.array_equal(case.data.train_x_all, picked)
+    assert len(np.unique(ids)) == case.NumDomain
+
+
+def test_rar_d_round_adds_anchors():
+    dde = _setup()
+    from ai4xde_b200 import algorithm, cases
+    from oracle import sampling
+
+    np.random.seed(1)
+    torch.manual_seed(1)
+    case = cases.Burgers(NumDomain=1000, layer_size=[2, 20, 20, 20, 1])
+    solver = algorithm.RAR_D(case, iter=1, k=2, c=0)
+    case.compile(solver.model, "adam", lr=1e-3)
+    before = case.data.train_x_all.copy()
+    np.random.seed(33)
+    state = np.random.get_state()
+    ids = solver.resample()
+    np.random.set_state(state)
+    X = case.geomtime.random_points(100000)
+    res = solver.model.predict(X, operator=case.pde)
+    ids_ref, picked = sampling.rar_d_select(X, res, 10, k=2, c=0)
+    assert np.array_equal(ids, ids_ref)
+    assert np.array_equal(case.data.train_x_all, np.vstack((picked, before)))
+
+
+def test_r3_round_equals_numpy_selection():
+    dde = _setup()
+    from ai4xde_b200 import algorithm, cases, resample
+    from oracle import sampling
+
+    np.random.seed(2)
+    torch.manual_seed(2)
+    case = cases.Helmholtz(NumDomain=20000, layer_size=[2] + [64] * 3 + [1], activation="tanh", honor_num_domain=True)
+    solver = algorithm.R3Sampling(case, max_iter=1)
+    case.compile(solver.model, "adam", lr=1e-3)
+    X = case.data.train_x_all.copy()
+    res_dev, n = resample.residual_matrix(solver.model, X, case.pde)
+    rs = sampling.r3_residual(res_dev[0, :n].cpu().numpy()[:, None])
+    thr, keep_ref, Xr = sampling.r3_select(X, rs)
+    np.random.seed(5)
+    keep = solver.resample()
+    assert np.array_equal(keep, keep_ref)
+    new_all = case.data.train_x_all
+    assert len(new_all) == len(X)                                   # population size is constant
+    assert np.array_equal(new_all[len(X) - len(Xr):], Xr)           # [new ; retained]  (R3Sampling.py:95-98)
+    # device-side compaction holds the same retained points (float32 mirror)
+    keep2, thr2, x_dev, nk = resample.r3_retain(solver.model, X, case.pde)
+    assert nk == int(keep_ref.sum()) and np.float32(thr) == np.float32(thr2)
+    got = x_dev[:, n - nk:n].t().cpu().numpy()
+    assert np.array_equal(got, Xr.astype(np.float32))
+
+
+def test_fbpinn_batched_nets_on_gpu():
+    dde = _setup()
+    from ai4xde_b200 import algorithm, cases
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = cases.Harmonic_Oscillator_1D(NumDomain=64, hard_condition=True, layer_size=[1, 64, 64, 64, 1])
+    solver = algorithm.FBPINN(case, segment=8, iter=1)
+    x = torch.rand(100, 1, device="cuda").requires_grad_()
+    for engine in ("fp32", "tf32"):
+        dde.config.set_engine(engine)
+        y = solver.get_predict(x)
+        ref = sum(m.net(x) for m in solver.model_list)
+        tol = 1e-5 if engine == "fp32" else 5e-3
+        assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+        dde.grad.clear()
+    dde.config.set_engine("auto")
+    dde.optimizers.set_LBFGS_options(maxiter=3)
+    solver.train_step(iterations=3, eval=False)
+    assert np.isfinite(solver.losshistory.loss_train[-1]).all()
+    dde.optimizers.set_LBFGS_options()
+
+
+def test_pinn_short_training_tracks_oracle_loss_curve():
+    """1 % loss-curve agreement over the first 200 Adam steps, FP32 engine vs float64 oracle
+    (cfg1: Burgers soft constraints, 2540+80+160 points)."""
+    dde = _setup()
+    from ai4xde_b200 import cases as pc
+    from oracle import cases as oc, ddelite
+
+    ddelite.config.set_default_float("float64")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    odata, onet, _ = oc.build("cfg1", 2540)
+    omodel = ddelite.Model(odata, onet)
+    omodel.compile("adam", lr=1e-3)
+    state = {k: v.detach().float() for k, v in onet.state_dict().items()}
+    olh, _ = omodel.train(iterations=200, display_every=20)
+    ddelite.config.set_default_float("float32")
+    torch.set_default_dtype(torch.float32)
+    case = pc.Burgers(NumDomain=0, layer_size=[2, 20, 20, 20, 1], soft_constraints=True)
+    case.data = dde.data.TimePDE(case.geomtime, case.pde, case.data.bcs, num_domain=0, anchors=odata.train_x_all,
+                                 train_distribution="pseudo")
+    case.net.load_state_dict(state)
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3)
+    lh, _ = model.train(iterations=200, display_every=20)
+    a, b = np.array(lh.loss_train).sum(1), np.array(olh.loss_train).sum(1)
+    assert np.abs(a - b).max() / b.max() < 1e-2

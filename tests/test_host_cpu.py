@@ -1,0 +1,244 @@
+"""Host side of the fused path on a CPU box: the product's own dde namespace / cases / Model /
+algorithms driven with the plain-PyTorch Taylor-mode double in place of the two kernel calls
+(tests/_taylor_double.py), checked against the reference goldens and the oracle.  This covers
+stream discovery, grad interception (raw and through output transforms), per-term losses, BC
+slicing, loss weights, Adam/L-BFGS loops, anchors bookkeeping and the FBPINN bank."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import _taylor_double as td
+from parity_util import product_vs_oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(autouse=True)
+def double(monkeypatch):
+    td.install(monkeypatch)
+    warnings.simplefilter("ignore")
+    yield
+
+
+def _product_case(name, g):
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    dde.config.set_default_float("float64")
+    ls = [int(v) for v in g["layer_size"]]
+    X = g["train_x_all"]
+    lw = None
+    if name == "heat_soft":
+        case = pc.Heat(NumDomain=1, layer_size=ls)
+        data = dde.data.TimePDE(case.geomtime, case.pde, case.data.bcs, num_domain=0, anchors=X, train_distribution="pseudo")
+    elif name == "burgers_hard":
+        case = pc.Burgers(NumDomain=1, layer_size=ls)
+        data = dde.data.TimePDE(case.geomtime, case.pde, [], num_domain=0, anchors=X, train_distribution="pseudo")
+    elif name == "allencahn":
+        case = pc.AllenCahn(NumDomain=1, layer_size=ls)
+        data = dde.data.TimePDE(case.geomtime, case.pde, [], num_domain=0, anchors=X, train_distribution="pseudo")
+    elif name == "ns_cavity":
+        case = pc.NS_Flow_in_LidDriven_Cavity(NumDomain=1, layer_size=ls, train_distribution="pseudo")
+        data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=X, train_distribution="pseudo")
+    elif name in ("helmholtz_tanh", "helmholtz_sin"):
+        case = pc.Helmholtz(layer_size=ls, activation="sin" if name.endswith("sin") else "tanh")
+        data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=X, train_distribution="pseudo")
+        lw = case.loss_weights
+    elif name == "poisson1d_multiscale":
+        case = pc.Poisson_1D_Fourier_Net(NumDomain=1, layer_size=ls)
+        data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=X, train_distribution="pseudo")
+    case.data = data
+    off, sd = 0, {}
+    for i, lin in enumerate(case.net.linears):
+        for nm, p in (("weight", lin.weight), ("bias", lin.bias)):
+            n = p.numel()
+            sd[f"linears.{i}.{nm}"] = torch.as_tensor(g["params"][off:off + n], dtype=torch.float32).reshape(p.shape)
+            off += n
+    case.net.load_state_dict(sd)
+    return case, lw
+
+
+@pytest.mark.parametrize("name", ["heat_soft", "burgers_hard", "allencahn", "ns_cavity", "helmholtz_tanh",
+                                  "helmholtz_sin", "poisson1d_multiscale"])
+def test_product_host_path_matches_reference_goldens(name):
+    import ai4xde_b200.dde as dde
+
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    case, lw = _product_case(name, g)
+    assert np.array_equal(case.data.train_x, g["train_x"])
+    assert list(case.data.num_bcs) == list(g["num_bcs"])
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3, loss_weights=lw)
+    res = model.predict_on_device(case.data.train_x, case.pde)
+    res = list(res) if isinstance(res, (list, tuple)) else [res]
+    outs, losses = model.outputs_losses_train(case.data.train_x, None, None)
+    case.net.zero_grad()
+    losses.sum().backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in case.net.parameters()]).numpy()
+
+    def rel(a, b):
+        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+    assert rel(outs.detach().numpy(), g["outputs"]) < 2e-5
+    assert rel(np.stack([r.numpy() for r in res]), g["residuals"]) < 5e-5
+    assert rel(losses.detach().numpy(), g["losses"]) < 2e-5
+    assert rel(grad, g["grad"]) < 1e-4
+
+
+@pytest.mark.parametrize("cfg,n", [("cfg1", 400), ("cfg2", 300), ("cfg3", 256), ("cfg4", 200), ("cfg5", 300)])
+def test_baseline_configs_match_oracle(cfg, n):
+    r = product_vs_oracle(cfg, n)
+    assert r["loss_rel"] < 1e-5 and r["out_rel"] < 1e-5, r
+    assert r["grad_rel"] < 2e-5 and r["res_rel"] < 5e-5, r
+
+
+def test_stream_discovery():
+    """The dry run asks the kernels for exactly what the case's pde/BCs use."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    def spec_of(case, lw=None):
+        m = dde.Model(case.data, case.net)
+        m.compile("adam", lr=1e-3, loss_weights=lw)
+        m.outputs_losses_train(case.data.train_x, None, None)
+        return [v for k, v in m._specs.items() if k[0] == "losses"][0]
+
+    np.random.seed(0)
+    s = spec_of(pc.Burgers(NumDomain=20, layer_size=[2, 8, 1]))
+    assert s.dirs == (0, 1) and s.pairs == ((0, 0),)                      # {u, u_x, u_t, u_xx}
+    s = spec_of(pc.Helmholtz(layer_size=[2, 8, 1], activation="tanh"), [1, 100])
+    assert s.dirs == (0, 1) and s.pairs == ((0, 0), (1, 1))               # {u, (u_x, u_y), u_xx, u_yy}
+    s = spec_of(pc.Poisson_1D_Dirichlet(NumDomain=8, layer_size=[1, 8, 1]))
+    assert s.dirs == (0,) and s.pairs == ((0, 0),)
+    s = spec_of(pc.Harmonic_Oscillator_1D(NumDomain=8, layer_size=[1, 8, 1]))   # Neumann BC + u''
+    assert s.dirs == (0,) and s.pairs == ((0, 0),)
+
+
+def test_grad_signatures_and_errors():
+    import ai4xde_b200.dde as dde
+
+    np.random.seed(0)
+    net = dde.nn.FNN([2, 8, 3], "tanh", "Glorot uniform")
+    x = torch.rand(5, 2).requires_grad_()
+    y = net(x)
+    assert dde.grad.jacobian(y, x, i=1, j=0).shape == (5, 1)
+    assert dde.grad.jacobian(y, x, i=2).shape == (5, 2)
+    assert dde.grad.hessian(y, x, component=1, i=0, j=1).shape == (5, 1)
+    with pytest.raises(ValueError):
+        dde.grad.jacobian(y, x, i=3)
+    with pytest.raises(ValueError):
+        dde.grad.jacobian(y, x, i=0, j=2)
+    with pytest.raises(ValueError, match="component of y is missing"):
+        dde.grad.hessian(y, x, i=0, j=0)
+    # derived tensors go through autograd down to the jet leaves and agree with the direct streams
+    mu = 2 * (x[:, 0:1] + x[:, 1:2]) * y[:, 0:1]
+    d_mu = dde.grad.jacobian(mu, x, i=0, j=0)
+    direct = 2 * y[:, 0:1] + 2 * (x[:, 0:1] + x[:, 1:2]) * dde.grad.jacobian(y, x, i=0, j=0)
+    assert torch.allclose(d_mu, direct, atol=1e-6)
+    dde.grad.clear()
+    y1 = dde.nn.FNN([2, 8, 1], "tanh", "Glorot uniform")(x)
+    with pytest.raises(ValueError, match="Do not use component"):
+        dde.grad.hessian(y1, x, component=0)
+    with pytest.raises(NotImplementedError, match="third"):
+        h = dde.grad.hessian(y1, x, i=0, j=0)
+        dde.grad.jacobian(h, x, i=0, j=0)
+    dde.grad.clear()
+
+
+def test_training_loop_adam_then_lbfgs_and_loss_curve():
+    """PINNSolver two-phase schedule runs; the float32 fused-path loss curve tracks the float64
+    oracle within 1 % over the first steps (same points, same weights, Adam 1e-3)."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import algorithm, cases as pc
+    from oracle import cases as oc, ddelite
+
+    ddelite.config.set_default_float("float64")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    odata, onet, _ = oc.build("cfg1", 300)
+    omodel = ddelite.Model(odata, onet)
+    omodel.compile("adam", lr=1e-3)
+    state = {k: v.detach().float() for k, v in onet.state_dict().items()}
+    olh, _ = omodel.train(iterations=60, display_every=10)
+    ddelite.config.set_default_float("float32")
+    torch.set_default_dtype(torch.float32)
+
+    case = pc.Burgers(NumDomain=0, layer_size=[2, 20, 20, 20, 1], soft_constraints=True)
+    case.data = dde.data.TimePDE(case.geomtime, case.pde, case.data.bcs, num_domain=0, anchors=odata.train_x_all,
+                                 train_distribution="pseudo")
+    case.net.load_state_dict(state)
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3)
+    lh, ts = model.train(iterations=60, display_every=10)
+    a, b = np.array(lh.loss_train).sum(1), np.array(olh.loss_train).sum(1)
+    assert lh.steps == olh.steps
+    assert np.abs(a - b).max() / b.max() < 1e-2
+    dde.optimizers.set_LBFGS_options(maxiter=5)
+    solver = algorithm.PINN(pc.Burgers(NumDomain=50, layer_size=[2, 8, 8, 1]), iteration=3)
+    solver.train()
+    assert solver.train_state.step >= 3 and np.isfinite(solver.losshistory.loss_train[-1]).all()
+    dde.optimizers.set_LBFGS_options()
+
+
+def test_anchor_bookkeeping_matches_oracle():
+    import ai4xde_b200.dde as dde
+    from oracle import ddelite
+
+    for mod in (dde, ddelite):
+        mod.config.set_default_float("float64")
+    try:
+        def build(m):
+            np.random.seed(3)
+            gt = m.geometry.GeometryXTime(m.geometry.Interval(-1, 1), m.geometry.TimeDomain(0, 1))
+            bc = m.icbc.DirichletBC(gt, lambda x: 0, lambda _, on: on)
+            ic = m.icbc.IC(gt, lambda x: 0 * x[:, 0:1], lambda _, on: on)
+            return m.data.TimePDE(gt, lambda x, y: y, [bc, ic], num_domain=30, num_boundary=8, num_initial=6,
+                                  train_distribution="pseudo")
+
+        a, b = build(dde), build(ddelite)
+        assert np.array_equal(a.train_x, b.train_x) and a.num_bcs == b.num_bcs
+        rng = np.random.RandomState(0)
+        extra, repl = rng.rand(5, 2), rng.rand(7, 2)
+        for d in (a, b):
+            d.add_anchors(extra)
+        assert np.array_equal(a.train_x, b.train_x) and np.array_equal(a.train_x_all, b.train_x_all)
+        for d in (a, b):
+            d.replace_with_anchors(repl)
+            d.add_anchors(extra)
+        assert np.array_equal(a.train_x, b.train_x) and np.array_equal(a.train_x_all, b.train_x_all)
+        np.random.seed(9)
+        a.resample_train_points()
+        np.random.seed(9)
+        b.resample_train_points()
+        assert np.array_equal(a.train_x, b.train_x)
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+
+
+def test_fbpinn_bank_matches_sum_of_nets():
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import algorithm, cases as pc
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = pc.Harmonic_Oscillator_1D(NumDomain=40, hard_condition=True, layer_size=[1, 16, 16, 1])
+    solver = algorithm.FBPINN(case, segment=4, iter=1)
+    lims = solver.domains.limits
+    assert len(lims) == 4 and lims[0][0] == 0 and lims[-1][1] == 1
+    assert abs(lims[1][0] - (0.25 - 0.025)) < 1e-12 and abs(lims[1][1] - (0.5 + 0.025)) < 1e-12   # FBPINN.py:52-63
+    x = torch.rand(11, 1).requires_grad_()
+    y = solver.get_predict(x)
+    ref = sum(m.net(x) for m in solver.model_list)          # the reference's get_predict loop
+    assert torch.allclose(y, ref, atol=1e-6)
+    dde.grad.clear()
+    # one subdomain step only moves that subdomain's net
+    before = solver.bank.flat.clone()
+    model, pde = solver.model_list[1], solver.domains.pdeCase_list[1]
+    solver.compile(pde, model, "adam", lr=1e-3)
+    model.train(iterations=2)
+    moved = (solver.bank.flat - before).abs().sum(dim=1)
+    assert moved[1] > 0 and moved[0] == 0 and moved[2] == 0 and moved[3] == 0
