@@ -162,6 +162,32 @@ class Model:
             return operator(x, y, self.net.auxiliary_vars)
         raise ValueError("operator must take 2 or 3 arguments")
 
+    # ---- data parallel -----------------------------------------------------------------------
+    def _dp_term_scale(self, losses, inputs):
+        """Per-term factor n_local * world / n_global that turns the all-reduce MEAN of the ranks'
+        local means into the exact global mean (sums and global counts), cached per
+        point-set version.  None for a single process or for batches that are not the training set."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+        data = self.data
+        if inputs is not data.train_x or getattr(data, "num_bcs", None) is None:
+            return None
+        key = (getattr(data, "version", None), losses.numel())
+        hit = getattr(self, "_dp_scale_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        n_bc = [int(c) for c in data.num_bcs]
+        n_res = losses.numel() - len(n_bc)
+        counts = [len(data.train_x) - sum(n_bc)] * n_res + n_bc
+        local = torch.tensor(counts, dtype=torch.float64, device=losses.device)
+        glob = local.clone()
+        dist.all_reduce(glob, op=dist.ReduceOp.SUM)
+        scale = (local * dist.get_world_size() / glob.clamp_min(1)).to(torch.float32)
+        self._dp_scale_cache = (key, scale)
+        return scale
+
     # ---- compile -----------------------------------------------------------------------------
     def compile(self, optimizer, lr=None, loss="MSE", metrics=None, decay=None, loss_weights=None,
                 external_trainable_variables=None):
@@ -203,6 +229,9 @@ class Model:
                 if self._weights_dev is None:
                     self._weights_dev = torch.as_tensor(self.loss_weights, dtype=torch.float32, device=losses.device)
                 losses = losses * self._weights_dev
+            scale = self._dp_term_scale(losses, inputs)
+            if scale is not None:
+                losses = losses * scale
             grad.clear()
             return outputs_, losses
 

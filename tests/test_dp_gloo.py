@@ -1,6 +1,7 @@
-"""Data-parallel semantics on CPU (world_size 2, gloo): each rank owns half of the collocation points
-(BC rows replicated), the flat gradient is all-reduced (mean) inside dde.Model's closure, and the
-result equals the single-process gradient on the concatenated point set."""
+"""Data-parallel semantics on CPU (world_size 2, gloo): each rank owns a (deliberately unequal) shard
+of the collocation and boundary points, per-term losses are weighted by n_local * world / n_global,
+the flat gradient is all-reduced (mean) inside dde.Model's closure, and the result equals the
+single-process gradient on the concatenated point set (sums and global counts)."""
 import os
 import sys
 
@@ -26,8 +27,9 @@ def _build(points_all, rank=None, world=1):
     bdry = points_all[:16]
     dom = points_all[16:]
     if rank is not None:
-        per = len(dom) // world
-        dom = dom[rank * per:(rank + 1) * per]
+        # unequal shards on purpose: the exchange must weight by global counts, not average means
+        bdry = bdry[:6] if rank == 0 else bdry[6:]
+        dom = dom[:40] if rank == 0 else dom[40:]
     X = np.vstack((bdry, dom))
     data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=X, train_distribution="pseudo")
     model = dde.Model(data, case.net)

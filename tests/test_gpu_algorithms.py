@@ -106,9 +106,17 @@ def test_fbpinn_batched_nets_on_gpu():
         assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
         dde.grad.clear()
     dde.config.set_engine("auto")
+    # train a decomposition whose sub-cases all own boundary rows (sub-cases are built with the
+    # parent's class defaults, FBPINN.py:42, so the oscillator's t=0 conditions would be empty -> NaN
+    # on every subdomain but the first, exactly as in the reference)
+    np.random.seed(1)
+    case = cases.Poisson_1D_Dirichlet(NumDomain=64, layer_size=[1, 64, 64, 64, 1])
+    solver = algorithm.FBPINN(case, segment=4, iter=1)
     dde.optimizers.set_LBFGS_options(maxiter=3)
-    solver.train_step(iterations=3, eval=False)
+    before = solver.bank.flat.clone()
+    solver.train_step(iterations=3, eval=True)
     assert np.isfinite(solver.losshistory.loss_train[-1]).all()
+    assert bool(((solver.bank.flat - before).abs().sum(dim=1) > 0).all())
     dde.optimizers.set_LBFGS_options()
 
 
