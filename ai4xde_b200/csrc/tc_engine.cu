@@ -617,22 +617,40 @@ __global__ void k_tc_first(const float *__restrict__ W, const float *__restrict_
   }
 }
 
-// output layer forward: jets[s][c][p] = sum_k Wout[c][k] A[(p,s)][k] (+ b_c for s = 0); warp per row
-__global__ void k_tc_last_fwd(const float *__restrict__ Wout, const float *__restrict__ bout,
-                              const float *__restrict__ actL, int H, int C, int S, long long n, long long ldn,
-                              float *__restrict__ jets) {
+// output layer forward: jets[s][c][p] = sum_k Wout[c][k] A[(p,s)][k] (+ b_c for s = 0).
+// A warp owns 4 rows at a time (4 x H/32 independent loads in flight per lane), lanes over k.
+__global__ void __launch_bounds__(256)
+k_tc_last_fwd(const float *__restrict__ Wout, const float *__restrict__ bout, const float *__restrict__ actL,
+              int H, int C, int S, long long n, long long ldn, float *__restrict__ jets) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = warp_global; row < n * S; row += nwarps) {
-    const long long p = row / S;
-    const int s = (int)(row - p * S);
-    const float *a = actL + row * H;
+  const long long rows = n * S;
+  const int KL = H / 32;  // <= 8
+  for (long long row0 = warp_global * 4; row0 < rows; row0 += nwarps * 4) {
+    float a[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        a[r][j] = (j < KL && row0 + r < rows) ? __ldg(actL + (row0 + r) * H + lane + 32 * j) : 0.0f;
     for (int c = 0; c < C; ++c) {
-      float acc = 0.0f;
-      for (int k = lane; k < H; k += 32) acc = fmaf(__ldg(Wout + (long long)c * H + k), a[k], acc);
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) jets[((long long)s * C + c) * ldn + p] = acc + (s == 0 ? __ldg(bout + c) : 0.0f);
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = j < KL ? __ldg(Wout + (long long)c * H + lane + 32 * j) : 0.0f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(w[j], a[r][j], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const long long row = row0 + r;
+        if (lane == 0 && row < rows) {
+          const long long p = row / S;
+          const int s_ = (int)(row - p * S);
+          jets[((long long)s_ * C + c) * ldn + p] = acc + (s_ == 0 ? __ldg(bout + c) : 0.0f);
+        }
+      }
     }
   }
 }
@@ -640,9 +658,10 @@ __global__ void k_tc_last_fwd(const float *__restrict__ Wout, const float *__res
 // output layer backward: zbar_{L-1} from jets_bar; per-block partials of dWout, dbout, db_{L-1}
 // block = H threads (unit k), PB points per block.  partial layout per block: [C*H | C | H]
 template <class P>
-__global__ void k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar,
-                              const float *__restrict__ actL, int H, int C, long long n, long long ldn,
-                              int pts_per_block, float *__restrict__ gout, float *__restrict__ partial, int act) {
+__global__ void __launch_bounds__(256)
+k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar,
+              const float *__restrict__ actL, int H, int C, long long n, long long ldn,
+              int pts_per_block, float *__restrict__ gout, float *__restrict__ partial, int act) {
   constexpr int S = P::S;
   const int k = threadIdx.x;
   if (k >= H) return;
@@ -655,29 +674,40 @@ __global__ void k_tc_last_bwd(const float *__restrict__ Wout, const float *__res
   }
   float dbh = 0.0f;
   const long long p_beg = (long long)blockIdx.x * pts_per_block;
-  for (int pp = 0; pp < pts_per_block; ++pp) {
-    const long long p = p_beg + pp;
-    if (p >= n) break;
-    float A[S], ab[S], zb[S];
+  constexpr int U = 4;  // points in flight per thread
+  for (int pp = 0; pp < pts_per_block; pp += U) {
+    if (p_beg + pp >= n) break;
+    float A[U][S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      A[s] = actL[(p * S + s) * H + k];
-      float acc = 0.0f;
+    for (int u = 0; u < U; ++u) {
+      const long long p = p_beg + pp + u;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < C) {
-          const float ob = __ldg(jets_bar + ((long long)s * C + c) * ldn + p);
-          acc = fmaf(wc[c], ob, acc);
-          dw[c] = fmaf(ob, A[s], dw[c]);
-          if (s == 0) dbo[c] += ob;
-        }
-      ab[s] = acc;
+      for (int s = 0; s < S; ++s) A[u][s] = (p < n) ? __ldg(actL + (p * S + s) * H + k) : 0.0f;
     }
-    jet_adjoint_A<P>(act, A, ab, zb);
-    dbh += zb[0];
-    float *dst = gout + (p * S) * H + k;
 #pragma unroll
-    for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(zb[s]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = p_beg + pp + u;
+      if (p >= n) break;
+      float ab[S], zb[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < C) {
+            const float ob = __ldg(jets_bar + ((long long)s * C + c) * ldn + p);
+            acc = fmaf(wc[c], ob, acc);
+            dw[c] = fmaf(ob, A[u][s], dw[c]);
+            if (s == 0) dbo[c] += ob;
+          }
+        ab[s] = acc;
+      }
+      jet_adjoint_A<P>(act, A[u], ab, zb);
+      dbh += zb[0];
+      float *dst = gout + (p * S) * H + k;
+#pragma unroll
+      for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(zb[s]);
+    }
   }
   float *part = partial + (long long)blockIdx.x * ((long long)C * H + C + H);
   for (int c = 0; c < C; ++c) part[(long long)c * H + k] = dw[c];
@@ -698,20 +728,29 @@ __global__ void k_tc_first_bwd(const float *__restrict__ g0, const float *__rest
 #pragma unroll
   for (int d = 0; d < 8; ++d) acc[d] = 0.0f;
   const long long p_beg = (long long)blockIdx.x * pts_per_block;
-  for (int pp = 0; pp < pts_per_block; ++pp) {
-    const long long p = p_beg + pp;
-    if (p >= n) break;
-    const float *src = g0 + (p * S) * H + i;
-    const float z0 = src[0];
+  constexpr int U = 8;  // points in flight per thread
+  for (int pp = 0; pp < pts_per_block; pp += U) {
+    if (p_beg + pp >= n) break;
+    float zz[U][1 + P::N1];
 #pragma unroll
-    for (int d = 0; d < 8; ++d)
-      if (d < d_in) acc[d] = fmaf(z0, __ldg(x + (long long)d * ldn + p), acc[d]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = p_beg + pp + u;
 #pragma unroll
-    for (int j = 0; j < P::N1; ++j) {
-      const float zj = src[(long long)(1 + j) * H];
+      for (int s = 0; s < 1 + P::N1; ++s) zz[u][s] = (p < n) ? __ldg(g0 + (p * S + s) * H + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p_beg + pp + u;
+      if (p >= n) break;
 #pragma unroll
       for (int d = 0; d < 8; ++d)
-        if (d == dirs.d[j]) acc[d] += zj;
+        if (d < d_in) acc[d] = fmaf(zz[u][0], __ldg(x + (long long)d * ldn + p), acc[d]);
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          if (d == dirs.d[j]) acc[d] += zz[u][1 + j];
+      }
     }
   }
   float *part = partial + (long long)blockIdx.x * ((long long)H * d_in);
@@ -858,8 +897,8 @@ static int reduce_to(const float *partial, long long stride, long long sub, int 
   return 0;
 }
 
-constexpr int kLastPts = 256;   // points per block of the output-layer backward
-constexpr int kFirstPts = 256;  // points per block of the first-layer backward
+constexpr int kLastPts = 128;   // points per block of the output-layer backward
+constexpr int kFirstPts = 128;  // points per block of the first-layer backward
 
 static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id == 4 || id == 5 || id == 6; }
 
@@ -958,7 +997,7 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
     }
     {
       KernelTimer t("tc_last_fwd", a.stream, 2.0 * S * H * C * (double)a.n, 4.0 * S * H * (double)a.n);
-      const int blocks = sm_count() * 8;
+      const int blocks = sm_count() * 16;
       k_tc_last_fwd<<<blocks, 256, 0, a.stream>>>(prm + g.w_off[g.L], prm + g.b_off[g.L], slot(g.L - 1), H, C, S,
                                                   a.n, a.ldn, jets);
     }
