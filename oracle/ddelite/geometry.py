@@ -66,6 +66,59 @@ class Geometry:
     def periodic_point(self, x, component):
         raise NotImplementedError
 
+    def __sub__(self, other):
+        return CSGDifference(self, other)
+
+
+class CSGDifference(Geometry):
+    """geom1 - geom2 (DeepXDE csg.CSGDifference), used at /root/reference/AI4XDE/cases/PDECases.py:679,831."""
+
+    def __init__(self, geom1, geom2):
+        if geom1.dim != geom2.dim:
+            raise ValueError("{} - {} failed (dimensions do not match).".format(geom1.idstr, geom2.idstr))
+        super().__init__(geom1.dim, geom1.bbox, geom1.diam)
+        self.geom1, self.geom2 = geom1, geom2
+
+    def inside(self, x):
+        return np.logical_and(self.geom1.inside(x), ~self.geom2.inside(x))
+
+    def on_boundary(self, x):
+        return np.logical_or(
+            np.logical_and(self.geom1.on_boundary(x), ~self.geom2.inside(x)),
+            np.logical_and(self.geom1.inside(x), self.geom2.on_boundary(x)),
+        )
+
+    def boundary_normal(self, x):
+        return np.logical_and(self.geom1.on_boundary(x), ~self.geom2.inside(x))[:, np.newaxis] * self.geom1.boundary_normal(x) \
+            + np.logical_and(self.geom1.inside(x), self.geom2.on_boundary(x))[:, np.newaxis] * -self.geom2.boundary_normal(x)
+
+    def random_points(self, n, random="pseudo"):
+        x = np.empty(shape=(n, self.dim), dtype=config.real(np))
+        i = 0
+        while i < n:
+            tmp = self.geom1.random_points(n, random=random)
+            tmp = tmp[~self.geom2.inside(tmp)]
+            if len(tmp) > n - i:
+                tmp = tmp[: n - i]
+            x[i : i + len(tmp)] = tmp
+            i += len(tmp)
+        return x
+
+    def random_boundary_points(self, n, random="pseudo"):
+        x = np.empty(shape=(n, self.dim), dtype=config.real(np))
+        i = 0
+        while i < n:
+            g1 = self.geom1.random_boundary_points(n, random=random)
+            g1 = g1[~self.geom2.inside(g1)]
+            g2 = self.geom2.random_boundary_points(n, random=random)
+            g2 = g2[self.geom1.inside(g2)]
+            tmp = np.random.permutation(np.concatenate((g1, g2)))
+            if len(tmp) > n - i:
+                tmp = tmp[: n - i]
+            x[i : i + len(tmp)] = tmp
+            i += len(tmp)
+        return x
+
 
 class Interval(Geometry):
     def __init__(self, l, r):

@@ -1,0 +1,116 @@
+"""Drop-in check with the UNMODIFIED reference package (container-only; skipped where /root/reference
+is absent, e.g. on the GPU box): the reference's own case classes are imported twice -- once on the
+oracle (`deepxde` := oracle.ddelite, float64) and once on the fused path (`deepxde` :=
+ai4xde_b200.dde, kernels replaced by the plain-PyTorch double on this CPU box) -- given the same
+points and weights, and their per-term losses and parameter gradients must agree."""
+import importlib
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import _taylor_double as td
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+_DDE_SUBMODULES = ("backend", "callbacks", "config", "data", "geometry", "gradients", "icbc", "losses",
+                   "metrics", "nn", "optimizers", "utils")
+
+
+def _purge():
+    for k in [k for k in sys.modules if k == "AI4XDE" or k.startswith("AI4XDE.") or k == "deepxde"
+              or k.startswith("deepxde.")]:
+        del sys.modules[k]
+
+
+def load_reference(backend):
+    """Fresh import of /root/reference/AI4XDE bound to `backend` ('oracle' | 'fused')."""
+    _purge()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.tri", "matplotlib.colors", "mpl_toolkits",
+                 "mpl_toolkits.axes_grid1", "skopt", "skopt.space", "skopt.utils", "skopt.plots", "skopt.sampler"):
+        ref_import._stub(name)
+    if backend == "oracle":
+        from oracle import ddelite
+
+        ddelite.install_as_deepxde()
+    else:
+        import ai4xde_b200
+
+        ai4xde_b200.install_as_deepxde()
+    if ref_import.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_import.REFERENCE_ROOT)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pkg = importlib.import_module("AI4XDE")
+    return pkg, sys.modules["deepxde"]
+
+
+CASES = [
+    ("Burgers", dict(NumDomain=150, layer_size=[2, 16, 16, 1])),
+    ("AllenCahn", dict(NumDomain=150, layer_size=[2, 16, 16, 1])),
+    ("Heat", dict(NumDomain=150)),
+    ("Helmholtz", dict(layer_size=[2, 16, 16, 1])),                       # reference default: sin activation
+    ("Helmholtz_Sound_hard_Absorbing", dict(layer_size=[2, 16, 16, 2])),  # Neumann + Robin BCs, 2 outputs
+    ("NS_Flow_in_LidDriven_Cavity", dict(NumDomain=150, layer_size=[2, 16, 16, 3])),
+    ("Kovasznay_Flow", dict(layer_size=[2, 16, 16, 3])),
+    ("Klein_Gordon", dict()),                                             # OperatorBC with a first derivative
+    ("Schrodinger", dict(layer_size=[2, 16, 16, 2])),                     # PeriodicBC order 0 and 1
+    ("Poisson_1D_Dirichlet_Robin", dict()),
+    ("Poisson_1D_Dirichlet_PointSetOperator", dict()),
+    ("Bimodal_2D", dict(layer_size=[2, 16, 16, 1])),                      # jacobian of a derived tensor
+    ("Beltrami_flow", dict(NumDomain=60, layer_size=[4, 16, 16, 4])),     # 4 inputs, 15 J + 9 H
+    ("Diffusion_Reaction_Inverse", dict()),                               # dde.Variable inside the pde
+    ("Convection_1D_Periodic", dict()),
+]
+
+
+def _evaluate(dde, case):
+    model = dde.Model(case.data, case.net)
+    case.compile(model, "adam", lr=1e-3)
+    _, losses = model.outputs_losses_train(case.data.train_x, case.data.train_y, None)
+    case.net.zero_grad()
+    losses.sum().backward()
+    g = torch.cat([p.grad.reshape(-1).double().cpu() for p in case.net.parameters()]).numpy()
+    return losses.detach().double().cpu().numpy(), g
+
+
+@pytest.mark.parametrize("name,kwargs", CASES)
+def test_unmodified_reference_case_runs_on_the_fused_path(name, kwargs, monkeypatch):
+    td.install(monkeypatch)
+    try:
+        A, dde_o = load_reference("oracle")                # float64 (PDESolver.py:6 runs at import)
+        np.random.seed(0)
+        torch.manual_seed(0)
+        case_o = getattr(A.cases, name)(**kwargs)
+        ref_losses, ref_grad = _evaluate(dde_o, case_o)
+        state = {k: v.detach().float() for k, v in case_o.net.state_dict().items()}
+        X_all = case_o.data.train_x_all.copy()
+        dde_o.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+
+        B, dde_f = load_reference("fused")
+        np.random.seed(0)
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            case_f = getattr(B.cases, name)(**kwargs)
+        # same collocation points (the two backends' quasi-random samplers are not the same code)
+        if not np.array_equal(case_f.data.train_x_all, X_all):
+            case_f.data.replace_with_anchors(X_all)
+            case_f.data.train_x_bc = None
+            case_f.data.replace_with_anchors(X_all)
+        assert case_f.data.train_x.shape == case_o.data.train_x.shape
+        case_f.net.load_state_dict(state)
+        losses, g = _evaluate(dde_f, case_f)
+    finally:
+        _purge()
+        from oracle import ddelite
+
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    assert losses.shape == ref_losses.shape
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-3, atol=1e-6 * np.abs(ref_losses).max())
+    assert np.abs(g - ref_grad).max() / max(np.abs(ref_grad).max(), 1e-30) < 2e-3
