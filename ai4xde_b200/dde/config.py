@@ -10,7 +10,7 @@ import warnings
 import numpy as np
 import torch
 
-_state = {"host": np.float32, "warned": False, "engine": "auto"}
+_state = {"host": np.float32, "warned": False, "engine": "auto", "graphs": "auto", "graph_max_rows": 300000}
 
 
 def real(package):
@@ -50,6 +50,19 @@ def set_engine(name):
 
 def engine():
     return _state["engine"]
+
+
+def set_cuda_graphs(mode, max_rows=None):
+    """'auto' (capture the Adam step of small problems, which are launch-bound), True, or False."""
+    if mode not in ("auto", True, False):
+        raise ValueError(mode)
+    _state["graphs"] = mode
+    if max_rows is not None:
+        _state["graph_max_rows"] = int(max_rows)
+
+
+def cuda_graphs():
+    return _state["graphs"], _state["graph_max_rows"]
 
 
 def device():

@@ -162,6 +162,61 @@ class Model:
             return operator(x, y, self.net.auxiliary_vars)
         raise ValueError("operator must take 2 or 3 arguments")
 
+    # ---- CUDA-graph replay of the small-problem step -------------------------------------------
+    def _graphed_step(self, inputs, targets, auxiliary_vars, closure):
+        """Launch-bound regime (cfg1 is ~60 MFLOP per step): after three eager
+        steps on an unchanged point set the whole closure + Adam update is captured once into a CUDA
+        graph and replayed.  Returns True if this call was served by the graph."""
+        import torch.distributed as dist
+
+        mode, max_rows = config.cuda_graphs()
+        st = self.__dict__.setdefault("_graph_state", {"key": None, "seen": 0, "graph": None})
+        if mode is False or not torch.cuda.is_available():
+            return False
+        n_rows = len(inputs) if hasattr(inputs, "__len__") else 0
+        eligible = (
+            (mode is True or n_rows <= max_rows)
+            and not optimizers.is_external_optimizer(self.opt_name)
+            and self.lr_scheduler is None
+            and targets is None and auxiliary_vars is None
+            and isinstance(self.opt, (torch.optim.Adam, torch.optim.AdamW))
+            and self.opt.defaults.get("capturable", False)
+            and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+            and self.train_step.__qualname__.startswith("Model.compile")
+            and self.outputs_losses_train.__qualname__.startswith("Model.compile")
+        )
+        key = (id(inputs), getattr(self.data, "version", None), id(self.opt), id(self.data.pde))
+        if not eligible:
+            st.update(key=None, seen=0, graph=None)
+            return False
+        if st["key"] != key:
+            st.update(key=key, seen=0, graph=None, holder=inputs)
+        if st["graph"] is not None:
+            st["graph"].replay()
+            return True
+        st["seen"] += 1
+        if st["seen"] <= 3:
+            return False                      # eager warm-up (also runs the stream-set probe, BC uploads)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.opt.step(closure)        # THIS call's step, eagerly, on a side stream (capture warm-up)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g):         # records the next steps; nothing executes here
+                self.opt.step(closure)
+            st["graph"] = g
+            return True
+        except Exception as e:                # capture is an optimisation: stay on the eager fused path
+            import warnings
+
+            warnings.warn(f"ai4xde_b200: CUDA-graph capture of the train step failed ({e}); running eagerly")
+            config.set_cuda_graphs(False)
+            torch.cuda.synchronize()
+            return False
+
     # ---- data parallel -----------------------------------------------------------------------
     def _dp_term_scale(self, losses, inputs):
         """Per-term factor n_local * world / n_global that turns the all-reduce MEAN of the ranks'
@@ -254,6 +309,8 @@ class Model:
                 self.last_total_loss = total_loss.detach()
                 return total_loss
 
+            if self._graphed_step(inputs, targets, auxiliary_vars, closure):
+                return
             self.opt.step(closure)
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()

@@ -146,3 +146,64 @@ def test_pinn_short_training_tracks_oracle_loss_curve():
     lh, _ = model.train(iterations=200, display_every=20)
     a, b = np.array(lh.loss_train).sum(1), np.array(olh.loss_train).sum(1)
     assert np.abs(a - b).max() / b.max() < 1e-2
+
+
+def test_cuda_graph_step_matches_eager():
+    """Small problems replay the captured Adam step; the trajectory must equal the eager one."""
+    dde = _setup()
+    from ai4xde_b200 import cases as pc
+
+    def run(graphs):
+        dde.config.set_cuda_graphs(graphs)
+        np.random.seed(0)
+        torch.manual_seed(0)
+        case = pc.Burgers(NumDomain=2540, layer_size=[2, 20, 20, 20, 1], soft_constraints=True)
+        model = dde.Model(case.data, case.net)
+        case.compile(model, "adam", lr=1e-3)
+        lh, _ = model.train(iterations=60, display_every=20)
+        served = model.__dict__.get("_graph_state", {}).get("graph") is not None
+        return np.array(lh.loss_train), served, torch.cat([p.detach().reshape(-1) for p in case.net.parameters()]).cpu()
+
+    try:
+        a, served_a, pa = run(True)
+        b, served_b, pb = run(False)
+    finally:
+        dde.config.set_cuda_graphs("auto")
+    assert served_a and not served_b
+    assert np.abs(a - b).max() / np.abs(b).max() < 1e-4
+    assert float((pa - pb).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("cfg,n,engine,tol", [("cfg1", 2540, "fp32", 1e-2), ("cfg2", 3000, "tf32", 1e-2)])
+def test_loss_curve_within_one_percent_over_1k_steps(cfg, n, engine, tol):
+    """north_star gate: loss curves agree within 1 % over 1k Adam steps (same points, same weights):
+    fused path (FP32 engine for the narrow net, TF32 tensor-core engine for the 64-wide net, CUDA-graph
+    replay where it applies) against the float64 CPU oracle."""
+    dde = _setup()
+    from oracle import cases as oc, ddelite
+    from parity_util import build_product
+
+    ddelite.config.set_default_float("float64")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    odata, onet, _ = oc.build(cfg, n)
+    state0 = {k: v.detach().clone() for k, v in onet.state_dict().items()}
+    omodel = ddelite.Model(odata, onet)
+    omodel.compile("adam", lr=1e-3)
+    olh, _ = omodel.train(iterations=1000, display_every=100)
+    onet.load_state_dict(state0)
+    ddelite.config.set_default_float("float32")
+    torch.set_default_dtype(torch.float32)
+    case = build_product(cfg, odata, onet)
+    dde.config.set_engine(engine)
+    try:
+        model = dde.Model(case.data, case.net)
+        model.compile("adam", lr=1e-3)
+        lh, _ = model.train(iterations=1000, display_every=100)
+    finally:
+        dde.config.set_engine("auto")
+    a, b = np.array(lh.loss_train).sum(1), np.array(olh.loss_train).sum(1)
+    assert lh.steps == olh.steps and len(a) == 11
+    rel = np.abs(a - b) / b
+    print(cfg, engine, "max rel loss-curve deviation", rel.max())
+    assert rel.max() < tol
