@@ -102,6 +102,7 @@ static bool pattern_equals(const ax_jet_desc *jet) {
 
 int match_pattern(const ax_jet_desc *jet) {
   if (!jet || jet->n1 < 0 || jet->n1 > AX_MAX_FIRST || jet->n2 < 0 || jet->n2 > AX_MAX_SECOND) return -1;
+  // (pa, pb) = (15, 15) is the trace stream of the P_*_T patterns
 #define AX_MATCH(ID, PAT) \
   if (pattern_equals<PAT>(jet)) return ID;
   AX_FOR_EACH_PATTERN(AX_MATCH)

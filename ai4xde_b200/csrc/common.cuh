@@ -65,11 +65,17 @@ using P_3_F = Pattern<3, 6, 0x211000ull, 0x221210ull>;  // aa,ab,ac,bb,bc,cc
 using P_4 = Pattern<4, 0, 0x0ull, 0x0ull>;
 using P_4_D = Pattern<4, 4, 0x3210ull, 0x3210ull>;
 using P_4_F = Pattern<4, 10, 0x3221110000ull, 0x3323213210ull>;
+// "trace" patterns: ONE second-order stream carrying the Laplacian over all first-order streams
+// (pair code 15/15).  sum_j a_jj = s2 * sum_j z_j^2 + s1 * sum_j z_jj is closed under the layer map, so a
+// PDE that only uses u_aa + u_bb (+ u_cc) needs S = 2 + N1 streams instead of 1 + 2 N1.
+using P_2_T = Pattern<2, 1, 0xFull, 0xFull>;        // {0,a,b,aa+bb}
+using P_3_T = Pattern<3, 1, 0xFull, 0xFull>;        // {0,a,b,c,aa+bb+cc}
+constexpr int kTracePair = 15;
 
 #define AX_FOR_EACH_PATTERN(X) \
   X(0, P_V) X(1, P_1) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F) X(7, P_3) \
-  X(8, P_3_D) X(9, P_3_F) X(10, P_4) X(11, P_4_D) X(12, P_4_F)
-constexpr int kNumPatterns = 13;
+  X(8, P_3_D) X(9, P_3_F) X(10, P_4) X(11, P_4_D) X(12, P_4_F) X(13, P_2_T) X(14, P_3_T)
+constexpr int kNumPatterns = 15;
 
 // returns pattern id or -1
 int match_pattern(const ax_jet_desc *jet);
@@ -126,8 +132,16 @@ __device__ __forceinline__ void jet_reconstruct(int act, const float (&st)[P::S]
 #pragma unroll
   for (int j = 0; j < P::N1; ++j) A[1 + j] = d.s1 * st[1 + j];
 #pragma unroll
-  for (int q = 0; q < P::N2; ++q)
-    A[1 + P::N1 + q] = fmaf(d.s2 * st[1 + P::pa(q)], st[1 + P::pb(q)], d.s1 * st[1 + P::N1 + q]);
+  for (int q = 0; q < P::N2; ++q) {
+    if (P::pa(q) == kTracePair) {
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) sq = fmaf(st[1 + j], st[1 + j], sq);
+      A[1 + P::N1 + q] = fmaf(d.s2, sq, d.s1 * st[1 + P::N1 + q]);
+    } else {
+      A[1 + P::N1 + q] = fmaf(d.s2 * st[1 + (P::pa(q) & 3)], st[1 + (P::pb(q) & 3)], d.s1 * st[1 + P::N1 + q]);
+    }
+  }
 }
 
 // reverse of jet_reconstruct: given stash streams and adjoints of A, adjoints of z
@@ -143,12 +157,23 @@ __device__ __forceinline__ void jet_adjoint(int act, const float (&st)[P::S], co
   }
 #pragma unroll
   for (int q = 0; q < P::N2; ++q) {
-    const float za = st[1 + P::pa(q)], zc = st[1 + P::pb(q)], zq = st[1 + P::N1 + q];
+    const float zq = st[1 + P::N1 + q];
     const float aq = ab[1 + P::N1 + q];
     zb[1 + P::N1 + q] = d.s1 * aq;
-    zb[1 + P::pa(q)] = fmaf(d.s2 * zc, aq, zb[1 + P::pa(q)]);
-    zb[1 + P::pb(q)] = fmaf(d.s2 * za, aq, zb[1 + P::pb(q)]);
-    z0b = fmaf(fmaf(d.s3 * za, zc, d.s2 * zq), aq, z0b);
+    if (P::pa(q) == kTracePair) {
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) {
+        sq = fmaf(st[1 + j], st[1 + j], sq);
+        zb[1 + j] = fmaf(2.0f * d.s2 * st[1 + j], aq, zb[1 + j]);
+      }
+      z0b = fmaf(fmaf(d.s3, sq, d.s2 * zq), aq, z0b);
+    } else {
+      const float za = st[1 + (P::pa(q) & 3)], zc = st[1 + (P::pb(q) & 3)];
+      zb[1 + (P::pa(q) & 3)] = fmaf(d.s2 * zc, aq, zb[1 + (P::pa(q) & 3)]);
+      zb[1 + (P::pb(q) & 3)] = fmaf(d.s2 * za, aq, zb[1 + (P::pb(q) & 3)]);
+      z0b = fmaf(fmaf(d.s3 * za, zc, d.s2 * zq), aq, z0b);
+    }
   }
   zb[0] = z0b;
 }

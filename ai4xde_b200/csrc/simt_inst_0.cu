@@ -9,4 +9,8 @@ template int simt_forward<P_1_D>(const FwdArgs &);
 template int simt_backward<P_1_D>(const BwdArgs &);
 template int simt_forward<P_2>(const FwdArgs &);
 template int simt_backward<P_2>(const BwdArgs &);
+template int simt_forward<P_2_T>(const FwdArgs &);
+template int simt_backward<P_2_T>(const BwdArgs &);
+template int simt_forward<P_3_T>(const FwdArgs &);
+template int simt_backward<P_3_T>(const BwdArgs &);
 }  // namespace ax

@@ -171,8 +171,16 @@ __device__ __forceinline__ void jet_forward_A(int act, float (&z)[P::S], float (
 #pragma unroll
   for (int j = 0; j < P::N1; ++j) A[1 + j] = s1 * z[1 + j];
 #pragma unroll
-  for (int q = 0; q < P::N2; ++q)
-    A[1 + P::N1 + q] = fmaf(s2 * z[1 + P::pa(q)], z[1 + P::pb(q)], s1 * z[1 + P::N1 + q]);
+  for (int q = 0; q < P::N2; ++q) {
+    if (P::pa(q) == kTracePair) {
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) sq = fmaf(z[1 + j], z[1 + j], sq);
+      A[1 + P::N1 + q] = fmaf(s2, sq, s1 * z[1 + P::N1 + q]);
+    } else {
+      A[1 + P::N1 + q] = fmaf(s2 * z[1 + (P::pa(q) & 3)], z[1 + (P::pb(q) & 3)], s1 * z[1 + P::N1 + q]);
+    }
+  }
 }
 
 // Adjoint through the activation expressed in the stored POST-activation streams A:
@@ -201,12 +209,24 @@ __device__ __forceinline__ void jet_adjoint_A(int act, const float (&A)[P::S], c
   }
 #pragma unroll
   for (int q = 0; q < P::N2; ++q) {
-    const float aa = A[1 + P::pa(q)], ac = A[1 + P::pb(q)], aq = A[1 + P::N1 + q];
+    const float aq = A[1 + P::N1 + q];
     const float g = ab[1 + P::N1 + q];
     zb[1 + P::N1 + q] = s1 * g;
-    zb[1 + P::pa(q)] = fmaf(c1 * ac, g, zb[1 + P::pa(q)]);
-    zb[1 + P::pb(q)] = fmaf(c1 * aa, g, zb[1 + P::pb(q)]);
-    z0b = fmaf(fmaf(c2 * aa, ac, c1 * aq), g, z0b);
+    if (P::pa(q) == kTracePair) {
+      // Laplacian stream: d a_T/d z_j = 2 c1 a_j ;  d a_T/d z0 = c2 sum_j a_j^2 + c1 a_T
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) {
+        sq = fmaf(A[1 + j], A[1 + j], sq);
+        zb[1 + j] = fmaf(2.0f * c1 * A[1 + j], g, zb[1 + j]);
+      }
+      z0b = fmaf(fmaf(c2, sq, c1 * aq), g, z0b);
+    } else {
+      const float aa = A[1 + (P::pa(q) & 3)], ac = A[1 + (P::pb(q) & 3)];
+      zb[1 + (P::pa(q) & 3)] = fmaf(c1 * ac, g, zb[1 + (P::pa(q) & 3)]);
+      zb[1 + (P::pb(q) & 3)] = fmaf(c1 * aa, g, zb[1 + (P::pb(q) & 3)]);
+      z0b = fmaf(fmaf(c2 * aa, ac, c1 * aq), g, z0b);
+    }
   }
   zb[0] = z0b;
 }
@@ -900,7 +920,7 @@ static int reduce_to(const float *partial, long long stride, long long sub, int 
 constexpr int kLastPts = 128;   // points per block of the output-layer backward
 constexpr int kFirstPts = 128;  // points per block of the first-layer backward
 
-static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id == 4 || id == 5 || id == 6; }
+static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id == 4 || id == 5 || id == 6 || id == 13; }
 
 bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
   if (engine != AX_ENGINE_TF32) return false;
@@ -1093,7 +1113,7 @@ int tc_debug_wgrad(const float *zbar, const float *a, long long rows, int H, flo
   return reduce_to(ws, (long long)H * H, 0, grid, (long long)H * H, out, st);
 }
 
-#define AX_TC_PATTERNS(X) X(0, P_V) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F)
+#define AX_TC_PATTERNS(X) X(0, P_V) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F) X(13, P_2_T)
 
 int tc_forward(const NetGeom &g, const FwdArgs &a, int engine) {
   const int id = match_pattern(a.jet), H = g.widths[1];

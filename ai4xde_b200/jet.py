@@ -21,6 +21,8 @@ class JetSpec:
     the smallest compiled superset.
     """
 
+    TRACE = 15  # pair code of the Laplacian stream (csrc/common.cuh kTracePair)
+
     def __init__(self, dirs, pairs):
         self.dirs = tuple(int(d) for d in dirs)
         self.pairs = tuple((int(a), int(b)) for a, b in pairs)
@@ -28,11 +30,20 @@ class JetSpec:
         self.S = 1 + self.n1 + self.n2
         self.first_of_dim = {d: j for j, d in enumerate(self.dirs)}
         self.second_of_dims = {}
+        self.trace = None  # index q of the Laplacian stream, if this is a trace pattern
         for q, (a, b) in enumerate(self.pairs):
+            if a == self.TRACE and b == self.TRACE:
+                self.trace = q
+                continue
             da, db = self.dirs[a], self.dirs[b]
             self.second_of_dims[(da, db)] = q
             self.second_of_dims[(db, da)] = q
         self.desc = _lib.make_jet_desc(self.dirs, self.pairs)
+
+    @staticmethod
+    def laplacian(dims):
+        """{value, d/dx_j for j in dims, sum_j d2/dx_j^2}: S = 2 + len(dims) streams."""
+        return JetSpec(sorted(dims), [(JetSpec.TRACE, JetSpec.TRACE)])
 
     def key(self):
         return (self.dirs, self.pairs)
@@ -197,6 +208,16 @@ class JetOutput:
         return torch.cat(cols, dim=1)
 
     def second(self, comp, dim_i, dim_j):
+        if self.spec.trace is not None:
+            # Laplacian pattern (adopted only after the dry run showed the caller uses nothing but the
+            # sum of the pure second derivatives): the whole sum is handed out as the first one
+            if dim_i != dim_j or dim_i not in self.spec.first_of_dim:
+                return None
+            qt = self.spec.trace
+            if qt not in self._second:
+                self._second[qt] = _Leaf2.apply(self.x, self.streams[1 + self.spec.n1 + qt])
+            lap = self._second[qt][:, comp : comp + 1]
+            return lap if dim_i == self.spec.dirs[0] else torch.zeros_like(lap)
         q = self.spec.second_of_dims.get((dim_i, dim_j))
         if q is None:
             return None
@@ -210,7 +231,7 @@ def make_leaf(x, spec, streams):
     return _Leaf0.apply(x, spec, streams[0], *streams[1:])
 
 
-def probe_streams(x, n_out, fn):
+def probe_streams(x, n_out, fn, allow_trace=True):
     """Find which derivative streams `fn(x, y)` really uses.
 
     fn receives the input tensor and a stand-in network output whose value / first / second
@@ -240,7 +261,7 @@ def probe_streams(x, n_out, fn):
             total = t if total is None else total + t
         if total is None:
             return JetSpec.value_only()
-        grads = torch.autograd.grad(total, streams[1:], allow_unused=True)
+        grads = torch.autograd.grad(total, streams[1:], allow_unused=True, retain_graph=True)
     need1, need2 = [], []
     for j in range(full.n1):
         g = grads[j]
@@ -250,4 +271,52 @@ def probe_streams(x, n_out, fn):
         g = grads[full.n1 + q]
         if g is not None and bool((g != 0).any()):
             need2.append((full.dirs[a], full.dirs[b]))
-    return JetSpec.covering(need1, need2)
+    cover = JetSpec.covering(need1, need2)
+    lap = _try_laplacian(x, fn, full, streams, cover, need2, total, allow_trace)
+    return lap if lap is not None else cover
+
+
+def _try_laplacian(x, fn, full, streams, cover, need2, total_full, allow_trace):
+    """If the caller only ever uses the SUM of the pure second derivatives over all carried
+    directions (Helmholtz, steady Navier-Stokes: u_xx + u_yy), one Laplacian stream replaces them.
+    Adopted only when re-running the caller's own code on the Laplacian pattern -- fed the sum of the
+    same random second-order streams -- reproduces the loss and its stream gradients exactly."""
+    if not allow_trace or len(need2) < 2 or any(j != k for j, k in need2):
+        return None
+    dims = sorted(j for j, _ in need2)
+    if dims != sorted(cover.dirs) or len(dims) > 3:
+        return None
+    from .dde import gradients as grad  # local import: jet <-> dde.gradients
+
+    spec = JetSpec.laplacian(dims)
+    n1f = full.n1
+    firsts = [streams[1 + full.first_of_dim[d]] for d in spec.dirs]
+    lap = sum(streams[1 + n1f + full.second_of_dims[(d, d)]] for d in dims)
+    t_streams = [streams[0]] + firsts + [lap]
+    with torch.enable_grad():
+        y = make_leaf(x, spec, t_streams)
+        grad.register(y, JetOutput(x, spec, t_streams))
+        try:
+            outs = fn(x, y)
+        except Exception:
+            return None
+        outs = outs if isinstance(outs, (list, tuple)) else [outs]
+        total = None
+        for o in outs:
+            if o is None or not torch.is_tensor(o) or not o.requires_grad:
+                continue
+            t = (o.to(x.dtype) ** 2).sum()
+            total = t if total is None else total + t
+        if total is None:
+            return None
+        leaves = [streams[0]] + firsts
+        g_t = torch.autograd.grad(total, leaves, allow_unused=True)
+        g_f = torch.autograd.grad(total_full, leaves, allow_unused=True, retain_graph=True)
+    if not torch.allclose(total, total_full, rtol=1e-5, atol=0.0):
+        return None
+    for a, b in zip(g_t, g_f):
+        if (a is None) != (b is None):
+            return None
+        if a is not None and not torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(b.abs().max())):
+            return None
+    return spec

@@ -51,7 +51,11 @@ def taylor_streams(net, jet, flat, x):
     for W, b in layers[1:]:
         a, s1, s2 = _act(net.activation, z[0])
         A = [a] + [s1 * z[1 + j] for j in range(n1)]
-        A += [s2 * z[1 + pa] * z[1 + pb] + s1 * z[1 + n1 + q] for q, (pa, pb) in enumerate(pairs)]
+        for q, (pa, pb) in enumerate(pairs):
+            if pa == 15 and pb == 15:      # Laplacian stream over all first-order streams
+                A.append(s2 * sum(z[1 + j] * z[1 + j] for j in range(n1)) + s1 * z[1 + n1 + q])
+            else:
+                A.append(s2 * z[1 + pa] * z[1 + pb] + s1 * z[1 + n1 + q])
         z = [A[0] @ W.t() + b] + [As @ W.t() for As in A[1:]]
     return z
 

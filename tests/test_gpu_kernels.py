@@ -21,6 +21,8 @@ SPECS = {
     "3d": ((0, 1, 2), ((0, 0), (1, 1), (2, 2))),
     "3f": ((0, 1, 2), ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))),
     "4f": ((0, 1, 2, 3), tuple((a, b) for a in range(4) for b in range(a, 4))),
+    "2t": ((0, 1), ((15, 15),)),          # Laplacian stream u_xx + u_yy
+    "3t": ((0, 1, 2), ((15, 15),)),
 }
 
 CASES = [
@@ -38,6 +40,9 @@ CASES = [
     ([2, 32, 32, 1], "tanh", "v", 1, 1),
     ([1, 20, 20, 1], "tanh", "1", 31, 2),
     ([2, 20, 20, 1], "tanh", "2", 33, 1),
+    ([2, 256, 256, 256, 1], "tanh", "2t", 515, 1),
+    ([2, 150, 150, 1], "sin", "2t", 300, 1),
+    ([3, 40, 40, 2], "sigmoid", "3t", 65, 2),
 ]
 
 

@@ -39,6 +39,8 @@ def _rel(a, b):
     ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((0, 0), (1, 1))), 20000),
     ([2, 128, 128, 128, 2], "sigmoid", ((0, 1), ((0, 0), (0, 1), (1, 1))), 777),
     ([2, 64, 64, 1], "tanh", ((0, 1), ()), 95),
+    ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((15, 15),)), 20000),     # Laplacian stream (cfg4 as run)
+    ([2, 128, 128, 128, 3], "sigmoid", ((0, 1), ((15, 15),)), 3000),
 ])
 def test_tf32_engine_matches_double(widths, act, spec, n):
     dev = torch.device("cuda:0")

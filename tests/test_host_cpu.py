@@ -110,7 +110,11 @@ def test_stream_discovery():
     s = spec_of(pc.Burgers(NumDomain=20, layer_size=[2, 8, 1]))
     assert s.dirs == (0, 1) and s.pairs == ((0, 0),)                      # {u, u_x, u_t, u_xx}
     s = spec_of(pc.Helmholtz(layer_size=[2, 8, 1], activation="tanh"), [1, 100])
-    assert s.dirs == (0, 1) and s.pairs == ((0, 0), (1, 1))               # {u, (u_x, u_y), u_xx, u_yy}
+    assert s.dirs == (0, 1) and s.trace == 0 and s.S == 4                 # {u, u_x, u_y, u_xx + u_yy}
+    s = spec_of(pc.NS_Flow_in_LidDriven_Cavity(NumDomain=30, layer_size=[2, 8, 3], train_distribution="pseudo"))
+    assert s.dirs == (0, 1) and s.trace == 0 and s.S == 4                 # momentum eqs use only the Laplacians
+    s = spec_of(pc.Heat(NumDomain=30, layer_size=[2, 8, 1]))
+    assert s.trace is None and s.pairs == ((0, 0),)                       # u_t - a u_xx: no Laplacian pattern
     s = spec_of(pc.Poisson_1D_Dirichlet(NumDomain=8, layer_size=[1, 8, 1]))
     assert s.dirs == (0,) and s.pairs == ((0, 0),)
     s = spec_of(pc.Harmonic_Oscillator_1D(NumDomain=8, layer_size=[1, 8, 1]))   # Neumann BC + u''
