@@ -250,6 +250,14 @@ struct GemmArgs {
   const float *stash_in;  // dgrad: POST-activation streams of the destination layer [rows][H]
   float *out;             // fwd: act of this layer; dgrad: zbar of the previous layer  [rows][H]
   float *db_partial;      // dgrad: [grid][H] per-CTA sums of zbar_0 (bias gradient of the dest layer)
+  // dgrad into the FIRST hidden layer: zbar_0 is consumed on the spot -- dW0[o][d] = sum_p zbar_0 x_d +
+  // sum_j [dir_j == d] zbar_j accumulates in registers and `out` is never written (saves S*H*4 B/point
+  // of HBM write + the re-read by a separate first-layer kernel)
+  const float *first_x;   // x_soa [d_in][ldn] or nullptr
+  float *dw0_partial;     // [grid][H][4]
+  long long ldn;
+  int d_in;
+  JetDirs dirs;
   long long n;            // points
   int num_tiles;
   int act;
@@ -363,8 +371,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     uint32_t tphase = 0;
     float dbsum[NH];
     float bias[NH];
+    float dw0[NH][4];
+    const bool fuse_first = (MODE == 1) && (g.first_x != nullptr);
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) dw0[h][d] = 0.0f;
       dbsum[h] = 0.0f;
       const int o = h * 128 + q * 32 + lane;
       bias[h] = (MODE == 0 && o < H) ? __ldg(g.bias + o) : 0.0f;
@@ -412,6 +424,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
           for (int i = 0; i < 8 * S; ++i) cur[i] = st[i];
           if (item + 2 < ITEMS) prefetch(item + 2);
         }
+        float dba = 0.0f, dwa[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // per-item register accumulators
         if (o < H) {
 #pragma unroll
           for (int pp = 0; pp < 8; ++pp) {
@@ -422,7 +435,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
               for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
               float *dst = outp + (p * S) * H + o;
               if (MODE == 0) {
-                z[0] += bias[h];
+                z[0] += (h == 0) ? bias[0] : bias[NH - 1];
                 jet_forward_A<P>(g.act, z, w);
                 dst[0] = w[0];
 #pragma unroll
@@ -432,11 +445,35 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
 #pragma unroll
                 for (int s = 0; s < S; ++s) a[s] = cur[pp * S + s];
                 jet_adjoint_A<P>(g.act, a, z, w);
-                dbsum[h] += w[0];
+                dba += w[0];
+                if (fuse_first) {
 #pragma unroll
-                for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+                  for (int d = 0; d < 4; ++d)
+                    if (d < g.d_in) dwa[d] = fmaf(w[0], __ldg(g.first_x + (long long)d * g.ldn + p), dwa[d]);
+#pragma unroll
+                  for (int j = 0; j < P::N1; ++j) {
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+                      if (d == g.dirs.d[j]) dwa[d] += w[1 + j];
+                  }
+                } else {
+#pragma unroll
+                  for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+                }
               }
             }
+          }
+        }
+        if (MODE == 1) {
+          // one indexed update per item (h is a run-time index: keep it out of the point loop)
+          if (h == 0) {
+            dbsum[0] += dba;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) dw0[0][d] += dwa[d];
+          } else {
+            dbsum[NH - 1] += dba;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) dw0[NH - 1][d] += dwa[d];
           }
         }
       }
@@ -444,17 +481,28 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     }
     if (MODE == 1) {
       // two warps share each unit: combine through shared memory in a fixed order
-      float *red = reinterpret_cast<float *>(tmem_slot + 4);  // [2][NH][128]
+      float *red = reinterpret_cast<float *>(tmem_slot + 4);  // [2][NH][128][5]
 #pragma unroll
-      for (int h = 0; h < NH; ++h) red[(sub * NH + h) * 128 + q * 32 + lane] = dbsum[h];
+      for (int h = 0; h < NH; ++h) {
+        float *r5 = red + ((sub * NH + h) * 128 + q * 32 + lane) * 5;
+        r5[0] = dbsum[h];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) r5[1 + d] = dw0[h][d];
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (sub == 0) {
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           const int o = h * 128 + q * 32 + lane;
-          if (o < H)
-            g.db_partial[(long long)blockIdx.x * H + o] =
-                red[(0 * NH + h) * 128 + q * 32 + lane] + red[(1 * NH + h) * 128 + q * 32 + lane];
+          if (o < H) {
+            const float *r0 = red + ((0 * NH + h) * 128 + q * 32 + lane) * 5;
+            const float *r1 = red + ((1 * NH + h) * 128 + q * 32 + lane) * 5;
+            g.db_partial[(long long)blockIdx.x * H + o] = r0[0] + r1[0];
+            if (fuse_first) {
+              for (int d = 0; d < g.d_in; ++d)
+                g.dw0_partial[((long long)blockIdx.x * H + o) * 4 + d] = r0[1 + d] + r1[1 + d];
+            }
+          }
         }
       }
     }
@@ -789,6 +837,16 @@ __global__ void k_tc_round_copy(const float *__restrict__ src, float *__restrict
     dst[idx] = v;
 }
 
+__global__ void k_tc_reduce_dw0(const float *__restrict__ partial, int nblocks, int H, int d_in,
+                                float *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H * d_in) return;
+  const int o = j / d_in, d = j - o * d_in;
+  float s = 0.0f;
+  for (int b = 0; b < nblocks; ++b) s += partial[((long long)b * H + o) * 4 + d];
+  out[j] = s;
+}
+
 // out[off + j] = sum_b partial[b * stride + sub + j]
 __global__ void k_tc_reduce(const float *__restrict__ partial, long long stride, long long sub, int nblocks,
                             long long count, float *__restrict__ out) {
@@ -860,7 +918,7 @@ static int launch_gemm(const float *wop, const float *in, const GemmArgs &ga, lo
   constexpr int S = P::S, N = TileOf<S>::N, NH = (H + 127) / 128, HM = NH * 128;
   constexpr int STAGE_BYTES = (HM + N) * 128;
   constexpr int NSTAGE = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
-  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256 + 2 * NH * 128 * sizeof(float);
+  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256 + 2 * NH * 128 * 5 * sizeof(float);
   CUtensorMap mw, mi;
   if (make_map(&mw, wop, H, H, HM, 1)) return 1;
   if (make_map(&mi, in, rows, H, N, 1)) return 1;
@@ -951,7 +1009,7 @@ static void plan_bwd_ws(const NetGeom &g, int S, long long ldn, BwdWs *w, void *
   size_t pf = (size_t)(sm_count() + 1) * H * H;               // wgrad partials
   size_t a = nb_last * ((size_t)C * H + C + H);               // last-layer partials
   size_t b = nb_first * ((size_t)H * d_in);                   // first-layer partials
-  size_t c = (size_t)(sm_count() + 1) * H;                    // dgrad bias partials (kept separately)
+  size_t c = (size_t)(sm_count() + 1) * H * 5;                // dgrad bias (+ fused dW0) partials, kept separately
   if (a > pf) pf = a;
   if (b > pf) pf = b;
   float *p = (float *)base;
@@ -1039,7 +1097,9 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
     set_error("backward workspace too small: %zu < %zu", a.ws_bytes, w.total_bytes);
     return 1;
   }
-  float *dbpart = w.partial + (w.partial_floats - (size_t)(sm_count() + 1) * H);
+  float *dbpart = w.partial + (w.partial_floats - (size_t)(sm_count() + 1) * H * 5);
+  float *dw0part = dbpart + (size_t)(sm_count() + 1) * H;
+  const bool fuse_first = d_in <= 4;
   for (int net = 0; net < a.net->n_nets; ++net) {
     const float *prm = a.params + (long long)net * g.P;
     float *grad = a.grad + (long long)net * g.P;
@@ -1075,15 +1135,27 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       ga.stash_in = slot(l - 1);
       ga.out = w.g[cur ^ 1];
       ga.db_partial = dbpart;
+      if (l == 1 && fuse_first) {
+        ga.first_x = a.x;
+        ga.dw0_partial = dw0part;
+        ga.ldn = a.ldn;
+        ga.d_in = d_in;
+        ga.dirs = dirs;
+      }
       ga.n = a.n;
       ga.num_tiles = (int)((a.n + PT - 1) / PT);
       ga.act = act;
       if (launch_gemm<P, 1, H>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], ga, rows, a.stream)) return 1;
       const int grid = ga.num_tiles < sm_count() ? ga.num_tiles : sm_count();
       if (reduce_to(dbpart, H, 0, grid, H, grad + g.b_off[l - 1], a.stream)) return 1;
+      if (l == 1 && fuse_first) {
+        // dW0 partials are [grid][H][4]; W0 is [H][d_in]
+        k_tc_reduce_dw0<<<(H * d_in + 255) / 256, 256, 0, a.stream>>>(dw0part, grid, H, d_in, grad + g.w_off[0]);
+        AX_LAUNCH_OK();
+      }
       cur ^= 1;
     }
-    {
+    if (!fuse_first) {
       const int nb = (int)((a.n + kFirstPts - 1) / kFirstPts);
       {
         KernelTimer t("tc_first_bwd", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);

@@ -10,7 +10,10 @@ import warnings
 import numpy as np
 import torch
 
-_state = {"host": np.float32, "warned": False, "engine": "auto", "graphs": "auto", "graph_max_rows": 300000}
+import os
+
+_state = {"host": np.float32, "warned": False, "engine": "auto", "graphs": "auto",
+          "graph_max_rows": int(os.environ.get("AI4XDE_B200_GRAPH_MAX_ROWS", "300000"))}
 
 
 def real(package):
