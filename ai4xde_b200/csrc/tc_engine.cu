@@ -853,7 +853,8 @@ __global__ void k_tc_reduce(const float *__restrict__ partial, long long stride,
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   float s = 0.0f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * stride + sub + j];
+#pragma unroll 8
+  for (int b = 0; b < nblocks; ++b) s += __ldg(partial + (long long)b * stride + sub + j);
   out[j] = s;
 }
 
