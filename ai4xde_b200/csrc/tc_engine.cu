@@ -18,6 +18,7 @@
 // one elected thread issues tcgen05.mma; four epilogue warps drain TMEM with tcgen05.ld.
 // Reference behaviour replaced: see simt_kernels.cuh (same math, FP32 engine).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "simt_kernels.cuh"
 #include "tc_engine.cuh"
@@ -515,6 +516,275 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
   }
 }
 
+
+// -----------------------------------------------------------------------------------------
+// kernel A2: the same layer GEMM for H = 256 on a CTA PAIR (tcgen05 cta_group::2, M = 256).
+// Each CTA of the pair owns 128 output units: it stages only its half of W (16 KB per K block) and its
+// half of the (point, stream) rows; the pair's tensor cores read both halves.  Per CTA the accumulator
+// is 128 lanes x N columns, so TWO accumulators fit in TMEM: the MMA of tile t+1 overlaps the epilogue
+// of tile t, and the half-size stages give a 6-deep TMA ring (reads keep flowing during the stores).
+// Barrier protocol: full[] lives in the leader CTA (both CTAs' TMA loads complete_tx on it), empty[] and
+// tmem_full[] are signalled in both CTAs by multicast tcgen05.commit, tmem_empty[] in the leader collects
+// the 16 epilogue warps of the pair (remote mbarrier.arrive from the peer).
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0,
+                                                int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <class P, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_in, GemmArgs g) {
+  constexpr int S = P::S, H = 256;
+  constexpr int PT = TileOf<S>::PT, N = TileOf<S>::N, NHALF = N / 2;
+  constexpr int KB = H / 32;
+  constexpr int W_BYTES = 128 * 128, IN_BYTES = NHALF * 128;
+  constexpr int STAGE_BYTES = W_BYTES + ((IN_BYTES + 1023) / 1024) * 1024;
+  constexpr int NSTAGE = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
+  constexpr uint32_t IDESC = make_idesc_m256(N);
+  constexpr int G8 = PT / 8;
+  static_assert(NHALF % 8 == 0, "row halves must be whole swizzle atoms");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = (uint64_t *)(smem + NSTAGE * STAGE_BYTES);
+  uint64_t *empty = full + NSTAGE;
+  uint64_t *tmem_full = empty + NSTAGE;   // [2]
+  uint64_t *tmem_empty = tmem_full + 2;   // [2]
+  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
+  float *red = reinterpret_cast<float *>(tmem_slot + 4);  // [2][128][5]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
+        const int row0 = tile * N + (int)rank * NHALF;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t *sw = smem + stage * STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (W_BYTES + IN_BYTES));
+          const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
+          tma_load_3d_2sm(&map_w, leader_bar, sw, 0, (int)rank * 128, kb);
+          tma_load_3d_2sm(&map_in, leader_bar, sw + W_BYTES, 0, row0, kb);
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) --------------
+    if (rank == 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
+        const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[b], bphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sw = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sin = sw + W_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_desc(sw + ks * 32, 16, 1024);
+            const uint64_t db = make_desc(sin + ks * 32, 16, 1024);
+            umma_tf32_2sm(tmem_base + b * 256, da, db, IDESC, (kb | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[b]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 units) --------
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    constexpr int MY_ITEMS = (G8 + 1) / 2;
+    const int o = (int)rank * 128 + q * 32 + lane;
+    float dbsum = 0.0f, dw0[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float bias = (MODE == 0) ? __ldg(g.bias + o) : 0.0f;
+    const bool fuse_first = (MODE == 1) && (g.first_x != nullptr);
+    const float *__restrict__ stash_in = g.stash_in;
+    float *__restrict__ outp = g.out;
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
+      const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+      const long long p0 = (long long)tile * PT;
+      float st[MODE == 1 ? 8 * S : 1];
+      auto prefetch = [&](int grp) {
+        if (MODE == 1) {
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            const long long p = p0 + grp * 8 + pp;
+            const bool ok = p < g.n;
+#pragma unroll
+            for (int s = 0; s < S; ++s) st[pp * S + s] = ok ? __ldg(stash_in + (p * S + s) * H + o) : 0.0f;
+          }
+        }
+      };
+      if (sub < G8) prefetch(sub);
+      mbar_wait(&tmem_full[b], bphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < MY_ITEMS; ++k) {
+        const int grp = sub + 2 * k;
+        if (grp >= G8) break;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * 256 + grp * 8 * S;
+        float r[8 * S];
+        tmem_ld_cols<8 * S>(taddr, r);
+        tmem_ld_wait();
+        if (grp + 2 >= G8) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&tmem_empty[b], 0);   // leader's barrier (remote for the peer)
+        }
+        float cur[MODE == 1 ? 8 * S : 1];
+        if (MODE == 1) {
+#pragma unroll
+          for (int i = 0; i < 8 * S; ++i) cur[i] = st[i];
+          if (grp + 2 < G8) prefetch(grp + 2);
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const long long p = p0 + grp * 8 + pp;
+          if (p < g.n) {
+            float z[S], w[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
+            float *dst = outp + (p * S) * H + o;
+            if (MODE == 0) {
+              z[0] += bias;
+              jet_forward_A<P>(g.act, z, w);
+              dst[0] = w[0];
+#pragma unroll
+              for (int s = 1; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+            } else {
+              float a[S];
+#pragma unroll
+              for (int s = 0; s < S; ++s) a[s] = cur[pp * S + s];
+              jet_adjoint_A<P>(g.act, a, z, w);
+              dbsum += w[0];
+              if (fuse_first) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                  if (d < g.d_in) dw0[d] = fmaf(w[0], __ldg(g.first_x + (long long)d * g.ldn + p), dw0[d]);
+#pragma unroll
+                for (int j = 0; j < P::N1; ++j) {
+#pragma unroll
+                  for (int d = 0; d < 4; ++d)
+                    if (d == g.dirs.d[j]) dw0[d] += w[1 + j];
+                }
+              } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (MODE == 1) {
+      float *r5 = red + ((sub * 128) + q * 32 + lane) * 5;
+      r5[0] = dbsum;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) r5[1 + d] = dw0[d];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (sub == 0) {
+        const float *r0 = red + ((0 * 128) + q * 32 + lane) * 5;
+        const float *r1 = red + ((1 * 128) + q * 32 + lane) * 5;
+        g.db_partial[(long long)cluster_id * H + o] = r0[0] + r1[0];
+        if (fuse_first)
+          for (int d = 0; d < g.d_in; ++d) g.dw0_partial[((long long)cluster_id * H + o) * 4 + d] = r0[1 + d] + r1[1 + d];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be signalling / reading this CTA's barriers and smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // -----------------------------------------------------------------------------------------
 // kernel B:  dW[i][k] = sum_rows Zbar[row][i] * A[row][k]      (both operands MN-major)
 // each CTA reduces its own row range into a 256-lane x H-column FP32 accumulator and writes a
@@ -861,6 +1131,7 @@ __global__ void k_tc_reduce(const float *__restrict__ partial, long long stride,
 // =========================================================================================
 // host side
 // =========================================================================================
+static int g_use_pair = 1;  // AX_TC_PAIR=0 in the environment falls back to the single-CTA layer kernel
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -906,6 +1177,8 @@ static int make_map(CUtensorMap *m, const float *base, long long rows, int cols,
 static int sm_count() {
   static int n = 0;
   if (!n) {
+    const char *e = getenv("AX_TC_PAIR");
+    if (e && e[0] == '0') g_use_pair = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -935,6 +1208,33 @@ static int launch_gemm(const float *wop, const float *in, const GemmArgs &ga, lo
     k_tc_gemm<P, MODE, H><<<grid, kGemmThreads, smem, st>>>(mw, mi, ga);
   }
   AX_LAUNCH_OK();
+  return 0;
+}
+
+template <class P, int MODE>
+static int launch_gemm_pair(const float *wop, const float *in, const GemmArgs &ga, long long rows, cudaStream_t st,
+                            int *grid_units) {
+  constexpr int S = P::S, N = TileOf<S>::N, NHALF = N / 2, H = 256;
+  constexpr int STAGE_BYTES = 128 * 128 + ((NHALF * 128 + 1023) / 1024) * 1024;
+  constexpr int NSTAGE = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
+  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256 + 2 * 128 * 5 * sizeof(float);
+  CUtensorMap mw, mi;
+  if (make_map(&mw, wop, H, H, 128, 1)) return 1;
+  if (make_map(&mi, in, rows, H, NHALF, 1)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm2<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  int clusters = sm_count() / 2;
+  if (ga.num_tiles < clusters) clusters = ga.num_tiles;
+  {
+    KernelTimer t(MODE == 0 ? "tc_gemm_fwd" : "tc_gemm_dgrad", st, 2.0 * S * H * (double)H * (double)ga.n,
+                  4.0 * S * H * (double)ga.n * (MODE == 0 ? 2.0 : 3.0));
+    k_tc_gemm2<P, MODE><<<2 * clusters, kGemmThreads, smem, st>>>(mw, mi, ga);
+  }
+  AX_LAUNCH_OK();
+  *grid_units = clusters;
   return 0;
 }
 
@@ -1072,7 +1372,12 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       ga.n = a.n;
       ga.num_tiles = (int)((a.n + PT - 1) / PT);
       ga.act = act;
-      if (launch_gemm<P, 0, H>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream)) return 1;
+      if (H == 256 && g_use_pair) {
+        int units = 0;
+        if (launch_gemm_pair<P, 0>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream, &units)) return 1;
+      } else {
+        if (launch_gemm<P, 0, H>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream)) return 1;
+      }
     }
     {
       KernelTimer t("tc_last_fwd", a.stream, 2.0 * S * H * C * (double)a.n, 4.0 * S * H * (double)a.n);
@@ -1146,8 +1451,12 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       ga.n = a.n;
       ga.num_tiles = (int)((a.n + PT - 1) / PT);
       ga.act = act;
-      if (launch_gemm<P, 1, H>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], ga, rows, a.stream)) return 1;
-      const int grid = ga.num_tiles < sm_count() ? ga.num_tiles : sm_count();
+      int grid = ga.num_tiles < sm_count() ? ga.num_tiles : sm_count();
+      if (H == 256 && g_use_pair) {
+        if (launch_gemm_pair<P, 1>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], ga, rows, a.stream, &grid)) return 1;
+      } else {
+        if (launch_gemm<P, 1, H>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], ga, rows, a.stream)) return 1;
+      }
       if (reduce_to(dbpart, H, 0, grid, H, grad + g.b_off[l - 1], a.stream)) return 1;
       if (l == 1 && fuse_first) {
         // dW0 partials are [grid][H][4]; W0 is [H][d_in]
