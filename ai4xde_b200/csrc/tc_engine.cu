@@ -675,28 +675,60 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
     }
   } else {
     // ------------------------------ epilogue (both CTAs, own 128 units) --------
+    // The epilogue warps are latency-bound (2 warps per scheduler), so instructions per element are what
+    // counts: one 64-bit base pointer per tile, compile-time offsets below it, and no per-point bound
+    // checks on full tiles.
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
     constexpr int MY_ITEMS = (G8 + 1) / 2;
+    constexpr int GSTRIDE = 8 * S * H;   // floats between consecutive 8-point groups
     const int o = (int)rank * 128 + q * 32 + lane;
-    float dbsum = 0.0f, dw0[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float dbsum = 0.0f, dw0a = 0.0f, dw0b = 0.0f;
     const float bias = (MODE == 0) ? __ldg(g.bias + o) : 0.0f;
     const bool fuse_first = (MODE == 1) && (g.first_x != nullptr);
+    float m0[P::N1 > 0 ? P::N1 : 1], m1[P::N1 > 0 ? P::N1 : 1];   // first-order stream j differentiates x0 / x1 ?
+#pragma unroll
+    for (int j = 0; j < P::N1; ++j) {
+      m0[j] = (g.dirs.d[j] == 0) ? 1.0f : 0.0f;
+      m1[j] = (g.dirs.d[j] == 1) ? 1.0f : 0.0f;
+    }
     const float *__restrict__ stash_in = g.stash_in;
     float *__restrict__ outp = g.out;
+    const float *__restrict__ x0p = g.first_x;
+    const float *__restrict__ x1p = (g.first_x != nullptr && g.d_in > 1) ? g.first_x + g.ldn : g.first_x;
     uint32_t it = 0;
     for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
       const uint32_t b = it & 1, bphase = (it >> 1) & 1;
       const long long p0 = (long long)tile * PT;
+      const bool full_tile = (p0 + PT <= g.n);
+      const float *sbase = (MODE == 1) ? stash_in + (p0 * S) * H + o : nullptr;
+      float *obase = outp + (p0 * S) * H + o;
       float st[MODE == 1 ? 8 * S : 1];
+      float xs[MODE == 1 ? 16 : 1];   // x of the next group's points (fused first-layer gradient, d_in <= 2)
       auto prefetch = [&](int grp) {
         if (MODE == 1) {
+          const float *sp = sbase + grp * GSTRIDE;
+          if (full_tile) {
 #pragma unroll
-          for (int pp = 0; pp < 8; ++pp) {
-            const long long p = p0 + grp * 8 + pp;
-            const bool ok = p < g.n;
+            for (int i = 0; i < 8 * S; ++i) st[i] = __ldg(sp + i * H);
+            if (fuse_first) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) st[pp * S + s] = ok ? __ldg(stash_in + (p * S + s) * H + o) : 0.0f;
+              for (int pp = 0; pp < 8; ++pp) {
+                xs[2 * pp] = __ldg(x0p + p0 + grp * 8 + pp);
+                xs[2 * pp + 1] = __ldg(x1p + p0 + grp * 8 + pp);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const bool ok = p0 + grp * 8 + pp < g.n;
+#pragma unroll
+              for (int s = 0; s < S; ++s) st[pp * S + s] = ok ? __ldg(sp + (pp * S + s) * H) : 0.0f;
+              if (fuse_first) {
+                xs[2 * pp] = ok ? __ldg(x0p + p0 + grp * 8 + pp) : 0.0f;
+                xs[2 * pp + 1] = ok ? __ldg(x1p + p0 + grp * 8 + pp) : 0.0f;
+              }
+            }
           }
         }
       };
@@ -717,25 +749,28 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
           if (lane == 0) mbar_arrive_cta(&tmem_empty[b], 0);   // leader's barrier (remote for the peer)
         }
         float cur[MODE == 1 ? 8 * S : 1];
+        float xc[MODE == 1 ? 16 : 1];
         if (MODE == 1) {
 #pragma unroll
           for (int i = 0; i < 8 * S; ++i) cur[i] = st[i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xc[i] = xs[i];
           if (grp + 2 < G8) prefetch(grp + 2);
         }
+        float *op = obase + grp * GSTRIDE;
+        const int valid = full_tile ? 8 : (int)((g.n - p0 - grp * 8) < 8 ? (g.n - p0 - grp * 8) : 8);
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) {
-          const long long p = p0 + grp * 8 + pp;
-          if (p < g.n) {
+          if (full_tile || pp < valid) {
             float z[S], w[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
-            float *dst = outp + (p * S) * H + o;
             if (MODE == 0) {
               z[0] += bias;
               jet_forward_A<P>(g.act, z, w);
-              dst[0] = w[0];
+              op[(pp * S) * H] = w[0];
 #pragma unroll
-              for (int s = 1; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+              for (int s = 1; s < S; ++s) op[(pp * S + s) * H] = to_tf32(w[s]);
             } else {
               float a[S];
 #pragma unroll
@@ -743,24 +778,23 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
               jet_adjoint_A<P>(g.act, a, z, w);
               dbsum += w[0];
               if (fuse_first) {
-#pragma unroll
-                for (int d = 0; d < 4; ++d)
-                  if (d < g.d_in) dw0[d] = fmaf(w[0], __ldg(g.first_x + (long long)d * g.ldn + p), dw0[d]);
+                dw0a = fmaf(w[0], xc[2 * pp], dw0a);
+                dw0b = fmaf(w[0], xc[2 * pp + 1], dw0b);
 #pragma unroll
                 for (int j = 0; j < P::N1; ++j) {
-#pragma unroll
-                  for (int d = 0; d < 4; ++d)
-                    if (d == g.dirs.d[j]) dw0[d] += w[1 + j];
+                  dw0a = fmaf(m0[j], w[1 + j], dw0a);
+                  dw0b = fmaf(m1[j], w[1 + j], dw0b);
                 }
               } else {
 #pragma unroll
-                for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(w[s]);
+                for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = to_tf32(w[s]);
               }
             }
           }
         }
       }
     }
+    const float dw0[4] = {dw0a, dw0b, 0.0f, 0.0f};
     if (MODE == 1) {
       float *r5 = red + ((sub * 128) + q * 32 + lane) * 5;
       r5[0] = dbsum;
@@ -1405,7 +1439,7 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
   }
   float *dbpart = w.partial + (w.partial_floats - (size_t)(sm_count() + 1) * H * 5);
   float *dw0part = dbpart + (size_t)(sm_count() + 1) * H;
-  const bool fuse_first = d_in <= 4;
+  const bool fuse_first = d_in <= 2;
   for (int net = 0; net < a.net->n_nets; ++net) {
     const float *prm = a.params + (long long)net * g.P;
     float *grad = a.grad + (long long)net * g.P;
