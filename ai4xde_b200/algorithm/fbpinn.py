@@ -81,6 +81,7 @@ class FBPINN(PINNSolver):
         self.model_list = [dde.Model(pde.data, pde.net) for pde in self.domains.pdeCase_list]
         self.bank = dde.nn.NetBank([m.net for m in self.model_list])
         self._specs = {}
+        self._pick_combine()
 
     # ---- schedule (FBPINN.py:112-123) -------------------------------------------------------
     def train_step(self, lr=1e-3, iterations=1000, callbacks=None, eval=True):
@@ -97,8 +98,9 @@ class FBPINN(PINNSolver):
             self.train_step()
 
     # ---- sum over subdomain nets --------------------------------------------------------------
-    def _combine(self, x, y_all):
-        """sum_j T_j(x, N_j(x)) with T_j the sub-case's wired output transform (window * parent)."""
+    def _combine_loop(self, x, y_all):
+        """sum_j T_j(x, N_j(x)) with T_j the sub-case's wired output transform (window * parent):
+        the reference's get_predict loop (FBPINN.py:196-204), net by net."""
         C = self.bank.layer_sizes[-1]
         result = None
         for j, model in enumerate(self.model_list):
@@ -108,6 +110,48 @@ class FBPINN(PINNSolver):
                 y = tf(x, y)
             result = y if result is None else result + y
         return result
+
+    def _combine_vectorised(self, x, y_all):
+        """Same sum in a handful of batched ops: all K windows at once, the parent transform applied to
+        the (n, K) block (valid when it is elementwise in y, which _pick_combine verifies numerically)."""
+        K, C = self.bank.K, self.bank.layer_sizes[-1]
+        if not self._wired:
+            return y_all.view(-1, K, C).sum(dim=1)
+        y = y_all
+        parent = self._parent_transform
+        if parent is not None:
+            yp = parent(x, y)
+            if yp is not None:
+                y = yp
+        lo, hi = self._lims
+        w = torch.sigmoid(x - lo) * torch.sigmoid(hi - x)          # (n, K): FBPINN.py:45-50 for every subdomain
+        return (w * y).sum(dim=1, keepdim=True)
+
+    def _pick_combine(self):
+        """Use the vectorised sum only if it reproduces the net-by-net loop on a probe batch."""
+        K, C = self.bank.K, self.bank.layer_sizes[-1]
+        nets = [m.net for m in self.model_list]
+        self._wired = all(n._output_transform is not None for n in nets)
+        self._combine = self._combine_loop
+        if any(n._output_transform is not None for n in nets) and not self._wired:
+            return
+        if self._wired and C != 1:
+            return
+        dev = dconfig.device()
+        lims = np.array(self.domains.limits, dtype=np.float32)
+        self._lims = (torch.as_tensor(lims[:, 0], device=dev)[None, :], torch.as_tensor(lims[:, 1], device=dev)[None, :])
+        parent_cls = type(self.PDECase)
+        self._parent_transform = (lambda xx, yy: parent_cls.output_transform(self.PDECase, xx, yy)) if self._wired else None
+        try:
+            g = torch.Generator().manual_seed(0)
+            lo, hi = float(lims[:, 0].min()), float(lims[:, 1].max())
+            x = (torch.rand((7, 1), generator=g) * (hi - lo) + lo).to(dev)
+            y = torch.randn((7, K * C), generator=g).to(dev)
+            a, b = self._combine_loop(x, y), self._combine_vectorised(x, y)
+            if a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-6):
+                self._combine = self._combine_vectorised
+        except Exception:
+            self._combine = self._combine_loop
 
     def get_predict(self, input, active=None, spec=None, x_soa=None, param_grad=True):
         y_all = self.bank.forward_all(input, x_soa=x_soa, spec=spec, active=active, param_grad=param_grad)
