@@ -1,11 +1,9 @@
 """Algorithms available on the fused path (mirror of AI4XDE.algorithm).  HPO, FI_PINN, CausalPINN
 and the skopt-based Uniform sampler are outside the hot-path scope."""
-from .pinn import PINN
+from .basic import PINN, RAR_G, Random_R
 from .rad import RAD
 from .rar_d import RAR_D
-from .rar_g import RAR_G
 from .r3sampling import R3Sampling
-from .random_r import Random_R
 from .gpinn import gPINN
 from .fbpinn import FBPINN
 

@@ -2,11 +2,13 @@
 
 The residual of the whole population is evaluated with forward-only jets and the retain step
 (sum of |residual| over components, NumPy-order mean as threshold, `res > thr`, ordered compaction)
-runs on the device.  Deviations from the reference, both documented in SURVEY.md App. C:
+runs on the device (`ai4xde_b200.resample.r3_retain`).  Constructor, attributes (`gamma, alpha,
+max_iter, causally_sampling, beta_lr, tol`) and methods (`set_causal_pde, update_gamma, causal_weight,
+residual, closure`) keep the reference's names.  Deviations, both listed in SURVEY.md App. C:
   * R3Sampling.py:79 raises AxisError when `pde` returns ONE residual; the evident intent (sum over
     residual components, identity for one) is what runs here;
   * with `causally_sampling` the reference's 2-argument wrapper never applies its weight to the
-    residual (loop-variable rebinding, R3Sampling.py:43-44); that no-op is kept, and the causal gate on
+    residual (a loop variable is rebound, R3Sampling.py:43-44); that no-op is kept.  The causal gate on
     the sampling side (R3Sampling.py:80-82) runs in NumPy as in the reference."""
 import numpy as np
 
@@ -15,44 +17,57 @@ from ..dde import backend as bkd
 from ..solver import PINNSolver
 
 
+class _CausalGate:
+    """w(t) = (1 - tanh(alpha (t_hat - gamma))) / 2 with t_hat = t / (max t - min t); gamma creeps
+    forward by beta_lr * exp(-tol * mean gated residual) each round (R3Sampling.py:62-75)."""
+
+    def __init__(self, alpha=5, gamma=-0.5, beta_lr=0.001, tol=20):
+        self.alpha, self.gamma, self.beta_lr, self.tol = alpha, gamma, beta_lr, tol
+
+    def weight(self, X):
+        t = X[:, -1]
+        t_hat = t / (max(t) - min(t))
+        return ((1 - np.tanh(self.alpha * (t_hat - self.gamma))) / 2).reshape(-1)
+
+    def advance(self, gated_mean):
+        self.gamma += self.beta_lr * np.exp(-self.tol * gated_mean)
+
+
 class R3Sampling(PINNSolver):
     def __init__(self, PDECase, max_iter=100, causally_sampling=False, beta_lr=0.001, tol=20):
         dde.optimizers.config.set_LBFGS_options(maxiter=1000)
-        name = "R3Sampling"
-        if causally_sampling:
-            name += "_causal"
-            self.set_causal_pde(PDECase)
-        super().__init__(name=name, PDECase=PDECase)
-        self.gamma, self.alpha = -0.5, 5
+        self._gate = _CausalGate(beta_lr=beta_lr, tol=tol)
         self.max_iter = max_iter
         self.causally_sampling = causally_sampling
-        self.beta_lr, self.tol = beta_lr, tol
+        if causally_sampling:
+            self.set_causal_pde(PDECase)
+        super().__init__("R3Sampling_causal" if causally_sampling else "R3Sampling", PDECase)
 
-    def set_causal_pde(self, PDECase):
-        pde = PDECase.pde
-        nargs = dde.utils.get_num_args(pde)
-        if nargs == 2:
-            def g_pde(x, y):
-                res = pde(x, y)
-                return res if isinstance(res, list) else [res]      # weight not applied (reference no-op)
-        else:
-            def g_pde(x, y, ex):
-                res = pde(x, y, ex)
-                w = self.causal_weight(bkd.to_numpy(x), tensor=True)
-                res = res if isinstance(res, list) else [res]
-                return [r * w for r in res]
-        PDECase.set_pde(g_pde)
+    # reference attribute names, backed by the gate
+    gamma = property(lambda self: self._gate.gamma, lambda self, v: setattr(self._gate, "gamma", v))
+    alpha = property(lambda self: self._gate.alpha, lambda self, v: setattr(self._gate, "alpha", v))
+    beta_lr = property(lambda self: self._gate.beta_lr, lambda self, v: setattr(self._gate, "beta_lr", v))
+    tol = property(lambda self: self._gate.tol, lambda self, v: setattr(self._gate, "tol", v))
 
     def update_gamma(self, loss):
-        self.gamma += self.beta_lr * np.exp(-self.tol * loss)
+        self._gate.advance(loss)
 
     def causal_weight(self, X, tensor=False):
-        t = X[:, -1]
-        t = t / (max(t) - min(t))
-        weight = ((1 - np.tanh(self.alpha * (t - self.gamma))) / 2).reshape(-1)
-        if tensor:
-            weight = bkd.pow(bkd.from_numpy(weight), 1 / 2)
-        return weight
+        w = self._gate.weight(X)
+        return bkd.pow(bkd.from_numpy(w), 1 / 2) if tensor else w
+
+    def set_causal_pde(self, PDECase):
+        inner = PDECase.pde
+        if dde.utils.get_num_args(inner) == 2:
+            def gated(x, y):                       # reference: weight computed, never applied
+                out = inner(x, y)
+                return out if isinstance(out, list) else [out]
+        else:
+            def gated(x, y, ex):
+                out = inner(x, y, ex)
+                w = self.causal_weight(bkd.to_numpy(x), tensor=True)
+                return [r * w for r in (out if isinstance(out, list) else [out])]
+        PDECase.set_pde(gated)
 
     def residual(self, X, causally_sampling=False):
         res, n = resample.residual_matrix(self.model, X, self.PDECase.pde)
@@ -63,19 +78,19 @@ class R3Sampling(PINNSolver):
         return res
 
     def resample(self):
-        """One retain/refill round; returns the boolean keep mask over the old population."""
-        case = self.PDECase
-        X = case.data.train_x_all
+        """One retain / refill round; returns the boolean keep mask over the old population.
+        New population = [fresh uniform points ; retained points] (R3Sampling.py:92-98)."""
+        data, X = self.PDECase.data, self.PDECase.data.train_x_all
         if self.causally_sampling:
             res = self.residual(X, True)
             keep = res > np.mean(res)
         else:
-            keep, _thr, _x_dev, _nk = resample.r3_retain(self.model, X, case.pde)
-        X_retained = X[np.where(keep)]
-        case.data.replace_with_anchors(X_retained)
-        n_new = len(X) - len(X_retained)
-        if n_new > 0:
-            case.data.add_anchors(case.geomtime.random_points(n_new))
+            keep = resample.r3_retain(self.model, X, self.PDECase.pde)[0]
+        kept = X[np.where(keep)]
+        data.replace_with_anchors(kept)
+        released = len(X) - len(kept)
+        if released > 0:
+            data.add_anchors(self.PDECase.geomtime.random_points(released))
         return keep
 
     def closure(self):

@@ -45,3 +45,28 @@ class Visualization_2D(_Viz):
             ax.set_title(f"{title or ''} {name}")
             fig.colorbar(im, ax=ax)
         return fig, axes
+
+
+def plot_loss_curves(label, losshistory, train_cost, axes=None, train=False, use_time=False):
+    """Summed train / test loss versus step (or wall-clock seconds) on a log axis; matplotlib is an
+    optional dependency of the fused path and is imported only here."""
+    import numpy as np
+
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError as e:  # pragma: no cover
+        raise ImportError("plotting needs matplotlib, which is not part of the fused path") from e
+    fig, axes = plt.subplots() if axes is None else (axes.get_figure(), axes)
+    steps = np.asarray(losshistory.steps, dtype=float)
+    if use_time:
+        xs, xlabel = steps / steps[-1] * train_cost, "Time(s)"
+    else:
+        xs, xlabel = steps, "Steps"
+    curves = {"Test loss" if train else label: np.sum(losshistory.loss_test, axis=1)}
+    if train:
+        curves = {"Train loss": np.sum(losshistory.loss_train, axis=1), **curves}
+    for name, ys in curves.items():
+        axes.semilogy(xs, ys, label=name)
+    axes.set(xlabel=xlabel, ylabel="Loss", title=label)
+    axes.legend()
+    return fig, axes
