@@ -819,6 +819,323 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
   }
 }
 
+
+// -----------------------------------------------------------------------------------------
+// kernel C: fused backward of one hidden layer on a CTA pair (H = 256):
+//     zbar_{l-1} = adjoint( W_l^T zbar_l )      (dgrad, K-major operands, two accumulators in TMEM cols 0..255)
+//     dW_l      += zbar_l^T A_{l-1}             (wgrad, MN-major operands, accumulator in TMEM cols 256..511)
+// Both GEMMs consume the SAME (point,stream)-row tile of zbar_l and the same stash rows, so the tile comes
+// from HBM once (its second layout comes out of L2): per point and layer 3*S*H*4 bytes (read zbar, read
+// stash, write zbar') instead of 5*S*H*4 for separate kernels.
+// Shared memory: this CTA's 128 rows of W_l^T stay RESIDENT (128 KB, loaded once per launch), the rest is
+// a ring of 16 KB slots carrying two slot kinds per tile:
+//     D slot = two 32-wide K blocks of the CTA's zbar row half, K-major        (dgrad B operand)
+//     W slot = 16 rows x own 128 units of zbar and of the stash, MN-major      (wgrad A and B operands)
+// The dgrad accumulator is double-buffered (N <= 128 columns each), so the tensor pipe runs
+// dgrad(t+1) / wgrad(t+1) while the epilogue warps drain tile t; the epilogue prefetches its stash rows
+// one 8-point group ahead ACROSS tile boundaries, so its loads never drain.
+// -----------------------------------------------------------------------------------------
+template <int S>
+struct BwdTileOf {
+  // points per tile: N = S*PT <= 128, N a multiple of 16 (whole wgrad slots; MMA N granularity of a CTA
+  // pair), PT a multiple of 16 (two epilogue warps per lane quarter, 8-point groups)
+  static constexpr int PT = (S == 1) ? 128 : (S == 2) ? 64 : (S <= 4) ? 32 : (S <= 6) ? 16 : 0;
+  static constexpr int N = S * PT;
+};
+
+struct BwdArgs2 {
+  GemmArgs g;
+  float *dw_partial;   // [clusters][H][H]
+};
+
+constexpr int kBwdSlotBytes = 16384, kBwdSlots = 5, kBwdWres = 128 * 1024;
+constexpr size_t kBwdSmem = (size_t)kBwdWres + kBwdSlots * kBwdSlotBytes + 1024 + 256 + 2 * 128 * 5 * sizeof(float);
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_g_k,
+          const __grid_constant__ CUtensorMap map_g_mn, const __grid_constant__ CUtensorMap map_a_mn, BwdArgs2 args) {
+  constexpr int S = P::S, H = 256;
+  constexpr int PT = BwdTileOf<S>::PT, N = BwdTileOf<S>::N, NHALF = N / 2;
+  constexpr int KB = H / 32, DSLOTS = KB / 2;   // two K blocks per D slot
+  constexpr int CR = 16, WSLOTS = N / CR;       // rows per W slot
+  constexpr int SLOT = kBwdSlotBytes, NSLOT = kBwdSlots;
+  constexpr int D_BYTES = 2 * NHALF * 128, W_BYTES = 2 * CR * 512;   // per CTA and slot
+  constexpr uint32_t IDESC_D = make_idesc_m256(N);
+  constexpr uint32_t IDESC_W = make_idesc_m256(256) | (1u << 15) | (1u << 16);   // both operands MN-major
+  constexpr int G8 = PT / 8, MY = G8 / 2;
+  static_assert(N % 16 == 0 && NHALF % 8 == 0 && N <= 128 && G8 % 2 == 0, "bad backward tile");
+  static_assert(D_BYTES <= SLOT && W_BYTES <= SLOT, "slot too small");
+  const GemmArgs &g = args.g;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *wres = smem;                   // [KB][128 rows][32] : own rows of W^T, K-major, 128B swizzle
+  uint8_t *ring = smem + kBwdWres;
+  uint64_t *full = (uint64_t *)(ring + NSLOT * SLOT);
+  uint64_t *empty = full + NSLOT;
+  uint64_t *tmem_full = empty + NSLOT;    // [2] dgrad accumulator b ready
+  uint64_t *tmem_empty = tmem_full + 2;   // [2] dgrad accumulator b drained (16 epilogue warps of the pair)
+  uint64_t *w_full = tmem_empty + 2;      // wgrad accumulator complete (end of kernel)
+  uint64_t *wres_full = w_full + 1;       // resident W^T of both CTAs landed
+  uint32_t *tmem_slot = (uint32_t *)(wres_full + 1);
+  float *red = reinterpret_cast<float *>(ring + NSLOT * SLOT + 256);  // [2][128][5]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 2 * kEpiWarps);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(wres_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------
+    if (lane == 0) {
+      {
+        if (rank == 0) mbar_expect_tx(wres_full, 2 * kBwdWres);
+        const uint32_t leader_bar = smem_u32(wres_full) & 0xFEFFFFFFu;
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d_2sm(&map_wt, leader_bar, wres + kb * 16384, 0, (int)rank * 128, kb);
+      }
+      uint32_t slot = 0, phase = 0;
+      auto advance = [&]() {
+        if (++slot == NSLOT) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
+        const int row0 = tile * N;
+        for (int j = 0; j < DSLOTS; ++j) {   // K blocks 2j, 2j+1 of this CTA's row half of zbar
+          mbar_wait(&empty[slot], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[slot], 2 * D_BYTES);
+          const uint32_t leader_bar = smem_u32(&full[slot]) & 0xFEFFFFFFu;
+          tma_load_3d_2sm(&map_g_k, leader_bar, ring + slot * SLOT, 0, row0 + (int)rank * NHALF, 2 * j);
+          advance();
+        }
+        for (int c = 0; c < WSLOTS; ++c) {   // 16 rows x own 128 units of zbar and of the stash
+          mbar_wait(&empty[slot], phase ^ 1);
+          uint8_t *sp = ring + slot * SLOT;
+          if (rank == 0) mbar_expect_tx(&full[slot], 2 * W_BYTES);
+          const uint32_t leader_bar = smem_u32(&full[slot]) & 0xFEFFFFFFu;
+          tma_load_3d_2sm(&map_g_mn, leader_bar, sp, 0, row0 + c * CR, (int)rank * 4);
+          tma_load_3d_2sm(&map_a_mn, leader_bar, sp + CR * 512, 0, row0 + c * CR, (int)rank * 4);
+          advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) --------------
+    if (rank == 0 && lane == 0) {
+      uint32_t slot = 0, phase = 0, it = 0;
+      auto advance = [&]() {
+        if (++slot == NSLOT) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      mbar_wait(wres_full, 0);
+      tc_fence_after();
+      const uint32_t wr = smem_u32(wres);
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
+        const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[b], bphase ^ 1);
+        tc_fence_after();
+        for (int j = 0; j < DSLOTS; ++j) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t sp = smem_u32(ring + slot * SLOT);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32_2sm(tmem_base + b * 128, make_desc(wr + (2 * j + kk) * 16384 + ks * 32, 16, 1024),
+                            make_desc(sp + kk * (NHALF * 128) + ks * 32, 16, 1024), IDESC_D,
+                            (j | kk | ks) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[slot]);
+          advance();
+        }
+        umma_commit_2sm(&tmem_full[b]);
+        for (int c = 0; c < WSLOTS; ++c) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t sp = smem_u32(ring + slot * SLOT);
+          // MN-major, 32B-base swizzle: LBO = next 32-unit block (16 rows x 128 B), SBO = next 4 K-rows
+#pragma unroll
+          for (int ks = 0; ks < CR / 8; ++ks)
+            umma_tf32_2sm(tmem_base + 256, make_desc(sp + ks * 1024, CR * 128, 512, 1),
+                          make_desc(sp + CR * 512 + ks * 1024, CR * 128, 512, 1), IDESC_W,
+                          (it | (uint32_t)c | (uint32_t)ks) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[slot]);
+          advance();
+        }
+      }
+      umma_commit_2sm(w_full);
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 units) --------
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int o = (int)rank * 128 + q * 32 + lane;
+    float dbsum = 0.0f, dw0a = 0.0f, dw0b = 0.0f;
+    const bool fuse_first = (g.first_x != nullptr);
+    float m0[P::N1 > 0 ? P::N1 : 1], m1[P::N1 > 0 ? P::N1 : 1];
+#pragma unroll
+    for (int j = 0; j < P::N1; ++j) {
+      m0[j] = (g.dirs.d[j] == 0) ? 1.0f : 0.0f;
+      m1[j] = (g.dirs.d[j] == 1) ? 1.0f : 0.0f;
+    }
+    const float *__restrict__ stash_in = g.stash_in + o;
+    float *__restrict__ outp = g.out + o;
+    const float *__restrict__ x0p = g.first_x;
+    const float *__restrict__ x1p = (g.first_x != nullptr && g.d_in > 1) ? g.first_x + g.ldn : g.first_x;
+    const long long n = g.n;
+    float st[8 * S], xs[16];
+    // stash rows (and x) of the 8-point group starting at point pg
+    auto prefetch = [&](long long pg) {
+      const float *sp = stash_in + pg * (S * H);
+      if (pg + 8 <= n) {
+#pragma unroll
+        for (int i = 0; i < 8 * S; ++i) st[i] = __ldg(sp + i * H);
+        if (fuse_first) {
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            xs[2 * pp] = __ldg(x0p + pg + pp);
+            xs[2 * pp + 1] = __ldg(x1p + pg + pp);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const bool ok = pg + pp < n;
+#pragma unroll
+          for (int s = 0; s < S; ++s) st[pp * S + s] = ok ? __ldg(sp + (pp * S + s) * H) : 0.0f;
+          if (fuse_first) {
+            xs[2 * pp] = ok ? __ldg(x0p + pg + pp) : 0.0f;
+            xs[2 * pp + 1] = ok ? __ldg(x1p + pg + pp) : 0.0f;
+          }
+        }
+      }
+    };
+    if (cluster_id < g.num_tiles) prefetch((long long)cluster_id * PT + sub * 8);
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
+      const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+      const long long p0 = (long long)tile * PT;
+      mbar_wait(&tmem_full[b], bphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < MY; ++k) {
+        const int grp = sub + 2 * k;
+        const long long pg = p0 + grp * 8;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * 128 + grp * 8 * S;
+        float r[8 * S];
+        tmem_ld_cols<8 * S>(taddr, r);
+        tmem_ld_wait();
+        if (k == MY - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&tmem_empty[b], 0);
+        }
+        float cur[8 * S], xc[16];
+#pragma unroll
+        for (int i = 0; i < 8 * S; ++i) cur[i] = st[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xc[i] = xs[i];
+        if (k + 1 < MY)
+          prefetch(pg + 16);
+        else if (tile + num_clusters < g.num_tiles)
+          prefetch((long long)(tile + num_clusters) * PT + sub * 8);
+        float *op = outp + pg * (S * H);
+        const bool full_grp = pg + 8 <= n;
+        const int valid = full_grp ? 8 : (int)(n > pg ? n - pg : 0);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          if (full_grp || pp < valid) {
+            float z[S], w[S], a[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              z[s] = r[pp * S + s];
+              a[s] = cur[pp * S + s];
+            }
+            jet_adjoint_A<P>(g.act, a, z, w);
+            dbsum += w[0];
+            if (fuse_first) {
+              dw0a = fmaf(w[0], xc[2 * pp], dw0a);
+              dw0b = fmaf(w[0], xc[2 * pp + 1], dw0b);
+#pragma unroll
+              for (int j = 0; j < P::N1; ++j) {
+                dw0a = fmaf(m0[j], w[1 + j], dw0a);
+                dw0b = fmaf(m1[j], w[1 + j], dw0b);
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = to_tf32(w[s]);
+            }
+          }
+        }
+      }
+    }
+    // bias-gradient (and first-layer) partials of this cluster, fixed order
+    {
+      float *r5 = red + ((sub * 128) + q * 32 + lane) * 5;
+      r5[0] = dbsum;
+      r5[1] = dw0a;
+      r5[2] = dw0b;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (sub == 0) {
+        const float *r0 = red + ((0 * 128) + q * 32 + lane) * 5;
+        const float *r1 = red + ((1 * 128) + q * 32 + lane) * 5;
+        g.db_partial[(long long)cluster_id * H + o] = r0[0] + r1[0];
+        if (fuse_first)
+          for (int d = 0; d < g.d_in && d < 2; ++d)
+            g.dw0_partial[((long long)cluster_id * H + o) * 4 + d] = r0[1 + d] + r1[1 + d];
+      }
+    }
+    // weight-gradient partial of this cluster: lanes = own 128 rows i of dW, 256 columns k
+    {
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      float *part = args.dw_partial + (long long)cluster_id * H * H + (long long)o * H;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
+#pragma unroll 1
+      for (int c0 = sub * 32; c0 < H; c0 += 64) {
+        float r[32];
+        tmem_ld16(taddr + c0, &r[0]);
+        tmem_ld16(taddr + c0 + 16, &r[16]);
+        tmem_ld_wait();
+        float4 *dst = reinterpret_cast<float4 *>(part + c0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // -----------------------------------------------------------------------------------------
 // kernel B:  dW[i][k] = sum_rows Zbar[row][i] * A[row][k]      (both operands MN-major)
 // each CTA reduces its own row range into a 256-lane x H-column FP32 accumulator and writes a
@@ -1165,7 +1482,8 @@ __global__ void k_tc_reduce(const float *__restrict__ partial, long long stride,
 // =========================================================================================
 // host side
 // =========================================================================================
-static int g_use_pair = 1;  // AX_TC_PAIR=0 in the environment falls back to the single-CTA layer kernel
+static int g_use_pair = 1;       // AX_TC_PAIR=0 in the environment falls back to the single-CTA layer kernel
+static int g_use_fused_bwd = 1;  // AX_TC_FUSED_BWD=0 runs dgrad and wgrad as separate kernels
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1213,6 +1531,8 @@ static int sm_count() {
   if (!n) {
     const char *e = getenv("AX_TC_PAIR");
     if (e && e[0] == '0') g_use_pair = 0;
+    const char *f = getenv("AX_TC_FUSED_BWD");
+    if (f && f[0] == '0') g_use_fused_bwd = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -1269,6 +1589,35 @@ static int launch_gemm_pair(const float *wop, const float *in, const GemmArgs &g
   }
   AX_LAUNCH_OK();
   *grid_units = clusters;
+  return 0;
+}
+
+
+// fused dgrad + wgrad of one hidden layer (H = 256, CTA pairs); returns the number of clusters (= partials)
+template <class P>
+static int launch_bwd_pair(const float *wt, const float *gl, const float *stash_prev, GemmArgs ga, long long rows,
+                           float *dw_partial, int *clusters_out, cudaStream_t st) {
+  constexpr int S = P::S, PT = BwdTileOf<S>::PT, N = BwdTileOf<S>::N, H = 256;
+  CUtensorMap m_wt, m_gk, m_gmn, m_amn;
+  if (make_map(&m_wt, wt, H, H, 128, 1)) return 1;
+  if (make_map(&m_gk, gl, rows, H, N / 2, 2)) return 1;
+  if (make_map(&m_gmn, gl, rows, H, 16, 4, true)) return 1;
+  if (make_map(&m_amn, stash_prev, rows, H, 16, 4, true)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_tc_bwd2<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    attr = true;
+  }
+  ga.num_tiles = (int)((ga.n + PT - 1) / PT);
+  int clusters = sm_count() / 2;
+  if (ga.num_tiles < clusters) clusters = ga.num_tiles;
+  BwdArgs2 a2{ga, dw_partial};
+  {
+    KernelTimer t("tc_bwd_fused", st, 4.0 * S * H * (double)H * (double)ga.n, 4.0 * S * H * (double)ga.n * 3.0);
+    k_tc_bwd2<P><<<2 * clusters, kGemmThreads, kBwdSmem, st>>>(m_wt, m_gk, m_gmn, m_amn, a2);
+  }
+  AX_LAUNCH_OK();
+  *clusters_out = clusters;
   return 0;
 }
 
@@ -1466,6 +1815,34 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       if (reduce_to(w.partial, stride, (long long)C * H + C, nb, H, grad + g.b_off[L - 1], a.stream)) return 1;
     }
     for (int l = L - 1; l >= 1; --l) {
+      if (H == 256 && g_use_pair && g_use_fused_bwd && BwdTileOf<S>::PT > 0) {
+        // fused: zbar_{l-1} = adjoint(W_l^T zbar_l)  and  dW_l = zbar_l^T A_{l-1}  in one pass over the tile
+        GemmArgs ga{};
+        ga.stash_in = slot(l - 1);
+        ga.out = w.g[cur ^ 1];
+        ga.db_partial = dbpart;
+        if (l == 1 && fuse_first) {
+          ga.first_x = a.x;
+          ga.dw0_partial = dw0part;
+          ga.ldn = a.ldn;
+          ga.d_in = d_in;
+          ga.dirs = dirs;
+        }
+        ga.n = a.n;
+        ga.act = act;
+        int clusters = 0;
+        if (launch_bwd_pair<P>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], slot(l - 1), ga, rows, w.partial, &clusters,
+                               a.stream))
+          return 1;
+        if (reduce_to(w.partial, (long long)H * H, 0, clusters, (long long)H * H, grad + g.w_off[l], a.stream)) return 1;
+        if (reduce_to(dbpart, H, 0, clusters, H, grad + g.b_off[l - 1], a.stream)) return 1;
+        if (l == 1 && fuse_first) {
+          k_tc_reduce_dw0<<<(H * d_in + 255) / 256, 256, 0, a.stream>>>(dw0part, clusters, H, d_in, grad + g.w_off[0]);
+          AX_LAUNCH_OK();
+        }
+        cur ^= 1;
+        continue;
+      }
       // dW_l = zbar_l^T A_{l-1}
       int wg_grid = 0;
       if (launch_wgrad<H>(w.g[cur], slot(l - 1), rows, w.partial, &wg_grid, a.stream, S)) return 1;

@@ -41,6 +41,12 @@ def _rel(a, b):
     ([2, 64, 64, 1], "tanh", ((0, 1), ()), 95),
     ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((15, 15),)), 20000),     # Laplacian stream (cfg4 as run)
     ([2, 128, 128, 128, 3], "sigmoid", ((0, 1), ((15, 15),)), 3000),
+    # H = 256 backward = fused dgrad + wgrad kernel (k_tc_bwd2): every tile shape it is compiled for
+    ([2, 256, 256, 256, 1], "tanh", ((), ()), 333),                                  # S = 1, PT = 128
+    ([1, 256, 256, 256, 1], "tanh", ((0,), ((0, 0),)), 2053),                        # S = 3, PT = 32
+    ([2, 256, 256, 256, 256, 2], "tanh", ((1, 0), ((0, 0),)), 4100),                 # S = 4, PT = 32
+    ([2, 256, 256, 256, 1], "sigmoid", ((0, 1), ((0, 0), (0, 1), (1, 1))), 1501),    # S = 6, PT = 16
+    ([3, 256, 256, 256, 1], "tanh", ((0, 1), ((0, 0), (1, 1))), 9999),               # d_in = 3: separate first-layer bwd
 ])
 def test_tf32_engine_matches_double(widths, act, spec, n):
     dev = torch.device("cuda:0")
