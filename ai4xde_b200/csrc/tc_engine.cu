@@ -1803,10 +1803,15 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
     // output layer
     int cur = 0;
     {
-      const int nb = (int)((a.n + kLastPts - 1) / kLastPts);
+      // a few blocks per SM, each walking a contiguous point range: the partials stay few (the fixed-order
+      // reduce reads them serially per output) and never exceed the planned ceil(n / kLastPts) blocks
+      long long ppb = (a.n + 4 * sm_count() - 1) / (4 * sm_count());
+      ppb = (ppb + 3) / 4 * 4;
+      if (ppb < kLastPts) ppb = kLastPts;
+      const int nb = (int)((a.n + ppb - 1) / ppb);
       {
         KernelTimer t("tc_last_bwd", a.stream, 4.0 * S * H * C * (double)a.n, 8.0 * S * H * (double)a.n);
-        k_tc_last_bwd<P><<<nb, H, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn, kLastPts,
+        k_tc_last_bwd<P><<<nb, H, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn, (int)ppb,
                                                  w.g[cur], w.partial, act);
       }
       AX_LAUNCH_OK();
@@ -1877,10 +1882,13 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       cur ^= 1;
     }
     if (!fuse_first) {
-      const int nb = (int)((a.n + kFirstPts - 1) / kFirstPts);
+      long long ppb = (a.n + 4 * sm_count() - 1) / (4 * sm_count());
+      ppb = (ppb + 7) / 8 * 8;
+      if (ppb < kFirstPts) ppb = kFirstPts;
+      const int nb = (int)((a.n + ppb - 1) / ppb);
       {
         KernelTimer t("tc_first_bwd", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
-        k_tc_first_bwd<P><<<nb, H, 0, a.stream>>>(w.g[cur], a.x, d_in, dirs, H, a.n, a.ldn, kFirstPts, w.partial);
+        k_tc_first_bwd<P><<<nb, H, 0, a.stream>>>(w.g[cur], a.x, d_in, dirs, H, a.n, a.ldn, (int)ppb, w.partial);
       }
       AX_LAUNCH_OK();
       if (reduce_to(w.partial, (long long)H * d_in, 0, nb, (long long)H * d_in, grad + g.w_off[0], a.stream)) return 1;

@@ -271,7 +271,8 @@ def run_ours(args):
             # the layer GEMMs stream S*H*4 bytes per point and layer through HBM: ncu shows DRAM at
             # 70-80 % of peak and the tensor pipe at 25-45 % => the dominant kernel is HBM-bound; its
             # tensor-pipe rate is reported alongside.
-            hbm_bound = name.startswith("tc_")
+            # which roof the dominant kernel sits closer to decides the reported bound
+            hbm_bound = (gbs / hbm_peak) >= (tflops / tf32_peak)
             roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": name,
                         "achieved": gbs if hbm_bound else tflops,
                         "peak": hbm_peak if hbm_bound else tf32_peak,
