@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <utility>
+
 #include "simt_kernels.cuh"
 #include "tc_engine.cuh"
 
@@ -65,6 +67,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -821,6 +826,381 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
 
 
 // -----------------------------------------------------------------------------------------
+// kernel F: the whole hidden stack of the forward pass on a CTA pair (H = 256).
+// A tile of PT points runs through layer 0 (FP32, from x) and every hidden GEMM layer without its
+// activations leaving the SM pair: the epilogue writes layer l's post-activation streams straight into
+// the NEXT layer's B operand in shared memory (K-major, 128B-swizzled, exactly what TMA would have
+// staged; the half of the rows the peer CTA multiplies goes there over DSMEM).  When the caller keeps
+// the stash, a TMA bulk store copies that same operand image to HBM while the next layer's MMAs read
+// it.  HBM traffic per point and layer: S*H*4 bytes written (nothing read) instead of 2*S*H*4; the
+// residual probe (keep_all = 0) writes only the last layer.
+//   warp 0 : TMA producer -- streams this CTA's 128 rows of W_l, one 32-wide K block per 16 KB stage
+//   warp 1 : MMA issuer (leader CTA): per layer 8 K blocks x 4 tcgen05.mma.cta_group::2 (M = 256, N = S*PT)
+//   warp 2 : stash writer -- TMA stores of the finished operand image (each CTA its own row half)
+//   warps 3..18: epilogue -- TMEM lane = unit, so a thread owns all streams of a (unit, point) pair
+// The layer chain of one tile is serial (layer l+1 needs all units of layer l); the W ring and the
+// stash stores run under the MMAs, and the exp2/rcp activation keeps the epilogue short.
+// -----------------------------------------------------------------------------------------
+constexpr int kChainEpiWarps = 16;
+constexpr int kChainFirstEpi = 3;
+constexpr int kChainThreads = 32 * (kChainFirstEpi + kChainEpiWarps);
+constexpr int kChainSubs = kChainEpiWarps / 4;
+
+struct ChainArgs {
+  const float *x;                      // x_soa [d_in][ldn]
+  const float *w0, *b0;                // first layer (FP32)
+  const float *bias[AX_MAX_LINEAR];    // bias of hidden layer l, l = 1..L-1
+  int out_slot[AX_MAX_LINEAR];         // stash slot (4th TMA coordinate) of hidden layer l = 0..L-1, or -1
+  int L, d_in;
+  JetDirs dirs;
+  long long n, ldn;
+  int num_tiles;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// round-to-nearest (ties away) to TF32 in two integer instructions; identical to cvt.rna.tf32.f32 on
+// finite values and infinities (sm_100 emulates the cvt with three)
+__device__ __forceinline__ float to_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// activation jet with exp2/rcp special-function units: |error of a| ~ 1e-7 absolute, far below the TF32
+// rounding of the streams it feeds; s1 is formed from the stored a exactly as the adjoint re-forms it.
+template <class P, int ACT>
+__device__ __forceinline__ void jet_forward_fast(float (&z)[P::S], float (&A)[P::S]) {
+  float a, s1, s2;
+  if (ACT == AX_ACT_TANH) {
+    const float e = ex2_approx(z[0] * 2.8853900817779268f);
+    a = fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
+    s1 = fmaf(-a, a, 1.0f);
+    s2 = -2.0f * a * s1;
+  } else {
+    const float e = ex2_approx(z[0] * -1.4426950408889634f);
+    a = rcp_approx(1.0f + e);
+    s1 = a * (1.0f - a);
+    s2 = s1 * (1.0f - 2.0f * a);
+  }
+  A[0] = a;
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) A[1 + j] = s1 * z[1 + j];
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q) {
+    if (P::pa(q) == kTracePair) {
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) sq = fmaf(z[1 + j], z[1 + j], sq);
+      A[1 + P::N1 + q] = fmaf(s2, sq, s1 * z[1 + P::N1 + q]);
+    } else {
+      A[1 + P::N1 + q] = fmaf(s2 * z[1 + (P::pa(q) & 3)], z[1 + (P::pb(q) & 3)], s1 * z[1 + P::N1 + q]);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+template <int OFF>
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void st_cta_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cta.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v) : "memory");
+}
+// rows i = 0..NV-1 of one group (128 bytes apart) at compile-time offsets from the 8 swizzle bases
+template <int NV, bool REMOTE, int... I>
+__device__ __forceinline__ void store_rows(const uint32_t (&bc)[8], const float (&v)[NV],
+                                           std::integer_sequence<int, I...>) {
+  if (REMOTE)
+    (st_cluster_f32<I * 128>(bc[I & 7], v[I]), ...);
+  else
+    (st_cta_f32<I * 128>(bc[I & 7], v[I]), ...);
+}
+// arrive (release at cluster scope) on the same barrier in CTA `cta` of the pair
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t *bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// spin relaxed, then one cluster-scope acquire fence (an acquire.cluster try_wait invalidates L1 per poll)
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t *bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int S>
+struct ChainGeom {
+  static constexpr int PT = TileOf<S>::PT, N = TileOf<S>::N, NHALF = N / 2;
+  static constexpr int OPND_BYTES = 8 * NHALF * 128;   // [K block][NHALF rows][32 floats]
+  static constexpr int NSTAGE_RAW = (227 * 1024 - 3072 - OPND_BYTES) / 16384;
+  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
+  static constexpr size_t SMEM = (size_t)OPND_BYTES + (size_t)NSTAGE * 16384 + 1024 + 512;
+};
+
+template <class P, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
+k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+               const ChainArgs g) {
+  constexpr int S = P::S, H = 256;
+  using G = ChainGeom<S>;
+  constexpr int PT = G::PT, N = G::N, NHALF = G::NHALF, KB = H / 32;
+  constexpr int NSTAGE = G::NSTAGE, W_BYTES = 16384;
+  constexpr uint32_t IDESC = make_idesc_m256(N);
+  constexpr int G8 = PT / 8;
+  static_assert(NHALF % 8 == 0 && (PT / 2) % 8 == 0, "row halves must be whole 8-point groups");
+  static_assert(NSTAGE >= 3, "W ring too shallow");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *opnd = smem;
+  uint8_t *ring = smem + G::OPND_BYTES;
+  uint64_t *full = (uint64_t *)(ring + NSTAGE * W_BYTES);
+  uint64_t *empty = full + NSTAGE;
+  uint64_t *tmem_full = empty + NSTAGE;     // accumulator of the current layer complete (both CTAs, multicast)
+  uint64_t *opnd_full = tmem_full + 1;      // this CTA's operand image written by all 32 epilogue warps of the pair
+  uint64_t *store_done = opnd_full + 1;     // both CTAs' stash stores have finished reading their operand images
+  uint32_t *tmem_slot = (uint32_t *)(store_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int L = g.L;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(opnd_full, 2 * kChainEpiWarps);
+    mbar_init(store_done, 2);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs): W_l row half, K block by K block ------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
+        for (int l = 1; l < L; ++l) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * W_BYTES);
+            const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
+            tma_load_3d_2sm(&map_w, leader_bar, ring + stage * W_BYTES, 0, (l - 1) * H + (int)rank * 128, kb);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) --------------
+    if (rank == 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0, ver = 0;   // ver = operand image version (L per tile; the last has no MMA)
+      const uint32_t ob = smem_u32(opnd);
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
+        for (int l = 1; l <= L; ++l, ++ver) {
+          mbar_wait_acquire_cluster(opnd_full, ver & 1);   // every phase is observed, in order
+          if (l == L) continue;   // image of the last hidden layer: stash store only
+          tc_fence_after();
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sw = smem_u32(ring + stage * W_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32_2sm(tmem_base, make_desc(sw + ks * 32, 16, 1024),
+                            make_desc(ob + kb * (NHALF * 128) + ks * 32, 16, 1024), IDESC, (kb | ks) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[stage]);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit_2sm(tmem_full);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------ stash writer (both CTAs) ------------------
+    // image version v = tile-local layer index 0..L-1; store it (if that layer is kept) and tell both CTAs'
+    // epilogue warps when this CTA's image may be overwritten
+    if (lane == 0) {
+      uint32_t ver = 0;
+      for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
+        const int row0 = tile * N + (int)rank * NHALF;
+        for (int l = 0; l < L; ++l, ++ver) {
+          mbar_wait_acquire_cluster(opnd_full, ver & 1);
+          const int slot = g.out_slot[l];
+          if (slot >= 0) {
+            for (int kb = 0; kb < KB; ++kb) tma_store_4d(&map_out, opnd + kb * (NHALF * 128), 0, row0, kb, slot);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          mbar_arrive_release_cluster(store_done, 0);
+          mbar_arrive_release_cluster(store_done, 1);
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 units) --------
+    const int q = warp & 3;
+    const int sub = (warp - kChainFirstEpi) >> 2;
+    const int o = (int)rank * 128 + q * 32 + lane;
+    // operand address pieces: this thread's unit is column `lane` of K block (rank*4 + q); 128B swizzle:
+    // the 16-byte chunk index (lane/4) is XORed with (row & 7)
+    uint32_t xo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) xo[c] = ((((uint32_t)lane >> 2) ^ (uint32_t)c) << 4) + (((uint32_t)lane & 3u) << 2);
+    const uint32_t blk = smem_u32(opnd) + (uint32_t)((int)rank * 4 + q) * (NHALF * 128);
+    const uint32_t blk_peer = mapa_u32(blk, rank ^ 1u);
+    // first-layer weights of this unit
+    float w0[4], wd[P::N1 > 0 ? P::N1 : 1];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) w0[d] = d < g.d_in ? __ldg(g.w0 + (long long)o * g.d_in + d) : 0.0f;
+    const float b0 = __ldg(g.b0 + o);
+#pragma unroll
+    for (int j = 0; j < P::N1; ++j) wd[j] = __ldg(g.w0 + (long long)o * g.d_in + g.dirs.d[j]);
+    const float *__restrict__ x0p = g.x;
+    const float *__restrict__ x1p = g.d_in > 1 ? g.x + g.ldn : g.x;
+    const float *__restrict__ x2p = g.d_in > 2 ? g.x + 2 * g.ldn : g.x;
+    const float *__restrict__ x3p = g.d_in > 3 ? g.x + 3 * g.ldn : g.x;
+    const long long n = g.n;
+    uint32_t job = 0, ver = 0;
+
+    // one 8-point group's streams into the operand image of the CTA that multiplies those rows
+    auto emit = [&](int grp, float (&v)[8 * S]) {
+      const int row0 = grp * 8 * S;                     // tile row of the group's first stream
+      const uint32_t tgt = row0 >= NHALF ? 1u : 0u;     // which CTA of the pair multiplies these rows
+      const uint32_t roff = (uint32_t)(row0 - (int)tgt * NHALF) * 128u;
+      uint32_t bc[8];
+      if (tgt == rank) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bc[c] = blk + roff + xo[c];
+        store_rows<8 * S, false>(bc, v, std::make_integer_sequence<int, 8 * S>{});
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bc[c] = blk_peer + roff + xo[c];
+        store_rows<8 * S, true>(bc, v, std::make_integer_sequence<int, 8 * S>{});
+      }
+    };
+    // the image is complete from this warp's side: publish to the async proxy, hand TMEM back, tell both CTAs
+    auto signal_operand = [&]() {
+      fence_proxy_async_all();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_release_cluster(opnd_full, 0);
+        mbar_arrive_release_cluster(opnd_full, 1);
+      }
+    };
+    // the previous image has been consumed: its MMAs are complete (tmem_full, waited by the caller) and both
+    // stash stores have finished reading it
+    auto wait_image_free = [&]() {
+      if (ver > 0) mbar_wait_acquire_cluster(store_done, (ver - 1) & 1);
+    };
+
+    for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
+      const long long p0 = (long long)tile * PT;
+      // ---- layer 0 from x (FP32 FMA) ----
+      wait_image_free();
+      for (int grp = sub; grp < G8; grp += kChainSubs) {
+        const long long pg = p0 + grp * 8;
+        float v[8 * S];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const long long p = pg + pp;
+          const bool ok = p < n;
+          float z[S], A[S];
+          z[0] = fmaf(w0[0], ok ? __ldg(x0p + p) : 0.0f, b0);
+          z[0] = fmaf(w0[1], ok ? __ldg(x1p + p) : 0.0f, z[0]);
+          if (g.d_in > 2) {
+            z[0] = fmaf(w0[2], ok ? __ldg(x2p + p) : 0.0f, z[0]);
+            z[0] = fmaf(w0[3], ok ? __ldg(x3p + p) : 0.0f, z[0]);
+          }
+#pragma unroll
+          for (int j = 0; j < P::N1; ++j) z[1 + j] = wd[j];
+#pragma unroll
+          for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
+          jet_forward_fast<P, ACT>(z, A);
+          v[pp * S] = A[0];
+#pragma unroll
+          for (int s_ = 1; s_ < S; ++s_) v[pp * S + s_] = to_tf32_fast(A[s_]);
+        }
+        emit(grp, v);
+      }
+      signal_operand();
+      ++ver;
+      // ---- hidden GEMM layers ----
+      for (int l = 1; l < L; ++l, ++job, ++ver) {
+        const float bias = __ldg(g.bias[l] + o);
+        mbar_wait(tmem_full, job & 1);
+        tc_fence_after();
+        wait_image_free();
+        for (int grp = sub; grp < G8; grp += kChainSubs) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 8 * S;
+          float r[8 * S];
+          tmem_ld_cols<8 * S>(taddr, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            float z[S], A[S];
+#pragma unroll
+            for (int s_ = 0; s_ < S; ++s_) z[s_] = r[pp * S + s_];
+            z[0] += bias;
+            jet_forward_fast<P, ACT>(z, A);
+            r[pp * S] = A[0];
+#pragma unroll
+            for (int s_ = 1; s_ < S; ++s_) r[pp * S + s_] = to_tf32_fast(A[s_]);
+          }
+          emit(grp, r);
+        }
+        signal_operand();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 256);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
 // kernel C: fused backward of one hidden layer on a CTA pair (H = 256):
 //     zbar_{l-1} = adjoint( W_l^T zbar_l )      (dgrad, K-major operands, two accumulators in TMEM cols 0..255)
 //     dW_l      += zbar_l^T A_{l-1}             (wgrad, MN-major operands, accumulator in TMEM cols 256..511)
@@ -1484,6 +1864,7 @@ __global__ void k_tc_reduce(const float *__restrict__ partial, long long stride,
 // =========================================================================================
 static int g_use_pair = 1;       // AX_TC_PAIR=0 in the environment falls back to the single-CTA layer kernel
 static int g_use_fused_bwd = 1;  // AX_TC_FUSED_BWD=0 runs dgrad and wgrad as separate kernels
+static int g_use_chain = 0;      // AX_TC_CHAIN=1: whole-stack forward kernel (experimental: correct, but latency-bound -- DESIGN.md 2.2)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1526,6 +1907,29 @@ static int make_map(CUtensorMap *m, const float *base, long long rows, int cols,
   return 0;
 }
 
+// the stash as [slots][rows][cols] floats viewed as (32, rows, cols/32, slots); box = (32, box_rows, 1, 1).
+// rows past the end are clipped by TMA, so a partial last tile needs no guards.
+static int make_map4(CUtensorMap *m, const float *base, long long rows, int cols, int slots, size_t slot_floats,
+                     int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return 1;
+  }
+  cuuint64_t gdim[4] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32), (cuuint64_t)slots};
+  cuuint64_t gstr[3] = {(cuuint64_t)cols * 4, 128, (cuuint64_t)slot_floats * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D stash map) failed (%d) rows=%lld cols=%d slots=%d", (int)r, rows, cols, slots);
+    return 1;
+  }
+  return 0;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -1533,6 +1937,8 @@ static int sm_count() {
     if (e && e[0] == '0') g_use_pair = 0;
     const char *f = getenv("AX_TC_FUSED_BWD");
     if (f && f[0] == '0') g_use_fused_bwd = 0;
+    const char *c = getenv("AX_TC_CHAIN");
+    if (c && c[0] == '1') g_use_chain = 1;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -1742,6 +2148,43 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
                                                                 H, 0);
       AX_LAUNCH_OK();
     }
+    if (H == 256 && g_use_pair && g_use_chain && d_in <= 4) {
+      // whole hidden stack in one launch: activations stay in the SM pair, only the stash goes to HBM
+      using G = ChainGeom<S>;
+      ChainArgs ca{};
+      ca.x = a.x;
+      ca.w0 = prm + g.w_off[0];
+      ca.b0 = prm + g.b_off[0];
+      int kept = 0;
+      for (int l = 0; l < g.L; ++l) {
+        ca.bias[l] = prm + g.b_off[l];
+        ca.out_slot[l] = a.keep_all ? l : (l == g.L - 1 ? (l & 1) : -1);
+        kept += ca.out_slot[l] >= 0;
+      }
+      ca.L = g.L;
+      ca.d_in = d_in;
+      ca.dirs = dirs;
+      ca.n = a.n;
+      ca.ldn = a.ldn;
+      ca.num_tiles = (int)((a.n + G::PT - 1) / G::PT);
+      CUtensorMap mw, mo;
+      if (make_map(&mw, wr, (long long)(g.L - 1) * H, H, 128, 1)) return 1;
+      if (make_map4(&mo, stash, rows, H, slots, layer_fl, G::NHALF)) return 1;
+      auto kern = act == AX_ACT_TANH ? k_tc_fwd_chain<P, AX_ACT_TANH> : k_tc_fwd_chain<P, AX_ACT_SIGMOID>;
+      static bool attr[2] = {false, false};
+      if (!attr[act == AX_ACT_TANH]) {
+        AX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr[act == AX_ACT_TANH] = true;
+      }
+      int clusters = sm_count() / 2;
+      if (ca.num_tiles < clusters) clusters = ca.num_tiles;
+      {
+        KernelTimer t("tc_fwd_chain", a.stream, 2.0 * S * H * (double)H * (double)a.n * (g.L - 1) + 2.0 * d_in * H * (double)a.n,
+                      4.0 * S * H * (double)a.n * kept + 4.0 * d_in * (double)a.n);
+        kern<<<2 * clusters, kChainThreads, G::SMEM, a.stream>>>(mw, mo, ca);
+      }
+      AX_LAUNCH_OK();
+    } else {
     {
       KernelTimer t("tc_first_layer", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
       k_tc_first<P><<<(unsigned)((a.n + 31) / 32), H, 0, a.stream>>>(prm + g.w_off[0], prm + g.b_off[0], a.x, d_in,
@@ -1761,6 +2204,7 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       } else {
         if (launch_gemm<P, 0, H>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream)) return 1;
       }
+    }
     }
     {
       KernelTimer t("tc_last_fwd", a.stream, 2.0 * S * H * C * (double)a.n, 4.0 * S * H * (double)a.n);
