@@ -132,10 +132,28 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float *r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// round-to-nearest (ties away) to TF32 in two integer instructions: identical to cvt.rna.tf32.f32 on
+// finite values and infinities (ptxas emulates the cvt with three instructions on sm_100)
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// tanh / sigmoid on the exp2 and reciprocal special-function units (5 instructions): absolute error
+// ~1e-7, far below the TF32 rounding of the streams the value feeds; exact limits at +-infinity.
+__device__ __forceinline__ float tanh_fast(float z) {
+  return fmaf(-2.0f, rcp_approx(ex2_approx(z * 2.8853900817779268f) + 1.0f), 1.0f);
+}
+__device__ __forceinline__ float sigmoid_fast(float z) {
+  return rcp_approx(1.0f + ex2_approx(z * -1.4426950408889634f));
 }
 
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B)
@@ -165,11 +183,11 @@ template <class P>
 __device__ __forceinline__ void jet_forward_A(int act, float (&z)[P::S], float (&A)[P::S]) {
   float a, s1, s2;
   if (act == AX_ACT_TANH) {
-    a = tanhf(z[0]);
+    a = tanh_fast(z[0]);
     s1 = fmaf(-a, a, 1.0f);
     s2 = -2.0f * a * s1;
   } else {
-    a = 1.0f / (1.0f + expf(-z[0]));
+    a = sigmoid_fast(z[0]);
     s1 = a * (1.0f - a);
     s2 = s1 * (1.0f - 2.0f * a);
   }
@@ -857,34 +875,17 @@ struct ChainArgs {
   int num_tiles;
 };
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// round-to-nearest (ties away) to TF32 in two integer instructions; identical to cvt.rna.tf32.f32 on
-// finite values and infinities (sm_100 emulates the cvt with three)
-__device__ __forceinline__ float to_tf32_fast(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
 // activation jet with exp2/rcp special-function units: |error of a| ~ 1e-7 absolute, far below the TF32
 // rounding of the streams it feeds; s1 is formed from the stored a exactly as the adjoint re-forms it.
 template <class P, int ACT>
 __device__ __forceinline__ void jet_forward_fast(float (&z)[P::S], float (&A)[P::S]) {
   float a, s1, s2;
   if (ACT == AX_ACT_TANH) {
-    const float e = ex2_approx(z[0] * 2.8853900817779268f);
-    a = fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
+    a = tanh_fast(z[0]);
     s1 = fmaf(-a, a, 1.0f);
     s2 = -2.0f * a * s1;
   } else {
-    const float e = ex2_approx(z[0] * -1.4426950408889634f);
-    a = rcp_approx(1.0f + e);
+    a = sigmoid_fast(z[0]);
     s1 = a * (1.0f - a);
     s2 = s1 * (1.0f - 2.0f * a);
   }
@@ -1157,7 +1158,7 @@ k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           jet_forward_fast<P, ACT>(z, A);
           v[pp * S] = A[0];
 #pragma unroll
-          for (int s_ = 1; s_ < S; ++s_) v[pp * S + s_] = to_tf32_fast(A[s_]);
+          for (int s_ = 1; s_ < S; ++s_) v[pp * S + s_] = to_tf32(A[s_]);
         }
         emit(grp, v);
       }
@@ -1183,7 +1184,7 @@ k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             jet_forward_fast<P, ACT>(z, A);
             r[pp * S] = A[0];
 #pragma unroll
-            for (int s_ = 1; s_ < S; ++s_) r[pp * S + s_] = to_tf32_fast(A[s_]);
+            for (int s_ = 1; s_ < S; ++s_) r[pp * S + s_] = to_tf32(A[s_]);
           }
           emit(grp, r);
         }
@@ -1724,65 +1725,112 @@ k_tc_last_fwd(const float *__restrict__ Wout, const float *__restrict__ bout, co
   }
 }
 
-// output layer backward: zbar_{L-1} from jets_bar; per-block partials of dWout, dbout, db_{L-1}
-// block = H threads (unit k), PB points per block.  partial layout per block: [C*H | C | H]
+// output layer backward: zbar_{L-1} from jets_bar; per-block partials of dWout, dbout, db_{L-1}.
+// A thread owns FOUR consecutive units (128-bit loads and stores: a (p,s) row of H floats is one or two
+// warp instructions) and every 256/(H/4)-th point of the block's range; the row groups are combined in a
+// fixed order through shared memory.  partial layout per block: [C*H | C | H]
 template <class P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar,
               const float *__restrict__ actL, int H, int C, long long n, long long ldn,
               int pts_per_block, float *__restrict__ gout, float *__restrict__ partial, int act) {
   constexpr int S = P::S;
-  const int k = threadIdx.x;
-  if (k >= H) return;
-  float wc[4], dw[4], dbo[4];
+  constexpr int U = (S <= 4) ? 2 : 1;   // points in flight per thread (U*S 128-bit loads outstanding)
+  __shared__ float red[256 * 9];
+  const int HQ = H >> 2;         // unit quads per row
+  const int PR = 256 / HQ;       // points processed side by side
+  const int kq = threadIdx.x % HQ, pr = threadIdx.x / HQ;
+  float4 wc[4];
+  float dw[4][4], dbo[4], dbh[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    wc[c] = c < C ? __ldg(Wout + (long long)c * H + k) : 0.0f;
-    dw[c] = 0.0f;
+    wc[c] = c < C ? __ldg(reinterpret_cast<const float4 *>(Wout + (long long)c * H) + kq) : make_float4(0, 0, 0, 0);
     dbo[c] = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dw[c][u] = 0.0f;
   }
-  float dbh = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) dbh[u] = 0.0f;
   const long long p_beg = (long long)blockIdx.x * pts_per_block;
-  constexpr int U = 4;  // points in flight per thread
-  for (int pp = 0; pp < pts_per_block; pp += U) {
-    if (p_beg + pp >= n) break;
-    float A[U][S];
+  long long p_end = p_beg + pts_per_block;
+  if (p_end > n) p_end = n;
+  for (long long pb = p_beg + pr; pb < p_end; pb += (long long)U * PR) {
+    float4 A[U][S];
+    float jb[U][S][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long p = p_beg + pp + u;
+      const long long p = pb + (long long)u * PR;
+      const bool ok = p < p_end;
 #pragma unroll
-      for (int s = 0; s < S; ++s) A[u][s] = (p < n) ? __ldg(actL + (p * S + s) * H + k) : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long p = p_beg + pp + u;
-      if (p >= n) break;
-      float ab[S], zb[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float acc = 0.0f;
+      for (int s_ = 0; s_ < S; ++s_) {
+        A[u][s_] = ok ? __ldg(reinterpret_cast<const float4 *>(actL + (p * S + s_) * H) + kq) : make_float4(0, 0, 0, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c < C) {
-            const float ob = __ldg(jets_bar + ((long long)s * C + c) * ldn + p);
-            acc = fmaf(wc[c], ob, acc);
-            dw[c] = fmaf(ob, A[u][s], dw[c]);
-            if (s == 0) dbo[c] += ob;
-          }
-        ab[s] = acc;
+          jb[u][s_][c] = (ok && c < C) ? __ldg(jets_bar + ((long long)s_ * C + c) * ldn + p) : 0.0f;
       }
-      jet_adjoint_A<P>(act, A[u], ab, zb);
-      dbh += zb[0];
-      float *dst = gout + (p * S) * H + k;
+    }
 #pragma unroll
-      for (int s = 0; s < S; ++s) dst[(long long)s * H] = to_tf32(zb[s]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = pb + (long long)u * PR;
+      if (p >= p_end) break;
+      float zq[S][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a_[S], ab[S], zb[S];
+#pragma unroll
+        for (int s_ = 0; s_ < S; ++s_) {
+          const float av = e == 0 ? A[u][s_].x : e == 1 ? A[u][s_].y : e == 2 ? A[u][s_].z : A[u][s_].w;
+          a_[s_] = av;
+          float acc = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float w = e == 0 ? wc[c].x : e == 1 ? wc[c].y : e == 2 ? wc[c].z : wc[c].w;
+            acc = fmaf(w, jb[u][s_][c], acc);
+            dw[c][e] = fmaf(jb[u][s_][c], av, dw[c][e]);
+          }
+          ab[s_] = acc;
+        }
+        jet_adjoint_A<P>(act, a_, ab, zb);
+        dbh[e] += zb[0];
+#pragma unroll
+        for (int s_ = 0; s_ < S; ++s_) zq[s_][e] = to_tf32(zb[s_]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dbo[c] += jb[u][0][c];
+#pragma unroll
+      for (int s_ = 0; s_ < S; ++s_)
+        reinterpret_cast<float4 *>(gout + (p * S + s_) * H)[kq] = make_float4(zq[s_][0], zq[s_][1], zq[s_][2], zq[s_][3]);
     }
   }
+  // combine the PR row groups in a fixed order; thread (pr = 0, kq) then owns units 4kq..4kq+3
   float *part = partial + (long long)blockIdx.x * ((long long)C * H + C + H);
-  for (int c = 0; c < C; ++c) part[(long long)c * H + k] = dw[c];
-  if (k == 0)
-    for (int c = 0; c < C; ++c) part[(long long)C * H + c] = dbo[c];
-  part[(long long)C * H + C + k] = dbh;
+  for (int c = 0; c < C; ++c) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[threadIdx.x * 9 + e] = dw[c][e];
+    red[threadIdx.x * 9 + 4] = dbo[c];
+    if (c == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[threadIdx.x * 9 + 5 + e] = dbh[e];
+    }
+    __syncthreads();
+    if (pr == 0) {
+      float acc[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) acc[e] = 0.0f;
+      for (int r = 0; r < PR; ++r) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) acc[e] += red[(r * HQ + kq) * 9 + e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) part[(long long)c * H + 4 * kq + e] = acc[e];
+      if (kq == 0) part[(long long)C * H + c] = acc[4];
+      if (c == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) part[(long long)C * H + C + 4 * kq + e] = acc[5 + e];
+      }
+    }
+  }
 }
 
 // first layer backward: dW0[i][d] = sum_p zbar_0 x_d + sum_j [dir_j == d] zbar_j ; block = H threads
@@ -2250,12 +2298,12 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       // a few blocks per SM, each walking a contiguous point range: the partials stay few (the fixed-order
       // reduce reads them serially per output) and never exceed the planned ceil(n / kLastPts) blocks
       long long ppb = (a.n + 4 * sm_count() - 1) / (4 * sm_count());
-      ppb = (ppb + 3) / 4 * 4;
+      ppb = (ppb + 7) / 8 * 8;
       if (ppb < kLastPts) ppb = kLastPts;
       const int nb = (int)((a.n + ppb - 1) / ppb);
       {
         KernelTimer t("tc_last_bwd", a.stream, 4.0 * S * H * C * (double)a.n, 8.0 * S * H * (double)a.n);
-        k_tc_last_bwd<P><<<nb, H, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn, (int)ppb,
+        k_tc_last_bwd<P><<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn, (int)ppb,
                                                  w.g[cur], w.partial, act);
       }
       AX_LAUNCH_OK();
