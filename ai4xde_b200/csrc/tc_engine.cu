@@ -598,6 +598,81 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar, uint32_t cta) {
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// ---- warp-uniform issue: the WHOLE MMA warp runs the loop (so ptxas keeps descriptors and addresses in
+// uniform registers) and one elected lane's predicate guards the tcgen05 instructions.  Issuing from inside
+// `if (lane == 0)` costs a vector->uniform "waterfall" (ELECT / R2UR x5 / BRA.U.ANY, ~21 instructions) per MMA,
+// which made the issuing thread -- not the tensor pipe or HBM -- the bottleneck of the backward kernel.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t *bar, uint32_t bytes, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(bytes), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm_p(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0,
+                                                  int c1, int c2, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1,
+                                              int c2, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_p(uint64_t *bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t *bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
+}
 __host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
@@ -648,18 +723,19 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (both CTAs) ------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (both CTAs; whole warp, one elected lane issues) ----
+    {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
         const int row0 = tile * N + (int)rank * NHALF;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t *sw = smem + stage * STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (W_BYTES + IN_BYTES));
+          mbar_expect_tx_p(&full[stage], 2 * (W_BYTES + IN_BYTES), rank == 0 ? issue : 0u);
           const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
-          tma_load_3d_2sm(&map_w, leader_bar, sw, 0, (int)rank * 128, kb);
-          tma_load_3d_2sm(&map_in, leader_bar, sw + W_BYTES, 0, row0, kb);
+          tma_load_3d_2sm_p(&map_w, leader_bar, sw, 0, (int)rank * 128, kb, issue);
+          tma_load_3d_2sm_p(&map_in, leader_bar, sw + W_BYTES, 0, row0, kb, issue);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -668,10 +744,13 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA only) --------------
-    if (rank == 0 && lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only; whole warp, one elected lane issues) ----
+    if (rank == 0) {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
+      const uint64_t d_w = make_desc(smem_u32(smem), 16, 1024);
+      const uint64_t d_in = make_desc(smem_u32(smem) + W_BYTES, 16, 1024);
       for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
         const uint32_t b = it & 1, bphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[b], bphase ^ 1);
@@ -679,21 +758,18 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sw = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sin = sw + W_BYTES;
+          const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = make_desc(sw + ks * 32, 16, 1024);
-            const uint64_t db = make_desc(sin + ks * 32, 16, 1024);
-            umma_tf32_2sm(tmem_base + b * 256, da, db, IDESC, (kb | ks) != 0 ? 1u : 0u);
-          }
-          umma_commit_2sm(&empty[stage]);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32_2sm_p(tmem_base + b * 256, d_w + so + ((ks * 32) >> 4), d_in + so + ((ks * 32) >> 4), IDESC,
+                            (kb | ks) != 0 ? 1u : 0u, issue);
+          umma_commit_2sm_p(&empty[stage], issue);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[b]);
+        umma_commit_2sm_p(&tmem_full[b], issue);
       }
     }
   } else {
@@ -1288,12 +1364,14 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (both CTAs) ------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (both CTAs; whole warp, one elected lane issues) ----
+    {
+      const uint32_t issue = elect_one();
       {
-        if (rank == 0) mbar_expect_tx(wres_full, 2 * kBwdWres);
+        mbar_expect_tx_p(wres_full, 2 * kBwdWres, rank == 0 ? issue : 0u);
         const uint32_t leader_bar = smem_u32(wres_full) & 0xFEFFFFFFu;
-        for (int kb = 0; kb < KB; ++kb) tma_load_3d_2sm(&map_wt, leader_bar, wres + kb * 16384, 0, (int)rank * 128, kb);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_3d_2sm_p(&map_wt, leader_bar, wres + kb * 16384, 0, (int)rank * 128, kb, issue);
       }
       uint32_t slot = 0, phase = 0;
       auto advance = [&]() {
@@ -1306,25 +1384,26 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
         const int row0 = tile * N;
         for (int j = 0; j < DSLOTS; ++j) {   // K blocks 2j, 2j+1 of this CTA's row half of zbar
           mbar_wait(&empty[slot], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[slot], 2 * D_BYTES);
+          mbar_expect_tx_p(&full[slot], 2 * D_BYTES, rank == 0 ? issue : 0u);
           const uint32_t leader_bar = smem_u32(&full[slot]) & 0xFEFFFFFFu;
-          tma_load_3d_2sm(&map_g_k, leader_bar, ring + slot * SLOT, 0, row0 + (int)rank * NHALF, 2 * j);
+          tma_load_3d_2sm_p(&map_g_k, leader_bar, ring + slot * SLOT, 0, row0 + (int)rank * NHALF, 2 * j, issue);
           advance();
         }
         for (int c = 0; c < WSLOTS; ++c) {   // 16 rows x own 128 units of zbar and of the stash
           mbar_wait(&empty[slot], phase ^ 1);
           uint8_t *sp = ring + slot * SLOT;
-          if (rank == 0) mbar_expect_tx(&full[slot], 2 * W_BYTES);
+          mbar_expect_tx_p(&full[slot], 2 * W_BYTES, rank == 0 ? issue : 0u);
           const uint32_t leader_bar = smem_u32(&full[slot]) & 0xFEFFFFFFu;
-          tma_load_3d_2sm(&map_g_mn, leader_bar, sp, 0, row0 + c * CR, (int)rank * 4);
-          tma_load_3d_2sm(&map_a_mn, leader_bar, sp + CR * 512, 0, row0 + c * CR, (int)rank * 4);
+          tma_load_3d_2sm_p(&map_g_mn, leader_bar, sp, 0, row0 + c * CR, (int)rank * 4, issue);
+          tma_load_3d_2sm_p(&map_a_mn, leader_bar, sp + CR * 512, 0, row0 + c * CR, (int)rank * 4, issue);
           advance();
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA only) --------------
-    if (rank == 0 && lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only; whole warp, one elected lane issues) ----
+    if (rank == 0) {
+      const uint32_t issue = elect_one();
       uint32_t slot = 0, phase = 0, it = 0;
       auto advance = [&]() {
         if (++slot == NSLOT) {
@@ -1334,7 +1413,10 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
       };
       mbar_wait(wres_full, 0);
       tc_fence_after();
-      const uint32_t wr = smem_u32(wres);
+      // descriptors differ only in the 14-bit (address >> 4) field: build each view once, add offsets after
+      const uint64_t d_wres = make_desc(smem_u32(wres), 16, 1024);
+      const uint64_t d_ring_k = make_desc(smem_u32(ring), 16, 1024);
+      const uint64_t d_ring_mn = make_desc(smem_u32(ring), CR * 128, 512, 1);
       for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters, ++it) {
         const uint32_t b = it & 1, bphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[b], bphase ^ 1);
@@ -1342,33 +1424,32 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
         for (int j = 0; j < DSLOTS; ++j) {
           mbar_wait(&full[slot], phase);
           tc_fence_after();
-          const uint32_t sp = smem_u32(ring + slot * SLOT);
+          const uint64_t da = d_wres + (uint64_t)(2 * j * (16384 >> 4));
+          const uint64_t db = d_ring_k + (uint64_t)(slot * (SLOT >> 4));
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_tf32_2sm(tmem_base + b * 128, make_desc(wr + (2 * j + kk) * 16384 + ks * 32, 16, 1024),
-                            make_desc(sp + kk * (NHALF * 128) + ks * 32, 16, 1024), IDESC_D,
-                            (j | kk | ks) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty[slot]);
+              umma_tf32_2sm_p(tmem_base + b * 128, da + ((kk * 16384 + ks * 32) >> 4),
+                              db + ((kk * (NHALF * 128) + ks * 32) >> 4), IDESC_D, (j | kk | ks) != 0 ? 1u : 0u, issue);
+          umma_commit_2sm_p(&empty[slot], issue);
           advance();
         }
-        umma_commit_2sm(&tmem_full[b]);
+        umma_commit_2sm_p(&tmem_full[b], issue);
         for (int c = 0; c < WSLOTS; ++c) {
           mbar_wait(&full[slot], phase);
           tc_fence_after();
-          const uint32_t sp = smem_u32(ring + slot * SLOT);
           // MN-major, 32B-base swizzle: LBO = next 32-unit block (16 rows x 128 B), SBO = next 4 K-rows
+          const uint64_t dz = d_ring_mn + (uint64_t)(slot * (SLOT >> 4));
 #pragma unroll
           for (int ks = 0; ks < CR / 8; ++ks)
-            umma_tf32_2sm(tmem_base + 256, make_desc(sp + ks * 1024, CR * 128, 512, 1),
-                          make_desc(sp + CR * 512 + ks * 1024, CR * 128, 512, 1), IDESC_W,
-                          (it | (uint32_t)c | (uint32_t)ks) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty[slot]);
+            umma_tf32_2sm_p(tmem_base + 256, dz + ((ks * 1024) >> 4), dz + ((CR * 512 + ks * 1024) >> 4), IDESC_W,
+                            (it | (uint32_t)c | (uint32_t)ks) != 0 ? 1u : 0u, issue);
+          umma_commit_2sm_p(&empty[slot], issue);
           advance();
         }
       }
-      umma_commit_2sm(w_full);
+      umma_commit_2sm_p(w_full, issue);
     }
   } else {
     // ------------------------------ epilogue (both CTAs, own 128 units) --------
