@@ -1084,15 +1084,16 @@ k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs): W_l row half, K block by K block ------
-    if (lane == 0) {
+    {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
         for (int l = 1; l < L; ++l) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            if (rank == 0) mbar_expect_tx(&full[stage], 2 * W_BYTES);
+            mbar_expect_tx_p(&full[stage], 2 * W_BYTES, rank == 0 ? issue : 0u);
             const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
-            tma_load_3d_2sm(&map_w, leader_bar, ring + stage * W_BYTES, 0, (l - 1) * H + (int)rank * 128, kb);
+            tma_load_3d_2sm_p(&map_w, leader_bar, ring + stage * W_BYTES, 0, (l - 1) * H + (int)rank * 128, kb, issue);
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1;
@@ -1102,10 +1103,12 @@ k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA only) --------------
-    if (rank == 0 && lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only; whole warp, elected lane issues) ------
+    if (rank == 0) {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0, ver = 0;   // ver = operand image version (L per tile; the last has no MMA)
-      const uint32_t ob = smem_u32(opnd);
+      const uint64_t d_op = make_desc(smem_u32(opnd), 16, 1024);
+      const uint64_t d_w = make_desc(smem_u32(ring), 16, 1024);
       for (int tile = cluster_id; tile < g.num_tiles; tile += num_clusters) {
         for (int l = 1; l <= L; ++l, ++ver) {
           mbar_wait_acquire_cluster(opnd_full, ver & 1);   // every phase is observed, in order
@@ -1114,18 +1117,19 @@ k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint32_t sw = smem_u32(ring + stage * W_BYTES);
+            const uint64_t da = d_w + (uint64_t)(stage * (W_BYTES >> 4));
+            const uint64_t db = d_op + (uint64_t)(kb * ((NHALF * 128) >> 4));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_tf32_2sm(tmem_base, make_desc(sw + ks * 32, 16, 1024),
-                            make_desc(ob + kb * (NHALF * 128) + ks * 32, 16, 1024), IDESC, (kb | ks) != 0 ? 1u : 0u);
-            umma_commit_2sm(&empty[stage]);
+              umma_tf32_2sm_p(tmem_base, da + ((ks * 32) >> 4), db + ((ks * 32) >> 4), IDESC, (kb | ks) != 0 ? 1u : 0u,
+                              issue);
+            umma_commit_2sm_p(&empty[stage], issue);
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit_2sm(tmem_full);
+          umma_commit_2sm_p(tmem_full, issue);
         }
       }
     }
