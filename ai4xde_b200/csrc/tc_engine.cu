@@ -156,6 +156,81 @@ __device__ __forceinline__ float sigmoid_fast(float z) {
   return rcp_approx(1.0f + ex2_approx(z * -1.4426950408889634f));
 }
 
+// ---- warp-uniform issue: the WHOLE MMA warp runs the loop (so ptxas keeps descriptors and addresses in
+// uniform registers) and one elected lane's predicate guards the tcgen05 instructions.  Issuing from inside
+// `if (lane == 0)` costs a vector->uniform "waterfall" (ELECT / R2UR x5 / BRA.U.ANY, ~21 instructions) per MMA,
+// which made the issuing thread -- not the tensor pipe or HBM -- the bottleneck of the backward kernel.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t *bar, uint32_t bytes, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(bytes), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm_p(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0,
+                                                  int c1, int c2, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1,
+                                              int c2, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_p(uint64_t *bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t *bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
+}
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B)
 // layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (the only layout tcgen05 accepts for
 // MN-major 32-bit operands)
@@ -334,17 +409,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (whole warp, one elected lane issues) ------
+    {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         const int row0 = tile * N;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t *sw = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_3d(&map_w, &full[stage], sw, 0, 0, kb);
-          tma_load_3d(&map_in, &full[stage], sw + W_BYTES, 0, row0, kb);
+          mbar_expect_tx_p(&full[stage], STAGE_BYTES, issue);
+          tma_load_3d_p(&map_w, &full[stage], sw, 0, 0, kb, issue);
+          tma_load_3d_p(&map_in, &full[stage], sw + W_BYTES, 0, row0, kb, issue);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -353,33 +429,33 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (whole warp, one elected lane issues) --------
+    {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0, tphase = 0;
+      const uint64_t d_w = make_desc(smem_u32(smem), 16, 1024);
+      const uint64_t d_in = make_desc(smem_u32(smem) + W_BYTES, 16, 1024);
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         mbar_wait(tmem_empty, tphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sw = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sin = sw + W_BYTES;
+          const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t db = make_desc(sin + ks * 32, 16, 1024);
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-              const uint64_t da = make_desc(sw + h * (128 * 128) + ks * 32, 16, 1024);
-              umma_tf32(tmem_base + h * 256, da, db, IDESC, (kb | ks) != 0 ? 1u : 0u);
-            }
+            for (int h = 0; h < NH; ++h)
+              umma_tf32_p(tmem_base + h * 256, d_w + so + ((h * (128 * 128) + ks * 32) >> 4),
+                          d_in + so + ((ks * 32) >> 4), IDESC, (kb | ks) != 0 ? 1u : 0u, issue);
           }
-          umma_commit(&empty[stage]);
+          umma_commit_p(&empty[stage], issue);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(tmem_full);
+        umma_commit_p(tmem_full, issue);
         tphase ^= 1;
       }
     }
@@ -596,81 +672,6 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar, uint32_t cta) {
       "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
       "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
-      : "memory");
-}
-// ---- warp-uniform issue: the WHOLE MMA warp runs the loop (so ptxas keeps descriptors and addresses in
-// uniform registers) and one elected lane's predicate guards the tcgen05 instructions.  Issuing from inside
-// `if (lane == 0)` costs a vector->uniform "waterfall" (ELECT / R2UR x5 / BRA.U.ANY, ~21 instructions) per MMA,
-// which made the issuing thread -- not the tensor pipe or HBM -- the bottleneck of the backward kernel.
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred;
-}
-__device__ __forceinline__ void mbar_expect_tx_p(uint64_t *bar, uint32_t bytes, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
-      ::"r"(smem_u32(bar)), "r"(bytes), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm_p(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0,
-                                                  int c1, int c2, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %6, 0;\n\t"
-      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_p(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1,
-                                              int c2, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %6, 0;\n\t"
-      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm_p(uint64_t *bar, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-      ::"r"(smem_u32(bar)), "h"((uint16_t)3), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_p(uint64_t *bar, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(issue)
       : "memory");
 }
 __host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
@@ -1654,14 +1655,15 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CU
   const int chunks = r_beg < r_end ? (int)((r_end - r_beg + 31) / 32) : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0;
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t *sz = smem + stage * STAGE_BYTES;
-        mbar_expect_tx(&full[stage], STAGE_BYTES);
-        tma_load_3d(&map_z, &full[stage], sz, 0, (int)(r_beg + (long long)c * 32), 0);
-        tma_load_3d(&map_a, &full[stage], sz + Z_BYTES, 0, (int)(r_beg + (long long)c * 32), 0);
+        mbar_expect_tx_p(&full[stage], STAGE_BYTES, issue);
+        tma_load_3d_p(&map_z, &full[stage], sz, 0, (int)(r_beg + (long long)c * 32), 0, issue);
+        tma_load_3d_p(&map_a, &full[stage], sz + Z_BYTES, 0, (int)(r_beg + (long long)c * 32), 0, issue);
         if (++stage == NSTAGE) {
           stage = 0;
           phase ^= 1;
@@ -1669,31 +1671,31 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t issue = elect_one();
       uint32_t stage = 0, phase = 0;
+      // MN-major, 32B-base swizzle: 128B along MN x 4 K-rows per atom; LBO = next 32-unit block,
+      // SBO = next group of 4 K-rows; one MMA (K = 8) spans two groups
+      const uint64_t d_z = make_desc(smem_u32(smem), 4096, 512, 1);
+      const uint64_t d_a = make_desc(smem_u32(smem) + Z_BYTES, 4096, 512, 1);
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sz = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sa = sz + Z_BYTES;
+        const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          // MN-major, 32B-base swizzle: 128B along MN x 4 K-rows per atom; LBO = next 32-unit block,
-          // SBO = next group of 4 K-rows; one MMA (K = 8) spans two groups
-          const uint64_t db = make_desc(sa + ks * 1024, 4096, 512, 1);
 #pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            const uint64_t da = make_desc(sz + h * (4 * 4096) + ks * 1024, 4096, 512, 1);
-            umma_tf32(tmem_base + h * 256, da, db, IDESC, (c | ks) != 0 ? 1u : 0u);
-          }
+          for (int h = 0; h < NH; ++h)
+            umma_tf32_p(tmem_base + h * 256, d_z + so + ((h * (4 * 4096) + ks * 1024) >> 4),
+                        d_a + so + ((ks * 1024) >> 4), IDESC, (c | ks) != 0 ? 1u : 0u, issue);
         }
-        umma_commit(&empty[stage]);
+        umma_commit_p(&empty[stage], issue);
         if (++stage == NSTAGE) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(tmem_full);
+      umma_commit_p(tmem_full, issue);
     }
   } else {
     const int q = warp & 3;
