@@ -75,6 +75,11 @@ _SIGNATURES = {
         [_P, C.c_int32, C.c_int64, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P,
          _P, _P, _P, C.c_size_t, _P],
     ),
+    "ax_r3_abs_sum": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "ax_r3_retain_thr": (
+        C.c_int,
+        [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P],
+    ),
     "ax_gather_points": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
 }
@@ -293,6 +298,31 @@ def r3_retain(res, x_soa, n, place_at_end=True):
                           _ptr(res_sum), _ptr(ws), wsb, _stream())
     _check(rc, "ax_r3_retain")
     return x_out, n_keep, thr, res_sum
+
+
+def r3_abs_sum(res, n):
+    """res [n_res, ldr] f32 -> sum_r |res_r| [n] f32 (first half of the R3 retain step)."""
+    lib = load()
+    _need_cuda(res)
+    out = torch.empty((n,), dtype=torch.float32, device=res.device)
+    _check(lib.ax_r3_abs_sum(_ptr(res), res.shape[0], res.shape[1], int(n), _ptr(out), _stream()), "ax_r3_abs_sum")
+    return out
+
+
+def r3_retain_thr(res_sum, thr, x_soa, n, place_at_end=True):
+    """Compaction half of the R3 retain step against a given threshold (0-d / 1-element f32 device tensor)."""
+    lib = load()
+    _need_cuda(res_sum, thr, x_soa)
+    dev = x_soa.device
+    d, ldn = x_soa.shape
+    x_out = torch.empty_like(x_soa)
+    n_keep = torch.zeros((1,), dtype=torch.int64, device=dev)
+    thr = thr.reshape(1).to(torch.float32).contiguous()
+    ws, wsb = resample_ws(n, dev)
+    rc = lib.ax_r3_retain_thr(_ptr(res_sum), _ptr(thr), _ptr(x_soa), d, int(n), ldn, _ptr(x_out), ldn,
+                              int(bool(place_at_end)), _ptr(n_keep), _ptr(ws), wsb, _stream())
+    _check(rc, "ax_r3_retain_thr")
+    return x_out, n_keep
 
 
 def debug_tc_wgrad(zbar, a):

@@ -85,7 +85,9 @@ class R3Sampling(PINNSolver):
             res = self.residual(X, True)
             keep = res > np.mean(res)
         else:
-            keep = resample.r3_retain(self.model, X, self.PDECase.pde)[0]
+            # sharded population: global threshold (all-gather of the block residuals), local retain / refill
+            retain = resample.r3_retain_sharded if resample._world()[2] > 1 else resample.r3_retain
+            keep = retain(self.model, X, self.PDECase.pde)[0]
         kept = X[np.where(keep)]
         data.replace_with_anchors(kept)
         released = len(X) - len(kept)

@@ -15,9 +15,22 @@ class RAD(PINNSolver):
 
     def resample(self):
         case = self.PDECase
-        X = case.geomtime.random_points(case.NumDomain * 10)
-        ids = resample.rad_select(self.model, X, case.pde, case.NumDomain, k=self.k, c=self.c)
-        case.data.replace_with_anchors(X[ids])
+        _, rank, world = resample._world()
+        if world == 1:
+            X = case.geomtime.random_points(case.NumDomain * 10)
+            ids = resample.rad_select(self.model, X, case.pde, case.NumDomain, k=self.k, c=self.c)
+            case.data.replace_with_anchors(X[ids])
+            return ids
+        # point-sharded run: NumDomain is this rank's share.  Every rank draws the SAME
+        # global candidate set and uniforms (shared stream), probes its own block, and keeps its block of
+        # the globally selected points -- the selection equals the single-process one on world * NumDomain.
+        if getattr(self, "_shared", None) is None:
+            self._shared = resample.shared_numpy_stream()
+        with self._shared:
+            X = case.geomtime.random_points(case.NumDomain * 10 * world)
+            ids = resample.rad_select_sharded(self.model, X, case.pde, case.NumDomain * world, k=self.k, c=self.c)
+        lo, hi = resample.block_bounds(len(ids), rank, world)
+        case.data.replace_with_anchors(X[ids[lo:hi]])
         return ids
 
     def closure(self):

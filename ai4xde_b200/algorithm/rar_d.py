@@ -14,9 +14,22 @@ class RAR_D(PINNSolver):
 
     def resample(self):
         case = self.PDECase
-        X = case.geomtime.random_points(self.num_candidates)
-        ids = resample.rad_select(self.model, X, case.pde, case.NumDomain // 100, k=self.k, c=self.c)
-        case.data.add_anchors(X[ids])
+        _, rank, world = resample._world()
+        if world == 1:
+            X = case.geomtime.random_points(self.num_candidates)
+            ids = resample.rad_select(self.model, X, case.pde, case.NumDomain // 100, k=self.k, c=self.c)
+            case.data.add_anchors(X[ids])
+            return ids
+        # point-sharded run: same global candidates / uniforms on every rank, probe sharded, each rank
+        # adds its block of the globally selected anchors (see RAD.resample)
+        if getattr(self, "_shared", None) is None:
+            self._shared = resample.shared_numpy_stream()
+        with self._shared:
+            X = case.geomtime.random_points(self.num_candidates)
+            ids = resample.rad_select_sharded(self.model, X, case.pde, (case.NumDomain * world) // 100,
+                                              k=self.k, c=self.c)
+        lo, hi = resample.block_bounds(len(ids), rank, world)
+        case.data.add_anchors(X[ids[lo:hi]])
         return ids
 
     def closure(self):

@@ -499,6 +499,37 @@ int ax_choice_round(double *p, int64_t n, const double *u, int64_t n_draw, int64
   return 0;
 }
 
+int ax_r3_abs_sum(const float *res, int32_t n_res, int64_t ldr, int64_t n, float *res_sum_out, void *stream) {
+  if (n <= 0) return 0;
+  const int bs = 256;
+  k_abs_sum_f32<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(res, n_res, ldr, n, res_sum_out);
+  AX_LAUNCH_OK();
+  return 0;
+}
+
+int ax_r3_retain_thr(const float *res_sum, const float *thr, const float *x_soa, int32_t d, int64_t n,
+                     int64_t ldn, float *x_out, int64_t ldn_out, int32_t place_at_end, int64_t *n_keep_out,
+                     void *ws, size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  if (n > INT_MAX) {
+    set_error("r3_retain: n too large");
+    return 1;
+  }
+  WsLayout L;
+  if (carve(ws, ws_bytes, n, &L)) return 1;
+  const int per = kScanBlock * kScanItems;
+  const int nblocks = (int)((n + per - 1) / per);
+  k_keep_count<<<nblocks, kScanBlock, 0, st>>>(res_sum, n, thr, L.blocks);
+  AX_LAUNCH_OK();
+  k_scan_blocks<<<1, 1024, 0, st>>>(L.blocks, nblocks, n_keep_out);
+  AX_LAUNCH_OK();
+  k_keep_scatter<<<nblocks, kScanBlock, 0, st>>>(res_sum, n, thr, L.blocks, n_keep_out, x_soa, d, ldn, x_out,
+                                                 ldn_out, place_at_end);
+  AX_LAUNCH_OK();
+  return 0;
+}
+
 int ax_r3_retain(const float *res, int32_t n_res, int64_t ldr, const float *x_soa, int32_t d, int64_t n,
                  int64_t ldn, float *x_out, int64_t ldn_out, int32_t place_at_end, int64_t *n_keep_out,
                  float *thr_out, float *res_sum_out, void *ws, size_t ws_bytes, void *stream) {
@@ -510,20 +541,10 @@ int ax_r3_retain(const float *res, int32_t n_res, int64_t ldr, const float *x_so
   }
   WsLayout L;
   if (carve(ws, ws_bytes, n, &L)) return 1;
-  const int bs = 256;
-  k_abs_sum_f32<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(res, n_res, ldr, n, res_sum_out);
-  AX_LAUNCH_OK();
+  if (ax_r3_abs_sum(res, n_res, ldr, n, res_sum_out, stream)) return 1;
   if (pairwise_sum_impl<float>(res_sum_out, n, thr_out, (float)n, L.heap, L.heap_bytes, st)) return 1;
-  const int per = kScanBlock * kScanItems;
-  const int nblocks = (int)((n + per - 1) / per);
-  k_keep_count<<<nblocks, kScanBlock, 0, st>>>(res_sum_out, n, thr_out, L.blocks);
-  AX_LAUNCH_OK();
-  k_scan_blocks<<<1, 1024, 0, st>>>(L.blocks, nblocks, n_keep_out);
-  AX_LAUNCH_OK();
-  k_keep_scatter<<<nblocks, kScanBlock, 0, st>>>(res_sum_out, n, thr_out, L.blocks, n_keep_out, x_soa, d,
-                                                 ldn, x_out, ldn_out, place_at_end);
-  AX_LAUNCH_OK();
-  return 0;
+  return ax_r3_retain_thr(res_sum_out, thr_out, x_soa, d, n, ldn, x_out, ldn_out, place_at_end, n_keep_out, ws,
+                          ws_bytes, stream);
 }
 
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,

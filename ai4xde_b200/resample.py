@@ -58,3 +58,104 @@ def r3_retain(model, X, pde):
     x_out, n_keep, thr, res_sum = _lib.r3_retain(res, batch.soa, n, place_at_end=True)
     keep = (res_sum > thr).cpu().numpy()
     return keep, float(thr.item()), x_out, int(n_keep.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# Point-sharded selection.  The expensive part -- the residual probe over the candidate
+# set / the population -- is sharded: every rank evaluates its own contiguous block.  What crosses
+# NVLink is only the block residuals (4 bytes per point, all-gathered in rank order); the selection
+# arithmetic is then REPLICATED on every rank over the global residual vector, in the same kernels and
+# therefore in the same NumPy rounding order as a single process, so the selected global index set is
+# bit-identical to the single-process one on the same residuals and uniform stream, on every rank.
+# ------------------------------------------------------------------------------------------------
+def _world():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def block_bounds(n, rank, world):
+    """Contiguous row block of rank `rank` when n rows are split over `world` ranks (np.array_split order)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allgather_rows(local, n_local, n_total):
+    """[n_res, >= n_local] per-rank blocks -> [n_res, pad32(n_total)] global matrix, rank order, zero padded."""
+    dist, rank, world = _world()
+    n_res = local.shape[0]
+    out = torch.zeros((n_res, _lib.pad32(n_total)), dtype=local.dtype, device=local.device)
+    if dist is None:
+        out[:, :n_local] = local[:, :n_local]
+        return out
+    counts = [block_bounds(n_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in counts)
+    send = torch.zeros((n_res, width), dtype=local.dtype, device=local.device)
+    send[:, :n_local] = local[:, :n_local]
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send)
+    for (lo, hi), blk in zip(counts, recv):
+        out[:, lo:hi] = blk[:, :hi - lo]
+    return out
+
+
+def rad_select_sharded(model, X, pde, num, k=1, c=1, rand=None):
+    """RAD / RAR_D selection with the candidate probe sharded over ranks.  `X` is the GLOBAL candidate array
+    and `rand` the uniform source; both must be identical on every rank (a shared-seed stream, see
+    `shared_numpy_stream`).  Returns the global index array (identical on every rank)."""
+    dist, rank, world = _world()
+    n = len(X)
+    lo, hi = block_bounds(n, rank, world)
+    res_local, n_local = residual_matrix(model, X[lo:hi], pde)
+    res = allgather_rows(res_local, n_local, n)
+    p = _lib.rad_probabilities(res, n, k, c)
+    return choice_noreplace_device(p, num, rand).cpu().numpy()
+
+
+def r3_retain_sharded(model, X_local, pde):
+    """R3 retain on this rank's block of the population against the GLOBAL threshold: mean (NumPy pairwise
+    order) of sum|residual| over the rank-ordered concatenation of all blocks.  Returns (keep mask over the
+    local block, threshold, retained local points on the device, n_keep)."""
+    dist, rank, world = _world()
+    res_local, n_local = residual_matrix(model, X_local, pde)
+    res_sum = _lib.r3_abs_sum(res_local, n_local)
+    if dist is None:
+        n_total, glob = n_local, res_sum
+    else:
+        sizes = torch.zeros((world,), dtype=torch.int64, device=res_sum.device)
+        sizes[rank] = n_local
+        dist.all_reduce(sizes)
+        sizes = [int(v) for v in sizes.tolist()]
+        n_total, width = sum(sizes), max(sizes)
+        send = torch.zeros((width,), dtype=torch.float32, device=res_sum.device)
+        send[:n_local] = res_sum
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+        glob = torch.cat([blk[:m] for blk, m in zip(recv, sizes)])
+    thr = _lib.pairwise_sum(glob) / torch.tensor(float(n_total), dtype=torch.float32, device=glob.device)
+    batch = model.device_batch(X_local)
+    x_out, n_keep = _lib.r3_retain_thr(res_sum, thr, batch.soa, n_local, place_at_end=True)
+    keep = (res_sum > thr).cpu().numpy()
+    return keep, float(thr.item()), x_out, int(n_keep.item())
+
+
+class shared_numpy_stream:
+    """Context manager: run NumPy's GLOBAL legacy generator on a stream that is identical on every rank
+    (seeded once), and restore the rank's own stream afterwards.  RAD / RAR_D draw their candidates and
+    uniforms inside it when the point set is sharded, so every rank sees the same global candidate array."""
+
+    def __init__(self, seed=20240229):
+        self._state = np.random.RandomState(seed).get_state()
+
+    def __enter__(self):
+        self._own = np.random.get_state()
+        np.random.set_state(self._state)
+        return self
+
+    def __exit__(self, *exc):
+        self._state = np.random.get_state()
+        np.random.set_state(self._own)
+        return False

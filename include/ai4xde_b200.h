@@ -140,6 +140,18 @@ int ax_r3_retain(const float *res, int32_t n_res, int64_t ldr, const float *x_so
                  int64_t *n_keep_out, float *thr_out, float *res_sum_out, void *ws, size_t ws_bytes,
                  void *stream);
 
+/*
+ * The two halves of ax_r3_retain for a population sharded over ranks: each rank forms
+ * res_sum = sum_r |res_r| of its block (ax_r3_abs_sum), the blocks are all-gathered in rank order, the
+ * threshold is the NumPy-order mean of the GLOBAL vector (ax_pairwise_sum_f32 / n_global: the value a
+ * single process computes at R3Sampling.py:91), and each rank compacts its own block against that
+ * threshold (ax_r3_retain_thr; thr is a device pointer).
+ */
+int ax_r3_abs_sum(const float *res, int32_t n_res, int64_t ldr, int64_t n, float *res_sum_out, void *stream);
+int ax_r3_retain_thr(const float *res_sum, const float *thr, const float *x_soa, int32_t d, int64_t n,
+                     int64_t ldn, float *x_out, int64_t ldn_out, int32_t place_at_end,
+                     int64_t *n_keep_out, void *ws, size_t ws_bytes, void *stream);
+
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
                      float *x_out, int64_t ldn_out, void *stream);

@@ -152,3 +152,34 @@ def test_r3_retain_bit_exact(n, nres):
     assert nk == int(keep.sum())
     got = x_out[:, n - nk : n].t().cpu().numpy()
     assert np.array_equal(got, Xr)
+
+
+@pytest.mark.parametrize("n,nres,cuts", [(100000, 1, (0, 31000, 100000)), (4097, 3, (0, 5, 2000, 4097))])
+def test_r3_sharded_halves_equal_fused_entry(n, nres, cuts):
+    """ax_r3_abs_sum per block + ax_pairwise_sum over the rank-ordered concatenation + ax_r3_retain_thr per
+    block reproduce ax_r3_retain on the whole population (threshold and retained points, bit for bit)."""
+    rng = np.random.RandomState(7)
+    res = (rng.randn(nres, n) * np.exp(rng.randn(nres, n))).astype(np.float32)
+    X = rng.rand(n, 2).astype(np.float32)
+    dev = torch.device("cuda:0")
+    r = torch.zeros((nres, _lib.pad32(n)), dtype=torch.float32, device=dev)
+    r[:, :n] = torch.as_tensor(res).to(dev)
+    x_out, n_keep, thr_d, res_sum = _lib.r3_retain(r, to_soa(torch.as_tensor(X).to(dev)), n, place_at_end=True)
+    nk = int(n_keep.item())
+    whole = x_out[:, n - nk:n].cpu().numpy()
+    sums = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        blk = torch.zeros((nres, _lib.pad32(hi - lo)), dtype=torch.float32, device=dev)
+        blk[:, :hi - lo] = r[:, lo:hi]
+        sums.append(_lib.r3_abs_sum(blk, hi - lo))
+    glob = torch.cat(sums)
+    assert torch.equal(glob, res_sum)
+    thr = _lib.pairwise_sum(glob) / torch.tensor(float(n), dtype=torch.float32, device=dev)
+    assert thr.item() == thr_d.item()
+    parts = []
+    for (lo, hi), sm in zip(zip(cuts[:-1], cuts[1:]), sums):
+        xs = to_soa(torch.as_tensor(X[lo:hi]).to(dev))
+        xo, k = _lib.r3_retain_thr(sm, thr, xs, hi - lo, place_at_end=True)
+        k = int(k.item())
+        parts.append(xo[:, (hi - lo) - k:(hi - lo)].cpu().numpy())
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)
