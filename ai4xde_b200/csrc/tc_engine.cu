@@ -1738,39 +1738,52 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CU
 // =========================================================================================
 // small FP32 kernels either side of the tensor-core layers (this engine's layout)
 // =========================================================================================
-// layer 0: POST-activation streams from x.   block = H threads (unit), 32 points per block
+// layer 0: POST-activation streams from x.  A thread owns FOUR consecutive units (128-bit stores: one
+// (p,s) row of H floats is one or two warp instructions) and every (256 / (H/4))-th point of its block.
 template <class P>
-__global__ void k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float *__restrict__ x,
-                           int d_in, JetDirs dirs, int H, long long n, long long ldn, float *__restrict__ act0,
-                           int act) {
+__global__ void __launch_bounds__(256)
+k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float *__restrict__ x,
+           int d_in, JetDirs dirs, int H, long long n, long long ldn, float *__restrict__ act0, int act,
+           int pts_per_block) {
   constexpr int S = P::S;
-  const int o = threadIdx.x;
-  if (o >= H) return;
-  float w[8];
+  const int HQ = H >> 2, PR = 256 / HQ;
+  const int kq = threadIdx.x % HQ, pr = threadIdx.x / HQ;
+  float w[4][4], bo[4], wd[4][P::N1 > 0 ? P::N1 : 1];
 #pragma unroll
-  for (int d = 0; d < 8; ++d) w[d] = d < d_in ? __ldg(W + (long long)o * d_in + d) : 0.0f;
-  const float bo = __ldg(b + o);
-  float wd[P::N1 > 0 ? P::N1 : 1];
+  for (int e = 0; e < 4; ++e) {
+    const int o = 4 * kq + e;
 #pragma unroll
-  for (int j = 0; j < P::N1; ++j) wd[j] = __ldg(W + (long long)o * d_in + dirs.d[j]);
-  const long long p_beg = (long long)blockIdx.x * 32;
-  for (int pp = 0; pp < 32; ++pp) {
-    const long long p = p_beg + pp;
-    if (p >= n) break;
-    float z[S], A[S];
-    z[0] = bo;
+    for (int d = 0; d < 4; ++d) w[e][d] = d < d_in ? __ldg(W + (long long)o * d_in + d) : 0.0f;
+    bo[e] = __ldg(b + o);
 #pragma unroll
-    for (int d = 0; d < 8; ++d)
-      if (d < d_in) z[0] = fmaf(w[d], __ldg(x + (long long)d * ldn + p), z[0]);
+    for (int j = 0; j < P::N1; ++j) wd[e][j] = __ldg(W + (long long)o * d_in + dirs.d[j]);
+  }
+  const long long p_beg = (long long)blockIdx.x * pts_per_block;
+  long long p_end = p_beg + pts_per_block;
+  if (p_end > n) p_end = n;
+  for (long long p = p_beg + pr; p < p_end; p += PR) {
+    float xv[4];
 #pragma unroll
-    for (int j = 0; j < P::N1; ++j) z[1 + j] = wd[j];
+    for (int d = 0; d < 4; ++d) xv[d] = d < d_in ? __ldg(x + (long long)d * ldn + p) : 0.0f;
+    float out[S][4];
 #pragma unroll
-    for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
-    jet_forward_A<P>(act, z, A);
-    float *dst = act0 + (p * S) * H + o;
-    dst[0] = A[0];
+    for (int e = 0; e < 4; ++e) {
+      float z[S], A[S];
+      z[0] = bo[e];
 #pragma unroll
-    for (int s = 1; s < S; ++s) dst[(long long)s * H] = to_tf32(A[s]);
+      for (int d = 0; d < 4; ++d) z[0] = fmaf(w[e][d], xv[d], z[0]);
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) z[1 + j] = wd[e][j];
+#pragma unroll
+      for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
+      jet_forward_A<P>(act, z, A);
+      out[0][e] = A[0];
+#pragma unroll
+      for (int s_ = 1; s_ < S; ++s_) out[s_][e] = to_tf32(A[s_]);
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < S; ++s_)
+      reinterpret_cast<float4 *>(act0 + (p * S + s_) * H)[kq] = make_float4(out[s_][0], out[s_][1], out[s_][2], out[s_][3]);
   }
 }
 
@@ -2213,7 +2226,7 @@ bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *j
   if (H != 64 && H != 128 && H != 256) return false;
   for (int l = 1; l <= g.L; ++l)
     if (g.widths[l] != H) return false;
-  if (g.widths[g.L + 1] > 4) return false;
+  if (g.widths[g.L + 1] > 4 || g.widths[0] > 4) return false;   // first / output layers are compiled for <= 4
   return pattern_in_tc(match_pattern(jet));
 }
 
@@ -2322,8 +2335,9 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
     } else {
     {
       KernelTimer t("tc_first_layer", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
-      k_tc_first<P><<<(unsigned)((a.n + 31) / 32), H, 0, a.stream>>>(prm + g.w_off[0], prm + g.b_off[0], a.x, d_in,
-                                                                    dirs, H, a.n, a.ldn, slot(0), act);
+      const int ppb = 256;   // points per block
+      k_tc_first<P><<<(unsigned)((a.n + ppb - 1) / ppb), 256, 0, a.stream>>>(prm + g.w_off[0], prm + g.b_off[0], a.x,
+                                                                            d_in, dirs, H, a.n, a.ldn, slot(0), act, ppb);
     }
     AX_LAUNCH_OK();
     for (int l = 1; l < g.L; ++l) {

@@ -239,17 +239,34 @@ def run_ours(args):
     # ---- end-to-end arm: host buffers in, loss out, every step ----------------------------------
     host = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).pin_memory()
     views = [host.view_as(host) for _ in range(args.steps + args.warmup)]   # distinct objects -> no device cache hit
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    # every step's loss is read back to pinned host memory; the read of step i is consumed (event wait + float())
+    # while step i+1 is already queued -- the usual asynchronous logging pattern -- and the last one before the
+    # closing event, so all K device->host reads complete inside the timed region.
+    loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    losses_seen = []
+
+    def e2e_step(i, view):
+        model.train_step(view, None, None)
+        loss_ring[i & 1].copy_(model.last_total_loss, non_blocking=True)
+        loss_ev[i & 1].record()
+        if i > 0:
+            loss_ev[(i - 1) & 1].synchronize()
+            losses_seen.append(float(loss_ring[(i - 1) & 1]))
+
     for i in range(args.warmup):
         model.train_step(views[i], None, None)
-        loss_host.copy_(model.last_total_loss, non_blocking=False)
+        loss_ring[0].copy_(model.last_total_loss, non_blocking=False)
     barrier()
     ev0.record()
     for i in range(args.steps):
-        model.train_step(views[args.warmup + i], None, None)
-        loss_host.copy_(model.last_total_loss, non_blocking=False)
+        e2e_step(i, views[args.warmup + i])
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    losses_seen.append(float(loss_ring[(args.steps - 1) & 1]))
     ev1.record()
     barrier()
+    assert len(losses_seen) == args.steps
+    loss_host = loss_ring[(args.steps - 1) & 1]
     t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
