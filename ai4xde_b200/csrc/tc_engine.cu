@@ -1829,21 +1829,21 @@ k_tc_last_fwd(const float *__restrict__ Wout, const float *__restrict__ bout, co
 // A thread owns FOUR consecutive units (128-bit loads and stores: a (p,s) row of H floats is one or two
 // warp instructions) and every 256/(H/4)-th point of the block's range; the row groups are combined in a
 // fixed order through shared memory.  partial layout per block: [C*H | C | H]
-template <class P>
+template <class P, int CM>
 __global__ void __launch_bounds__(256, 2)
 k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar,
               const float *__restrict__ actL, int H, int C, long long n, long long ldn,
               int pts_per_block, float *__restrict__ gout, float *__restrict__ partial, int act) {
   constexpr int S = P::S;
-  constexpr int U = (S <= 4) ? 2 : 1;   // points in flight per thread (U*S 128-bit loads outstanding)
+  constexpr int U = (S * CM <= 4) ? 4 : (S <= 4) ? 2 : 1;   // points in flight per thread (U*S 128-bit loads outstanding)
   __shared__ float red[256 * 9];
   const int HQ = H >> 2;         // unit quads per row
   const int PR = 256 / HQ;       // points processed side by side
   const int kq = threadIdx.x % HQ, pr = threadIdx.x / HQ;
-  float4 wc[4];
-  float dw[4][4], dbo[4], dbh[4];
+  float4 wc[CM];
+  float dw[CM][4], dbo[CM], dbh[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < CM; ++c) {
     wc[c] = c < C ? __ldg(reinterpret_cast<const float4 *>(Wout + (long long)c * H) + kq) : make_float4(0, 0, 0, 0);
     dbo[c] = 0.0f;
 #pragma unroll
@@ -1856,7 +1856,7 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
   if (p_end > n) p_end = n;
   for (long long pb = p_beg + pr; pb < p_end; pb += (long long)U * PR) {
     float4 A[U][S];
-    float jb[U][S][4];
+    float jb[U][S][CM];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = pb + (long long)u * PR;
@@ -1865,7 +1865,7 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
       for (int s_ = 0; s_ < S; ++s_) {
         A[u][s_] = ok ? __ldg(reinterpret_cast<const float4 *>(actL + (p * S + s_) * H) + kq) : make_float4(0, 0, 0, 0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < CM; ++c)
           jb[u][s_][c] = (ok && c < C) ? __ldg(jets_bar + ((long long)s_ * C + c) * ldn + p) : 0.0f;
       }
     }
@@ -1883,7 +1883,7 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
           a_[s_] = av;
           float acc = 0.0f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < CM; ++c) {
             const float w = e == 0 ? wc[c].x : e == 1 ? wc[c].y : e == 2 ? wc[c].z : wc[c].w;
             acc = fmaf(w, jb[u][s_][c], acc);
             dw[c][e] = fmaf(jb[u][s_][c], av, dw[c][e]);
@@ -1896,7 +1896,7 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
         for (int s_ = 0; s_ < S; ++s_) zq[s_][e] = to_tf32(zb[s_]);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) dbo[c] += jb[u][0][c];
+      for (int c = 0; c < CM; ++c) dbo[c] += jb[u][0][c];
 #pragma unroll
       for (int s_ = 0; s_ < S; ++s_)
         reinterpret_cast<float4 *>(gout + (p * S + s_) * H)[kq] = make_float4(zq[s_][0], zq[s_][1], zq[s_][2], zq[s_][3]);
@@ -1904,7 +1904,9 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
   }
   // combine the PR row groups in a fixed order; thread (pr = 0, kq) then owns units 4kq..4kq+3
   float *part = partial + (long long)blockIdx.x * ((long long)C * H + C + H);
-  for (int c = 0; c < C; ++c) {
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    if (c >= C) break;
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 4; ++e) red[threadIdx.x * 9 + e] = dw[c][e];
@@ -2404,8 +2406,12 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       const int nb = (int)((a.n + ppb - 1) / ppb);
       {
         KernelTimer t("tc_last_bwd", a.stream, 4.0 * S * H * C * (double)a.n, 8.0 * S * H * (double)a.n);
-        k_tc_last_bwd<P><<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn, (int)ppb,
-                                                 w.g[cur], w.partial, act);
+        if (C == 1)
+          k_tc_last_bwd<P, 1><<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn,
+                                                        (int)ppb, w.g[cur], w.partial, act);
+        else
+          k_tc_last_bwd<P, 4><<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn,
+                                                        (int)ppb, w.g[cur], w.partial, act);
       }
       AX_LAUNCH_OK();
       const long long stride = (long long)C * H + C + H;
