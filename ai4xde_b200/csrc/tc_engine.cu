@@ -360,6 +360,11 @@ struct GemmArgs {
   long long n;            // points
   int num_tiles;
   int act;
+  // forward of the LAST hidden layer with one output and 8*S == 32: the output layer is folded into the
+  // epilogue -- jets_part[rank][s][p] = sum over this CTA's 128 units of Wout[o] * a_s(o, p) (fixed-order
+  // lane / quarter reduction); `out` may then be nullptr (residual probe: nothing but the jets leaves the SM)
+  const float *wout;      // [H] or nullptr
+  float *jets_part;       // [2][S][ldn]
 };
 
 // -----------------------------------------------------------------------------------------
@@ -699,6 +704,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
   uint64_t *tmem_empty = tmem_full + 2;   // [2]
   uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
   float *red = reinterpret_cast<float *>(tmem_slot + 4);  // [2][128][5]
+  float *jacc = red + 2 * 128 * 5;                        // [2 tiles][G8][4 quarters][32] (fused output layer)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -786,6 +792,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
     float dbsum = 0.0f, dw0a = 0.0f, dw0b = 0.0f;
     const float bias = (MODE == 0) ? __ldg(g.bias + o) : 0.0f;
     const bool fuse_first = (MODE == 1) && (g.first_x != nullptr);
+    constexpr bool kCanFuseOut = (MODE == 0) && (8 * S == 32);
+    const bool fuse_out = kCanFuseOut && (g.wout != nullptr);
+    const float wout_o = fuse_out ? __ldg(g.wout + o) : 0.0f;
     float m0[P::N1 > 0 ? P::N1 : 1], m1[P::N1 > 0 ? P::N1 : 1];   // first-order stream j differentiates x0 / x1 ?
 #pragma unroll
     for (int j = 0; j < P::N1; ++j) {
@@ -859,6 +868,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
         }
         float *op = obase + grp * GSTRIDE;
         const int valid = full_tile ? 8 : (int)((g.n - p0 - grp * 8) < 8 ? (g.n - p0 - grp * 8) : 8);
+        float t[kCanFuseOut ? 32 : 1];   // Wout[o] * stream value, 8 points x S streams of this unit
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) {
           if (full_tile || pp < valid) {
@@ -868,9 +878,16 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
             if (MODE == 0) {
               z[0] += bias;
               jet_forward_A<P>(g.act, z, w);
-              op[(pp * S) * H] = w[0];
 #pragma unroll
-              for (int s = 1; s < S; ++s) op[(pp * S + s) * H] = to_tf32(w[s]);
+              for (int s = 1; s < S; ++s) w[s] = to_tf32(w[s]);
+              if (outp != nullptr) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = w[s];
+              }
+              if (kCanFuseOut) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = wout_o * w[s];
+              }
             } else {
               float a[S];
 #pragma unroll
@@ -890,7 +907,37 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
                 for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = to_tf32(w[s]);
               }
             }
+          } else if (kCanFuseOut) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = 0.0f;
           }
+        }
+        if (kCanFuseOut && fuse_out) {
+          // transpose-reduce over the warp's 32 units: after the 5 steps lane L holds the sum of value L
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const bool up = (lane & step) != 0;
+#pragma unroll
+            for (int i = 0; i < step; ++i) {
+              const float send = up ? t[i] : t[i + step];
+              const float keep = up ? t[i + step] : t[i];
+              t[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+            }
+          }
+          jacc[(((it & 1) * G8 + grp) * 4 + q) * 32 + lane] = t[0];
+        }
+      }
+      if (kCanFuseOut && fuse_out) {
+        // the tile's 8 epilogue warps are done: sum the four lane quarters in a fixed order, one value per
+        // thread (G8 * 32 = 256 values = 256 epilogue threads)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int e = (sub * 4 + q) * 32 + lane;   // 0..255
+        if (e < G8 * 32) {
+          const int grp = e >> 5, v = e & 31;
+          const float *ja = jacc + (((it & 1) * G8 + grp) * 4) * 32 + v;
+          const float sum = (ja[0] + ja[32]) + (ja[64] + ja[96]);
+          const long long p = p0 + grp * 8 + v / S;
+          if (p < g.n) g.jets_part[((long long)rank * S + (v % S)) * g.ldn + p] = sum;
         }
       }
     }
@@ -1976,6 +2023,17 @@ __global__ void k_tc_first_bwd(const float *__restrict__ g0, const float *__rest
   for (int d = 0; d < d_in; ++d) part[(long long)i * d_in + d] = acc[d];
 }
 
+// fused output layer, second half: jets[s][p] = part[0][s][p] + part[1][s][p] (+ bias for the value stream)
+__global__ void k_tc_jets_combine(const float *__restrict__ part, const float *__restrict__ bout, int S, long long n,
+                                  long long ldn, float *__restrict__ jets) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)S * ldn) return;
+  const long long p = i % ldn;
+  if (p >= n) return;
+  const int s_ = (int)(i / ldn);
+  jets[i] = (part[i] + part[(long long)S * ldn + i]) + (s_ == 0 ? __ldg(bout) : 0.0f);
+}
+
 __global__ void k_tc_round_copy(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols,
                                 int transpose) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2014,6 +2072,7 @@ __global__ void k_tc_reduce(const float *__restrict__ partial, long long stride,
 // =========================================================================================
 static int g_use_pair = 1;       // AX_TC_PAIR=0 in the environment falls back to the single-CTA layer kernel
 static int g_use_fused_bwd = 1;  // AX_TC_FUSED_BWD=0 runs dgrad and wgrad as separate kernels
+static int g_use_fuse_out = 1;   // AX_TC_FUSE_OUT=0: output layer as its own kernel
 static int g_use_chain = 0;      // AX_TC_CHAIN=1: whole-stack forward kernel (experimental: correct, but latency-bound -- DESIGN.md 2.2)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -2087,6 +2146,8 @@ static int sm_count() {
     if (e && e[0] == '0') g_use_pair = 0;
     const char *f = getenv("AX_TC_FUSED_BWD");
     if (f && f[0] == '0') g_use_fused_bwd = 0;
+    const char *fo = getenv("AX_TC_FUSE_OUT");
+    if (fo && fo[0] == '0') g_use_fuse_out = 0;
     const char *c = getenv("AX_TC_CHAIN");
     if (c && c[0] == '1') g_use_chain = 1;
     int dev = 0;
@@ -2127,7 +2188,8 @@ static int launch_gemm_pair(const float *wop, const float *in, const GemmArgs &g
   constexpr int S = P::S, N = TileOf<S>::N, NHALF = N / 2, H = 256;
   constexpr int STAGE_BYTES = 128 * 128 + ((NHALF * 128 + 1023) / 1024) * 1024;
   constexpr int NSTAGE = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
-  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256 + 2 * 128 * 5 * sizeof(float);
+  const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024 + 256 + 2 * 128 * 5 * sizeof(float) +
+                      2 * 8 * 4 * 32 * sizeof(float);   // + the fused output layer's quarter sums
   CUtensorMap mw, mi;
   if (make_map(&mw, wop, H, H, 128, 1)) return 1;
   if (make_map(&mi, in, rows, H, NHALF, 1)) return 1;
@@ -2264,7 +2326,9 @@ static void plan_bwd_ws(const NetGeom &g, int S, long long ldn, BwdWs *w, void *
 size_t tc_forward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
   if (!tc_supported(g, net, jet, AX_ENGINE_TF32)) return 0;
   const int H = g.widths[1];
-  return (size_t)(g.L - 1) * H * H * sizeof(float) * net->n_nets;  // tf32-rounded weights
+  const int S = 1 + jet->n1 + jet->n2;
+  // tf32-rounded weights of every net + the two CTA halves of the fused output layer (one net at a time)
+  return (size_t)(g.L - 1) * H * H * sizeof(float) * net->n_nets + (size_t)2 * S * ldn * sizeof(float);
 }
 
 size_t tc_backward_ws_bytes(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
@@ -2282,7 +2346,8 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
   const size_t layer_fl = (size_t)a.ldn * S * H;
   const int slots = a.keep_all ? g.L : 2;
   const JetDirs dirs = make_dirs(a.jet);
-  const size_t need = (size_t)(g.L - 1) * H * H * sizeof(float) * a.net->n_nets;
+  const size_t need = (size_t)(g.L - 1) * H * H * sizeof(float) * a.net->n_nets + (size_t)2 * S * a.ldn * sizeof(float);
+  float *jets_part = (float *)a.ws + (size_t)(g.L - 1) * H * H * a.net->n_nets;
   if (a.ws_bytes < need || !a.ws) {
     set_error("forward workspace too small: %zu < %zu", a.ws_bytes, need);
     return 1;
@@ -2342,6 +2407,9 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
                                                                             d_in, dirs, H, a.n, a.ldn, slot(0), act, ppb);
     }
     AX_LAUNCH_OK();
+    // the output layer rides in the last hidden layer's epilogue when that kernel can carry it (CTA pair,
+    // one output, 8*S == 32): the residual probe then writes nothing but the jets
+    const bool fuse_out = (H == 256) && g_use_pair && g_use_fuse_out && C == 1 && 8 * S == 32 && g.L >= 2;
     for (int l = 1; l < g.L; ++l) {
       GemmArgs ga{};
       ga.bias = prm + g.b_off[l];
@@ -2349,12 +2417,25 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       ga.n = a.n;
       ga.num_tiles = (int)((a.n + PT - 1) / PT);
       ga.act = act;
+      if (fuse_out && l == g.L - 1) {
+        ga.wout = prm + g.w_off[g.L];
+        ga.jets_part = jets_part;
+        ga.ldn = a.ldn;
+        if (!a.keep_all) ga.out = nullptr;
+      }
       if (H == 256 && g_use_pair) {
         int units = 0;
         if (launch_gemm_pair<P, 0>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream, &units)) return 1;
       } else {
         if (launch_gemm<P, 0, H>(wr + (size_t)(l - 1) * H * H, slot(l - 1), ga, rows, a.stream)) return 1;
       }
+    }
+    if (fuse_out) {
+      const long long cnt = (long long)S * a.ldn;
+      k_tc_jets_combine<<<(unsigned)((cnt + 255) / 256), 256, 0, a.stream>>>(jets_part, prm + g.b_off[g.L], S, a.n, a.ldn,
+                                                                           jets);
+      AX_LAUNCH_OK();
+      continue;
     }
     }
     {
