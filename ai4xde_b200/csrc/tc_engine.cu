@@ -1651,6 +1651,282 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
 }
 
 // -----------------------------------------------------------------------------------------
+// kernel C1: the same fused backward of one hidden layer for H = 64 / 128 on ONE CTA (cta_group::1, M = 128,
+// units past H are zero rows staged by TMA).  W_l^T is resident ([H/32][128][32], <= 64 KB); the ring
+// carries D slots (two K blocks of all N zbar rows, K-major) and W slots (16 rows x H units of zbar and
+// of the stash, MN-major) of 32 KB; TMEM holds two 128-column dgrad accumulators and the H-column dW
+// accumulator, which lives for the whole launch.
+// -----------------------------------------------------------------------------------------
+constexpr int kBwd1SlotBytes = 32768, kBwd1Slots = 4;
+template <int H>
+constexpr size_t bwd1_smem() {
+  return (size_t)(H / 32) * 16384 + (size_t)kBwd1Slots * kBwd1SlotBytes + 1024 + 256 + 2 * 128 * 5 * sizeof(float);
+}
+
+template <class P, int H>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_tc_bwd1(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_g_k,
+          const __grid_constant__ CUtensorMap map_g_mn, const __grid_constant__ CUtensorMap map_a_mn, BwdArgs2 args) {
+  constexpr int S = P::S;
+  constexpr int PT = BwdTileOf<S>::PT, N = BwdTileOf<S>::N;
+  constexpr int KB = H / 32, KPS = KB < 2 ? KB : 2, DSLOTS = KB / KPS;   // K blocks per D slot
+  constexpr int CR = 16, WSLOTS = N / CR;
+  constexpr int SLOT = kBwd1SlotBytes, NSLOT = kBwd1Slots;
+  constexpr int WRES = KB * 16384;
+  constexpr int D_BYTES = KPS * N * 128, W_HALF = 4 * CR * 128, W_BYTES = 2 * W_HALF;   // 4 unit blocks staged
+  constexpr uint32_t IDESC_D = make_idesc(N, 0, 0);
+  constexpr uint32_t IDESC_W = make_idesc(H, 1, 1);
+  constexpr int G8 = PT / 8, MY = G8 / 2;
+  static_assert(N % 16 == 0 && N <= 128 && G8 % 2 == 0, "bad backward tile");
+  static_assert(D_BYTES <= SLOT && W_BYTES <= SLOT, "slot too small");
+  const GemmArgs &g = args.g;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *wres = smem;                   // [KB][128 rows][32] : W^T (rows past H zero), K-major, 128B swizzle
+  uint8_t *ring = smem + WRES;
+  uint64_t *full = (uint64_t *)(ring + NSLOT * SLOT);
+  uint64_t *empty = full + NSLOT;
+  uint64_t *tmem_full = empty + NSLOT;    // [2]
+  uint64_t *tmem_empty = tmem_full + 2;   // [2]
+  uint64_t *w_full = tmem_empty + 2;
+  uint64_t *wres_full = w_full + 1;
+  uint32_t *tmem_slot = (uint32_t *)(wres_full + 1);
+  float *red = reinterpret_cast<float *>(ring + NSLOT * SLOT + 256);  // [2][128][5]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, num_ctas = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], kEpiWarps);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(wres_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (whole warp, one elected lane issues) ----
+    const uint32_t issue = elect_one();
+    mbar_expect_tx_p(wres_full, WRES, issue);
+    for (int kb = 0; kb < KB; ++kb) tma_load_3d_p(&map_wt, wres_full, wres + kb * 16384, 0, 0, kb, issue);
+    uint32_t slot = 0, phase = 0;
+    auto advance = [&]() {
+      if (++slot == NSLOT) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    for (int tile = cta; tile < g.num_tiles; tile += num_ctas) {
+      const int row0 = tile * N;
+      for (int j = 0; j < DSLOTS; ++j) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        mbar_expect_tx_p(&full[slot], D_BYTES, issue);
+        tma_load_3d_p(&map_g_k, &full[slot], ring + slot * SLOT, 0, row0, KPS * j, issue);
+        advance();
+      }
+      for (int c = 0; c < WSLOTS; ++c) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        uint8_t *sp = ring + slot * SLOT;
+        mbar_expect_tx_p(&full[slot], W_BYTES, issue);
+        tma_load_3d_p(&map_g_mn, &full[slot], sp, 0, row0 + c * CR, 0, issue);
+        tma_load_3d_p(&map_a_mn, &full[slot], sp + W_HALF, 0, row0 + c * CR, 0, issue);
+        advance();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (whole warp, one elected lane issues) ------
+    const uint32_t issue = elect_one();
+    uint32_t slot = 0, phase = 0, it = 0;
+    auto advance = [&]() {
+      if (++slot == NSLOT) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    mbar_wait(wres_full, 0);
+    tc_fence_after();
+    const uint64_t d_wres = make_desc(smem_u32(wres), 16, 1024);
+    const uint64_t d_ring_k = make_desc(smem_u32(ring), 16, 1024);
+    const uint64_t d_ring_mn = make_desc(smem_u32(ring), CR * 128, 512, 1);
+    for (int tile = cta; tile < g.num_tiles; tile += num_ctas, ++it) {
+      const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[b], bphase ^ 1);
+      tc_fence_after();
+      for (int j = 0; j < DSLOTS; ++j) {
+        mbar_wait(&full[slot], phase);
+        tc_fence_after();
+        const uint64_t da = d_wres + (uint64_t)(KPS * j * (16384 >> 4));
+        const uint64_t db = d_ring_k + (uint64_t)(slot * (SLOT >> 4));
+#pragma unroll
+        for (int kk = 0; kk < KPS; ++kk)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32_p(tmem_base + b * 128, da + ((kk * 16384 + ks * 32) >> 4), db + ((kk * (N * 128) + ks * 32) >> 4),
+                        IDESC_D, (j | kk | ks) != 0 ? 1u : 0u, issue);
+        umma_commit_p(&empty[slot], issue);
+        advance();
+      }
+      umma_commit_p(&tmem_full[b], issue);
+      for (int c = 0; c < WSLOTS; ++c) {
+        mbar_wait(&full[slot], phase);
+        tc_fence_after();
+        const uint64_t dz = d_ring_mn + (uint64_t)(slot * (SLOT >> 4));
+#pragma unroll
+        for (int ks = 0; ks < CR / 8; ++ks)
+          umma_tf32_p(tmem_base + 256, dz + ((ks * 1024) >> 4), dz + ((W_HALF + ks * 1024) >> 4), IDESC_W,
+                      (it | (uint32_t)c | (uint32_t)ks) != 0 ? 1u : 0u, issue);
+        umma_commit_p(&empty[slot], issue);
+        advance();
+      }
+    }
+    umma_commit_p(w_full, issue);
+  } else {
+    // ------------------------------ epilogue: lane = unit (units past H idle) --------
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int o = q * 32 + lane;
+    const bool live = o < H;
+    float dbsum = 0.0f, dw0a = 0.0f, dw0b = 0.0f;
+    const bool fuse_first = (g.first_x != nullptr);
+    float m0[P::N1 > 0 ? P::N1 : 1], m1[P::N1 > 0 ? P::N1 : 1];
+#pragma unroll
+    for (int j = 0; j < P::N1; ++j) {
+      m0[j] = (g.dirs.d[j] == 0) ? 1.0f : 0.0f;
+      m1[j] = (g.dirs.d[j] == 1) ? 1.0f : 0.0f;
+    }
+    const float *__restrict__ stash_in = g.stash_in + (live ? o : 0);
+    float *__restrict__ outp = g.out + (live ? o : 0);
+    const float *__restrict__ x0p = g.first_x;
+    const float *__restrict__ x1p = (g.first_x != nullptr && g.d_in > 1) ? g.first_x + g.ldn : g.first_x;
+    const long long n = g.n;
+    float st[8 * S], xs[16];
+    auto prefetch = [&](long long pg) {
+      const float *sp = stash_in + pg * (S * H);
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        const bool ok = live && (pg + pp < n);
+#pragma unroll
+        for (int s_ = 0; s_ < S; ++s_) st[pp * S + s_] = ok ? __ldg(sp + (pp * S + s_) * H) : 0.0f;
+        if (fuse_first) {
+          xs[2 * pp] = ok ? __ldg(x0p + pg + pp) : 0.0f;
+          xs[2 * pp + 1] = ok ? __ldg(x1p + pg + pp) : 0.0f;
+        }
+      }
+    };
+    if (cta < g.num_tiles) prefetch((long long)cta * PT + sub * 8);
+    uint32_t it = 0;
+    for (int tile = cta; tile < g.num_tiles; tile += num_ctas, ++it) {
+      const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+      const long long p0 = (long long)tile * PT;
+      mbar_wait(&tmem_full[b], bphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < MY; ++k) {
+        const int grp = sub + 2 * k;
+        const long long pg = p0 + grp * 8;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * 128 + grp * 8 * S;
+        float r[8 * S];
+        tmem_ld_cols<8 * S>(taddr, r);
+        tmem_ld_wait();
+        if (k == MY - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[b]);
+        }
+        float cur[8 * S], xc[16];
+#pragma unroll
+        for (int i = 0; i < 8 * S; ++i) cur[i] = st[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xc[i] = xs[i];
+        if (k + 1 < MY)
+          prefetch(pg + 16);
+        else if (tile + num_ctas < g.num_tiles)
+          prefetch((long long)(tile + num_ctas) * PT + sub * 8);
+        float *op = outp + pg * (S * H);
+        const int valid = !live ? 0 : (pg + 8 <= n) ? 8 : (int)(n > pg ? n - pg : 0);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          if (pp < valid) {
+            float z[S], w[S], a[S];
+#pragma unroll
+            for (int s_ = 0; s_ < S; ++s_) {
+              z[s_] = r[pp * S + s_];
+              a[s_] = cur[pp * S + s_];
+            }
+            jet_adjoint_A<P>(g.act, a, z, w);
+            dbsum += w[0];
+            if (fuse_first) {
+              dw0a = fmaf(w[0], xc[2 * pp], dw0a);
+              dw0b = fmaf(w[0], xc[2 * pp + 1], dw0b);
+#pragma unroll
+              for (int j = 0; j < P::N1; ++j) {
+                dw0a = fmaf(m0[j], w[1 + j], dw0a);
+                dw0b = fmaf(m1[j], w[1 + j], dw0b);
+              }
+            } else {
+#pragma unroll
+              for (int s_ = 0; s_ < S; ++s_) op[(pp * S + s_) * H] = to_tf32(w[s_]);
+            }
+          }
+        }
+      }
+    }
+    {
+      float *r5 = red + ((sub * 128) + q * 32 + lane) * 5;
+      r5[0] = dbsum;
+      r5[1] = dw0a;
+      r5[2] = dw0b;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (sub == 0 && live) {
+        const float *r0 = red + ((0 * 128) + q * 32 + lane) * 5;
+        const float *r1 = red + ((1 * 128) + q * 32 + lane) * 5;
+        g.db_partial[(long long)cta * H + o] = r0[0] + r1[0];
+        if (fuse_first)
+          for (int d = 0; d < g.d_in && d < 2; ++d)
+            g.dw0_partial[((long long)cta * H + o) * 4 + d] = r0[1 + d] + r1[1 + d];
+      }
+    }
+    {
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      float *part = args.dw_partial + (long long)cta * H * H + (long long)(live ? o : 0) * H;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
+#pragma unroll 1
+      for (int c0 = sub * 32; c0 < H; c0 += 64) {
+        float r[32];
+        tmem_ld16(taddr + c0, &r[0]);
+        tmem_ld16(taddr + c0 + 16, &r[16]);
+        tmem_ld_wait();
+        if (live) {
+          float4 *dst = reinterpret_cast<float4 *>(part + c0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
 // kernel B:  dW[i][k] = sum_rows Zbar[row][i] * A[row][k]      (both operands MN-major)
 // each CTA reduces its own row range into a 256-lane x H-column FP32 accumulator and writes a
 // partial; a deterministic second pass sums the partials.
@@ -1835,39 +2111,74 @@ k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float
 }
 
 // output layer forward: jets[s][c][p] = sum_k Wout[c][k] A[(p,s)][k] (+ b_c for s = 0).
-// A warp owns 4 rows at a time (4 x H/32 independent loads in flight per lane), lanes over k.
+// A warp owns 8 rows at a time, lanes over k (coalesced 128-byte row segments, 32 loads in flight per lane);
+// the 8 x CM partial sums of a lane are combined by a transpose-reduce (fixed order; NV - 1 shuffles for
+// NV = 8*CM values plus log2(32/NV) butterfly steps), after which lane L < NV holds output c = L % CM of
+// row L / CM.  CM = outputs compiled for (1 or 4), KLM = K blocks compiled for (H/32 <= KLM).
+template <int CM, int KLM>
 __global__ void __launch_bounds__(256)
 k_tc_last_fwd(const float *__restrict__ Wout, const float *__restrict__ bout, const float *__restrict__ actL,
               int H, int C, int S, long long n, long long ldn, float *__restrict__ jets) {
+  constexpr int NV = 8 * CM;
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long rows = n * S;
-  const int KL = H / 32;  // <= 8
-  for (long long row0 = warp_global * 4; row0 < rows; row0 += nwarps * 4) {
-    float a[4][8];
+  const int KL = H / 32;  // <= KLM
+  float w[CM][KLM];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+  for (int c = 0; c < CM; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        a[r][j] = (j < KL && row0 + r < rows) ? __ldg(actL + (row0 + r) * H + lane + 32 * j) : 0.0f;
-    for (int c = 0; c < C; ++c) {
-      float w[8];
+    for (int j = 0; j < KLM; ++j) w[c][j] = (c < C && j < KL) ? __ldg(Wout + (long long)c * H + lane + 32 * j) : 0.0f;
+  const int cme = lane % CM;
+  const float bias = cme < C ? __ldg(bout + cme) : 0.0f;
+  for (long long row0 = warp_global * 8; row0 < rows; row0 += nwarps * 8) {
+    float t[NV];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] = j < KL ? __ldg(Wout + (long long)c * H + lane + 32 * j) : 0.0f;
+    for (int i = 0; i < NV; ++i) t[i] = 0.0f;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float acc = 0.0f;
+    for (int j0 = 0; j0 < KLM; j0 += 4) {   // 8 rows x 4 K blocks = 32 independent loads in flight per lane
+      if (j0 < KL) {
+        constexpr int JW = KLM < 4 ? KLM : 4;
+        float v[8][JW];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(w[j], a[r][j], acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const long long row = row0 + r;
-        if (lane == 0 && row < rows) {
-          const long long p = row / S;
-          const int s_ = (int)(row - p * S);
-          jets[((long long)s_ * C + c) * ldn + p] = acc + (s_ == 0 ? __ldg(bout + c) : 0.0f);
-        }
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int jj = 0; jj < JW; ++jj)
+            v[r][jj] = (j0 + jj < KL && row0 + r < rows) ? __ldg(actL + (row0 + r) * H + lane + 32 * (j0 + jj)) : 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < JW; ++jj)
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < CM; ++c) t[r * CM + c] = fmaf(w[c][j0 + jj], v[r][jj], t[r * CM + c]);
       }
+    }
+#pragma unroll
+    for (int step = NV / 2; step >= 1; step >>= 1) {
+      const bool up = (lane & step) != 0;
+#pragma unroll
+      for (int i = 0; i < step; ++i) {
+        const float send = up ? t[i] : t[i + step];
+        const float keep = up ? t[i + step] : t[i];
+        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+      }
+    }
+#pragma unroll
+    for (int step = NV; step < 32; step <<= 1) t[0] += __shfl_xor_sync(0xffffffffu, t[0], step);
+    const long long row = row0 + (lane % NV) / CM;
+    if (lane < NV && cme < C && row < rows) {
+      long long p;
+      int s_;
+      if (rows < 0x7fffffffll) {
+        const unsigned ru = (unsigned)row;
+        p = ru / (unsigned)S;
+        s_ = (int)(ru - (unsigned)p * (unsigned)S);
+      } else {
+        p = row / S;
+        s_ = (int)(row - p * S);
+      }
+      jets[((long long)s_ * C + cme) * ldn + p] = t[0] + (s_ == 0 ? bias : 0.0f);
     }
   }
 }
@@ -2239,6 +2550,35 @@ static int launch_bwd_pair(const float *wt, const float *gl, const float *stash_
   return 0;
 }
 
+// fused dgrad + wgrad of one hidden layer on single CTAs (H = 64 / 128); returns the number of CTAs (= partials)
+template <class P, int H>
+static int launch_bwd_single(const float *wt, const float *gl, const float *stash_prev, GemmArgs ga, long long rows,
+                             float *dw_partial, int *ctas_out, cudaStream_t st) {
+  constexpr int S = P::S, PT = BwdTileOf<S>::PT, N = BwdTileOf<S>::N;
+  constexpr int KB = H / 32, KPS = KB < 2 ? KB : 2;
+  CUtensorMap m_wt, m_gk, m_gmn, m_amn;
+  if (make_map(&m_wt, wt, H, H, 128, 1)) return 1;              // rows past H are zero-filled
+  if (make_map(&m_gk, gl, rows, H, N, KPS)) return 1;
+  if (make_map(&m_gmn, gl, rows, H, 16, 4, true)) return 1;     // unit blocks past H/32 are zero-filled
+  if (make_map(&m_amn, stash_prev, rows, H, 16, 4, true)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_tc_bwd1<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd1_smem<H>()));
+    attr = true;
+  }
+  ga.num_tiles = (int)((ga.n + PT - 1) / PT);
+  int ctas = sm_count();
+  if (ga.num_tiles < ctas) ctas = ga.num_tiles;
+  BwdArgs2 a2{ga, dw_partial};
+  {
+    KernelTimer t("tc_bwd_fused", st, 4.0 * S * H * (double)H * (double)ga.n, 4.0 * S * H * (double)ga.n * 3.0);
+    k_tc_bwd1<P, H><<<ctas, kGemmThreads, bwd1_smem<H>(), st>>>(m_wt, m_gk, m_gmn, m_amn, a2);
+  }
+  AX_LAUNCH_OK();
+  *ctas_out = ctas;
+  return 0;
+}
+
 template <int H>
 static int launch_wgrad(const float *zbar, const float *a, long long rows, float *partial, int *grid_out,
                         cudaStream_t st, int S) {
@@ -2441,8 +2781,12 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
     {
       KernelTimer t("tc_last_fwd", a.stream, 2.0 * S * H * C * (double)a.n, 4.0 * S * H * (double)a.n);
       const int blocks = sm_count() * 16;
-      k_tc_last_fwd<<<blocks, 256, 0, a.stream>>>(prm + g.w_off[g.L], prm + g.b_off[g.L], slot(g.L - 1), H, C, S,
-                                                  a.n, a.ldn, jets);
+      if (C == 1)
+        k_tc_last_fwd<1, H / 32><<<blocks, 256, 0, a.stream>>>(prm + g.w_off[g.L], prm + g.b_off[g.L], slot(g.L - 1), H,
+                                                               C, S, a.n, a.ldn, jets);
+      else
+        k_tc_last_fwd<4, H / 32><<<blocks, 256, 0, a.stream>>>(prm + g.w_off[g.L], prm + g.b_off[g.L], slot(g.L - 1), H,
+                                                               C, S, a.n, a.ldn, jets);
     }
     AX_LAUNCH_OK();
   }
@@ -2500,7 +2844,7 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       if (reduce_to(w.partial, stride, (long long)C * H + C, nb, H, grad + g.b_off[L - 1], a.stream)) return 1;
     }
     for (int l = L - 1; l >= 1; --l) {
-      if (H == 256 && g_use_pair && g_use_fused_bwd && BwdTileOf<S>::PT > 0) {
+      if (g_use_fused_bwd && BwdTileOf<S>::PT > 0 && (H != 256 || g_use_pair)) {
         // fused: zbar_{l-1} = adjoint(W_l^T zbar_l)  and  dW_l = zbar_l^T A_{l-1}  in one pass over the tile
         GemmArgs ga{};
         ga.stash_in = slot(l - 1);
@@ -2516,9 +2860,15 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
         ga.n = a.n;
         ga.act = act;
         int clusters = 0;
-        if (launch_bwd_pair<P>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], slot(l - 1), ga, rows, w.partial, &clusters,
-                               a.stream))
-          return 1;
+        if constexpr (H == 256) {
+          if (launch_bwd_pair<P>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], slot(l - 1), ga, rows, w.partial,
+                                 &clusters, a.stream))
+            return 1;
+        } else {
+          if (launch_bwd_single<P, H>(w.wround + (size_t)(l - 1) * H * H, w.g[cur], slot(l - 1), ga, rows, w.partial,
+                                      &clusters, a.stream))
+            return 1;
+        }
         if (reduce_to(w.partial, (long long)H * H, 0, clusters, (long long)H * H, grad + g.w_off[l], a.stream)) return 1;
         if (reduce_to(dbpart, H, 0, clusters, H, grad + g.b_off[l - 1], a.stream)) return 1;
         if (l == 1 && fuse_first) {
