@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=2**20, help="collocation points per GPU")
-    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32"])
     ap.add_argument("--cpu-points", type=int, default=2**11, help="points per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -35,7 +35,9 @@ extern "C" {
 #define AX_MAX_SECOND 10
 
 enum { AX_ACT_TANH = 0, AX_ACT_SIN = 1, AX_ACT_SIGMOID = 2 };
-/* arithmetic engines: FP32 FMA (any width) or tcgen05 tensor cores (hidden width multiple of 64) */
+/* arithmetic engines: FP32 FMA (any width) or tcgen05 tensor cores (hidden width 64 / 128 / 256).
+ * AX_ENGINE_TF32X3 (3-pass split TF32) is RESERVED: no kernel implements it, ax_engine_supported() answers 0
+ * for it and the compute entry points return an error -- never a silent substitute. */
 enum { AX_ENGINE_AUTO = 0, AX_ENGINE_FP32 = 1, AX_ENGINE_TF32 = 2, AX_ENGINE_TF32X3 = 3 };
 
 /* dde.nn.FNN(layer_size, activation, initializer): cases/PDECases.py:38-42 */
