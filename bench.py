@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=2**20, help="collocation points per GPU")
     ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32"])
-    ap.add_argument("--cpu-points", type=int, default=2**11, help="points per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-points", type=int, default=2**14, help="points per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -323,7 +323,7 @@ def run_ours(args):
                                     for kk, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(args.cpu_points, 3, 1)
+            r = cpu_reference_run(args.cpu_points, 5, 1)   # ~10 s of host work: 3 thread counts x 6 steps
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {
             "metric": "train collocation points/sec (residual+backward)", "value": value, "unit": "points/s",
