@@ -118,3 +118,45 @@ def test_tf32_engine_matches_oracle(cfg, n):
     assert r["loss_rel"] < tol["loss"], r
     assert r["grad_rel"] < tol["grad"], r
     assert r["res_rel"] < tol["res"], r
+
+
+def test_cfg4_full_size_properties():
+    """BASELINE cfg4 at its full size (2^20 + 80 rows, 2-[256]x6-1 tanh, Laplacian stream pattern) through
+    size-independent properties: (i) every point's jets do not depend on which tile / launch it rode in
+    (full batch == concatenation of two unequal shards, bit for bit); (ii) the parameter gradient is additive
+    over point shards (the data-parallel contract); (iii) the backward is linear in the jet adjoints (x2 is
+    exact in binary floating point, TF32 rounding included); (iv) a random 2048-point subset agrees with the
+    float64 double within the stated TF32 bound."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    widths = [2] + [256] * 6 + [1]
+    js = JetSpec((0, 1), ((15, 15),))
+    net = _lib.make_net_desc(widths, "tanh")
+    params = _glorot_params(widths, gen).to(dev)
+    n = 2**20 + 80
+    x = (torch.rand((n, 2), generator=gen) * 2 - 1).to(dev)
+    xs = to_soa(x)
+    jets, stash = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=True, engine="tf32")
+    cut = 400_003
+    ja, sa = _lib.jet_forward(net, js.desc, params, to_soa(x[:cut]), cut, keep_all=True, engine="tf32")
+    jb_, sb = _lib.jet_forward(net, js.desc, params, to_soa(x[cut:]), n - cut, keep_all=True, engine="tf32")
+    assert torch.equal(jets[..., :cut], ja[..., :cut])
+    assert torch.equal(jets[..., cut:n], jb_[..., :n - cut])
+    # (iv) subset against the float64 double
+    idx = torch.randperm(n, generator=gen)[:2048].to(dev)
+    ref, _ = td.jet_forward(net, js.desc, params.double(), to_soa(x[idx]).double(), 2048, True)
+    for s in range(js.S):
+        assert _rel(jets[0, s, :, idx].double(), ref[0, s, :, :2048]) < TF32_JET_TOL, f"stream {s}"
+    # (ii) additivity of the gradient over shards, (iii) linearity in the adjoints
+    jbar = torch.randn(jets.shape, generator=gen).to(dev)
+    jbar[..., n:] = 0
+    g_full = _lib.jet_backward(net, js.desc, params, xs, n, jbar, stash, engine="tf32")
+    bar_a = torch.zeros_like(ja)
+    bar_a[..., :cut] = jbar[..., :cut]
+    bar_b = torch.zeros_like(jb_)
+    bar_b[..., :n - cut] = jbar[..., cut:n]
+    g_a = _lib.jet_backward(net, js.desc, params, to_soa(x[:cut]), cut, bar_a, sa, engine="tf32")
+    g_b = _lib.jet_backward(net, js.desc, params, to_soa(x[cut:]), n - cut, bar_b, sb, engine="tf32")
+    assert _rel((g_a + g_b).double(), g_full.double()) < 1e-4     # FP32 partial sums in a different order
+    g2 = _lib.jet_backward(net, js.desc, params, xs, n, 2.0 * jbar, stash, engine="tf32")
+    assert torch.equal(g2, 2.0 * g_full)
