@@ -128,7 +128,7 @@ class Model:
                 grad.clear()
                 return out
 
-            spec = jet.probe_streams(x, self._n_out(), fn)
+            spec = jet.probe_streams(x, self._n_out(), fn, feature=getattr(self.net, "_input_transform", None))
             self._specs[key] = spec
             if Model.verbose:
                 print(f"[ai4xde_b200] streams for training losses: {spec}")
@@ -148,7 +148,7 @@ class Model:
             grad.clear()
             return out
 
-        spec = jet.probe_streams(x, self._n_out(), fn)
+        spec = jet.probe_streams(x, self._n_out(), fn, feature=getattr(self.net, "_input_transform", None))
         self._specs[key] = (operator, spec)
         if Model.verbose:
             print(f"[ai4xde_b200] streams for operator {getattr(operator, '__name__', operator)}: {spec}")

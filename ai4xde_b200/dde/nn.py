@@ -182,13 +182,15 @@ class FNN(NN):
             self._scope = prev
 
     def forward(self, inputs):
-        if self._input_transform is not None:
-            raise NotImplementedError(
-                "feature transforms are not in the fused jet path yet (the kernels differentiate "
-                "w.r.t. the raw network inputs)"
-            )
         sc = self._scope
         x = inputs
+        featured = self._input_transform is not None
+        if featured:
+            # net.apply_feature_transform(f) (cases/PDECases.py:212,405): the kernels differentiate w.r.t. the
+            # features phi = f(x); f itself is ordinary autograd, so dde.grad.* on the raw inputs chains through it
+            x = self._input_transform(inputs)
+            if x.shape[1] != self.layer_sizes[0]:
+                raise ValueError(f"feature transform returns {x.shape[1]} features, the net takes {self.layer_sizes[0]}")
         if sc.probe_streams is not None:
             y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
         else:
@@ -199,7 +201,10 @@ class FNN(NN):
                 spec = sc.spec
             else:
                 spec = jet.JetSpec.full(x.shape[1])
-            x_soa = sc.x_soa if sc.x_soa is not None and sc.x_soa.shape[1] >= x.shape[0] else jet.to_soa(x)
+            if featured or sc.x_soa is None or sc.x_soa.shape[1] < x.shape[0]:
+                x_soa = jet.to_soa(x.detach().to(torch.float32))
+            else:
+                x_soa = sc.x_soa
             params = self._param_list()
             need_bwd = bool(sc.param_grad and torch.is_grad_enabled() and any(p.requires_grad for p in params))
             streams = _FusedForward.apply(self, x_soa, x.shape[0], spec, config.engine(), need_bwd, *params)

@@ -231,25 +231,34 @@ def make_leaf(x, spec, streams):
     return _Leaf0.apply(x, spec, streams[0], *streams[1:])
 
 
-def probe_streams(x, n_out, fn, allow_trace=True):
+def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
     """Find which derivative streams `fn(x, y)` really uses.
+
+    With a feature transform (`net.apply_feature_transform(f)`) the kernels differentiate w.r.t. the
+    FEATURES phi = f(x): the stand-in output is a leaf over phi, `f` itself stays ordinary autograd, and the
+    streams found are those of d/dphi (the chain rule through `f` usually needs all of them).
 
     fn receives the input tensor and a stand-in network output whose value / first / second
     derivative streams are independent random tensors, and must return the tensors that the
     training loss (or the predict operator) is built from.  A stream is needed iff the result
     has a non-zero gradient w.r.t. it.  Returns JetSpec.covering(...).  No kernel is involved.
     """
-    n, d = x.shape
+    n = x.shape[0]
+    with torch.enable_grad():
+        leaf_in = x if feature is None else feature(x)
+    d = leaf_in.shape[1]
     if d > _lib.MAX_FIRST:
         # cannot even express the full second-order set; probe first order only
         raise NotImplementedError(f"probe for d_in={d} > {_lib.MAX_FIRST} inputs")
+    if feature is not None:
+        allow_trace = False
     full = JetSpec.full(d)
     gen = torch.Generator(device=x.device)
     gen.manual_seed(1234)
     mk = lambda: torch.randn((n, n_out), dtype=x.dtype, device=x.device, generator=gen).requires_grad_()
     streams = [mk() for _ in range(full.S)]
     with torch.enable_grad():
-        y = make_leaf(x, full, streams)
+        y = make_leaf(leaf_in, full, streams)
         outs = fn(x, y)
         if not isinstance(outs, (list, tuple)):
             outs = [outs]

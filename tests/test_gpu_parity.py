@@ -27,3 +27,56 @@ def test_fp32_engine_matches_oracle(cfg, n):
     assert r["loss_rel"] < tol["loss"], r
     assert r["grad_rel"] < tol["grad"], r
     assert r["res_rel"] < tol["res"], r
+
+
+@pytest.mark.parametrize("engine,width,tol", [("fp32", 32, 2e-5), ("tf32", 64, 2e-2)])
+def test_feature_transform_chains_through_the_jet_leaf(engine, width, tol):
+    """net.apply_feature_transform(f) (reference: cases/PDECases.py:399-405, Laplace on a disk in polar
+    coordinates): the kernels differentiate w.r.t. the features, `f` is ordinary autograd, and
+    dde.grad.jacobian / hessian w.r.t. the RAW inputs equal float64 autograd through a plain MLP."""
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float32")
+    dde.config.set_engine(engine)
+    try:
+        torch.manual_seed(4)
+        net = dde.nn.FNN([2, width, width, 1], "tanh", "Glorot normal")
+        feat = lambda x: torch.cat([x[:, 0:1] * torch.sin(x[:, 1:2]), x[:, 0:1] * torch.cos(x[:, 1:2])], dim=1)
+        net.apply_feature_transform(feat)
+        net.to("cuda")
+        x = (torch.rand((3000, 2)) * torch.tensor([1.0, 6.28])).to("cuda").requires_grad_()
+
+        def pde(xx, y):
+            dy_r = dde.grad.jacobian(y, xx, i=0, j=0)
+            dy_rr = dde.grad.hessian(y, xx, i=0, j=0)
+            dy_tt = dde.grad.hessian(y, xx, i=1, j=1)
+            return xx[:, 0:1] * dy_r + xx[:, 0:1] ** 2 * dy_rr + dy_tt
+
+        y = net(x)
+        r = pde(x, y)
+        dde.grad.clear()
+        loss = (r ** 2).mean()
+        net.zero_grad()
+        loss.backward()
+        g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu()
+
+        # float64 reference: the same weights in a plain torch MLP, autograd all the way
+        ps = [p.detach().double().cpu() for p in net.parameters()]
+        ps = [p.requires_grad_() for p in ps]
+        xr = x.detach().double().cpu().requires_grad_()
+        h = feat(xr)
+        for i in range(0, len(ps) - 2, 2):
+            h = torch.tanh(h @ ps[i].t() + ps[i + 1])
+        yr = h @ ps[-2].t() + ps[-1]
+        gy = torch.autograd.grad(yr.sum(), xr, create_graph=True)[0]
+        g_rr = torch.autograd.grad(gy[:, 0].sum(), xr, create_graph=True)[0][:, 0:1]
+        g_tt = torch.autograd.grad(gy[:, 1].sum(), xr, create_graph=True)[0][:, 1:2]
+        rr = xr[:, 0:1] * gy[:, 0:1] + xr[:, 0:1] ** 2 * g_rr + g_tt
+        lr = (rr ** 2).mean()
+        gr = torch.cat([(t if t is not None else torch.zeros_like(p_)).reshape(-1)      # the output bias drops out
+                        for t, p_ in zip(torch.autograd.grad(lr, ps, allow_unused=True), ps)])
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        assert rel(r.detach().double().cpu(), rr.detach()) < tol
+        assert rel(g, gr) < tol
+    finally:
+        dde.config.set_engine("auto")

@@ -64,6 +64,8 @@ CASES = [
     ("Beltrami_flow", dict(NumDomain=60, layer_size=[4, 16, 16, 4])),     # 4 inputs, 15 J + 9 H
     ("Diffusion_Reaction_Inverse", dict()),                               # dde.Variable inside the pde
     ("Convection_1D_Periodic", dict()),
+    ("Laplace_disk", dict(NumDomain=150, layer_size=[2, 16, 16, 1])),     # feature transform (polar -> cartesian)
+    ("LotkaVolterra", dict(NumDomain=120, layer_size=[1, 16, 16, 2])),    # feature + output transform, 2-output ODE
 ]
 
 
