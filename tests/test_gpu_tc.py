@@ -160,3 +160,20 @@ def test_cfg4_full_size_properties():
     assert _rel((g_a + g_b).double(), g_full.double()) < 1e-4     # FP32 partial sums in a different order
     g2 = _lib.jet_backward(net, js.desc, params, xs, n, 2.0 * jbar, stash, engine="tf32")
     assert torch.equal(g2, 2.0 * g_full)
+
+
+@pytest.mark.parametrize("flags", [{"AX_TC_CHAIN": "1"}, {"AX_TC_FUSED_BWD": "0", "AX_TC_FUSE_OUT": "0"},
+                                   {"AX_TC_PAIR": "0"}])
+def test_alternative_kernel_paths_stay_parity_green(flags):
+    """The library reads its kernel-selection switches once per process, so the non-default paths -- the
+    whole-stack forward kernel (AX_TC_CHAIN=1), separate dgrad / wgrad / output-layer kernels, single-CTA
+    layer kernels for H = 256 -- are exercised in a child process over the same parity cases."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, **flags)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_tc.py"), "-x", "-q",
+                        "-k", "test_tf32_engine_matches_double"], env=env, capture_output=True, text=True, cwd=here)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
