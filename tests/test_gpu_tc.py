@@ -47,6 +47,12 @@ def _rel(a, b):
     ([2, 256, 256, 256, 256, 2], "tanh", ((1, 0), ((0, 0),)), 4100),                 # S = 4, PT = 32
     ([2, 256, 256, 256, 1], "sigmoid", ((0, 1), ((0, 0), (0, 1), (1, 1))), 1501),    # S = 6, PT = 16
     ([3, 256, 256, 256, 1], "tanh", ((0, 1), ((0, 0), (1, 1))), 9999),               # d_in = 3: separate first-layer bwd
+    # ragged / tiny point sets: less than one tile, one point, not a multiple of the 8-point groups
+    ([2, 256, 256, 256, 1], "tanh", ((0, 1), ((15, 15),)), 1),
+    ([2, 256, 256, 256, 1], "tanh", ((0, 1), ((15, 15),)), 37),
+    ([2, 128, 128, 128, 3], "tanh", ((0, 1), ((15, 15),)), 1),
+    ([2, 128, 128, 128, 3], "tanh", ((0, 1), ((0, 0), (1, 1))), 45),
+    ([1, 64, 64, 64, 1], "sigmoid", ((0,), ((0, 0),)), 3),
 ])
 def test_tf32_engine_matches_double(widths, act, spec, n):
     dev = torch.device("cuda:0")
