@@ -311,5 +311,63 @@ class NetBank:
         return y
 
 
+class PFNN(NN):
+    """dde.nn.PFNN of the fused path (reference: cases/PoissonCases.py:625-626,
+    `[1, [20, 20], [20, 20], [20, 20], 2]`): one sub-network per output.  The fully split form with
+    structurally identical sub-networks -- what the reference builds -- is C independent FNNs with one
+    output each, evaluated by ONE fused kernel sequence through a NetBank (`n_nets = C`); their outputs form
+    a single (n, C) jet leaf, so `dde.grad.jacobian(y, x, i=c)` reads net c's streams directly.  Parameter
+    names follow DeepXDE (`layers.{i}.{j}.weight`).  A shared trunk before the split, or sub-networks of
+    different widths, are not in the fused path (NotImplementedError)."""
+
+    def __init__(self, layer_sizes, activation, kernel_initializer):
+        super().__init__()
+        if len(layer_sizes) <= 2 or not isinstance(layer_sizes[0], int) or not isinstance(layer_sizes[-1], int):
+            raise ValueError("PFNN needs integer input / output sizes and at least one hidden layer")
+        n_out = int(layer_sizes[-1])
+        hidden = layer_sizes[1:-1]
+        for h in hidden:
+            if not isinstance(h, (list, tuple)):
+                raise NotImplementedError("a shared layer before the split is not in the fused PFNN path")
+            if len(h) != n_out:
+                raise ValueError("number of sub-layers should equal number of network outputs")
+            if len(set(int(w) for w in h)) != 1:
+                raise NotImplementedError("sub-networks of different widths are not in the fused PFNN path")
+        self.layer_sizes = list(layer_sizes)
+        sub_sizes = [int(layer_sizes[0])] + [int(h[0]) for h in hidden] + [1]
+        subnets = [FNN(sub_sizes, activation, kernel_initializer) for _ in range(n_out)]
+        object.__setattr__(self, "_subnets", subnets)          # parameters are registered through `layers`
+        self.layers = torch.nn.ModuleList(
+            torch.nn.ModuleList(sub.linears[i] for sub in subnets) for i in range(len(sub_sizes) - 1))
+        object.__setattr__(self, "_bank", NetBank(subnets))
+        self._scope = _JetScope()
+
+    @contextlib.contextmanager
+    def jet_scope(self, spec=None, x_soa=None, param_grad=True, probe_streams=None):
+        prev = self._scope
+        self._scope = _JetScope(spec, x_soa, param_grad, probe_streams)
+        try:
+            yield
+        finally:
+            self._scope = prev
+
+    def forward(self, inputs):
+        sc = self._scope
+        x = inputs
+        featured = self._input_transform is not None
+        if featured:
+            x = self._input_transform(inputs)
+        if sc.probe_streams is not None:
+            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+        else:
+            wants_jets = x.requires_grad and torch.is_grad_enabled()
+            x_soa = None if featured else sc.x_soa
+            y = self._bank.forward_all(x, x_soa=x_soa, spec=sc.spec if wants_jets else None,
+                                       param_grad=sc.param_grad)
+        if self._output_transform is not None:
+            y = self._output_transform(inputs, y)
+        return y
+
+
 def get_supported_activations():
     return sorted(_lib.ACT)

@@ -96,3 +96,68 @@ class FNN(NN):
         if self._output_transform is not None:
             x = self._output_transform(inputs, x)
         return x
+
+
+
+class PFNN(NN):
+    """Parallel fully-connected network [DeepXDE-upstream `deepxde.nn.pytorch.PFNN`], restated: a layer size
+    given as a list of n_output widths splits the net into one sub-network per output from that layer on (a
+    plain int before the first split is a shared layer; re-joining after a split is an error).  Constructed
+    by the reference at /root/reference/AI4XDE/cases/PoissonCases.py:625-626 with
+    [1, [20, 20], [20, 20], [20, 20], 2].  Parameter names follow upstream: `layers.{i}.{j}.weight`."""
+
+    def __init__(self, layer_sizes, activation, kernel_initializer):
+        super().__init__()
+        self.activation = get_activation(activation)
+        initializer = get_initializer(kernel_initializer)
+        initializer_zero = get_initializer("zeros")
+        if len(layer_sizes) <= 1:
+            raise ValueError("must specify input and output sizes")
+        if not isinstance(layer_sizes[0], int) or not isinstance(layer_sizes[-1], int):
+            raise ValueError("input and output sizes must be integers")
+        n_output = layer_sizes[-1]
+
+        def make_linear(n_in, n_out):
+            lin = torch.nn.Linear(n_in, n_out, dtype=config.real(torch))
+            initializer(lin.weight)
+            initializer_zero(lin.bias)
+            return lin
+
+        self.layers = torch.nn.ModuleList()
+        for i in range(1, len(layer_sizes) - 1):
+            prev, cur = layer_sizes[i - 1], layer_sizes[i]
+            if isinstance(cur, (list, tuple)):
+                if len(cur) != n_output:
+                    raise ValueError("number of sub-layers should equal number of network outputs")
+                if isinstance(prev, (list, tuple)):
+                    self.layers.append(torch.nn.ModuleList([make_linear(prev[j], cur[j]) for j in range(n_output)]))
+                else:
+                    self.layers.append(torch.nn.ModuleList([make_linear(prev, cur[j]) for j in range(n_output)]))
+            else:
+                if not isinstance(prev, int):
+                    raise ValueError("cannot rejoin parallel subnetworks after splitting")
+                self.layers.append(make_linear(prev, cur))
+        if isinstance(layer_sizes[-2], (list, tuple)):
+            self.layers.append(torch.nn.ModuleList([make_linear(layer_sizes[-2][j], 1) for j in range(n_output)]))
+        else:
+            self.layers.append(make_linear(layer_sizes[-2], n_output))
+
+    def forward(self, inputs):
+        x = inputs
+        if self._input_transform is not None:
+            x = self._input_transform(x)
+        for layer in self.layers[:-1]:
+            if isinstance(layer, torch.nn.ModuleList):
+                if isinstance(x, list):
+                    x = [self.activation(f(x_)) for f, x_ in zip(layer, x)]
+                else:
+                    x = [self.activation(f(x)) for f in layer]
+            else:
+                x = self.activation(layer(x))
+        if isinstance(x, list):
+            x = torch.cat([f(x_) for f, x_ in zip(self.layers[-1], x)], dim=1)
+        else:
+            x = self.layers[-1](x)
+        if self._output_transform is not None:
+            x = self._output_transform(inputs, x)
+        return x

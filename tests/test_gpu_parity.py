@@ -80,3 +80,53 @@ def test_feature_transform_chains_through_the_jet_leaf(engine, width, tol):
         assert rel(g, gr) < tol
     finally:
         dde.config.set_engine("auto")
+
+
+def test_pfnn_sub_networks_ride_one_fused_launch_sequence():
+    """dde.nn.PFNN([1, [32, 32], [32, 32], 2]) (reference: cases/PoissonCases.py:625-626): two independent
+    sub-networks evaluated as a NetBank; values, first and second derivatives and parameter gradients equal
+    float64 autograd through the same weights in plain torch modules."""
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float32")
+    dde.config.set_engine("fp32")
+    try:
+        torch.manual_seed(7)
+        net = dde.nn.PFNN([1, [32, 32], [32, 32], 2], "tanh", "Glorot uniform")
+        net.to("cuda")
+        x = (torch.rand((2000, 1)) * 2 - 1).to("cuda").requires_grad_()
+        y = net(x)
+        u_xx = dde.grad.hessian(y, x, component=0, i=0, j=0)
+        q_x = dde.grad.jacobian(y, x, i=1, j=0)
+        r = u_xx - y[:, 1:2] + 0.3 * q_x
+        dde.grad.clear()
+        loss = (r ** 2).mean()
+        net.zero_grad()
+        loss.backward()
+        names = [k for k, _ in net.named_parameters()]
+        assert names[0] == "layers.0.0.weight" and "layers.2.1.bias" in names      # DeepXDE's parameter names
+        g = {k: p.grad.double().cpu() for k, p in net.named_parameters()}
+
+        sd = {k: v.detach().double().cpu().requires_grad_() for k, v in net.state_dict().items()}
+        xr = x.detach().double().cpu().requires_grad_()
+        outs = []
+        for j in range(2):
+            h = xr
+            for i in range(2):
+                h = torch.tanh(h @ sd[f"layers.{i}.{j}.weight"].t() + sd[f"layers.{i}.{j}.bias"])
+            outs.append(h @ sd[f"layers.2.{j}.weight"].t() + sd[f"layers.2.{j}.bias"])
+        u, q = outs
+        du = torch.autograd.grad(u.sum(), xr, create_graph=True)[0]
+        d2u = torch.autograd.grad(du.sum(), xr, create_graph=True)[0]
+        dq = torch.autograd.grad(q.sum(), xr, create_graph=True)[0]
+        rr = d2u - q + 0.3 * dq
+        lr = (rr ** 2).mean()
+        keys = list(sd)
+        gr = torch.autograd.grad(lr, [sd[k] for k in keys], allow_unused=True)
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        assert rel(r.detach().double().cpu(), rr.detach()) < 2e-5
+        for k, t in zip(keys, gr):
+            if t is not None and float(t.abs().max()) > 0:
+                assert rel(g[k], t) < 5e-5, k
+    finally:
+        dde.config.set_engine("auto")

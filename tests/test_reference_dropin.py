@@ -66,6 +66,7 @@ CASES = [
     ("Convection_1D_Periodic", dict()),
     ("Laplace_disk", dict(NumDomain=150, layer_size=[2, 16, 16, 1])),     # feature transform (polar -> cartesian)
     ("LotkaVolterra", dict(NumDomain=120, layer_size=[1, 16, 16, 2])),    # feature + output transform, 2-output ODE
+    ("Poisson_1D_Unknown_Forcing_Field_Inverse", dict()),                 # PFNN: one sub-network per output
 ]
 
 
