@@ -23,6 +23,7 @@ class NetDesc(C.Structure):
         ("widths", C.c_int32 * (MAX_LINEAR + 1)),
         ("activation", C.c_int32),
         ("n_nets", C.c_int32),
+        ("first_activation", C.c_int32),
     ]
 
 
@@ -139,7 +140,7 @@ def _need_cuda(*tensors):
             )
 
 
-def make_net_desc(widths, activation, n_nets=1):
+def make_net_desc(widths, activation, n_nets=1, first_activation=None):
     if len(widths) - 1 > MAX_LINEAR or len(widths) < 3:
         raise ValueError(f"layer_size {widths}: need 1..{MAX_LINEAR - 1} hidden layers")
     if activation not in ACT:
@@ -152,6 +153,10 @@ def make_net_desc(widths, activation, n_nets=1):
         d.widths[i] = int(w)
     d.activation = ACT[activation]
     d.n_nets = int(n_nets)
+    if first_activation is not None and first_activation != activation:
+        if first_activation not in ACT:
+            raise NotImplementedError(f"first-layer activation {first_activation!r} is not in the fused path")
+        d.first_activation = ACT[first_activation] + 1
     return d
 
 

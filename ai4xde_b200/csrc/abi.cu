@@ -66,6 +66,10 @@ int make_geom(const ax_net_desc *net, NetGeom *g) {
     set_error("net: unknown activation %d", net->activation);
     return 1;
   }
+  if (net->first_activation < 0 || net->first_activation > AX_ACT_SIGMOID + 1) {
+    set_error("net: unknown first_activation %d", net->first_activation);
+    return 1;
+  }
   g->n_linear = net->n_linear;
   g->L = net->n_linear - 1;
   g->Hmax = 0;

@@ -75,7 +75,8 @@ struct LayerArgs {
   int64_t dst_net_stride;
   int Ndim;
   int64_t n, ldn;
-  int act;
+  int act;      // activation of the layer whose stash is READ (src in the forward modes, aux in DGRAD)
+  int act_out;  // MODE_FWD_ACT: activation of the layer being produced
 };
 
 template <class P, int MODE, int UI, int NW>
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(NW * 32) k_layer(LayerArgs a) {
     for (int s = 0; s < S; ++s) z[s] = acc[s][u];
     if (MODE == MODE_FWD_ACT) {
       z[0] += __ldg(a.params + net * a.p_stride + a.b_off + o);
-      z[0] = stash_slot0(a.act, z[0]);
+      z[0] = stash_slot0(a.act_out, z[0]);
 #pragma unroll
       for (int s = 0; s < S; ++s) dst[((int64_t)s * a.Ndim + o) * a.ldn + p] = z[s];
     } else if (MODE == MODE_FWD_LIN) {
@@ -350,6 +351,8 @@ int simt_forward(const FwdArgs &a) {
   if (make_geom(a.net, &g)) return 1;
   constexpr int S = P::S;
   const int K = a.net->n_nets, act = a.net->activation;
+  const int act0 = a.net->first_activation > 0 ? a.net->first_activation - 1 : act;
+  auto act_of = [&](int l) { return l == 0 ? act0 : act; };   // activation of hidden layer l
   const int64_t layer_stride = (int64_t)S * g.Hmax * a.ldn;
   const int slots = a.keep_all ? g.L : (g.L < 2 ? g.L : 2);
   const int64_t stash_net_stride = layer_stride * slots;
@@ -362,7 +365,7 @@ int simt_forward(const FwdArgs &a) {
                         4.0 * S * g.widths[1] * (double)a.n * K);
       k_first_layer<P><<<grid, 256, 0, a.stream>>>(a.params, g.P, g.w_off[0], g.b_off[0], a.x,
                                                    g.widths[0], make_dirs(a.jet), g.widths[1], a.n,
-                                                   a.ldn, slot(0), stash_net_stride, act);
+                                                   a.ldn, slot(0), stash_net_stride, act0);
     }
     AX_LAUNCH_OK();
   }
@@ -382,7 +385,8 @@ int simt_forward(const FwdArgs &a) {
     la.Ndim = g.widths[l + 1];
     la.n = a.n;
     la.ldn = a.ldn;
-    la.act = act;
+    la.act = act_of(l - 1);
+    la.act_out = act_of(l);
     if (launch_layer<P, MODE_FWD_ACT>(la, K, a.stream)) return 1;
   }
   {
@@ -402,7 +406,7 @@ int simt_forward(const FwdArgs &a) {
     la.Ndim = g.widths[l + 1];
     la.n = a.n;
     la.ldn = a.ldn;
-    la.act = act;
+    la.act = act_of(l - 1);
     if (launch_layer<P, MODE_FWD_LIN>(la, K, a.stream)) return 1;
   }
   return 0;
@@ -464,6 +468,8 @@ int simt_backward(const BwdArgs &a) {
   if (make_geom(a.net, &g)) return 1;
   constexpr int S = P::S;
   const int K = a.net->n_nets, act = a.net->activation;
+  const int act0 = a.net->first_activation > 0 ? a.net->first_activation - 1 : act;
+  auto act_of = [&](int l) { return l == 0 ? act0 : act; };
   const int64_t layer_stride = (int64_t)S * g.Hmax * a.ldn;
   const int64_t stash_net_stride = layer_stride * g.L;
   const size_t need = simt_backward_ws_bytes(g, S, a.ldn, K);
@@ -495,7 +501,7 @@ int simt_backward(const BwdArgs &a) {
     wa.partial = partial;
     wa.n = a.n;
     wa.ldn = a.ldn;
-    wa.act = act;
+    wa.act = act_of(l > 0 ? l - 1 : 0);
     if (launch_wgrad<P>(wa, K, a.grad, g.P, g.w_off[l], a.stream)) return 1;
     if (l == 0) break;
     LayerArgs la{};
@@ -515,7 +521,7 @@ int simt_backward(const BwdArgs &a) {
     la.Ndim = Hin;
     la.n = a.n;
     la.ldn = a.ldn;
-    la.act = act;
+    la.act = act_of(l - 1);
     if (launch_layer<P, MODE_DGRAD>(la, K, a.stream)) return 1;
     zb = gbuf[cur];
     zb_net_stride = layer_stride;

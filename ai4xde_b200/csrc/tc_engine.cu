@@ -2625,6 +2625,7 @@ static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id =
 bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
   if (engine != AX_ENGINE_TF32) return false;
   if (net->activation != AX_ACT_TANH && net->activation != AX_ACT_SIGMOID) return false;
+  if (net->first_activation > 0 && net->first_activation - 1 != net->activation) return false;   // FP32 engine
   if (g.L < 2) return false;
   const int H = g.widths[1];
   if (H != 64 && H != 128 && H != 256) return false;

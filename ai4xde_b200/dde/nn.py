@@ -369,5 +369,131 @@ class PFNN(NN):
         return y
 
 
+class _FusedRowsForward(torch.autograd.Function):
+    """K structurally identical nets whose parameter rows [K, P] are ordinary differentiable tensors (built
+    from tied / sliced nn.Parameters by torch ops): one fused launch sequence evaluates all of them, the
+    outputs are SUMMED over the nets, and the kernels' flat row gradients flow back through autograd."""
+
+    @staticmethod
+    def forward(ctx, desc, rows, x_soa, n, spec, engine, need_backward):
+        rows_c = rows.detach().contiguous()
+        jets, stash = _lib.jet_forward(desc, spec.desc, rows_c, x_soa, n, keep_all=need_backward, engine=engine)
+        ctx.desc, ctx.spec, ctx.engine, ctx.n = desc, spec, engine, n
+        ctx.rows, ctx.x_soa, ctx.stash, ctx.kept = rows_c, x_soa, stash, bool(need_backward)
+        return tuple(jets[:, s, :, :n].sum(dim=0).t() for s in range(spec.S))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        if not ctx.kept:
+            raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
+        K, n, spec = ctx.rows.shape[0], ctx.n, ctx.spec
+        ldn = ctx.x_soa.shape[1]
+        c_out = ctx.desc.widths[ctx.desc.n_linear]
+        jets_bar = torch.zeros((K, spec.S, c_out, ldn), dtype=torch.float32, device=ctx.rows.device)
+        for s, g in enumerate(gouts):
+            if g is not None:
+                jets_bar[:, s, :, :n] = g.t().unsqueeze(0)
+        g_rows = _lib.jet_backward(ctx.desc, spec.desc, ctx.rows, ctx.x_soa, n, jets_bar, ctx.stash, engine=ctx.engine)
+        ctx.stash = None
+        return None, g_rows, None, None, None, None, None
+
+
+class MsFFN(NN):
+    """dde.nn.MsFFN of the fused path (reference: cases/PoissonCases.py:478-479, sigmas [1, 10]).
+
+    For every sigma the network is an ordinary MLP whose FIRST layer is the fixed Fourier embedding
+    [cos(x b), sin(x b)] = sin(W0 x + phase) with W0 = [b^T; b^T] and phase = [pi/2 ... ; 0 ...], whose hidden
+    layers are the shared `linears` and whose output layer is that sigma's column slice of `_dense` -- and the
+    MsFFN output is the SUM of those K nets.  So it runs as K nets in one fused launch sequence
+    (`n_nets = K`, `first_activation = sin`, FP32 engine); the parameter rows are assembled from the shared
+    nn.Parameters by torch ops, which routes the kernels' row gradients back to `linears` / `_dense` (the
+    embedding rows get no update: `b` are plain tensors, as in DeepXDE)."""
+
+    def __init__(self, layer_sizes, activation, kernel_initializer, sigmas, dropout_rate=0):
+        super().__init__()
+        if dropout_rate:
+            raise NotImplementedError("dropout is not in the fused path")
+        if not isinstance(activation, str):
+            raise NotImplementedError("callable activations are not in the fused path (tanh, sin, sigmoid are)")
+        if len(layer_sizes) < 4:
+            raise ValueError("MsFFN needs at least one hidden layer after the Fourier embedding")
+        self.layer_sizes = [int(w) for w in layer_sizes]
+        self.sigmas = list(sigmas)
+        self.activation_name = activation
+        half = self.layer_sizes[1] // 2
+        if 2 * half != self.layer_sizes[2 - 1]:
+            raise ValueError("layer_sizes[1] must be even (cos and sin halves of the embedding)")
+        init = _INIT[kernel_initializer]
+        self.b = [torch.normal(mean=0.0, std=float(sg), size=(self.layer_sizes[0], half)) for sg in self.sigmas]
+        self.linears = torch.nn.ModuleList()
+        for i in range(2, len(self.layer_sizes) - 1):
+            lin = torch.nn.Linear(self.layer_sizes[i - 1], self.layer_sizes[i], dtype=torch.float32)
+            init(lin.weight)
+            torch.nn.init.zeros_(lin.bias)
+            self.linears.append(lin)
+        self._dense = torch.nn.Linear(self.layer_sizes[-2] * len(self.sigmas), self.layer_sizes[-1], dtype=torch.float32)
+        init(self._dense.weight)
+        torch.nn.init.zeros_(self._dense.bias)
+        self.net_desc = _lib.make_net_desc(self.layer_sizes, activation, n_nets=len(self.sigmas), first_activation="sin")
+        self._scope = _JetScope()
+        self.to(config.device())
+
+    @contextlib.contextmanager
+    def jet_scope(self, spec=None, x_soa=None, param_grad=True, probe_streams=None):
+        prev = self._scope
+        self._scope = _JetScope(spec, x_soa, param_grad, probe_streams)
+        try:
+            yield
+        finally:
+            self._scope = prev
+
+    def _rows(self):
+        dev = self._dense.weight.device
+        K, h = len(self.sigmas), self.layer_sizes[-2]
+        half = self.layer_sizes[1] // 2
+        phase = torch.cat([torch.full((half,), torch.pi / 2), torch.zeros(half)]).to(dev)
+        shared = [t.reshape(-1) for lin in self.linears for t in (lin.weight, lin.bias)]
+        rows = []
+        for k, b in enumerate(self.b):
+            bt = b.to(device=dev, dtype=torch.float32).t()
+            w0 = torch.cat([bt, bt], dim=0).reshape(-1)                   # (2*half, d_in): cos rows, then sin rows
+            w_out = self._dense.weight[:, k * h:(k + 1) * h].reshape(-1)
+            rows.append(torch.cat([w0, phase] + shared + [w_out, self._dense.bias / K]))
+        return torch.stack(rows)
+
+    def forward(self, inputs):
+        sc = self._scope
+        x = inputs
+        featured = self._input_transform is not None
+        if featured:
+            x = self._input_transform(inputs)
+        if sc.probe_streams is not None:
+            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+        else:
+            wants_jets = x.requires_grad and torch.is_grad_enabled()
+            if not wants_jets:
+                spec = jet.JetSpec.value_only()
+            elif sc.spec is not None:
+                spec = sc.spec
+            else:
+                spec = jet.JetSpec.full(x.shape[1])
+            if featured or sc.x_soa is None or sc.x_soa.shape[1] < x.shape[0]:
+                x_soa = jet.to_soa(x.detach().to(torch.float32))
+            else:
+                x_soa = sc.x_soa
+            rows = self._rows()
+            need_bwd = bool(sc.param_grad and torch.is_grad_enabled() and rows.requires_grad)
+            streams = _FusedRowsForward.apply(self.net_desc, rows, x_soa, x.shape[0], spec, config.engine(), need_bwd)
+            if wants_jets:
+                y = jet.make_leaf(x, spec, streams)
+                grad.register(y, jet.JetOutput(x, spec, streams))
+            else:
+                y = streams[0]
+        if self._output_transform is not None:
+            y = self._output_transform(inputs, y)
+        return y
+
+
 def get_supported_activations():
     return sorted(_lib.ACT)

@@ -46,6 +46,10 @@ typedef struct ax_net_desc {
   int32_t widths[AX_MAX_LINEAR + 1]; /* widths[0]=d_in ... widths[n_linear]=d_out */
   int32_t activation;                /* AX_ACT_* */
   int32_t n_nets;                    /* K nets evaluated on the same points (FBPINN) */
+  int32_t first_activation;          /* 0: the first hidden layer uses `activation` too; AX_ACT_x + 1: it uses
+                                        AX_ACT_x (Fourier-feature first layers of dde.nn.MsFFN,
+                                        cases/PoissonCases.py:478-479: sin(x B + phase), then tanh layers).
+                                        FP32 engine only. */
 } ax_net_desc;
 
 /* which derivatives the case's pde()/BCs ask of dde.grad.jacobian / hessian */

@@ -161,3 +161,49 @@ class PFNN(NN):
         if self._output_transform is not None:
             x = self._output_transform(inputs, x)
         return x
+
+
+
+class MsFFN(NN):
+    """Multi-scale Fourier feature network [DeepXDE-upstream `deepxde.nn.pytorch.MsFFN`], restated: for each
+    sigma a FIXED random matrix b ~ N(0, sigma^2) of shape (d_in, layer_sizes[1] // 2) embeds the input as
+    [cos(x b), sin(x b)]; every embedding runs through the SAME hidden Linear + activation stack
+    (`linears`, sizes layer_sizes[2:-1]); the results are concatenated and mapped by `_dense`.  The `b` are
+    plain tensors (not parameters, not in the state dict), as upstream.  Constructed by the reference at
+    /root/reference/AI4XDE/cases/PoissonCases.py:478-479 with sigmas [1, 10]."""
+
+    def __init__(self, layer_sizes, activation, kernel_initializer, sigmas, dropout_rate=0):
+        super().__init__()
+        self.activation = get_activation(activation)
+        self.dropout_rate = dropout_rate
+        self.sigmas = list(sigmas)
+        initializer = get_initializer(kernel_initializer)
+        initializer_zero = get_initializer("zeros")
+        self.b = [torch.normal(mean=0.0, std=float(sigma), size=(layer_sizes[0], layer_sizes[1] // 2)).to(config.real(torch))
+                  for sigma in self.sigmas]
+        self.linears = torch.nn.ModuleList()
+        for i in range(2, len(layer_sizes) - 1):
+            self.linears.append(torch.nn.Linear(layer_sizes[i - 1], layer_sizes[i], dtype=config.real(torch)))
+            initializer(self.linears[-1].weight)
+            initializer_zero(self.linears[-1].bias)
+        self._dense = torch.nn.Linear(layer_sizes[-2] * len(self.sigmas), layer_sizes[-1], dtype=config.real(torch))
+        initializer(self._dense.weight)
+        initializer_zero(self._dense.bias)
+
+    def forward(self, inputs):
+        x = inputs
+        if self._input_transform is not None:
+            x = self._input_transform(x)
+        ys = []
+        for b in self.b:
+            xb = torch.matmul(x, b.to(x.dtype))
+            y = torch.cat([torch.cos(xb), torch.sin(xb)], dim=1)
+            for linear in self.linears:
+                y = self.activation(linear(y))
+                if self.dropout_rate > 0:
+                    y = torch.nn.functional.dropout(y, p=self.dropout_rate, training=self.training)
+            ys.append(y)
+        y = self._dense(torch.cat(ys, dim=1))
+        if self._output_transform is not None:
+            y = self._output_transform(inputs, y)
+        return y

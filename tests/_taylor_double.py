@@ -48,8 +48,9 @@ def taylor_streams(net, jet, flat, x):
     z = [x @ W.t() + b]
     z += [W[:, d].unsqueeze(0).expand(x.shape[0], -1) for d in dirs]
     z += [torch.zeros_like(z[0]) for _ in pairs]
-    for W, b in layers[1:]:
-        a, s1, s2 = _act(net.activation, z[0])
+    first = getattr(net, "first_activation", 0)
+    for li, (W, b) in enumerate(layers[1:]):
+        a, s1, s2 = _act(first - 1 if (li == 0 and first > 0) else net.activation, z[0])
         A = [a] + [s1 * z[1 + j] for j in range(n1)]
         for q, (pa, pb) in enumerate(pairs):
             if pa == 15 and pb == 15:      # Laplacian stream over all first-order streams

@@ -130,3 +130,49 @@ def test_pfnn_sub_networks_ride_one_fused_launch_sequence():
                 assert rel(g[k], t) < 5e-5, k
     finally:
         dde.config.set_engine("auto")
+
+
+def test_msffn_runs_as_fourier_first_layer_nets():
+    """dde.nn.MsFFN([1, 64, 64, 64, 1], sigmas [1, 10]) (reference: cases/PoissonCases.py:478-479) on the
+    kernels' `first_activation = sin` path: residual u'' - f and parameter gradients against the float64
+    oracle restatement of DeepXDE's MsFFN with the same embeddings and weights."""
+    import ai4xde_b200.dde as dde
+    from oracle import ddelite
+
+    dde.config.set_default_float("float32")
+    dde.config.set_engine("auto")
+    torch.manual_seed(11)
+    net = dde.nn.MsFFN([1, 64, 64, 64, 1], "tanh", "Glorot uniform", sigmas=[1, 10])
+    x = torch.rand((3000, 1)).to("cuda").requires_grad_()
+    y = net(x)
+    u_xx = dde.grad.hessian(y, x)
+    u_x = dde.grad.jacobian(y, x)
+    r = u_xx + 0.5 * u_x - torch.sin(6.0 * x)
+    dde.grad.clear()
+    loss = (r ** 2).mean()
+    net.zero_grad()
+    loss.backward()
+    g = {k: p.grad.double().cpu() for k, p in net.named_parameters()}
+
+    ddelite.config.set_default_float("float64")
+    try:
+        ref = ddelite.nn.MsFFN([1, 64, 64, 64, 1], "tanh", "Glorot uniform", sigmas=[1, 10])
+        ref.load_state_dict({k: v.detach().double().cpu() for k, v in net.state_dict().items()})
+        ref.b = [b.detach().double().cpu() for b in net.b]
+        xr = x.detach().double().cpu().requires_grad_()
+        yr = ref(xr)
+        d1 = torch.autograd.grad(yr.sum(), xr, create_graph=True)[0]
+        d2 = torch.autograd.grad(d1.sum(), xr, create_graph=True)[0]
+        rr = d2 + 0.5 * d1 - torch.sin(6.0 * xr)
+        lr = (rr ** 2).mean()
+        names = [k for k, _ in ref.named_parameters()]
+        gr = torch.autograd.grad(lr, [p for _, p in ref.named_parameters()], allow_unused=True)
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert rel(y.detach().double().cpu(), yr.detach()) < 1e-5
+    assert rel(r.detach().double().cpu(), rr.detach()) < 5e-5     # second derivatives scale with sigma^2 = 100
+    for k, t in zip(names, gr):
+        if t is not None and float(t.abs().max()) > 0:
+            assert rel(g[k], t) < 1e-4, k
