@@ -82,6 +82,11 @@ _SIGNATURES = {
         [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P],
     ),
     "ax_gather_points": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
+    "ax_lbfgs_ws_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "ax_lbfgs_iterate": (
+        C.c_int,
+        [_P, _P, _P, C.c_int64, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, _P],
+    ),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
 }
 
@@ -328,6 +333,19 @@ def r3_retain_thr(res_sum, thr, x_soa, n, place_at_end=True):
                               int(bool(place_at_end)), _ptr(n_keep), _ptr(ws), wsb, _stream())
     _check(rc, "ax_r3_retain_thr")
     return x_out, n_keep
+
+
+def lbfgs_ws_floats(n_params, history):
+    return int(load().ax_lbfgs_ws_floats(int(n_params), int(history)))
+
+
+def lbfgs_iterate(x, g, loss, ws, state, history, lr, tol_grad, tol_change, begin_step):
+    """One device-resident L-BFGS iteration on the flat parameter vector (csrc/lbfgs.cu)."""
+    lib = load()
+    _need_cuda(x, g, loss, ws, state)
+    rc = lib.ax_lbfgs_iterate(_ptr(x), _ptr(g), _ptr(loss), x.numel(), _ptr(ws), _ptr(state), int(history),
+                              float(lr), float(tol_grad), float(tol_change), int(begin_step), _stream())
+    _check(rc, "ax_lbfgs_iterate")
 
 
 def debug_tc_wgrad(zbar, a):

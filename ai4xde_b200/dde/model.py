@@ -311,6 +311,10 @@ class Model:
 
             if self._graphed_step(inputs, targets, auxiliary_vars, closure):
                 return
+            if targets is None and auxiliary_vars is None and hasattr(inputs, "__len__"):
+                # lets DeviceLBFGS decide whether its per-iteration sequence may be replayed from a CUDA graph
+                closure.graph_rows = len(inputs)
+                closure.graph_key = (id(inputs), getattr(self.data, "version", None), id(self.data.pde))
             self.opt.step(closure)
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()

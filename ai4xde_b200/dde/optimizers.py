@@ -31,11 +31,16 @@ def get(params, optimizer, learning_rate=None, decay=None, weight_decay=0):
     elif is_external_optimizer(optimizer):
         if weight_decay > 0:
             raise ValueError("L-BFGS optimizer doesn't support weight_decay > 0")
-        optim = torch.optim.LBFGS(
-            params, lr=1, max_iter=LBFGS_options["iter_per_step"], max_eval=LBFGS_options["fun_per_step"],
-            tolerance_grad=LBFGS_options["gtol"], tolerance_change=LBFGS_options["ftol"],
-            history_size=LBFGS_options["maxcor"], line_search_fn=None,
-        )
+        kw = dict(lr=1, max_iter=LBFGS_options["iter_per_step"], max_eval=LBFGS_options["fun_per_step"],
+                  tolerance_grad=LBFGS_options["gtol"], tolerance_change=LBFGS_options["ftol"],
+                  history_size=LBFGS_options["maxcor"])
+        params = list(params)
+        if params and all(p.is_cuda for p in params):
+            from .lbfgs import DeviceLBFGS     # one kernel launch per iteration, no per-iteration host sync
+
+            optim = DeviceLBFGS(params, **kw)
+        else:                                  # host-logic tests on CPU tensors (the kernels are doubled there)
+            optim = torch.optim.LBFGS(params, line_search_fn=None, **kw)
     else:
         if learning_rate is None:
             raise ValueError("No learning rate for {}.".format(optimizer))

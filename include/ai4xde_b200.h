@@ -158,6 +158,34 @@ int ax_r3_retain_thr(const float *res_sum, const float *thr, const float *x_soa,
                      int64_t ldn, float *x_out, int64_t ldn_out, int32_t place_at_end,
                      int64_t *n_keep_out, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- device-resident L-BFGS (the second phase of every train_step, solver/PDESolver.py:79-85) ------ */
+
+/* 48-byte state block living in device memory; zero it to start a fresh optimisation */
+typedef struct ax_lbfgs_state {
+  int32_t n_iter;        /* iterations performed since the state was zeroed */
+  int32_t hist_count;    /* curvature pairs in the history ring (<= history) */
+  int32_t hist_head;     /* ring slot of the next pair */
+  int32_t done;          /* 1: a stopping test fired in the current step() call; later launches are no-ops */
+  int32_t func_evals;    /* evaluations consumed */
+  int32_t step_iter;     /* iterations within the current step() call */
+  float H_diag, t, prev_loss, pending_dt_max;
+  int32_t reserved[2];
+} ax_lbfgs_state;
+
+/* floats of workspace: previous gradient, direction, history ring (2 * history vectors), rho, alpha */
+size_t ax_lbfgs_ws_floats(int64_t n_params, int32_t history);
+
+/*
+ * One L-BFGS iteration in one launch, on the flat parameter vector x[n_params] given the loss (device
+ * scalar) and gradient g just evaluated AT x: stopping tests, curvature-pair update, two-loop recursion,
+ * step length and x += t d -- torch.optim.LBFGS(lr, history_size, tolerance_grad, tolerance_change,
+ * line_search_fn=None).step, statement by statement (csrc/lbfgs.cu).  begin_step != 0 marks the first
+ * evaluation of a step() call (clears `done`).  Nothing is read back by the host.
+ */
+int ax_lbfgs_iterate(float *x, const float *g, const float *loss, int64_t n_params, float *ws,
+                     ax_lbfgs_state *state, int32_t history, float lr, float tol_grad, float tol_change,
+                     int32_t begin_step, void *stream);
+
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
                      float *x_out, int64_t ldn_out, void *stream);

@@ -1,0 +1,92 @@
+"""Device-resident L-BFGS (csrc/lbfgs.cu, dde/lbfgs.py) against torch.optim.LBFGS -- the optimiser DeepXDE's
+PyTorch backend builds for the second phase of every AI4XDE train_step (solver/PDESolver.py:79-85)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(seed, n=96, d=40):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn((n, d), generator=g).cuda()
+    y = torch.randn((n,), generator=g).cuda()
+    w0 = (torch.randn((d,), generator=g) * 0.3).cuda()
+
+    def make():
+        w1 = torch.nn.Parameter(w0[: d // 2].clone())
+        w2 = torch.nn.Parameter(w0[d // 2:].clone())
+
+        def closure():
+            for p in (w1, w2):
+                p.grad = None
+            w = torch.cat([w1, w2])
+            r = torch.tanh(A @ w) - 0.5 * y           # non-quadratic, smooth
+            loss = (r ** 2).mean() + 1e-3 * (w ** 2).sum()
+            loss.backward()
+            return loss
+
+        return [w1, w2], closure
+
+    return make
+
+
+@pytest.mark.parametrize("history", [5, 100])
+def test_device_lbfgs_follows_torch_lbfgs(history):
+    from ai4xde_b200.dde.lbfgs import DeviceLBFGS
+
+    make = _problem(0)
+    pa, ca = make()
+    pb, cb = make()
+    kw = dict(lr=1, max_iter=30, max_eval=1000, tolerance_grad=1e-12, tolerance_change=0, history_size=history)
+    ref = torch.optim.LBFGS(pa, line_search_fn=None, **kw)
+    dev = DeviceLBFGS(pb, sync_every=7, **kw)
+    ref.step(ca)
+    dev.step(cb)
+    wa, wb = torch.cat([p.detach() for p in pa]), torch.cat([p.detach() for p in pb])
+    assert ref.state_dict()["state"][0]["n_iter"] == dev.state_dict()["state"][0]["n_iter"] == 30
+    assert float((wa - wb).abs().max() / wa.abs().max()) < 2e-3      # float32 reductions in a different order
+    la, lb = float(ca()), float(cb())
+    assert abs(la - lb) / la < 1e-3
+    # a second call continues from the kept history (state persists across step() calls, as in torch)
+    ref.step(ca)
+    dev.step(cb)
+    assert ref.state_dict()["state"][0]["n_iter"] == dev.state_dict()["state"][0]["n_iter"] == 60
+    assert abs(float(ca()) - float(cb())) / float(ca()) < 1e-3
+
+
+def test_device_lbfgs_stops_on_gradient_tolerance():
+    from ai4xde_b200.dde.lbfgs import DeviceLBFGS
+
+    make = _problem(1)
+    pb, cb = make()
+    dev = DeviceLBFGS(pb, lr=1, max_iter=2000, max_eval=2500, tolerance_grad=1e-5, tolerance_change=0,
+                      history_size=50, sync_every=10)
+    dev.step(cb)
+    n1 = dev.state_dict()["state"][0]["n_iter"]
+    assert 3 < n1 < 2000                                              # converged well before max_iter
+    cb()
+    assert float(torch.cat([p.grad.reshape(-1) for p in pb]).abs().max()) <= 1e-5 * 1.01
+    dev.step(cb)                                                      # already converged: no further iteration
+    assert dev.state_dict()["state"][0]["n_iter"] == n1
+
+
+def test_solver_lbfgs_phase_runs_on_the_device_optimiser():
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases, solver
+    from ai4xde_b200.dde.lbfgs import DeviceLBFGS
+
+    dde.config.set_default_float("float64")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    dde.optimizers.set_LBFGS_options(maxiter=300)
+    try:
+        case = cases.Burgers(NumDomain=1000, layer_size=[2] + [20] * 3 + [1])
+        s = solver.PINNSolver("pinn", case)
+        s.train_step(lr=1e-3, iterations=300)
+        assert isinstance(s.model.opt, DeviceLBFGS)
+        lh = np.array(s.losshistory.loss_train).sum(1)
+        assert s.model.train_state.step > 300 + 50                    # the L-BFGS phase really iterated
+        assert lh[-1] < lh[1]                                         # and kept reducing the loss
+    finally:
+        dde.optimizers.set_LBFGS_options()
