@@ -145,6 +145,16 @@ def main():
     print("sampling", {k: v.shape for k, v in sel.items()})
 
 
+def burgers_solution_subset():
+    """A 64 x 50 subset of the reference's own Burgers solution (/root/reference/AI4XDE/data/Burgers.npz, the
+    file `Burgers.gen_testdata` loads at cases/PDECases.py:1096-1101): the end-of-training known answer of
+    tests/test_gpu_algorithms.py::test_end_to_end_training_reaches_the_reference_solutions."""
+    d = np.load(os.path.join(ref_import.REFERENCE_ROOT, "AI4XDE", "data", "Burgers.npz"))
+    np.savez_compressed(os.path.join(OUT, "burgers_usol_subset.npz"), x=d["x"][::4], t=d["t"][::2],
+                        usol=d["usol"][::4, ::2])
+
+
 if __name__ == "__main__":
     rng2 = np.random.RandomState(1)
     main()
+    burgers_solution_subset()
