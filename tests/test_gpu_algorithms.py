@@ -198,6 +198,9 @@ def _oracle_curve(cfg, n, dtype, X=None, state=None, iters=1000):
         torch.set_default_dtype(torch.float32)
 
 
+_ORACLE_CURVES = {}
+
+
 @pytest.mark.parametrize("cfg,n,engine,tol,smooth_until,late_tol", [
     ("cfg1", 2540, "fp32", 1e-2, 1000, 0.6), ("cfg2", 3000, "fp32", 1e-2, 200, 0.6),
     ("cfg2", 3000, "tf32", 5e-2, 200, 0.6),
@@ -218,9 +221,12 @@ def test_loss_curve_over_1k_steps(cfg, n, engine, tol, smooth_until, late_tol):
     dde = _setup()
     from parity_util import build_product
 
-    odata, onet, ref, steps = _oracle_curve(cfg, n, "float64")
-    state = {k: v.detach().clone() for k, v in onet.state_dict().items()}
-    _, _, ref32, _ = _oracle_curve(cfg, n, "float32", X=odata.train_x_all.copy(), state=state)
+    if (cfg, n) not in _ORACLE_CURVES:      # the CPU oracle runs once per (config, size); engines share it
+        odata, onet, ref, steps = _oracle_curve(cfg, n, "float64")
+        state = {k: v.detach().clone() for k, v in onet.state_dict().items()}
+        _, _, ref32, _ = _oracle_curve(cfg, n, "float32", X=odata.train_x_all.copy(), state=state)
+        _ORACLE_CURVES[(cfg, n)] = (odata, onet, ref, steps, ref32)
+    odata, onet, ref, steps, ref32 = _ORACLE_CURVES[(cfg, n)]
     case = build_product(cfg, odata, onet)
     dde.config.set_engine(engine)
     try:
@@ -267,7 +273,11 @@ def test_end_to_end_training_reaches_the_reference_solutions():
     torch.manual_seed(0)
     case = cases.Helmholtz()
     s = solver.PINNSolver("pinn", case)
-    s.train_step(lr=1e-3, iterations=5000)
+    dde.optimizers.set_LBFGS_options(maxiter=3000)       # 15 000 by default: 0.11 % then; bounded here for time
+    try:
+        s.train_step(lr=1e-3, iterations=5000)
+    finally:
+        dde.optimizers.set_LBFGS_options()
     X, y = case.get_testdata()
     err = dde.metrics.l2_relative_error(y, s.model.predict(X))
     print("Helmholtz (reference-default sin net) L2 relative error", err)
