@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 def _problem(seed, n=96, d=40):
     g = torch.Generator().manual_seed(seed)
-    A = torch.randn((n, d), generator=g).cuda()
+    A = (torch.randn((n, d), generator=g) * (40.0 / d) ** 0.5).cuda()     # A w stays O(1) for every d
     y = torch.randn((n,), generator=g).cuda()
     w0 = (torch.randn((d,), generator=g) * 0.3).cuda()
 
@@ -31,11 +31,14 @@ def _problem(seed, n=96, d=40):
     return make
 
 
-@pytest.mark.parametrize("history", [5, 100])
-def test_device_lbfgs_follows_torch_lbfgs(history):
+@pytest.mark.parametrize("history,d", [(5, 40), (100, 40)])
+def test_device_lbfgs_follows_torch_lbfgs(history, d):
+    """Whole trajectories against torch.optim.LBFGS on a small well-conditioned problem (iterates of the
+    no-line-search method drift apart chaotically on ill-conditioned ones, torch against torch included; the
+    per-launch arithmetic of both kernels is pinned by test_lbfgs_iteration_kernel_matches_two_loop_reference)."""
     from ai4xde_b200.dde.lbfgs import DeviceLBFGS
 
-    make = _problem(0)
+    make = _problem(0, d=d)
     pa, ca = make()
     pb, cb = make()
     kw = dict(lr=1, max_iter=30, max_eval=1000, tolerance_grad=1e-12, tolerance_change=0, history_size=history)
@@ -93,3 +96,54 @@ def test_solver_lbfgs_phase_runs_on_the_device_optimiser():
         assert np.isfinite(lh).all() and lh[-1] < 0.5 * lh[0]
     finally:
         dde.optimizers.set_LBFGS_options()
+
+
+@pytest.mark.parametrize("P,m", [(100, 6), (5000, 100), (50000, 6), (200001, 20)])
+def test_lbfgs_iteration_kernel_matches_two_loop_reference(P, m):
+    """ax_lbfgs_iterate (single-CTA kernel below 32 768 parameters, cooperative-grid kernel above) against a
+    float64 transcription of torch.optim.LBFGS's update on a prescribed sequence of (loss, gradient) inputs:
+    the iterates must agree after every launch."""
+    from ai4xde_b200 import _lib
+
+    gen = torch.Generator().manual_seed(5)
+    x = torch.zeros(P, device="cuda")
+    ws = torch.zeros(_lib.lbfgs_ws_floats(P, m), device="cuda")
+    st = torch.zeros(12, dtype=torch.int32, device="cuda")
+    xr = torch.zeros(P, dtype=torch.float64)
+    old_dirs, old_stps, ro = [], [], []
+    d = t = prev_g = H = None
+    for it in range(3 * m // 2 + 4):
+        # gradients correlated with the iterate so that y.s > 0 most of the time (as on a convex problem)
+        g64 = 0.5 * xr + 0.05 * torch.randn(P, generator=gen, dtype=torch.float64) + 0.3
+        g = g64.float().cuda()
+        g64 = g.double().cpu()
+        loss = torch.tensor([1.0 / (1 + it)], device="cuda")
+        _lib.lbfgs_iterate(x, g, loss, ws, st, m, 1.0, 0.0, 0.0, 1 if it == 0 else 0)
+        # reference (torch.optim.LBFGS.step body, no line search)
+        if it == 0:
+            d, H = -g64, 1.0
+        else:
+            y, s = g64 - prev_g, step_taken        # the step the DEVICE took: histories stay in sync
+            ys = float(y.dot(s))
+            if ys > 1e-10:
+                if len(old_dirs) == m:
+                    old_dirs.pop(0); old_stps.pop(0); ro.pop(0)
+                old_dirs.append(y); old_stps.append(s); ro.append(1.0 / ys)
+                H = ys / float(y.dot(y))
+            q = -g64.clone()
+            al = [0.0] * len(old_dirs)
+            for i in range(len(old_dirs) - 1, -1, -1):
+                al[i] = float(old_stps[i].dot(q)) * ro[i]
+                q.add_(old_dirs[i], alpha=-al[i])
+            d = q * H
+            for i in range(len(old_dirs)):
+                be = float(old_dirs[i].dot(d)) * ro[i]
+                d.add_(old_stps[i], alpha=al[i] - be)
+        prev_g = g64.clone()
+        t = min(1.0, 1.0 / float(g64.abs().sum())) if it == 0 else 1.0
+        x_new = x.double().cpu()
+        step_taken = x_new - xr
+        err = float((step_taken - t * d).abs().max() / (t * d).abs().max().clamp_min(1e-30))
+        assert err < 5e-3, (it, err)
+        xr = x_new                     # follow the device iterate: the check is per launch, not of accumulated drift
+    assert int(st[0]) == 3 * m // 2 + 4 and int(st[1]) == min(m, 3 * m // 2 + 3)
