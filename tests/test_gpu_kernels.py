@@ -43,6 +43,10 @@ CASES = [
     ([2, 256, 256, 256, 1], "tanh", "2t", 515, 1),
     ([2, 150, 150, 1], "sin", "2t", 300, 1),
     ([3, 40, 40, 2], "sigmoid", "3t", 65, 2),
+    # large point sets (many point tiles per output block, ragged tails)
+    ([2, 150, 150, 150, 1], "sin", "2t", 40001, 1),
+    ([2, 64, 64, 3], "tanh", "2a", 38000, 2),
+    ([1, 48, 48, 1], "sigmoid", "1d", 50003, 1),
 ]
 
 
