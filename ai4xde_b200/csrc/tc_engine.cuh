@@ -1,4 +1,4 @@
-// tc_engine.cuh -- tcgen05 (TF32) engine entry points; see tc_engine.cu.
+// tc_engine.cuh -- tcgen05 (TF32) engine entry points; see tc_fwd.cu / tc_bwd.cu (shared device code: tc_common.cuh).
 #pragma once
 #include "common.cuh"
 
