@@ -265,6 +265,85 @@ class Disk(Geometry):
         return (self.radius * np.hstack([np.cos(theta), np.sin(theta)]) + self.center).astype(_real())
 
 
+class Polygon(Geometry):
+    """Simple polygon given by its vertices in order (either orientation; stored clockwise as DeepXDE does) --
+    `dde.geometry.Polygon([[0, 0], [1, 0], [1, -1], [-1, -1], [-1, 1], [0, 1]])` is the L-shaped domain of
+    /root/reference/AI4XDE/cases/PoissonCases.py:515-516.  `inside` is the winding-number test, `on_boundary`
+    the closed-segment test |x - v_i| + |x - v_{i+1}| = |v_{i+1} - v_i| (np.isclose), `boundary_normal` the
+    outward unit normal of the segment a point lies on; points come from rejection sampling in the bounding
+    box (interior) and from arc-length sampling of the perimeter (boundary)."""
+
+    dim = 2
+
+    def __init__(self, vertices):
+        v = np.array(vertices, dtype=_real())
+        if v.ndim != 2 or v.shape[1] != 2 or len(v) < 3:
+            raise ValueError("Polygon needs an (n >= 3, 2) array of vertices")
+        if len(v) == 3:
+            raise ValueError("The polygon is a triangle. Use Triangle instead.")
+        area2 = float(np.sum(v[:, 0] * np.roll(v[:, 1], -1) - np.roll(v[:, 0], -1) * v[:, 1]))
+        if area2 > 0:                                  # counter-clockwise input -> store clockwise
+            v = np.flipud(v)
+        self.area = abs(area2) / 2
+        self.vertices = v
+        self.nvertices = len(v)
+        self.bbox = (np.min(v, axis=0), np.max(v, axis=0))
+        self.diam = float(max(np.linalg.norm(a - b) for a in v for b in v))
+        self.segments = np.roll(v, -1, axis=0) - v     # segment i: v_i -> v_{i+1}
+        self.lengths = np.linalg.norm(self.segments, axis=1)
+        self.perimeter = float(self.lengths.sum())
+        # clockwise orientation: the outward normal is the segment direction rotated by +90 degrees
+        n = np.stack([-self.segments[:, 1], self.segments[:, 0]], axis=1)
+        self.normal = n / np.linalg.norm(n, axis=1, keepdims=True)
+
+    def inside(self, x):
+        x = np.atleast_2d(x)
+        a, b = self.vertices, np.roll(self.vertices, -1, axis=0)
+        wn = np.zeros(len(x), dtype=int)
+        for p, q in zip(a, b):
+            left = (q[0] - p[0]) * (x[:, 1] - p[1]) - (x[:, 0] - p[0]) * (q[1] - p[1])
+            up = (p[1] <= x[:, 1]) & (q[1] > x[:, 1]) & (left > 0)
+            down = (p[1] > x[:, 1]) & (q[1] <= x[:, 1]) & (left < 0)
+            wn += up.astype(int) - down.astype(int)
+        return (wn != 0) | self.on_boundary(x)
+
+    def _segment_mask(self, x):
+        x = np.atleast_2d(x)
+        a, b = self.vertices, np.roll(self.vertices, -1, axis=0)
+        l1 = np.linalg.norm(x[:, None, :] - a[None], axis=-1)
+        l2 = np.linalg.norm(x[:, None, :] - b[None], axis=-1)
+        return np.isclose(l1 + l2, self.lengths[None])
+
+    def on_boundary(self, x):
+        return self._segment_mask(x).any(axis=1)
+
+    def boundary_normal(self, x):
+        m = self._segment_mask(x)
+        first = np.argmax(m, axis=1)                   # a corner takes the normal of its first segment
+        return (self.normal[first] * m.any(axis=1, keepdims=True)).astype(_real())
+
+    def random_points(self, n, random="pseudo"):
+        out = np.empty((0, 2), dtype=_real())
+        lo, hi = self.bbox
+        while len(out) < n:
+            cand = sample(n, 2, "pseudo" if len(out) else random) * (hi - lo) + lo
+            cand = cand[self.inside(cand) & ~self.on_boundary(cand)]
+            out = np.vstack((out, cand.astype(_real())))
+        return out[:n]
+
+    def _at_arclength(self, s):
+        edges = np.concatenate(([0.0], np.cumsum(self.lengths)))
+        i = np.clip(np.searchsorted(edges, s, side="right") - 1, 0, self.nvertices - 1)
+        t = (s - edges[i]) / self.lengths[i]
+        return (self.vertices[i] + t[:, None] * self.segments[i]).astype(_real())
+
+    def uniform_boundary_points(self, n):
+        return self._at_arclength(np.linspace(0, self.perimeter, num=n, endpoint=False))
+
+    def random_boundary_points(self, n, random="pseudo"):
+        return self._at_arclength(np.ravel(sample(n, 1, random)) * self.perimeter)
+
+
 class CSGDifference(Geometry):
     """geom1 - geom2 (e.g. rectangle minus disk, /root/reference/AI4XDE/cases/PDECases.py:679)."""
 
