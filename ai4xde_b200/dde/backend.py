@@ -46,6 +46,8 @@ def as_tensor(data, dtype=None):
 
 
 def from_numpy(a):
+    if isinstance(a, _torch.Tensor):      # DeepXDE's is torch.as_tensor: a tensor passes through, graph intact
+        return a                          # (the reference's IDE cases call it on the network output)
     t = _torch.as_tensor(np.asarray(a))
     if t.is_floating_point():
         t = t.to(config.real(_torch))

@@ -158,6 +158,94 @@ class PDE(Data):
         return np.vstack((self.train_x_bc, x))
 
 
+class IDE(PDE):
+    """dde.data.IDE: integro-differential equations by Gauss-Legendre quadrature (reference call sites:
+    /root/reference/AI4XDE/cases/PDECases.py:2015-2025 and :2068-2085).  Every collocation point x brings
+    `quad_deg` quadrature nodes (quad_x + 1) x / 2 of int_0^x; the batch is
+    `train_x = [BC rows ; train_x_all ; quadrature nodes]`, and `pde(x, y, int_mat)` receives the
+    (n_bc + n_f) x n_rows matrix whose row i holds `w_q x_i / 2 * kernel(x_i, node)` at that point's nodes, so
+    `int_mat @ y` is the integral at every collocation point.  The network is evaluated once on the whole
+    batch by the fused kernels; `dde.grad.jacobian` reads its first-order stream."""
+
+    def __init__(self, geometry, ide, bcs, quad_deg, kernel=None, num_domain=0, num_boundary=0,
+                 train_distribution="Hammersley", anchors=None, solution=None, num_test=None):
+        self.kernel = kernel if kernel is not None else (lambda x, s: np.ones((len(x), 1)))
+        self.quad_deg = quad_deg
+        qx, qw = np.polynomial.legendre.leggauss(quad_deg)
+        self.quad_x, self.quad_w = qx.astype(config.real(np)), qw.astype(config.real(np))
+        self._int_cache = {}
+        super().__init__(geometry, ide, bcs, num_domain, num_boundary, train_distribution=train_distribution,
+                         anchors=anchors, solution=solution, num_test=num_test)
+
+    def quad_points(self, X):
+        return np.hstack([(self.quad_x + 1) * xi[0] / 2 for xi in X])[:, None].astype(config.real(np))
+
+    def _assemble(self):
+        bc_rows = self.bc_points()
+        self.train_x = np.vstack((bc_rows, self.train_x_all, self.quad_points(self.train_x_all)))
+        self._int_cache = {}
+        self._refresh_targets()
+
+    def train_next_batch(self, batch_size=None):
+        if self.train_x is None and self.train_y is None and self.train_aux_vars is None:
+            self.train_x_all = self.train_points()
+            self._assemble()
+        return self.train_x, self.train_y, self.train_aux_vars
+
+    def test(self):
+        if self.test_x is None and self.test_y is None and self.test_aux_vars is None:
+            x = self.train_x_all if self.num_test is None else self.geom.uniform_points(self.num_test, True)
+            self._n_test_f = len(x)
+            self.test_x = np.vstack((x, self.quad_points(x)))
+            self.test_y = self.soln(self.test_x) if self.soln else None
+        return self.test_x, self.test_y, self.test_aux_vars
+
+    def get_int_matrix(self, training):
+        hit = self._int_cache.get(bool(training))
+        if hit is not None:
+            return hit
+        if training:
+            n_bc, X, n_f = int(sum(self.num_bcs)), self.train_x, len(self.train_x_all)
+        else:
+            n_bc, X, n_f = 0, self.test_x, self._n_test_f
+        mat = np.zeros((n_bc + n_f, X.size), dtype=config.real(np))
+        for i in range(n_f):
+            x = X[i + n_bc, 0]
+            beg = n_f + n_bc + self.quad_deg * i
+            end = beg + self.quad_deg
+            K = np.ravel(self.kernel(np.full((self.quad_deg, 1), x), X[beg:end]))
+            mat[i + n_bc, beg:end] = self.quad_w * x / 2 * K
+        self._int_cache[bool(training)] = mat
+        return mat
+
+    def _residual_losses(self, training, outputs, loss_fn, inputs, n_bc):
+        f = self.pde(inputs, outputs, self.get_int_matrix(training))
+        f = list(f) if isinstance(f, (list, tuple)) else [f]
+        if not isinstance(loss_fn, (list, tuple)):
+            loss_fn = [loss_fn] * (len(f) + len(self.bcs))
+        out = []
+        for i, fi in enumerate(f):
+            err = fi[n_bc:]
+            out.append(loss_fn[i](torch.zeros_like(err), err))
+        return out, loss_fn, len(f)
+
+    def losses_train(self, targets, outputs, loss_fn, inputs, model, aux=None):
+        starts = [0]
+        for c in self.num_bcs:
+            starts.append(starts[-1] + int(c))
+        out, loss_fn, nf = self._residual_losses(True, outputs, loss_fn, inputs, starts[-1])
+        for i, bc in enumerate(self.bcs):
+            err = bc.error(self.train_x, inputs, outputs, starts[i], starts[i + 1])
+            out.append(loss_fn[nf + i](torch.zeros_like(err), err))
+        return out
+
+    def losses_test(self, targets, outputs, loss_fn, inputs, model, aux=None):
+        out, _, _ = self._residual_losses(False, outputs, loss_fn, inputs, 0)
+        return out + [torch.zeros((), dtype=out[0].dtype, device=out[0].device) for _ in self.bcs]
+
+    losses = losses_train
+
+
 class TimePDE(PDE):
     def __init__(self, geometryxtime, pde, ic_bcs, num_domain=0, num_boundary=0, num_initial=0,
                  train_distribution="Hammersley", anchors=None, exclusions=None, solution=None,

@@ -179,6 +179,88 @@ class PDE(Data):
         return x
 
 
+class IDE(PDE):
+    """Integro-differential equation data [DeepXDE-upstream `deepxde.data.IDE`], restated: Gauss-Legendre nodes
+    (quad_x + 1) x / 2 of int_0^x for every collocation point are appended to the batch,
+    train_x = [bc points ; train_x_all ; quadrature points], and the residual function receives `int_mat`
+    with int_mat[i + n_bc, nodes of point i] = quad_w x_i / 2 * kernel(x_i, node).  Pinned in
+    tests/test_oracle_pins.py by int_0^x sin(2 pi t) dt and by the analytic solutions of the two reference
+    cases (cases/PDECases.py:1977-2092)."""
+
+    def __init__(self, geometry, ide, bcs, quad_deg, kernel=None, num_domain=0, num_boundary=0,
+                 train_distribution="Hammersley", anchors=None, solution=None, num_test=None):
+        self.kernel = kernel if kernel is not None else (lambda x, s: np.ones((len(x), 1)))
+        self.quad_deg = quad_deg
+        self.quad_x, self.quad_w = np.polynomial.legendre.leggauss(quad_deg)
+        self.quad_x = self.quad_x.astype(config.real(np))
+        self.quad_w = self.quad_w.astype(config.real(np))
+        super().__init__(geometry, ide, bcs, num_domain=num_domain, num_boundary=num_boundary,
+                         train_distribution=train_distribution, anchors=anchors, solution=solution,
+                         num_test=num_test)
+
+    def losses_train(self, targets, outputs, loss_fn, inputs, model, aux=None):
+        bcs_start = list(map(int, np.cumsum([0] + self.num_bcs)))
+        f = self.pde(inputs, outputs, self.get_int_matrix(True))
+        if not isinstance(f, (list, tuple)):
+            f = [f]
+        f = [fi[bcs_start[-1]:] for fi in f]
+        losses = [loss_fn(torch.zeros_like(fi), fi) for fi in f]
+        for i, bc in enumerate(self.bcs):
+            beg, end = bcs_start[i], bcs_start[i + 1]
+            error = bc.error(self.train_x, inputs, outputs, beg, end)
+            losses.append(loss_fn(torch.zeros_like(error), error))
+        return losses
+
+    def losses_test(self, targets, outputs, loss_fn, inputs, model, aux=None):
+        f = self.pde(inputs, outputs, self.get_int_matrix(False))
+        if not isinstance(f, (list, tuple)):
+            f = [f]
+        return [loss_fn(torch.zeros_like(fi), fi) for fi in f] + [
+            torch.zeros((), dtype=outputs.dtype) for _ in self.bcs]
+
+    losses = losses_train
+
+    @run_if_all_none("train_x", "train_y", "train_aux_vars")
+    def train_next_batch(self, batch_size=None):
+        self.train_x_all = self.train_points()
+        x_bc = self.bc_points()
+        x_quad = self.quad_points(self.train_x_all)
+        self.train_x = np.vstack((x_bc, self.train_x_all, x_quad))
+        self.train_y = self.soln(self.train_x) if self.soln else None
+        return self.train_x, self.train_y, self.train_aux_vars
+
+    @run_if_all_none("test_x", "test_y", "test_aux_vars")
+    def test(self):
+        x = self.train_x_all if self.num_test is None else self.geom.uniform_points(self.num_test, True)
+        self._n_test_f = len(x)
+        self.test_x = np.vstack((x, self.quad_points(x)))
+        self.test_y = self.soln(self.test_x) if self.soln else None
+        return self.test_x, self.test_y, self.test_aux_vars
+
+    def replace_with_anchors(self, anchors):
+        self.anchors = anchors.astype(config.real(np))
+        self.train_x_all = self.anchors
+        self.train_x = np.vstack((self.bc_points(), self.train_x_all, self.quad_points(self.train_x_all)))
+        self.train_y = self.soln(self.train_x) if self.soln else None
+
+    def quad_points(self, X):
+        return np.hstack([(self.quad_x + 1) * xi[0] / 2 for xi in X])[:, None].astype(config.real(np))
+
+    def get_int_matrix(self, training):
+        if training:
+            num_bc, X, num_f = int(sum(self.num_bcs)), self.train_x, len(self.train_x_all)
+        else:
+            num_bc, X, num_f = 0, self.test_x, self._n_test_f
+        int_mat = np.zeros((num_bc + num_f, X.size), dtype=config.real(np))
+        for i in range(num_f):
+            x = X[i + num_bc, 0]
+            beg = num_f + num_bc + self.quad_deg * i
+            end = beg + self.quad_deg
+            K = np.ravel(self.kernel(np.full((self.quad_deg, 1), x), X[beg:end]))
+            int_mat[i + num_bc, beg:end] = self.quad_w * x / 2 * K
+        return int_mat
+
+
 class TimePDE(PDE):
     def __init__(
         self,

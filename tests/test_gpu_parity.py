@@ -176,3 +176,53 @@ def test_msffn_runs_as_fourier_first_layer_nets():
     for k, t in zip(names, gr):
         if t is not None and float(t.abs().max()) > 0:
             assert rel(g[k], t) < 1e-4, k
+
+
+def test_ide_data_on_the_fused_path_matches_the_oracle():
+    """dde.data.IDE on the GPU (the reference's Volterra IDE, cases/PDECases.py:2054-2085: 3-argument residual,
+    quadrature matrix, kernel e^{s-x}, IC): per-term losses and parameter gradients against the float64 oracle."""
+    import ai4xde_b200.dde as dde
+    from oracle import ddelite
+
+    def build(d, bkd):
+        def ide(x, y, int_mat):
+            rhs = bkd.matmul(bkd.from_numpy(int_mat), bkd.from_numpy(y))
+            return (d.grad.jacobian(y, x, i=0, j=0) + y)[: bkd.size(rhs)] - rhs
+
+        geom = d.geometry.TimeDomain(0, 5)
+        ic = d.icbc.IC(geom, lambda x: np.exp(-x) * np.cosh(x), lambda _, on_initial: on_initial)
+        data = d.data.IDE(geom, ide, ic, 20, kernel=lambda x, s: np.exp(s - x), num_domain=40, num_boundary=2,
+                          train_distribution="uniform")
+        net = d.nn.FNN([1] + [20] * 3 + [1], "tanh", "Glorot uniform")
+        return data, net
+
+    ddelite.config.set_default_float("float64")
+    try:
+        torch.manual_seed(2)
+        odata, onet = build(ddelite, ddelite.backend)
+        omodel = ddelite.Model(odata, onet)
+        omodel.compile("adam", lr=1e-3)
+        _, ol = omodel.outputs_losses_train(odata.train_x, None, None)
+        onet.zero_grad()
+        ol.sum().backward()
+        og = torch.cat([p.grad.reshape(-1) for p in onet.parameters()]).double()
+        state = {k: v.detach().float() for k, v in onet.state_dict().items()}
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    dde.config.set_default_float("float64")
+    dde.config.set_engine("fp32")
+    try:
+        data, net = build(dde, dde.backend)
+        assert np.allclose(data.train_x, odata.train_x)
+        net.load_state_dict(state)
+        model = dde.Model(data, net)
+        model.compile("adam", lr=1e-3)
+        _, l = model.outputs_losses_train(data.train_x, None, None)
+        net.zero_grad()
+        l.sum().backward()
+        g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu()
+    finally:
+        dde.config.set_engine("auto")
+    assert float((l.detach().double().cpu() - ol.detach().double()).abs().max() / ol.detach().abs().max()) < 2e-5
+    assert float((g - og).abs().max() / og.abs().max()) < 5e-5

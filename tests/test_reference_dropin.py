@@ -69,6 +69,8 @@ CASES = [
     ("Poisson_1D_Unknown_Forcing_Field_Inverse", dict()),                 # PFNN: one sub-network per output
     ("Poisson_1D_Fourier_Net", dict(layer_size=[1, 32, 32, 32, 1])),                 # MsFFN, sigmas [1, 10]
     ("Poisson_2D_L_Shaped", dict(NumDomain=200, layer_size=[2, 16, 16, 1])),          # dde.geometry.Polygon
+    ("IDE", dict()),                                                                  # dde.data.IDE, 3-argument residual
+    ("Volterra_IDE", dict()),                                                         # ... with a kernel, uniform points
 ]
 
 
