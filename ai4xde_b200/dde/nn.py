@@ -495,5 +495,208 @@ class MsFFN(NN):
         return y
 
 
+class _FusedRowsEach(torch.autograd.Function):
+    """As _FusedRowsForward with the K nets' outputs kept apart: S tensors (K, n, C)."""
+
+    @staticmethod
+    def forward(ctx, desc, rows, x_soa, n, spec, engine, need_backward):
+        rows_c = rows.detach().contiguous()
+        jets, stash = _lib.jet_forward(desc, spec.desc, rows_c, x_soa, n, keep_all=need_backward, engine=engine)
+        ctx.desc, ctx.spec, ctx.engine, ctx.n = desc, spec, engine, n
+        ctx.rows, ctx.x_soa, ctx.stash, ctx.kept = rows_c, x_soa, stash, bool(need_backward)
+        return tuple(jets[:, s, :, :n].transpose(1, 2) for s in range(spec.S))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        if not ctx.kept:
+            raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
+        K, n, spec = ctx.rows.shape[0], ctx.n, ctx.spec
+        ldn = ctx.x_soa.shape[1]
+        c_out = ctx.desc.widths[ctx.desc.n_linear]
+        jets_bar = torch.zeros((K, spec.S, c_out, ldn), dtype=torch.float32, device=ctx.rows.device)
+        for s, g in enumerate(gouts):
+            if g is not None:
+                jets_bar[:, s, :, :n] = g.transpose(1, 2)
+        g_rows = _lib.jet_backward(ctx.desc, spec.desc, ctx.rows, ctx.x_soa, n, jets_bar, ctx.stash, engine=ctx.engine)
+        ctx.stash = None
+        return None, g_rows, None, None, None, None, None
+
+
+def _activation_jet(name, z0):
+    """value, first and second derivative of the activation at the pre-activation z0 (torch ops, differentiable)."""
+    if name == "tanh":
+        a = torch.tanh(z0)
+        s1 = 1 - a * a
+        return a, s1, -2 * a * s1
+    if name == "sin":
+        a = torch.sin(z0)
+        return a, torch.cos(z0), -a
+    if name == "sigmoid":
+        a = torch.sigmoid(z0)
+        s1 = a * (1 - a)
+        return a, s1, s1 * (1 - 2 * a)
+    raise NotImplementedError(f"activation {name!r} is not in the fused path (tanh, sin, sigmoid are)")
+
+
+class STMsFFN(NN):
+    """dde.nn.STMsFFN of the fused path (reference: cases/WaveCases.py:125-128, sigmas_x=[1], sigmas_t=[1, 10]).
+
+    The last input column is time.  Every space scale and every time scale is an ordinary MLP over its own
+    columns -- fixed Fourier embedding as a `sin` first layer (as MsFFN above), the shared `linears` behind it --
+    so the K_x space nets and the K_t time nets each run as ONE fused launch sequence whose output layer is the
+    last shared Linear (pre-activation, with its value / first / second derivative streams).  What the kernels do
+    not do is cheap and stays in torch on the device: the last activation applied to the jets, the point-wise
+    product of every (space, time) pair (a space jet times a time jet: d/dx acts on one factor, d/dt on the other)
+    and `_dense`.  The result is handed to dde.grad.* as the streams of the requested pattern, so a case's
+    jacobian / hessian calls read them exactly as they do for an FNN."""
+
+    def __init__(self, layer_sizes, activation, kernel_initializer, sigmas_x, sigmas_t, dropout_rate=0):
+        super().__init__()
+        if dropout_rate:
+            raise NotImplementedError("dropout is not in the fused path")
+        if not isinstance(activation, str):
+            raise NotImplementedError("callable activations are not in the fused path (tanh, sin, sigmoid are)")
+        if len(layer_sizes) < 4:
+            raise ValueError("STMsFFN needs at least one hidden layer after the Fourier embedding")
+        if layer_sizes[0] < 2:
+            raise ValueError("STMsFFN needs at least one space column before the time column")
+        self.layer_sizes = [int(w) for w in layer_sizes]
+        self.sigmas_x, self.sigmas_t = list(sigmas_x), list(sigmas_t)
+        self.sigmas = self.sigmas_x + self.sigmas_t
+        self.activation_name = activation
+        _activation_jet(activation, torch.zeros(1))
+        d_in, half = self.layer_sizes[0], self.layer_sizes[1] // 2
+        if 2 * half != self.layer_sizes[1]:
+            raise ValueError("layer_sizes[1] must be even (cos and sin halves of the embedding)")
+        init = _INIT[kernel_initializer]
+        # draws in DeepXDE's order: MsFFN.__init__ (b of the joint scales, linears, its _dense), then b_x, b_t, _dense
+        for sg in self.sigmas:
+            torch.normal(mean=0.0, std=float(sg), size=(d_in, half))
+        self.linears = torch.nn.ModuleList()
+        for i in range(2, len(self.layer_sizes) - 1):
+            lin = torch.nn.Linear(self.layer_sizes[i - 1], self.layer_sizes[i], dtype=torch.float32)
+            init(lin.weight)
+            torch.nn.init.zeros_(lin.bias)
+            self.linears.append(lin)
+        init(torch.empty(self.layer_sizes[-1], self.layer_sizes[-2] * len(self.sigmas)))
+        self.b_x = [torch.normal(mean=0.0, std=float(sg), size=(d_in - 1, half)) for sg in self.sigmas_x]
+        self.b_t = [torch.normal(mean=0.0, std=float(sg), size=(1, half)) for sg in self.sigmas_t]
+        self._dense = torch.nn.Linear(self.layer_sizes[-2] * len(self.sigmas_x) * len(self.sigmas_t),
+                                      self.layer_sizes[-1], dtype=torch.float32)
+        init(self._dense.weight)
+        torch.nn.init.zeros_(self._dense.bias)
+        hidden = self.layer_sizes[1:-1]
+        self._desc_x = _lib.make_net_desc([d_in - 1] + hidden, activation, n_nets=len(self.sigmas_x),
+                                          first_activation="sin")
+        self._desc_t = _lib.make_net_desc([1] + hidden, activation, n_nets=len(self.sigmas_t), first_activation="sin")
+        self._scope = _JetScope()
+        self.to(config.device())
+
+    @contextlib.contextmanager
+    def jet_scope(self, spec=None, x_soa=None, param_grad=True, probe_streams=None):
+        prev = self._scope
+        self._scope = _JetScope(spec, x_soa, param_grad, probe_streams)
+        try:
+            yield
+        finally:
+            self._scope = prev
+
+    def _rows(self, bs):
+        dev = self._dense.weight.device
+        half = self.layer_sizes[1] // 2
+        phase = torch.cat([torch.full((half,), torch.pi / 2), torch.zeros(half)]).to(dev)
+        shared = [t.reshape(-1) for lin in self.linears for t in (lin.weight, lin.bias)]
+        rows = []
+        for b in bs:
+            bt = b.to(device=dev, dtype=torch.float32).t()
+            rows.append(torch.cat([torch.cat([bt, bt], dim=0).reshape(-1), phase] + shared))
+        return torch.stack(rows)
+
+    def _branch(self, desc, bs, cols, n, spec, need_bwd):
+        """Activated hidden jets of one family of nets: (a, {dim: a_dim}, {(dim, dim'): a_dim_dim'}), each (K, n, H);
+        dims are the family's own column indices."""
+        rows = self._rows(bs)
+        z = _FusedRowsEach.apply(desc, rows, jet.to_soa(cols), n, spec, config.engine(),
+                                 bool(need_bwd and rows.requires_grad))
+        a, s1, s2 = _activation_jet(self.activation_name, z[0])
+        first = {spec.dirs[j]: s1 * z[1 + j] for j in range(spec.n1)}
+        second = {}
+        for q, (pa, pb) in enumerate(spec.pairs):
+            da, db = spec.dirs[pa], spec.dirs[pb]
+            second[(da, db)] = second[(db, da)] = s2 * z[1 + pa] * z[1 + pb] + s1 * z[1 + spec.n1 + q]
+        return a, first, second
+
+    def _streams(self, x, spec, need_bwd):
+        n, d = x.shape
+        t_dim = d - 1
+        xs, ts = [p for p in spec.dirs if p < t_dim], [p for p in spec.dirs if p == t_dim]
+        need2 = set()
+        for pa, pb in spec.pairs:
+            if pa == jet.JetSpec.TRACE and pb == jet.JetSpec.TRACE:
+                need2 |= {(p, p) for p in spec.dirs}
+            else:
+                need2.add(tuple(sorted((spec.dirs[pa], spec.dirs[pb]))))
+        sx = jet.JetSpec.covering(xs, [pq for pq in need2 if pq[1] < t_dim])
+        st = jet.JetSpec.covering([0] if ts else [], [(0, 0)] if (t_dim, t_dim) in need2 else [])
+        xd = x.detach().to(torch.float32)
+        ax, ax1, ax2 = self._branch(self._desc_x, self.b_x, xd[:, :t_dim], n, sx, need_bwd)
+        at, at1, at2 = self._branch(self._desc_t, self.b_t, xd[:, t_dim:], n, st, need_bwd)
+        at1 = {t_dim: v for v in at1.values()}
+        at2 = {(t_dim, t_dim): v for v in at2.values()}
+
+        def pair_product(fx, ft):   # (Kx, n, H) x (Kt, n, H) -> (n, Kx * Kt * H), space index outer
+            return (fx.unsqueeze(1) * ft.unsqueeze(0)).permute(2, 0, 1, 3).reshape(n, -1)
+
+        def second(p, q):
+            if p == t_dim and q == t_dim:
+                return pair_product(ax, at2[(t_dim, t_dim)])
+            if p == t_dim or q == t_dim:
+                return pair_product(ax1[min(p, q)], at1[t_dim])
+            return pair_product(ax2[(p, q)], at)
+
+        feats = [pair_product(ax, at)]
+        for p in spec.dirs:
+            feats.append(pair_product(ax, at1[t_dim]) if p == t_dim else pair_product(ax1[p], at))
+        for pa, pb in spec.pairs:
+            if pa == jet.JetSpec.TRACE and pb == jet.JetSpec.TRACE:
+                lap = None
+                for p in spec.dirs:
+                    term = second(p, p)
+                    lap = term if lap is None else lap + term
+                feats.append(lap)
+            else:
+                feats.append(second(spec.dirs[pa], spec.dirs[pb]))
+        w = self._dense.weight.t()
+        return [feats[0] @ w + self._dense.bias] + [f @ w for f in feats[1:]]
+
+    def forward(self, inputs):
+        sc = self._scope
+        x = inputs
+        if self._input_transform is not None:
+            x = self._input_transform(inputs)
+        if x.shape[1] != self.layer_sizes[0]:
+            raise ValueError(f"the net takes {self.layer_sizes[0]} columns (space..., time), got {x.shape[1]}")
+        if sc.probe_streams is not None:
+            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+        else:
+            wants_jets = x.requires_grad and torch.is_grad_enabled()
+            if not wants_jets:
+                spec = jet.JetSpec.value_only()
+            elif sc.spec is not None:
+                spec = sc.spec
+            else:
+                spec = jet.JetSpec.full(x.shape[1])
+            streams = self._streams(x, spec, sc.param_grad and torch.is_grad_enabled())
+            if wants_jets:
+                y = jet.make_leaf(x, spec, streams)
+                grad.register(y, jet.JetOutput(x, spec, streams))
+            else:
+                y = streams[0]
+        if self._output_transform is not None:
+            y = self._output_transform(inputs, y)
+        return y
+
+
 def get_supported_activations():
     return sorted(_lib.ACT)

@@ -207,3 +207,49 @@ class MsFFN(NN):
         if self._output_transform is not None:
             y = self._output_transform(inputs, y)
         return y
+
+
+class STMsFFN(MsFFN):
+    """Spatio-temporal multi-scale Fourier feature network [DeepXDE-upstream `deepxde.nn.pytorch.STMsFFN`;
+    the package is an absent, unpinned dependency of the reference, so this restates its published
+    algorithm -- parity unpinned against upstream, pinned against the closed-form check in
+    tests/test_oracle_pins.py], constructed by the reference at
+    /root/reference/AI4XDE/cases/WaveCases.py:125-128 with sigmas_x=[1], sigmas_t=[1, 10].
+
+    The last input column is time.  Space columns are embedded by fixed b_x ~ N(0, sigma_x^2) of shape
+    (d_in - 1, layer_sizes[1] // 2), time by fixed b_t ~ N(0, sigma_t^2) of shape (1, layer_sizes[1] // 2); every
+    embedding [cos(. b), sin(. b)] runs through the SAME hidden Linear + activation stack; the hidden outputs are
+    multiplied point-wise for every (space, time) pair (space index outer), concatenated and mapped by `_dense`."""
+
+    def __init__(self, layer_sizes, activation, kernel_initializer, sigmas_x, sigmas_t, dropout_rate=0):
+        super().__init__(layer_sizes, activation, kernel_initializer, list(sigmas_x) + list(sigmas_t), dropout_rate)
+        self.sigmas_x, self.sigmas_t = list(sigmas_x), list(sigmas_t)
+        half = layer_sizes[1] // 2
+        real = config.real(torch)
+        self.b_x = [torch.normal(mean=0.0, std=float(s), size=(layer_sizes[0] - 1, half)).to(real) for s in self.sigmas_x]
+        self.b_t = [torch.normal(mean=0.0, std=float(s), size=(1, half)).to(real) for s in self.sigmas_t]
+        self._dense = torch.nn.Linear(layer_sizes[-2] * len(self.sigmas_x) * len(self.sigmas_t), layer_sizes[-1],
+                                      dtype=real)
+        get_initializer(kernel_initializer)(self._dense.weight)
+        get_initializer("zeros")(self._dense.bias)
+
+    def _branch(self, x, b):
+        xb = torch.matmul(x, b.to(x.dtype))
+        y = torch.cat([torch.cos(xb), torch.sin(xb)], dim=1)
+        for linear in self.linears:
+            y = self.activation(linear(y))
+            if self.dropout_rate > 0:
+                y = torch.nn.functional.dropout(y, p=self.dropout_rate, training=self.training)
+        return y
+
+    def forward(self, inputs):
+        x = inputs
+        if self._input_transform is not None:
+            x = self._input_transform(x)
+        y_x = [self._branch(x[:, :-1], b) for b in self.b_x]
+        y_t = [self._branch(x[:, -1:], b) for b in self.b_t]
+        y = torch.cat([torch.mul(a, c) for a in y_x for c in y_t], dim=1)
+        y = self._dense(y)
+        if self._output_transform is not None:
+            y = self._output_transform(inputs, y)
+        return y

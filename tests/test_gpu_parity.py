@@ -178,6 +178,55 @@ def test_msffn_runs_as_fourier_first_layer_nets():
             assert rel(g[k], t) < 1e-4, k
 
 
+def test_stmsffn_space_and_time_nets_on_the_kernels():
+    """dde.nn.STMsFFN([2, 64, 64, 64, 1], sigmas_x [1], sigmas_t [1, 10]) (reference: cases/WaveCases.py:125-128):
+    the space net and the two time nets run on the kernels with a 64-wide output layer carrying value / first /
+    second streams; wave residual u_tt - 4 u_xx (+ mixed and first-order terms) and parameter gradients against
+    the float64 oracle restatement with the same embeddings and weights."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import _lib
+    from oracle import ddelite
+
+    dde.config.set_default_float("float32")
+    dde.config.set_engine("auto")
+    torch.manual_seed(12)
+    ls = [2, 64, 64, 64, 1]
+    net = dde.nn.STMsFFN(ls, "tanh", "Glorot uniform", sigmas_x=[1], sigmas_t=[1, 10])
+    x = torch.rand((3000, 2)).to("cuda").requires_grad_()
+    before = _lib.launch_count()
+    y = net(x)
+    assert _lib.launch_count() > before
+    r = (dde.grad.hessian(y, x, i=1, j=1) - 4 * dde.grad.hessian(y, x, i=0, j=0) + 0.3 * dde.grad.hessian(y, x, i=0, j=1)
+         + dde.grad.jacobian(y, x, i=0, j=1) + y)
+    dde.grad.clear()
+    net.zero_grad()
+    (r ** 2).mean().backward()
+    g = {k: p.grad.double().cpu() for k, p in net.named_parameters()}
+
+    ddelite.config.set_default_float("float64")
+    try:
+        ref = ddelite.nn.STMsFFN(ls, "tanh", "Glorot uniform", sigmas_x=[1], sigmas_t=[1, 10])
+        ref.load_state_dict({k: v.detach().double().cpu() for k, v in net.state_dict().items()})
+        ref.b_x = [b.detach().double().cpu() for b in net.b_x]
+        ref.b_t = [b.detach().double().cpu() for b in net.b_t]
+        xr = x.detach().double().cpu().requires_grad_()
+        yr = ref(xr)
+        d1 = torch.autograd.grad(yr.sum(), xr, create_graph=True)[0]
+        d0 = torch.autograd.grad(d1[:, 0].sum(), xr, create_graph=True)[0]
+        dt = torch.autograd.grad(d1[:, 1].sum(), xr, create_graph=True)[0]
+        rr = dt[:, 1:2] - 4 * d0[:, 0:1] + 0.3 * d0[:, 1:2] + d1[:, 1:2] + yr
+        names = [k for k, _ in ref.named_parameters()]
+        gr = torch.autograd.grad((rr ** 2).mean(), [p for _, p in ref.named_parameters()])
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert rel(y.detach().double().cpu(), yr.detach()) < 1e-5
+    assert rel(r.detach().double().cpu(), rr.detach()) < 5e-5     # second derivatives scale with sigma^2 = 100
+    for k, t in zip(names, gr):
+        assert rel(g[k], t) < 1e-4, k
+
+
 def test_ide_data_on_the_fused_path_matches_the_oracle():
     """dde.data.IDE on the GPU (the reference's Volterra IDE, cases/PDECases.py:2054-2085: 3-argument residual,
     quadrature matrix, kernel e^{s-x}, IC): per-term losses and parameter gradients against the float64 oracle."""

@@ -246,3 +246,46 @@ def test_fbpinn_bank_matches_sum_of_nets():
     model.train(iterations=2)
     moved = (solver.bank.flat - before).abs().sum(dim=1)
     assert moved[1] > 0 and moved[0] == 0 and moved[2] == 0 and moved[3] == 0
+
+
+@pytest.mark.parametrize("d_in,act", [(2, "tanh"), (3, "sin")])
+def test_stmsffn_product_matches_oracle(d_in, act):
+    """dde.nn.STMsFFN of the fused path (K_x space nets and K_t time nets through the kernel double, last
+    activation / pair products / _dense in torch) against the oracle restatement: value, a residual made of first,
+    pure and mixed second derivatives, and every parameter gradient; 1 and 2 space columns."""
+    import ai4xde_b200.dde as dde
+    from oracle import ddelite
+
+    dde.config.set_default_float("float32")
+    torch.manual_seed(3)
+    ls = [d_in, 16, 16, 16, 1]
+    net = dde.nn.STMsFFN(ls, act, "Glorot uniform", sigmas_x=[1, 2], sigmas_t=[1, 10])
+    x = torch.rand(120, d_in).requires_grad_()
+    t = d_in - 1
+    y = net(x)
+    r = (dde.grad.hessian(y, x, i=t, j=t) - 4 * dde.grad.hessian(y, x, i=0, j=0) + 0.3 * dde.grad.hessian(y, x, i=0, j=t)
+         + dde.grad.jacobian(y, x, i=0, j=t) + dde.grad.jacobian(y, x, i=0, j=0) + y)
+    dde.grad.clear()
+    net.zero_grad()
+    (r ** 2).mean().backward()
+    g = {k: p.grad.double() for k, p in net.named_parameters()}
+    ddelite.config.set_default_float("float64")
+    try:
+        ref = ddelite.nn.STMsFFN(ls, act, "Glorot uniform", sigmas_x=[1, 2], sigmas_t=[1, 10])
+        ref.load_state_dict({k: v.detach().double() for k, v in net.state_dict().items()})
+        ref.b_x, ref.b_t = [b.double() for b in net.b_x], [b.double() for b in net.b_t]
+        xr = x.detach().double().requires_grad_()
+        yr = ref(xr)
+        d1 = torch.autograd.grad(yr.sum(), xr, create_graph=True)[0]
+        d0 = torch.autograd.grad(d1[:, 0].sum(), xr, create_graph=True)[0]
+        dt = torch.autograd.grad(d1[:, t].sum(), xr, create_graph=True)[0]
+        rr = dt[:, t:t + 1] - 4 * d0[:, 0:1] + 0.3 * d0[:, t:t + 1] + d1[:, t:t + 1] + d1[:, 0:1] + yr
+        gr = torch.autograd.grad((rr ** 2).mean(), [p for _, p in ref.named_parameters()])
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(y.detach().double(), yr.detach()) < 1e-5
+    assert rel(r.detach().double(), rr.detach()) < 1e-5
+    for (k, _), tr in zip(ref.named_parameters(), gr):
+        assert rel(g[k], tr) < 1e-5, k

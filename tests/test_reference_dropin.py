@@ -71,6 +71,7 @@ CASES = [
     ("Poisson_2D_L_Shaped", dict(NumDomain=200, layer_size=[2, 16, 16, 1])),          # dde.geometry.Polygon
     ("IDE", dict()),                                                                  # dde.data.IDE, 3-argument residual
     ("Volterra_IDE", dict()),                                                         # ... with a kernel, uniform points
+    ("Wave_1D_STMsFFN", dict(layer_size=[2, 32, 32, 32, 1])),                         # STMsFFN, sigmas_x [1], sigmas_t [1, 10]
 ]
 
 
@@ -116,6 +117,9 @@ def test_unmodified_reference_case_runs_on_the_fused_path(name, kwargs, monkeypa
         case_f.net.load_state_dict(state)
         if hasattr(case_o.net, "b"):      # MsFFN: the fixed Fourier matrices are plain tensors, not in the state dict
             case_f.net.b = [t.detach().float().clone() for t in case_o.net.b]
+        for nm in ("b_x", "b_t"):         # STMsFFN: likewise
+            if hasattr(case_o.net, nm):
+                setattr(case_f.net, nm, [t.detach().float().clone() for t in getattr(case_o.net, nm)])
         losses, g = _evaluate(dde_f, case_f)
     finally:
         _purge()
