@@ -20,12 +20,12 @@ from test_reference_dropin import load_reference
 td.install()
 A, dde = load_reference("fused")
 ok, bad = [], []
-mods = [getattr(A.cases, m) for m in ("PDECases", "PoissonCases", "WaveCases", "FuncCases", "InverseCases")
-        if hasattr(A.cases, m)]
+mods = [getattr(A.cases, m) for m in ("PDECases", "PoissonCases", "WaveCases", "ConvectionCases", "FuncCases",
+                                     "InverseCases") if hasattr(A.cases, m)]
 seen = set()
 for mod in mods:
     for name, cls in inspect.getmembers(mod, inspect.isclass):
-        if cls.__module__ != mod.__name__ or inspect.isabstract(cls) or name in seen:
+        if cls.__module__ != mod.__name__ or inspect.isabstract(cls) or cls.__subclasses__() or name in seen:
             continue
         seen.add(name)
         try:

@@ -72,13 +72,30 @@ CASES = [
     ("IDE", dict()),                                                                  # dde.data.IDE, 3-argument residual
     ("Volterra_IDE", dict()),                                                         # ... with a kernel, uniform points
     ("Wave_1D_STMsFFN", dict(layer_size=[2, 32, 32, 32, 1])),                         # STMsFFN, sigmas_x [1], sigmas_t [1, 10]
+    ("A_Simple_ODE", dict()),
+    ("SecondOrderODE", dict()),
+    ("Diffusion", dict()),
+    ("Diffusion_reaction", dict()),
+    ("Harmonic_Oscillator_1D", dict()),
+    ("Helmholtz_Hole", dict(layer_size=[2, 16, 16, 1])),
+    ("Poisson_1D_Dirichlet", dict()),
+    ("Poisson_1D_Dirichlet_Neumann", dict()),
+    ("Poisson_1D_Dirichlet_Periodic", dict()),
+    ("Poisson_1D_Hard_Boundary", dict()),
+    ("Poisson_2D_Peak", dict()),
+    ("Wave_1D_Hard_Boundary", dict()),
+    ("Brinkman_Forchheimer_Inverse", dict()),
+    ("Diffusion_Inverse", dict()),
+    ("Lorenz_Inverse", dict()),
+    ("Lorenz_Exogenous_Input_Inverse", dict()),
 ]
 
 
 def _evaluate(dde, case):
     model = dde.Model(case.data, case.net)
     case.compile(model, "adam", lr=1e-3)
-    _, losses = model.outputs_losses_train(case.data.train_x, case.data.train_y, None)
+    aux = getattr(case.data, "train_aux_vars", None)      # Lorenz_Exogenous_Input_Inverse: auxiliary_var_function
+    _, losses = model.outputs_losses_train(case.data.train_x, case.data.train_y, aux)
     case.net.zero_grad()
     # a reference case may carry a degenerate term (Poisson_1D_Fourier_Net asks for a Dirichlet BC but samples no
     # boundary points, cases/PoissonCases.py:480-492: MSE over an empty set = NaN on every backend) -- the
