@@ -37,9 +37,14 @@ class _FusedForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x_soa, n, spec, engine, need_backward, *params):
         flat = net.flat_params()
-        jets, stash = _lib.jet_forward(net.net_desc, spec.desc, flat, x_soa, n,
-                                       keep_all=need_backward, engine=engine)
-        ctx.net, ctx.spec, ctx.engine, ctx.n = net, spec, engine, n
+        pad = net._tc_pad if engine in ("auto", "tf32") else None
+        if pad is not None and not _lib.engine_supported(pad.desc, spec.desc, "tf32"):
+            pad = None                       # stream pattern outside the tensor-core engine: nothing to gain
+        if pad is not None:
+            flat = pad.widen(flat)
+        desc = net.net_desc if pad is None else pad.desc
+        jets, stash = _lib.jet_forward(desc, spec.desc, flat, x_soa, n, keep_all=need_backward, engine=engine)
+        ctx.net, ctx.spec, ctx.engine, ctx.n, ctx.desc, ctx.pad = net, spec, engine, n, desc, pad
         ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = x_soa, stash, bool(need_backward), flat
         ctx.shapes = [p.shape for p in params]
         return tuple(jets[0, s, :, :n].t() for s in range(spec.S))
@@ -56,8 +61,10 @@ class _FusedForward(torch.autograd.Function):
         for s, g in enumerate(gouts):
             if g is not None:
                 jets_bar[0, s, :, :n] = g.t()
-        g_flat = _lib.jet_backward(net.net_desc, spec.desc, ctx.flat, ctx.x_soa, n, jets_bar, ctx.stash,
+        g_flat = _lib.jet_backward(ctx.desc, spec.desc, ctx.flat, ctx.x_soa, n, jets_bar, ctx.stash,
                                    engine=ctx.engine)[0]
+        if ctx.pad is not None:
+            g_flat = ctx.pad.narrow(g_flat)
         ctx.stash = None
         outs, off = [], 0
         for shp in ctx.shapes:
@@ -67,6 +74,54 @@ class _FusedForward(torch.autograd.Function):
             outs.append(g_flat[off : off + cnt].view(shp))
             off += cnt
         return (None, None, None, None, None, None) + tuple(outs)
+
+
+class _TensorCorePad:
+    """Zero-padded image of an FNN whose uniform hidden width H lies strictly between the widths the tcgen05
+    engine is compiled for (64 / 128 / 256): the same function on the next compiled width.  Padded units see
+    zero incoming weights and bias (pre-activation 0, derivative streams 0) and feed zero outgoing weights, so
+    value, jets and the gradient of every real parameter are unchanged; the gradients of padded entries are
+    dropped.  One scatter per evaluation builds the image from the flat master buffer, one gather brings the
+    gradient back.  Used under engine 'auto' / 'tf32' only -- 'fp32' keeps the net as it is on the FP32 engine."""
+
+    def __init__(self, layer_sizes, activation, h_pad):
+        d_in, d_out, n_hidden = layer_sizes[0], layer_sizes[-1], len(layer_sizes) - 2
+        padded = [d_in] + [h_pad] * n_hidden + [d_out]
+        self.desc = _lib.make_net_desc(padded, activation)
+        idx, off = [], 0
+        for l in range(len(layer_sizes) - 1):
+            o, i = layer_sizes[l + 1], layer_sizes[l]
+            po, pi = padded[l + 1], padded[l]
+            rows = torch.arange(o).unsqueeze(1) * pi + torch.arange(i).unsqueeze(0)
+            idx.append((off + rows).reshape(-1))
+            off += po * pi
+            idx.append(off + torch.arange(o))
+            off += po
+        self.count = off
+        self.index = torch.cat(idx)
+        self._image = None
+
+    @staticmethod
+    def plan(layer_sizes, activation):
+        hidden = layer_sizes[1:-1]
+        if activation not in ("tanh", "sigmoid") or len(hidden) < 2 or len(set(hidden)) != 1:
+            return None
+        if layer_sizes[0] > 4 or layer_sizes[-1] > 4:
+            return None
+        h = hidden[0]
+        if h <= 64 or h >= 256 or h == 128:   # narrower nets stay on FP32 FMA; 64 / 128 / 256 need no padding
+            return None
+        return _TensorCorePad(layer_sizes, activation, 128 if h < 128 else 256)
+
+    def widen(self, flat):
+        if self._image is None or self._image.device != flat.device:
+            self._image = torch.zeros((1, self.count), dtype=torch.float32, device=flat.device)
+            self.index = self.index.to(flat.device)
+        self._image[0, self.index] = flat.detach().reshape(-1)
+        return self._image
+
+    def narrow(self, g_padded):
+        return g_padded.reshape(-1)[self.index]
 
 
 class NN(torch.nn.Module):
@@ -107,6 +162,7 @@ class FNN(NN):
         self.layer_sizes = [int(w) for w in layer_sizes]
         self.activation_name = activation
         self.net_desc = _lib.make_net_desc(self.layer_sizes, activation)
+        self._tc_pad = _TensorCorePad.plan(self.layer_sizes, activation)
         init = _INIT[kernel_initializer]
         self.linears = torch.nn.ModuleList()
         for i in range(1, len(self.layer_sizes)):

@@ -183,3 +183,37 @@ def test_alternative_kernel_paths_stay_parity_green(flags):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_tc.py"), "-x", "-q",
                         "-k", "test_tf32_engine_matches_double"], env=env, capture_output=True, text=True, cwd=here)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_fnn_between_compiled_widths_rides_the_tensor_cores_padded():
+    """dde.nn.FNN([2, 100, 100, 100, 100, 2], tanh) (the reference's Schrodinger net, cases/PDECases.py:1833) under
+    engine 'auto': evaluated on its zero-padded 128-wide image by the tcgen05 kernels (timing hooks name them), and
+    value / residual / real-parameter gradients agree with the same net on the FP32 engine within the TF32 bound."""
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float32")
+    torch.manual_seed(5)
+    net = dde.nn.FNN([2] + [100] * 4 + [2], "tanh", "Glorot normal")
+    x = (torch.rand((20011, 2)) * 2 - 1).to("cuda").requires_grad_()
+    out = {}
+    try:
+        for eng in ("fp32", "auto"):
+            dde.config.set_engine(eng)
+            _lib.timing_report()
+            _lib.timing_enable(True)
+            y = net(x)
+            r = dde.grad.hessian(y, x, component=0, i=0, j=0) + dde.grad.jacobian(y, x, i=1, j=1) + y[:, :1] * y[:, 1:]
+            dde.grad.clear()
+            net.zero_grad()
+            (r ** 2).mean().backward()
+            _lib.timing_enable(False)
+            names = set(_lib.timing_report())
+            assert any(k.startswith("tc_") for k in names) == (eng == "auto"), names
+            out[eng] = (y.detach().double(), r.detach().double(), torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double())
+    finally:
+        _lib.timing_enable(False)
+        dde.config.set_engine("auto")
+    (y0, r0, g0), (y1, r1, g1) = out["fp32"], out["auto"]
+    assert _rel(y1, y0) < TF32_JET_TOL
+    assert _rel(r1, r0) < 1e-2
+    assert _rel(g1, g0) < 2e-2

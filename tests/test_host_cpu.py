@@ -289,3 +289,35 @@ def test_stmsffn_product_matches_oracle(d_in, act):
     assert rel(r.detach().double(), rr.detach()) < 1e-5
     for (k, _), tr in zip(ref.named_parameters(), gr):
         assert rel(g[k], tr) < 1e-5, k
+
+
+@pytest.mark.parametrize("ls,act", [([2, 100, 100, 100, 2], "tanh"), ([3, 150, 150, 1], "sigmoid"), ([2, 70, 70, 70, 70, 1], "tanh")])
+def test_tensor_core_padding_is_the_same_function(ls, act):
+    """An FNN whose hidden width lies between the tensor-core engine's compiled widths is evaluated on a
+    zero-padded image (engine 'auto'): value, residual and the gradient of every real parameter equal the
+    unpadded evaluation (engine 'fp32'); widths the engine is compiled for, narrow nets and sin nets get no image."""
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float32")
+    torch.manual_seed(0)
+    net = dde.nn.FNN(ls, act, "Glorot normal")
+    assert net._tc_pad is not None and net._tc_pad.desc.widths[1] == (128 if ls[1] < 128 else 256)
+    x = torch.rand(97, ls[0]).requires_grad_()
+    out = {}
+    try:
+        for eng in ("fp32", "auto"):
+            dde.config.set_engine(eng)
+            y = net(x)
+            r = (dde.grad.hessian(y, x, component=0, i=0, j=0) if ls[-1] > 1 else dde.grad.hessian(y, x, i=0, j=0)) \
+                + dde.grad.jacobian(y, x, i=ls[-1] - 1, j=1) + y[:, :1]
+            dde.grad.clear()
+            net.zero_grad()
+            (r ** 2).mean().backward()
+            out[eng] = (y.detach().clone(), r.detach().clone(), torch.cat([p.grad.reshape(-1) for p in net.parameters()]))
+    finally:
+        dde.config.set_engine("auto")
+    for a, b in zip(out["fp32"], out["auto"]):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-6
+    for other in ([2, 64, 64, 1], [2, 128, 128, 1], [2, 256, 256, 1], [2, 20, 20, 20, 1], [2, 300, 300, 1], [2, 100, 1], [5, 100, 100, 1]):
+        assert dde.nn.FNN(other, "tanh", "Glorot normal")._tc_pad is None
+    assert dde.nn.FNN([2, 100, 100, 1], "sin", "Glorot normal")._tc_pad is None
