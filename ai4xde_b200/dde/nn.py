@@ -37,7 +37,9 @@ class _FusedForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x_soa, n, spec, engine, need_backward, *params):
         flat = net.flat_params()
-        pad = net._tc_pad if engine in ("auto", "tf32") else None
+        pad = net._tc_pad
+        if pad is not None and not (engine == "tf32" or (engine == "auto" and pad.auto_ok)):
+            pad = None
         if pad is not None and not _lib.engine_supported(pad.desc, spec.desc, "tf32"):
             pad = None                       # stream pattern outside the tensor-core engine: nothing to gain
         if pad is not None:
@@ -82,7 +84,8 @@ class _TensorCorePad:
     zero incoming weights and bias (pre-activation 0, derivative streams 0) and feed zero outgoing weights, so
     value, jets and the gradient of every real parameter are unchanged; the gradients of padded entries are
     dropped.  One scatter per evaluation builds the image from the flat master buffer, one gather brings the
-    gradient back.  Used under engine 'auto' / 'tf32' only -- 'fp32' keeps the net as it is on the FP32 engine."""
+    gradient back.  Used under engine 'auto' for widths above 64 and under an explicit 'tf32' also for widths
+    33..63 (padded to 64); 'fp32' keeps the net as it is on the FP32 engine."""
 
     def __init__(self, layer_sizes, activation, h_pad):
         d_in, d_out, n_hidden = layer_sizes[0], layer_sizes[-1], len(layer_sizes) - 2
@@ -109,9 +112,11 @@ class _TensorCorePad:
         if layer_sizes[0] > 4 or layer_sizes[-1] > 4:
             return None
         h = hidden[0]
-        if h <= 64 or h >= 256 or h == 128:   # narrower nets stay on FP32 FMA; 64 / 128 / 256 need no padding
+        if h <= 32 or h >= 256 or h in (64, 128):   # 64 / 128 / 256 need no padding
             return None
-        return _TensorCorePad(layer_sizes, activation, 128 if h < 128 else 256)
+        pad = _TensorCorePad(layer_sizes, activation, 64 if h < 64 else 128 if h < 128 else 256)
+        pad.auto_ok = h > 64    # narrower nets stay on FP32 FMA unless the caller asks for engine 'tf32'
+        return pad
 
     def widen(self, flat):
         if self._image is None or self._image.device != flat.device:

@@ -14,10 +14,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 dde.config.set_default_float("float32")
 torch.manual_seed(0)
 out = {"points": n}
-for widths in ([2] + [100] * 4 + [2], [2] + [150] * 3 + [1]):
+for widths in ([2] + [100] * 4 + [2], [2] + [150] * 3 + [1], [2] + [50] * 4 + [3]):
     net = dde.nn.FNN(widths, "tanh", "Glorot normal")
     x = (torch.rand((n, 2)) * 2 - 1).to("cuda").requires_grad_()
-    for eng in ("fp32", "auto"):
+    for eng in ("fp32", "auto", "tf32"):
         dde.config.set_engine(eng)
 
         def step():

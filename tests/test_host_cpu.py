@@ -320,4 +320,6 @@ def test_tensor_core_padding_is_the_same_function(ls, act):
         assert float((a - b).abs().max() / b.abs().max()) < 1e-6
     for other in ([2, 64, 64, 1], [2, 128, 128, 1], [2, 256, 256, 1], [2, 20, 20, 20, 1], [2, 300, 300, 1], [2, 100, 1], [5, 100, 100, 1]):
         assert dde.nn.FNN(other, "tanh", "Glorot normal")._tc_pad is None
+    narrow = dde.nn.FNN([2, 50, 50, 50, 3], "tanh", "Glorot normal")._tc_pad     # only on an explicit 'tf32'
+    assert narrow is not None and narrow.desc.widths[1] == 64 and not narrow.auto_ok
     assert dde.nn.FNN([2, 100, 100, 1], "sin", "Glorot normal")._tc_pad is None
