@@ -71,18 +71,34 @@ using P_4_F = Pattern<4, 10, 0x3221110000ull, 0x3323213210ull>;
 using P_2_T = Pattern<2, 1, 0xFull, 0xFull>;        // {0,a,b,aa+bb}
 using P_3_T = Pattern<3, 1, 0xFull, 0xFull>;        // {0,a,b,c,aa+bb+cc}
 constexpr int kTracePair = 15;
+// one-input higher-order patterns (Euler beam u_xxxx, cases/PDECases.py:454-464; gPINN on 1-D problems):
+// after the second-order stream aa come the third (pair code 14/14) and fourth (13/13) derivative along a.
+using P_1_3 = Pattern<1, 2, 0xE0ull, 0xE0ull>;      // {0,a,aa,aaa}
+using P_1_4 = Pattern<1, 3, 0xDE0ull, 0xDE0ull>;    // {0,a,aa,aaa,aaaa}
+constexpr int kThirdPair = 14, kFourthPair = 13;
+// highest derivative order a pattern carries
+template <class P>
+__host__ __device__ constexpr int pattern_order() {
+  int ord = P::N2 > 0 ? 2 : (P::N1 > 0 ? 1 : 0);
+  for (int q = 0; q < P::N2; ++q) {
+    if (P::pa(q) == kThirdPair && ord < 3) ord = 3;
+    if (P::pa(q) == kFourthPair) ord = 4;
+  }
+  return ord;
+}
 
 #define AX_FOR_EACH_PATTERN(X) \
   X(0, P_V) X(1, P_1) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F) X(7, P_3) \
-  X(8, P_3_D) X(9, P_3_F) X(10, P_4) X(11, P_4_D) X(12, P_4_F) X(13, P_2_T) X(14, P_3_T)
-constexpr int kNumPatterns = 15;
+  X(8, P_3_D) X(9, P_3_F) X(10, P_4) X(11, P_4_D) X(12, P_4_F) X(13, P_2_T) X(14, P_3_T) X(15, P_1_3) \
+  X(16, P_1_4)
+constexpr int kNumPatterns = 17;
 
 // returns pattern id or -1
 int match_pattern(const ax_jet_desc *jet);
 
 // ---- activation derivatives -------------------------------------------------------------
 struct ActD {
-  float a, s1, s2, s3;
+  float a, s1, s2, s3, s4, s5;
 };
 
 // full-accuracy tanh for the FP32 engine (libdevice tanhf: ~1 ulp)
@@ -98,15 +114,20 @@ __device__ __forceinline__ float stash_slot0(int act, float z) {
   return act_value(act, z);
 }
 
-// derivatives of the activation from stash slot 0
-template <bool NEED3>
+// derivatives of the activation from stash slot 0, up to order ORD (<= 5; the adjoint of an order-k jet
+// needs order k + 1)
+template <int ORD>
 __device__ __forceinline__ ActD act_from_stash(int act, float v) {
   ActD d;
+  d.s3 = d.s4 = d.s5 = 0.0f;
   if (act == AX_ACT_TANH) {
+    const float v2 = v * v;
     d.a = v;
     d.s1 = fmaf(-v, v, 1.0f);
     d.s2 = -2.0f * v * d.s1;
-    d.s3 = NEED3 ? -2.0f * d.s1 * fmaf(-3.0f * v, v, 1.0f) : 0.0f;
+    if (ORD >= 3) d.s3 = -2.0f * d.s1 * fmaf(-3.0f * v, v, 1.0f);
+    if (ORD >= 4) d.s4 = 8.0f * v * d.s1 * fmaf(-3.0f, v2, 2.0f);
+    if (ORD >= 5) d.s5 = d.s1 * fmaf(v2, fmaf(120.0f, v2, -120.0f), 16.0f);
   } else if (act == AX_ACT_SIN) {
     float s, c;
     sincosf(v, &s, &c);
@@ -114,11 +135,15 @@ __device__ __forceinline__ ActD act_from_stash(int act, float v) {
     d.s1 = c;
     d.s2 = -s;
     d.s3 = -c;
+    d.s4 = s;
+    d.s5 = c;
   } else {
     d.a = v;
     d.s1 = v * (1.0f - v);
     d.s2 = d.s1 * (1.0f - 2.0f * v);
-    d.s3 = NEED3 ? d.s1 * fmaf(6.0f * v, v - 1.0f, 1.0f) : 0.0f;
+    if (ORD >= 3) d.s3 = d.s1 * fmaf(6.0f * v, v - 1.0f, 1.0f);
+    if (ORD >= 4) d.s4 = d.s2 * fmaf(12.0f * v, v - 1.0f, 1.0f);
+    if (ORD >= 5) d.s5 = d.s1 * fmaf(v, fmaf(v, fmaf(v, fmaf(120.0f, v, -240.0f), 150.0f), -30.0f), 1.0f);
   }
   return d;
 }
@@ -127,13 +152,23 @@ __device__ __forceinline__ ActD act_from_stash(int act, float v) {
 // streams (slot 0 replaced) ; A[S] post-activation streams via jet_reconstruct.
 template <class P>
 __device__ __forceinline__ void jet_reconstruct(int act, const float (&st)[P::S], float (&A)[P::S]) {
-  ActD d = act_from_stash<false>(act, st[0]);
+  constexpr int ORD = pattern_order<P>() < 2 ? 2 : pattern_order<P>();
+  ActD d = act_from_stash<ORD>(act, st[0]);
   A[0] = d.a;
 #pragma unroll
   for (int j = 0; j < P::N1; ++j) A[1 + j] = d.s1 * st[1 + j];
 #pragma unroll
   for (int q = 0; q < P::N2; ++q) {
-    if (P::pa(q) == kTracePair) {
+    if (P::pa(q) == kThirdPair) {
+      // P_1_3 / P_1_4: st[1..3] = first, second, third derivative of z (Faa di Bruno, one variable)
+      const float z1 = st[1], z2 = st[2], z3 = st[3];
+      A[1 + P::N1 + q] = fmaf(d.s3 * z1 * z1, z1, fmaf(3.0f * d.s2 * z1, z2, d.s1 * z3));
+    } else if (P::pa(q) == kFourthPair) {
+      const float z1 = st[1], z2 = st[2], z3 = st[3], z4 = st[P::S - 1];
+      const float z11 = z1 * z1;
+      A[1 + P::N1 + q] = fmaf(d.s4 * z11, z11,
+                              fmaf(6.0f * d.s3 * z11, z2, fmaf(d.s2, fmaf(3.0f * z2, z2, 4.0f * z1 * z3), d.s1 * z4)));
+    } else if (P::pa(q) == kTracePair) {
       float sq = 0.0f;
 #pragma unroll
       for (int j = 0; j < P::N1; ++j) sq = fmaf(st[1 + j], st[1 + j], sq);
@@ -148,7 +183,8 @@ __device__ __forceinline__ void jet_reconstruct(int act, const float (&st)[P::S]
 template <class P>
 __device__ __forceinline__ void jet_adjoint(int act, const float (&st)[P::S], const float (&ab)[P::S],
                                             float (&zb)[P::S]) {
-  ActD d = act_from_stash<true>(act, st[0]);
+  constexpr int ORD = pattern_order<P>() < 2 ? 3 : pattern_order<P>() + 1;
+  ActD d = act_from_stash<ORD>(act, st[0]);
   float z0b = d.s1 * ab[0];
 #pragma unroll
   for (int j = 0; j < P::N1; ++j) {
@@ -160,7 +196,23 @@ __device__ __forceinline__ void jet_adjoint(int act, const float (&st)[P::S], co
     const float zq = st[1 + P::N1 + q];
     const float aq = ab[1 + P::N1 + q];
     zb[1 + P::N1 + q] = d.s1 * aq;
-    if (P::pa(q) == kTracePair) {
+    if (P::pa(q) == kThirdPair) {
+      // A3 = s3 z1^3 + 3 s2 z1 z2 + s1 z3   (zb[2] of the second-order stream is already set: q ascends)
+      const float z1 = st[1], z2 = st[2], z3 = st[3];
+      z0b = fmaf(fmaf(d.s4 * z1 * z1, z1, fmaf(3.0f * d.s3 * z1, z2, d.s2 * z3)), aq, z0b);
+      zb[1] = fmaf(3.0f * fmaf(d.s3 * z1, z1, d.s2 * z2), aq, zb[1]);
+      zb[2] = fmaf(3.0f * d.s2 * z1, aq, zb[2]);
+    } else if (P::pa(q) == kFourthPair) {
+      // A4 = s4 z1^4 + 6 s3 z1^2 z2 + 3 s2 z2^2 + 4 s2 z1 z3 + s1 z4
+      const float z1 = st[1], z2 = st[2], z3 = st[3], z4 = st[P::S - 1];
+      const float z11 = z1 * z1;
+      z0b = fmaf(fmaf(d.s5 * z11, z11,
+                      fmaf(6.0f * d.s4 * z11, z2, fmaf(d.s3, fmaf(3.0f * z2, z2, 4.0f * z1 * z3), d.s2 * z4))),
+                 aq, z0b);
+      zb[1] = fmaf(4.0f * fmaf(d.s4 * z11, z1, fmaf(3.0f * d.s3 * z1, z2, d.s2 * z3)), aq, zb[1]);
+      zb[2] = fmaf(6.0f * fmaf(d.s3, z11, d.s2 * z2), aq, zb[2]);
+      zb[3] = fmaf(4.0f * d.s2 * z1, aq, zb[3]);
+    } else if (P::pa(q) == kTracePair) {
       float sq = 0.0f;
 #pragma unroll
       for (int j = 0; j < P::N1; ++j) {

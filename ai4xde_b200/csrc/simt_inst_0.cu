@@ -13,4 +13,8 @@ template int simt_forward<P_2_T>(const FwdArgs &);
 template int simt_backward<P_2_T>(const BwdArgs &);
 template int simt_forward<P_3_T>(const FwdArgs &);
 template int simt_backward<P_3_T>(const BwdArgs &);
+template int simt_forward<P_1_3>(const FwdArgs &);
+template int simt_backward<P_1_3>(const BwdArgs &);
+template int simt_forward<P_1_4>(const FwdArgs &);
+template int simt_backward<P_1_4>(const BwdArgs &);
 }  // namespace ax

@@ -253,7 +253,7 @@ class FNN(NN):
             if x.shape[1] != self.layer_sizes[0]:
                 raise ValueError(f"feature transform returns {x.shape[1]} features, the net takes {self.layer_sizes[0]}")
         if sc.probe_streams is not None:
-            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+            y = jet.make_leaf(x, jet.probe_spec(x.shape[1]), sc.probe_streams)
         else:
             wants_jets = x.requires_grad and torch.is_grad_enabled()
             if not wants_jets:
@@ -419,7 +419,7 @@ class PFNN(NN):
         if featured:
             x = self._input_transform(inputs)
         if sc.probe_streams is not None:
-            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+            y = jet.make_leaf(x, jet.probe_spec(x.shape[1]), sc.probe_streams)
         else:
             wants_jets = x.requires_grad and torch.is_grad_enabled()
             x_soa = None if featured else sc.x_soa
@@ -530,7 +530,7 @@ class MsFFN(NN):
         if featured:
             x = self._input_transform(inputs)
         if sc.probe_streams is not None:
-            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+            y = jet.make_leaf(x, jet.probe_spec(x.shape[1]), sc.probe_streams)
         else:
             wants_jets = x.requires_grad and torch.is_grad_enabled()
             if not wants_jets:
@@ -739,7 +739,7 @@ class STMsFFN(NN):
         if x.shape[1] != self.layer_sizes[0]:
             raise ValueError(f"the net takes {self.layer_sizes[0]} columns (space..., time), got {x.shape[1]}")
         if sc.probe_streams is not None:
-            y = jet.make_leaf(x, jet.JetSpec.full(x.shape[1]), sc.probe_streams)
+            y = jet.make_leaf(x, jet.probe_spec(x.shape[1]), sc.probe_streams)
         else:
             wants_jets = x.requires_grad and torch.is_grad_enabled()
             if not wants_jets:

@@ -22,6 +22,7 @@ class JetSpec:
     """
 
     TRACE = 15  # pair code of the Laplacian stream (csrc/common.cuh kTracePair)
+    THIRD, FOURTH = 14, 13  # pair codes of the one-direction third / fourth derivative streams (P_1_3, P_1_4)
 
     def __init__(self, dirs, pairs):
         self.dirs = tuple(int(d) for d in dirs)
@@ -31,9 +32,18 @@ class JetSpec:
         self.first_of_dim = {d: j for j, d in enumerate(self.dirs)}
         self.second_of_dims = {}
         self.trace = None  # index q of the Laplacian stream, if this is a trace pattern
+        self.third = self.fourth = None  # index q of the third / fourth derivative stream (one direction only)
         for q, (a, b) in enumerate(self.pairs):
             if a == self.TRACE and b == self.TRACE:
                 self.trace = q
+                continue
+            if a == b and a in (self.THIRD, self.FOURTH):
+                if self.n1 != 1 or self.pairs[0] != (0, 0):
+                    raise ValueError("third / fourth order streams follow the (0, 0) stream of a one-direction pattern")
+                if a == self.THIRD:
+                    self.third = q
+                else:
+                    self.fourth = q
                 continue
             da, db = self.dirs[a], self.dirs[b]
             self.second_of_dims[(da, db)] = q
@@ -56,6 +66,16 @@ class JetSpec:
         return JetSpec((), ())
 
     @staticmethod
+    def one_direction(dim, order):
+        """{value, d/dx, ..., d^order/dx^order} along input `dim` (order 2..4)."""
+        pairs = [(0, 0), (JetSpec.THIRD, JetSpec.THIRD), (JetSpec.FOURTH, JetSpec.FOURTH)][: order - 1]
+        return JetSpec([dim], pairs)
+
+    def higher(self):
+        """indices (into the streams after the value) of the third / fourth derivative streams that exist"""
+        return [self.n1 + q for q in (self.third, self.fourth) if q is not None]
+
+    @staticmethod
     def full(d_in):
         if d_in > _lib.MAX_FIRST:
             raise NotImplementedError(
@@ -66,10 +86,17 @@ class JetSpec:
         return JetSpec(dirs, pairs)
 
     @staticmethod
-    def covering(need1, need2):
+    def covering(need1, need2, order=2):
         """Smallest compiled pattern covering first-order dims `need1` and second-order dim
-        pairs `need2` (iterables of ints / of (j, k))."""
+        pairs `need2` (iterables of ints / of (j, k)); `order` 3 / 4: derivatives up to that order along the
+        single direction all of them share."""
         need2 = {tuple(sorted(p)) for p in need2}
+        if order > 2:
+            dims = sorted(set(need1) | {d for p in need2 for d in p})
+            if len(dims) != 1:
+                raise NotImplementedError(
+                    "third- and fourth-order derivatives are compiled for one input direction only")
+            return JetSpec.one_direction(dims[0], order)
         dims = sorted(set(need1) | {d for p in need2 for d in p})
         n1 = len(dims)
         if n1 > _lib.MAX_FIRST:
@@ -100,8 +127,12 @@ def to_soa(x):
 
 
 # ---- functions with known derivatives -------------------------------------------------------
-class _Leaf2(Function):
-    """Second-order stream as a function of x; differentiating it again is third order."""
+_HIGHER_MSG = ("third- and higher-order derivatives of the network are not in the fused jet "
+               "kernels (second order is the compiled maximum; one-input networks go to fourth order)")
+
+
+class _Leaf4(Function):
+    """Fourth-order stream as a function of x; differentiating it again is fifth order."""
 
     @staticmethod
     def forward(ctx, x, h):
@@ -110,11 +141,69 @@ class _Leaf2(Function):
     @staticmethod
     def backward(ctx, g):
         if ctx.needs_input_grad[0] and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "third- and higher-order derivatives of the network are not in the fused jet "
-                "kernels (second order is the compiled maximum)"
-            )
+            raise NotImplementedError("fifth- and higher-order derivatives of the network are not in the fused jet kernels")
         return None, g
+
+
+class _Leaf3(Function):
+    """Third-order stream (one direction) as a function of x: d/dx = the fourth-order stream, if carried."""
+
+    @staticmethod
+    def forward(ctx, x, dim, h, *fourth):
+        ctx.dim = dim
+        ctx.save_for_backward(x, *fourth)
+        return h.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *fourth = ctx.saved_tensors
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if not fourth:
+                if torch.is_grad_enabled():
+                    raise NotImplementedError(_HIGHER_MSG)
+            else:
+                f = fourth[0]
+                if torch.is_grad_enabled():
+                    f = _Leaf4.apply(x, f)
+                gx = torch.zeros_like(x)
+                gx[:, ctx.dim] = (g * f).sum(dim=1)
+        return (gx, None, g) + (None,) * len(fourth)
+
+
+class _Leaf2(Function):
+    """Second-order stream as a function of x; differentiating it again is third order: available along the
+    single direction of the P_1_3 / P_1_4 patterns (`higher` = the third [and fourth] derivative streams)."""
+
+    @staticmethod
+    def forward(ctx, x, dim, h, *higher):
+        ctx.dim = dim
+        ctx.save_for_backward(x, *higher)
+        return h.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *higher = ctx.saved_tensors
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if not higher:
+                if torch.is_grad_enabled():
+                    raise NotImplementedError(_HIGHER_MSG)
+            else:
+                t = higher[0]
+                if torch.is_grad_enabled():
+                    t = _Leaf3.apply(x, ctx.dim, t, *higher[1:])
+                gx = torch.zeros_like(x)
+                gx[:, ctx.dim] = (g * t).sum(dim=1)
+        return (gx, None, g) + (None,) * len(higher)
+
+
+def _second_leaf(x, spec, q, after_value):
+    """_Leaf2 over second-order stream q; `after_value` = the streams after the value (firsts, then seconds)."""
+    h = after_value[spec.n1 + q]
+    if q == 0 and spec.third is not None:
+        return _Leaf2.apply(x, spec.dirs[0], h, *[after_value[i] for i in spec.higher()])
+    return _Leaf2.apply(x, 0, h)
 
 
 class _Leaf1(Function):
@@ -141,7 +230,7 @@ class _Leaf1(Function):
                     continue
                 h = seconds[q]
                 if torch.is_grad_enabled():
-                    h = _Leaf2.apply(x, h)
+                    h = _second_leaf(x, spec, q, (None,) * spec.n1 + tuple(seconds))
                 cols.append((gd * h).sum(dim=1))
             gx = torch.stack(cols, dim=1)
         return (gx, None, None, gd) + (None,) * len(seconds)
@@ -215,20 +304,25 @@ class JetOutput:
                 return None
             qt = self.spec.trace
             if qt not in self._second:
-                self._second[qt] = _Leaf2.apply(self.x, self.streams[1 + self.spec.n1 + qt])
+                self._second[qt] = _Leaf2.apply(self.x, 0, self.streams[1 + self.spec.n1 + qt])
             lap = self._second[qt][:, comp : comp + 1]
             return lap if dim_i == self.spec.dirs[0] else torch.zeros_like(lap)
         q = self.spec.second_of_dims.get((dim_i, dim_j))
         if q is None:
             return None
         if q not in self._second:
-            self._second[q] = _Leaf2.apply(self.x, self.streams[1 + self.spec.n1 + q])
+            self._second[q] = _second_leaf(self.x, self.spec, q, self.streams[1:])
         return self._second[q][:, comp : comp + 1]
 
 
 def make_leaf(x, spec, streams):
     """streams: S tensors (n, C). Returns y (n, C) differentiable w.r.t. x via the streams."""
     return _Leaf0.apply(x, spec, streams[0], *streams[1:])
+
+
+def probe_spec(d):
+    """The widest pattern a probe hands out for d inputs: everything to second order; to fourth for one input."""
+    return JetSpec.full(d) if d > 1 else JetSpec.one_direction(0, 4)
 
 
 def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
@@ -252,7 +346,7 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
         raise NotImplementedError(f"probe for d_in={d} > {_lib.MAX_FIRST} inputs")
     if feature is not None:
         allow_trace = False
-    full = JetSpec.full(d)
+    full = probe_spec(d)
     gen = torch.Generator(device=x.device)
     gen.manual_seed(1234)
     mk = lambda: torch.randn((n, n_out), dtype=x.dtype, device=x.device, generator=gen).requires_grad_()
@@ -276,10 +370,16 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
         g = grads[j]
         if g is not None and bool((g != 0).any()):
             need1.append(full.dirs[j])
+    order = 2
     for q, (a, b) in enumerate(full.pairs):
         g = grads[full.n1 + q]
         if g is not None and bool((g != 0).any()):
-            need2.append((full.dirs[a], full.dirs[b]))
+            if q == full.third or q == full.fourth:
+                order = max(order, 3 if q == full.third else 4)
+            else:
+                need2.append((full.dirs[a], full.dirs[b]))
+    if order > 2:
+        return JetSpec.covering(need1 or [full.dirs[0]], need2, order=order)
     cover = JetSpec.covering(need1, need2)
     lap = _try_laplacian(x, fn, full, streams, cover, need2, total, allow_trace)
     return lap if lap is not None else cover

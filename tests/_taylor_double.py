@@ -11,19 +11,24 @@ import torch
 
 
 def _act(name, z):
+    """value and first four derivatives of the activation at z"""
     if name == 0:
         a = torch.tanh(z)
         s1 = 1 - a * a
         s2 = -2 * a * s1
+        s3 = -2 * s1 * (1 - 3 * a * a)
+        s4 = 8 * a * s1 * (2 - 3 * a * a)
     elif name == 1:
         a = torch.sin(z)
         s1 = torch.cos(z)
-        s2 = -a
+        s2, s3, s4 = -a, -s1, a
     else:
         a = torch.sigmoid(z)
         s1 = a * (1 - a)
         s2 = s1 * (1 - 2 * a)
-    return a, s1, s2
+        s3 = s1 * (1 + 6 * a * (a - 1))
+        s4 = s2 * (1 + 12 * a * (a - 1))
+    return a, s1, s2, s3, s4
 
 
 def _unpack(net, flat):
@@ -50,11 +55,15 @@ def taylor_streams(net, jet, flat, x):
     z += [torch.zeros_like(z[0]) for _ in pairs]
     first = getattr(net, "first_activation", 0)
     for li, (W, b) in enumerate(layers[1:]):
-        a, s1, s2 = _act(first - 1 if (li == 0 and first > 0) else net.activation, z[0])
+        a, s1, s2, s3, s4 = _act(first - 1 if (li == 0 and first > 0) else net.activation, z[0])
         A = [a] + [s1 * z[1 + j] for j in range(n1)]
         for q, (pa, pb) in enumerate(pairs):
             if pa == 15 and pb == 15:      # Laplacian stream over all first-order streams
                 A.append(s2 * sum(z[1 + j] * z[1 + j] for j in range(n1)) + s1 * z[1 + n1 + q])
+            elif pa == 14 and pb == 14:    # third derivative along the single direction (streams 1..3: orders 1..3 of z)
+                A.append(s3 * z[1] ** 3 + 3 * s2 * z[1] * z[2] + s1 * z[3])
+            elif pa == 13 and pb == 13:    # fourth derivative
+                A.append(s4 * z[1] ** 4 + 6 * s3 * z[1] ** 2 * z[2] + 3 * s2 * z[2] ** 2 + 4 * s2 * z[1] * z[3] + s1 * z[4])
             else:
                 A.append(s2 * z[1 + pa] * z[1 + pb] + s1 * z[1 + n1 + q])
         z = [A[0] @ W.t() + b] + [As @ W.t() for As in A[1:]]

@@ -23,6 +23,9 @@ SPECS = {
     "4f": ((0, 1, 2, 3), tuple((a, b) for a in range(4) for b in range(a, 4))),
     "2t": ((0, 1), ((15, 15),)),          # Laplacian stream u_xx + u_yy
     "3t": ((0, 1, 2), ((15, 15),)),
+    "1o3": ((0,), ((0, 0), (14, 14))),            # one direction to third order (gPINN on a 1-D second-order problem)
+    "1o4": ((0,), ((0, 0), (14, 14), (13, 13))),  # ... to fourth order (Euler beam)
+    "1o4y": ((1,), ((0, 0), (14, 14), (13, 13))), # the direction need not be input 0
 }
 
 CASES = [
@@ -43,6 +46,11 @@ CASES = [
     ([2, 256, 256, 256, 1], "tanh", "2t", 515, 1),
     ([2, 150, 150, 1], "sin", "2t", 300, 1),
     ([3, 40, 40, 2], "sigmoid", "3t", 65, 2),
+    ([1, 20, 20, 20, 1], "tanh", "1o4", 1003, 1),       # the reference's Euler beam net (cases/PDECases.py:428)
+    ([1, 20, 20, 20, 1], "tanh", "1o3", 517, 2),
+    ([1, 40, 24, 2], "sin", "1o4", 300, 1),
+    ([1, 32, 32, 32, 1], "sigmoid", "1o4", 65, 3),
+    ([2, 64, 64, 1], "tanh", "1o4y", 2000, 1),
     # large point sets (many point tiles per output block, ragged tails)
     ([2, 150, 150, 150, 1], "sin", "2t", 40001, 1),
     ([2, 64, 64, 3], "tanh", "2a", 38000, 2),

@@ -227,6 +227,64 @@ def test_stmsffn_space_and_time_nets_on_the_kernels():
         assert rel(g[k], t) < 1e-4, k
 
 
+def test_euler_beam_fourth_order_on_the_kernels():
+    """The reference's Euler beam (cases/PDECases.py:428-500: 1-[20]x3-1 tanh, residual u_xxxx + 1, BCs on u, u_x,
+    u_xx, u_xxx) through dde.Model on the GPU: the probe picks the one-direction fourth-order pattern, per-term
+    losses and parameter gradients agree with the float64 oracle (nested autograd) on the same points and weights."""
+    import ai4xde_b200.dde as dde
+    from oracle import ddelite
+
+    def build(d):
+        geom = d.geometry.Interval(0, 1)
+
+        def pde(x, y):
+            dy_xx = d.grad.hessian(y, x)
+            return d.grad.hessian(dy_xx, x) + 1
+
+        left = lambda x, on: on and np.isclose(x[0], 0)
+        right = lambda x, on: on and np.isclose(x[0], 1)
+        bcs = [
+            d.icbc.DirichletBC(geom, lambda x: 0, left),
+            d.icbc.NeumannBC(geom, lambda x: 0, left),
+            d.icbc.OperatorBC(geom, lambda x, y, _: d.grad.hessian(y, x), right),
+            d.icbc.OperatorBC(geom, lambda x, y, _: d.grad.jacobian(d.grad.hessian(y, x), x), right),
+        ]
+        data = d.data.PDE(geom, pde, bcs, num_domain=200, num_boundary=2, train_distribution="uniform")
+        net = d.nn.FNN([1] + [20] * 3 + [1], "tanh", "Glorot uniform")
+        return data, net
+
+    ddelite.config.set_default_float("float64")
+    try:
+        torch.manual_seed(4)
+        odata, onet = build(ddelite)
+        omodel = ddelite.Model(odata, onet)
+        omodel.compile("adam", lr=1e-3)
+        X, yt, aux = odata.train_next_batch()
+        _, ol = omodel.outputs_losses_train(X, yt, aux)
+        onet.zero_grad()
+        ol.sum().backward()
+        og = torch.cat([p.grad.reshape(-1) for p in onet.parameters()]).numpy()
+        ol = ol.detach().numpy()
+        state = {k: v.detach().float() for k, v in onet.state_dict().items()}
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    dde.config.set_default_float("float32")
+    dde.config.set_engine("auto")
+    data, net = build(dde)
+    net.load_state_dict(state)
+    model = dde.Model(data, net)
+    model.compile("adam", lr=1e-3)
+    Xf, yf, auxf = data.train_next_batch()
+    np.testing.assert_allclose(Xf, X.astype(np.float32), atol=1e-7)
+    _, fl = model.outputs_losses_train(Xf, yf, auxf)
+    net.zero_grad()
+    fl.sum().backward()
+    fg = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu().numpy()
+    np.testing.assert_allclose(fl.detach().double().cpu().numpy(), ol, rtol=1e-4)
+    assert np.abs(fg - og).max() / np.abs(og).max() < 1e-4
+
+
 def test_ide_data_on_the_fused_path_matches_the_oracle():
     """dde.data.IDE on the GPU (the reference's Volterra IDE, cases/PDECases.py:2054-2085: 3-argument residual,
     quadrature matrix, kernel e^{s-x}, IC): per-term losses and parameter gradients against the float64 oracle."""

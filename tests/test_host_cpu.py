@@ -323,3 +323,72 @@ def test_tensor_core_padding_is_the_same_function(ls, act):
     narrow = dde.nn.FNN([2, 50, 50, 50, 3], "tanh", "Glorot normal")._tc_pad     # only on an explicit 'tf32'
     assert narrow is not None and narrow.desc.widths[1] == 64 and not narrow.auto_ok
     assert dde.nn.FNN([2, 100, 100, 1], "sin", "Glorot normal")._tc_pad is None
+
+
+@pytest.mark.parametrize("act", ["tanh", "sin", "sigmoid"])
+def test_one_input_nets_go_to_fourth_order(act):
+    """One-direction third / fourth order streams (patterns P_1_3 / P_1_4; Euler beam, cases/PDECases.py:454-464):
+    the host leaves hand `jacobian(hessian(y, x), x)` and `hessian(hessian(y, x), x)` the kernels' streams, and the
+    Faa-di-Bruno double used as the GPU tests' reference is itself held to NESTED torch.autograd in float64
+    (an independent route) -- derivatives and parameter gradients."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import jet
+
+    dde.config.set_default_float("float32")
+    torch.manual_seed(0)
+    net = dde.nn.FNN([1, 20, 20, 20, 2], act, "Glorot normal")
+    x = (torch.rand(50, 1) * 2 - 1).requires_grad_()
+    with net.jet_scope(jet.JetSpec.one_direction(0, 4)):
+        y = net(x)
+    d2 = dde.grad.hessian(y, x, component=1)
+    d3 = dde.grad.jacobian(d2, x)
+    d4 = dde.grad.hessian(d2, x)
+    dde.grad.clear()
+    r = d4 + 0.5 * d3 + d2 + y[:, 1:]
+    net.zero_grad()
+    (r ** 2).mean().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double()
+    xr = x.detach().double().requires_grad_()
+    ps = [p.detach().double().requires_grad_() for p in net.parameters()]
+    f = {"tanh": torch.tanh, "sin": torch.sin, "sigmoid": torch.sigmoid}[act]
+    h = xr
+    for i in range(0, len(ps) - 2, 2):
+        h = f(h @ ps[i].t() + ps[i + 1])
+    u = (h @ ps[-2].t() + ps[-1])[:, 1:]
+    ds, cur = [], u
+    for _ in range(4):
+        cur = torch.autograd.grad(cur.sum(), xr, create_graph=True)[0]
+        ds.append(cur)
+    rr = ds[3] + 0.5 * ds[2] + ds[1] + u
+    gr = torch.cat([t.reshape(-1) for t in torch.autograd.grad((rr ** 2).mean(), ps)])
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(d3.detach().double(), ds[2].detach()) < 1e-5
+    assert rel(d4.detach().double(), ds[3].detach()) < 1e-5
+    assert rel(g, gr) < 1e-5
+    # a second-order pattern still refuses the third derivative, loudly
+    with net.jet_scope(jet.JetSpec.full(1)):
+        y = net(x)
+    d2 = dde.grad.hessian(y, x, component=0)
+    with pytest.raises(NotImplementedError):
+        dde.grad.jacobian(d2, x)
+    dde.grad.clear()
+
+
+def test_probe_finds_the_order_a_one_input_problem_needs():
+    from ai4xde_b200 import jet
+    import ai4xde_b200.dde as dde
+
+    x = torch.rand(16, 1).requires_grad_()
+    beam = lambda x, y: dde.grad.hessian(dde.grad.hessian(y, x), x) + 1
+    third = lambda x, y: dde.grad.jacobian(dde.grad.hessian(y, x), x) - y
+    second = lambda x, y: dde.grad.hessian(y, x) - y
+    assert jet.probe_streams(x, 1, beam).key() == jet.JetSpec.one_direction(0, 4).key()
+    dde.grad.clear()
+    assert jet.probe_streams(x, 1, third).key() == jet.JetSpec.one_direction(0, 3).key()
+    dde.grad.clear()
+    assert jet.probe_streams(x, 1, second).key() == ((0,), ((0, 0),))
+    dde.grad.clear()
+    x2 = torch.rand(16, 2).requires_grad_()
+    with pytest.raises(NotImplementedError):     # two inputs: third order is not compiled
+        jet.probe_streams(x2, 1, lambda x, y: dde.grad.jacobian(dde.grad.hessian(y, x, i=0, j=0), x, j=0))
+    dde.grad.clear()

@@ -72,6 +72,7 @@ CASES = [
     ("IDE", dict()),                                                                  # dde.data.IDE, 3-argument residual
     ("Volterra_IDE", dict()),                                                         # ... with a kernel, uniform points
     ("Wave_1D_STMsFFN", dict(layer_size=[2, 32, 32, 32, 1])),                         # STMsFFN, sigmas_x [1], sigmas_t [1, 10]
+    ("Euler_Beam", dict()),                                               # fourth-order jets of a one-input net
     ("A_Simple_ODE", dict()),
     ("SecondOrderODE", dict()),
     ("Diffusion", dict()),
