@@ -273,7 +273,9 @@ class FNN(NN):
                 y = jet.make_leaf(x, spec, streams)
                 grad.register(y, jet.JetOutput(x, spec, streams))
             else:
-                y = streams[0]
+                # a fresh tensor, not a view of the kernels' jet buffer: callers update it in place
+                # (algorithm/FBPINN.py:203 `result += y`)
+                y = streams[0].clone()
         if self._output_transform is not None:
             y = self._output_transform(inputs, y)
         return y
@@ -550,7 +552,9 @@ class MsFFN(NN):
                 y = jet.make_leaf(x, spec, streams)
                 grad.register(y, jet.JetOutput(x, spec, streams))
             else:
-                y = streams[0]
+                # a fresh tensor, not a view of the kernels' jet buffer: callers update it in place
+                # (algorithm/FBPINN.py:203 `result += y`)
+                y = streams[0].clone()
         if self._output_transform is not None:
             y = self._output_transform(inputs, y)
         return y
@@ -753,7 +757,9 @@ class STMsFFN(NN):
                 y = jet.make_leaf(x, spec, streams)
                 grad.register(y, jet.JetOutput(x, spec, streams))
             else:
-                y = streams[0]
+                # a fresh tensor, not a view of the kernels' jet buffer: callers update it in place
+                # (algorithm/FBPINN.py:203 `result += y`)
+                y = streams[0].clone()
         if self._output_transform is not None:
             y = self._output_transform(inputs, y)
         return y
