@@ -282,3 +282,37 @@ def test_end_to_end_training_reaches_the_reference_solutions():
     err = dde.metrics.l2_relative_error(y, s.model.predict(X))
     print("Helmholtz (reference-default sin net) L2 relative error", err)
     assert err < 0.02
+
+
+def test_causal_pinn_round_on_device():
+    """CausalPINN mirror (reference: algorithm/CausalPINN.py:82-120) on the GPU: the slab weights computed from the
+    device's residual probe equal the reference's formula evaluated in NumPy on those residuals; the weighted pde
+    scales the residual by the slab weight of each point; a short weighted training phase stays finite."""
+    dde = _setup()
+    from ai4xde_b200 import algorithm, cases
+
+    np.random.seed(3)
+    torch.manual_seed(3)
+    case = cases.AllenCahn(NumDomain=2000, layer_size=[2] + [64] * 3 + [1])
+    solver = algorithm.CausalPINN(case, t_num=5, num_per_t=100, iter=1, warmup_iter=5)
+    case.compile(solver.model, "adam", lr=1e-3)
+    solver.model.train(iterations=5)
+    base_pde = case.pde
+    edges = solver._edges()
+    X = solver._probe_points(edges)
+    Y = np.abs(solver.model.predict(X, operator=base_pde)).astype(np.float64).squeeze()
+    solver.update_weights()
+    err = np.power(Y, 1) / np.power(Y, 1).mean() + 0
+    err = err / sum(err)
+    per_t = np.array([err[i * 100:(i + 1) * 100].mean() for i in range(5)])
+    want = np.array([1.0] + [np.exp(-100 * per_t[: i - 1].sum()) for i in range(1, 5)])
+    np.testing.assert_allclose(solver.weight, want, rtol=1e-12)
+    assert solver.weight[0] == solver.weight[1] == 1.0 and np.all(np.diff(solver.weight) <= 0)
+    pts = case.geomtime.random_points(500)
+    plain = solver.model.predict(pts, operator=base_pde)
+    weighted = solver.model.predict(pts, operator=case.pde)
+    slab = np.minimum(np.searchsorted(edges, pts[:, -1], side="right") - 1, 4)
+    np.testing.assert_allclose(weighted[:, 0], plain[:, 0] * solver.weight[slab], rtol=1e-5, atol=1e-7)
+    case.compile(solver.model, "adam", lr=1e-3)
+    losshistory, _ = solver.model.train(iterations=20)
+    assert np.isfinite(np.asarray(losshistory.loss_train[-1])).all()

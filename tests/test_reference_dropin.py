@@ -238,3 +238,48 @@ def test_unmodified_reference_algorithm_runs_on_the_fused_path(name, monkeypatch
     same = {tuple(np.round(r, 5)) for r in x_o} & {tuple(np.round(r, 5)) for r in x_f}
     assert len(same) >= 0.9 * len(x_o), (len(same), len(x_o))
     assert np.abs(p_f - p_o).max() / np.abs(p_o).max() < 2e-2
+
+
+def test_causal_pinn_mirror_matches_the_unmodified_reference(monkeypatch):
+    """ai4xde_b200.algorithm.CausalPINN against the reference's CausalPINN.py run unmodified on the same backend,
+    weights and seed: slab weights after each of two rounds, the weight function on points that include slab edges
+    and both ends of the time axis, and the network weights after the closure."""
+    td.install(monkeypatch)
+    try:
+        A, dde_f = load_reference("fused")
+        dde_f.config.set_default_float("float32")
+        import ai4xde_b200.algorithm as p_alg
+        import ai4xde_b200.cases as p_cases
+
+        kw = dict(t_num=4, num_per_t=50, iter=2, warmup_iter=3)
+        out = []
+        for make in (lambda: A.algorithm.CausalPINN(A.cases.AllenCahn(**_SMALL), **kw),
+                     lambda: p_alg.CausalPINN(p_cases.AllenCahn(**_SMALL), **kw)):
+            np.random.seed(0)
+            torch.manual_seed(0)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                solver = make()
+                if out:
+                    solver.model.net.load_state_dict(out[0]["state"])
+                state = {k: v.detach().clone() for k, v in solver.model.net.state_dict().items()}
+                _cap_train_step(type(solver), dde_f)
+                seen = []
+                upd = solver.update_weights
+                solver.update_weights = lambda upd=upd, solver=solver: (upd(), seen.append(solver.weight.copy()))
+                np.random.seed(1)
+                solver.closure()
+            edges = np.linspace(0, 1, 5)
+            probe = torch.tensor([[0.3, t] for t in [0.0, 0.1, 0.25, 0.4999, 0.5, 0.75, 0.9, 1.0]], dtype=torch.float32)
+            wf = solver.get_weight_func(np.array([1.0, 0.5, 0.25, 0.125]), edges)(probe)
+            out.append(dict(state=state, seen=seen, wf=wf.detach().numpy().reshape(-1),
+                            params=torch.cat([p.detach().reshape(-1) for p in solver.model.net.parameters()]).numpy()))
+    finally:
+        _purge()
+    ref, mine = out
+    assert len(ref["seen"]) == len(mine["seen"]) == 2
+    for a, b in zip(ref["seen"], mine["seen"]):
+        np.testing.assert_allclose(b, a, rtol=1e-6)
+    np.testing.assert_array_equal(mine["wf"], ref["wf"])
+    np.testing.assert_array_equal(ref["wf"], np.array([1, 1, 0.5, 0.5, 0.25, 0.125, 0.125, 0], dtype=np.float32))
+    np.testing.assert_allclose(mine["params"], ref["params"], rtol=1e-4, atol=1e-6)
