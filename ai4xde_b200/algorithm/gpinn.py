@@ -1,8 +1,9 @@
 """gPINN: gradient-enhanced residuals (/root/reference/AI4XDE/algorithm/gPINN.py:4-74).
-The wrapped pde differentiates the residual once more (`jacobian(res_i, x, j)`), i.e. asks for
-third-order derivatives of the network.  The fused kernels carry jets up to second order, so for
-second-order PDEs this raises NotImplementedError from the jet leaves (loudly, at the first
-evaluation); first-order PDEs run."""
+The wrapped pde differentiates the residual once more (`jacobian(res_i, x, j)`), i.e. asks for one more order
+of network derivatives than the PDE itself.  The kernels carry third order along one or two inputs (patterns
+P_1_3 / P_2_3, FP32 engine) and fourth along one, which covers second-order PDEs in x or (x, t) -- the
+reference's own example is Burgers (gPINN.py:77-81); beyond that the jet leaves raise NotImplementedError
+(loudly, at the first evaluation)."""
 from .. import dde
 from ..solver import PINNSolver
 

@@ -76,12 +76,17 @@ constexpr int kTracePair = 15;
 using P_1_3 = Pattern<1, 2, 0xE0ull, 0xE0ull>;      // {0,a,aa,aaa}
 using P_1_4 = Pattern<1, 3, 0xDE0ull, 0xDE0ull>;    // {0,a,aa,aaa,aaaa}
 constexpr int kThirdPair = 14, kFourthPair = 13;
+// two-input third order (gPINN on a second-order PDE in (x, t): the reference's own gPINN example is Burgers,
+// algorithm/gPINN.py:77-81): after aa, ab, bb come aaa, aab, abb, bbb -- pair code 8 + (number of b's).
+using P_2_3 = Pattern<2, 7, 0xBA98100ull, 0xBA98110ull>;  // {0,a,b,aa,ab,bb,aaa,aab,abb,bbb}
+constexpr int kTripleBase = 8;
+__host__ __device__ constexpr bool is_triple(int code) { return code >= kTripleBase && code < kTripleBase + 4; }
 // highest derivative order a pattern carries
 template <class P>
 __host__ __device__ constexpr int pattern_order() {
   int ord = P::N2 > 0 ? 2 : (P::N1 > 0 ? 1 : 0);
   for (int q = 0; q < P::N2; ++q) {
-    if (P::pa(q) == kThirdPair && ord < 3) ord = 3;
+    if ((P::pa(q) == kThirdPair || is_triple(P::pa(q))) && ord < 3) ord = 3;
     if (P::pa(q) == kFourthPair) ord = 4;
   }
   return ord;
@@ -90,8 +95,8 @@ __host__ __device__ constexpr int pattern_order() {
 #define AX_FOR_EACH_PATTERN(X) \
   X(0, P_V) X(1, P_1) X(2, P_1_D) X(3, P_2) X(4, P_2_A) X(5, P_2_D) X(6, P_2_F) X(7, P_3) \
   X(8, P_3_D) X(9, P_3_F) X(10, P_4) X(11, P_4_D) X(12, P_4_F) X(13, P_2_T) X(14, P_3_T) X(15, P_1_3) \
-  X(16, P_1_4)
-constexpr int kNumPatterns = 17;
+  X(16, P_1_4) X(17, P_2_3)
+constexpr int kNumPatterns = 18;
 
 // returns pattern id or -1
 int match_pattern(const ax_jet_desc *jet);
@@ -163,6 +168,14 @@ __device__ __forceinline__ void jet_reconstruct(int act, const float (&st)[P::S]
       // P_1_3 / P_1_4: st[1..3] = first, second, third derivative of z (Faa di Bruno, one variable)
       const float z1 = st[1], z2 = st[2], z3 = st[3];
       A[1 + P::N1 + q] = fmaf(d.s3 * z1 * z1, z1, fmaf(3.0f * d.s2 * z1, z2, d.s1 * z3));
+    } else if (is_triple(P::pa(q))) {
+      // P_2_3: triple (i, j, k), i <= j <= k in {a = 0, b = 1}; st[1 + i] first, st[3 + i + j] second order
+      const int m = P::pa(q) - kTripleBase;
+      const int i = m >= 3 ? 1 : 0, j = m >= 2 ? 1 : 0, k = m >= 1 ? 1 : 0;
+      const float zi = st[1 + i], zj = st[1 + j], zk = st[1 + k];
+      const float zij = st[3 + i + j], zik = st[3 + i + k], zjk = st[3 + j + k];
+      A[1 + P::N1 + q] = fmaf(d.s3 * zi * zj, zk,
+                              fmaf(d.s2, fmaf(zij, zk, fmaf(zik, zj, zjk * zi)), d.s1 * st[1 + P::N1 + q]));
     } else if (P::pa(q) == kFourthPair) {
       const float z1 = st[1], z2 = st[2], z3 = st[3], z4 = st[P::S - 1];
       const float z11 = z1 * z1;
@@ -202,6 +215,20 @@ __device__ __forceinline__ void jet_adjoint(int act, const float (&st)[P::S], co
       z0b = fmaf(fmaf(d.s4 * z1 * z1, z1, fmaf(3.0f * d.s3 * z1, z2, d.s2 * z3)), aq, z0b);
       zb[1] = fmaf(3.0f * fmaf(d.s3 * z1, z1, d.s2 * z2), aq, zb[1]);
       zb[2] = fmaf(3.0f * d.s2 * z1, aq, zb[2]);
+    } else if (is_triple(P::pa(q))) {
+      // A_ijk = s3 zi zj zk + s2 (zij zk + zik zj + zjk zi) + s1 zijk
+      const int m = P::pa(q) - kTripleBase;
+      const int i = m >= 3 ? 1 : 0, j = m >= 2 ? 1 : 0, k = m >= 1 ? 1 : 0;
+      const float zi = st[1 + i], zj = st[1 + j], zk = st[1 + k];
+      const float zij = st[3 + i + j], zik = st[3 + i + k], zjk = st[3 + j + k];
+      const float mix = fmaf(zij, zk, fmaf(zik, zj, zjk * zi));
+      z0b = fmaf(fmaf(d.s4 * zi * zj, zk, fmaf(d.s3, mix, d.s2 * zq)), aq, z0b);
+      zb[1 + i] = fmaf(fmaf(d.s3 * zj, zk, d.s2 * zjk), aq, zb[1 + i]);
+      zb[1 + j] = fmaf(fmaf(d.s3 * zi, zk, d.s2 * zik), aq, zb[1 + j]);
+      zb[1 + k] = fmaf(fmaf(d.s3 * zi, zj, d.s2 * zij), aq, zb[1 + k]);
+      zb[3 + i + j] = fmaf(d.s2 * zk, aq, zb[3 + i + j]);
+      zb[3 + i + k] = fmaf(d.s2 * zj, aq, zb[3 + i + k]);
+      zb[3 + j + k] = fmaf(d.s2 * zi, aq, zb[3 + j + k]);
     } else if (P::pa(q) == kFourthPair) {
       // A4 = s4 z1^4 + 6 s3 z1^2 z2 + 3 s2 z2^2 + 4 s2 z1 z3 + s1 z4
       const float z1 = st[1], z2 = st[2], z3 = st[3], z4 = st[P::S - 1];

@@ -7,4 +7,6 @@ template int simt_forward<P_2_D>(const FwdArgs &);
 template int simt_backward<P_2_D>(const BwdArgs &);
 template int simt_forward<P_2_F>(const FwdArgs &);
 template int simt_backward<P_2_F>(const BwdArgs &);
+template int simt_forward<P_2_3>(const FwdArgs &);
+template int simt_backward<P_2_3>(const BwdArgs &);
 }  // namespace ax

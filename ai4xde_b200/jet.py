@@ -23,6 +23,7 @@ class JetSpec:
 
     TRACE = 15  # pair code of the Laplacian stream (csrc/common.cuh kTracePair)
     THIRD, FOURTH = 14, 13  # pair codes of the one-direction third / fourth derivative streams (P_1_3, P_1_4)
+    TRIPLE = 8              # pair code 8 + m: third derivative with m factors along dirs[1], 3 - m along dirs[0] (P_2_3)
 
     def __init__(self, dirs, pairs):
         self.dirs = tuple(int(d) for d in dirs)
@@ -33,7 +34,13 @@ class JetSpec:
         self.second_of_dims = {}
         self.trace = None  # index q of the Laplacian stream, if this is a trace pattern
         self.third = self.fourth = None  # index q of the third / fourth derivative stream (one direction only)
+        self.triples = {}                # m -> index q of the two-direction third derivative stream
         for q, (a, b) in enumerate(self.pairs):
+            if a == b and self.TRIPLE <= a < self.TRIPLE + 4:
+                if self.n1 != 2 or self.pairs[:3] != ((0, 0), (0, 1), (1, 1)):
+                    raise ValueError("two-direction third order streams follow the (0,0), (0,1), (1,1) streams")
+                self.triples[a - self.TRIPLE] = q
+                continue
             if a == self.TRACE and b == self.TRACE:
                 self.trace = q
                 continue
@@ -71,9 +78,23 @@ class JetSpec:
         pairs = [(0, 0), (JetSpec.THIRD, JetSpec.THIRD), (JetSpec.FOURTH, JetSpec.FOURTH)][: order - 1]
         return JetSpec([dim], pairs)
 
-    def higher(self):
-        """indices (into the streams after the value) of the third / fourth derivative streams that exist"""
-        return [self.n1 + q for q in (self.third, self.fourth) if q is not None]
+    @staticmethod
+    def two_direction_third(dim_a, dim_b):
+        """everything to third order along two inputs: {u, a, b, aa, ab, bb, aaa, aab, abb, bbb}"""
+        t = JetSpec.TRIPLE
+        return JetSpec([dim_a, dim_b], [(0, 0), (0, 1), (1, 1)] + [(t + m, t + m) for m in range(4)])
+
+    def children_of_second(self, q):
+        """What differentiating second-order stream q once more gives: {input dim: (index of that third-order
+        stream in the list of streams after the value, children of that stream)} -- empty if this pattern stops
+        at second order."""
+        if q == 0 and self.third is not None:
+            fourth = {} if self.fourth is None else {self.dirs[0]: (self.n1 + self.fourth, {})}
+            return {self.dirs[0]: (self.n1 + self.third, fourth)}
+        if self.triples and q < 3:
+            ia, ib = self.pairs[q]
+            return {self.dirs[k]: (self.n1 + self.triples[ia + ib + k], {}) for k in (0, 1)}
+        return {}
 
     @staticmethod
     def full(d_in):
@@ -93,10 +114,12 @@ class JetSpec:
         need2 = {tuple(sorted(p)) for p in need2}
         if order > 2:
             dims = sorted(set(need1) | {d for p in need2 for d in p})
-            if len(dims) != 1:
-                raise NotImplementedError(
-                    "third- and fourth-order derivatives are compiled for one input direction only")
-            return JetSpec.one_direction(dims[0], order)
+            if len(dims) == 1:
+                return JetSpec.one_direction(dims[0], order)
+            if len(dims) == 2 and order == 3:
+                return JetSpec.two_direction_third(*dims)
+            raise NotImplementedError(
+                "third-order derivatives are compiled for one or two input directions, fourth-order for one")
         dims = sorted(set(need1) | {d for p in need2 for d in p})
         n1 = len(dims)
         if n1 > _lib.MAX_FIRST:
@@ -127,83 +150,60 @@ def to_soa(x):
 
 
 # ---- functions with known derivatives -------------------------------------------------------
-_HIGHER_MSG = ("third- and higher-order derivatives of the network are not in the fused jet "
-               "kernels (second order is the compiled maximum; one-input networks go to fourth order)")
+_HIGHER_MSG = ("third- and higher-order derivatives of the network are not in the fused jet kernels beyond: "
+               "third order along one or two inputs, fourth order along one")
 
 
-class _Leaf4(Function):
-    """Fourth-order stream as a function of x; differentiating it again is fifth order."""
+class _LeafHigher(Function):
+    """A second- or higher-order stream as a function of x.  `children` = {input dim: (index into `tensors`,
+    children of that stream)} names the carried streams that are its x-derivatives; a stream without children
+    is the end of what the kernels carry, differentiating it raises."""
 
     @staticmethod
-    def forward(ctx, x, h):
+    def forward(ctx, x, children, h, *tensors):
+        ctx.children = children
+        ctx.save_for_backward(x, *tensors)
         return h.clone()
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.needs_input_grad[0] and torch.is_grad_enabled():
-            raise NotImplementedError("fifth- and higher-order derivatives of the network are not in the fused jet kernels")
-        return None, g
-
-
-class _Leaf3(Function):
-    """Third-order stream (one direction) as a function of x: d/dx = the fourth-order stream, if carried."""
-
-    @staticmethod
-    def forward(ctx, x, dim, h, *fourth):
-        ctx.dim = dim
-        ctx.save_for_backward(x, *fourth)
-        return h.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        x, *fourth = ctx.saved_tensors
+        x, *tensors = ctx.saved_tensors
         gx = None
         if ctx.needs_input_grad[0]:
-            if not fourth:
+            if not ctx.children:
                 if torch.is_grad_enabled():
                     raise NotImplementedError(_HIGHER_MSG)
             else:
-                f = fourth[0]
-                if torch.is_grad_enabled():
-                    f = _Leaf4.apply(x, f)
                 gx = torch.zeros_like(x)
-                gx[:, ctx.dim] = (g * f).sum(dim=1)
-        return (gx, None, g) + (None,) * len(fourth)
+                cols = []
+                for dim in range(x.shape[1]):
+                    hit = ctx.children.get(dim)
+                    if hit is None:
+                        cols.append(torch.zeros_like(g[:, 0]))
+                        continue
+                    t = tensors[hit[0]]
+                    if torch.is_grad_enabled():
+                        t = _LeafHigher.apply(x, hit[1], t, *tensors)
+                    cols.append((g * t).sum(dim=1))
+                gx = torch.stack(cols, dim=1)
+        return (gx, None, g) + (None,) * len(tensors)
 
 
-class _Leaf2(Function):
-    """Second-order stream as a function of x; differentiating it again is third order: available along the
-    single direction of the P_1_3 / P_1_4 patterns (`higher` = the third [and fourth] derivative streams)."""
-
-    @staticmethod
-    def forward(ctx, x, dim, h, *higher):
-        ctx.dim = dim
-        ctx.save_for_backward(x, *higher)
-        return h.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        x, *higher = ctx.saved_tensors
-        gx = None
-        if ctx.needs_input_grad[0]:
-            if not higher:
-                if torch.is_grad_enabled():
-                    raise NotImplementedError(_HIGHER_MSG)
-            else:
-                t = higher[0]
-                if torch.is_grad_enabled():
-                    t = _Leaf3.apply(x, ctx.dim, t, *higher[1:])
-                gx = torch.zeros_like(x)
-                gx[:, ctx.dim] = (g * t).sum(dim=1)
-        return (gx, None, g) + (None,) * len(higher)
+def _compact(children, after_value, keep):
+    """children with indices into `after_value` -> the same tree with indices into the list `keep` collects"""
+    out = {}
+    for dim, (idx, sub) in children.items():
+        keep.append(after_value[idx])
+        pos = len(keep) - 1
+        out[dim] = (pos, _compact(sub, after_value, keep))
+    return out
 
 
 def _second_leaf(x, spec, q, after_value):
-    """_Leaf2 over second-order stream q; `after_value` = the streams after the value (firsts, then seconds)."""
-    h = after_value[spec.n1 + q]
-    if q == 0 and spec.third is not None:
-        return _Leaf2.apply(x, spec.dirs[0], h, *[after_value[i] for i in spec.higher()])
-    return _Leaf2.apply(x, 0, h)
+    """Leaf over second-order stream q; `after_value` = the streams after the value (firsts, then seconds)."""
+    keep = []
+    children = _compact(spec.children_of_second(q), after_value, keep)
+    return _LeafHigher.apply(x, children, after_value[spec.n1 + q], *keep)
 
 
 class _Leaf1(Function):
@@ -304,7 +304,7 @@ class JetOutput:
                 return None
             qt = self.spec.trace
             if qt not in self._second:
-                self._second[qt] = _Leaf2.apply(self.x, 0, self.streams[1 + self.spec.n1 + qt])
+                self._second[qt] = _LeafHigher.apply(self.x, {}, self.streams[1 + self.spec.n1 + qt])
             lap = self._second[qt][:, comp : comp + 1]
             return lap if dim_i == self.spec.dirs[0] else torch.zeros_like(lap)
         q = self.spec.second_of_dims.get((dim_i, dim_j))
@@ -321,8 +321,11 @@ def make_leaf(x, spec, streams):
 
 
 def probe_spec(d):
-    """The widest pattern a probe hands out for d inputs: everything to second order; to fourth for one input."""
-    return JetSpec.full(d) if d > 1 else JetSpec.one_direction(0, 4)
+    """The widest pattern a probe hands out for d inputs: everything to second order; to third for two inputs,
+    to fourth for one."""
+    if d == 1:
+        return JetSpec.one_direction(0, 4)
+    return JetSpec.two_direction_third(0, 1) if d == 2 else JetSpec.full(d)
 
 
 def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
@@ -376,10 +379,12 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
         if g is not None and bool((g != 0).any()):
             if q == full.third or q == full.fourth:
                 order = max(order, 3 if q == full.third else 4)
+            elif q in full.triples.values():
+                order = max(order, 3)
             else:
                 need2.append((full.dirs[a], full.dirs[b]))
     if order > 2:
-        return JetSpec.covering(need1 or [full.dirs[0]], need2, order=order)
+        return JetSpec.covering(full.dirs if full.triples else (need1 or [full.dirs[0]]), need2, order=order)
     cover = JetSpec.covering(need1, need2)
     lap = _try_laplacian(x, fn, full, streams, cover, need2, total, allow_trace)
     return lap if lap is not None else cover

@@ -60,7 +60,10 @@ typedef struct ax_jet_desc {
   int32_t pa[AX_MAX_SECOND];   /* stream q is d2/d(dir1[pa[q]]) d(dir1[pb[q]]), pa<=pb; pa=pb=15: the
                                   Laplacian over all first-order streams (sum_j d2/d(dir1[j])^2);
                                   with n1 = 1 and stream 0 = (0, 0): pa=pb=14 is d3/d(dir1[0])^3 and
-                                  pa=pb=13 is d4/d(dir1[0])^4 (Euler beam, cases/PDECases.py:454-464) */
+                                  pa=pb=13 is d4/d(dir1[0])^4 (Euler beam, cases/PDECases.py:454-464);
+                                  with n1 = 2 and streams 0..2 = (0,0), (0,1), (1,1): pa=pb=8+m is the third
+                                  derivative with m factors d/d(dir1[1]) and 3-m factors d/d(dir1[0])
+                                  (gPINN on second-order PDEs, algorithm/gPINN.py:45-48) */
   int32_t pb[AX_MAX_SECOND];
 } ax_jet_desc;
 

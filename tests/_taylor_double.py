@@ -62,6 +62,11 @@ def taylor_streams(net, jet, flat, x):
                 A.append(s2 * sum(z[1 + j] * z[1 + j] for j in range(n1)) + s1 * z[1 + n1 + q])
             elif pa == 14 and pb == 14:    # third derivative along the single direction (streams 1..3: orders 1..3 of z)
                 A.append(s3 * z[1] ** 3 + 3 * s2 * z[1] * z[2] + s1 * z[3])
+            elif pa == pb and 8 <= pa < 12:  # two-direction third order: m factors along direction 1 (streams 1, 2 first; 3, 4, 5 = aa, ab, bb)
+                m = pa - 8
+                i, j, k = int(m >= 3), int(m >= 2), int(m >= 1)
+                A.append(s3 * z[1 + i] * z[1 + j] * z[1 + k]
+                         + s2 * (z[3 + i + j] * z[1 + k] + z[3 + i + k] * z[1 + j] + z[3 + j + k] * z[1 + i]) + s1 * z[1 + n1 + q])
             elif pa == 13 and pb == 13:    # fourth derivative
                 A.append(s4 * z[1] ** 4 + 6 * s3 * z[1] ** 2 * z[2] + 3 * s2 * z[2] ** 2 + 4 * s2 * z[1] * z[3] + s1 * z[4])
             else:

@@ -26,6 +26,8 @@ SPECS = {
     "1o3": ((0,), ((0, 0), (14, 14))),            # one direction to third order (gPINN on a 1-D second-order problem)
     "1o4": ((0,), ((0, 0), (14, 14), (13, 13))),  # ... to fourth order (Euler beam)
     "1o4y": ((1,), ((0, 0), (14, 14), (13, 13))), # the direction need not be input 0
+    "2o3": ((0, 1), ((0, 0), (0, 1), (1, 1), (8, 8), (9, 9), (10, 10), (11, 11))),   # two directions to third order (gPINN)
+    "2o3r": ((2, 0), ((0, 0), (0, 1), (1, 1), (8, 8), (9, 9), (10, 10), (11, 11))),  # ... any two inputs, any order
 }
 
 CASES = [
@@ -51,6 +53,10 @@ CASES = [
     ([1, 40, 24, 2], "sin", "1o4", 300, 1),
     ([1, 32, 32, 32, 1], "sigmoid", "1o4", 65, 3),
     ([2, 64, 64, 1], "tanh", "1o4y", 2000, 1),
+    ([2, 20, 20, 20, 1], "tanh", "2o3", 2540, 1),       # gPINN on the reference's Burgers (algorithm/gPINN.py:77-81)
+    ([2, 64, 64, 64, 1], "tanh", "2o3", 1001, 2),
+    ([2, 48, 32, 2], "sin", "2o3", 333, 1),
+    ([3, 40, 40, 1], "sigmoid", "2o3r", 130, 1),
     # large point sets (many point tiles per output block, ragged tails)
     ([2, 150, 150, 150, 1], "sin", "2t", 40001, 1),
     ([2, 64, 64, 3], "tanh", "2a", 38000, 2),

@@ -388,7 +388,58 @@ def test_probe_finds_the_order_a_one_input_problem_needs():
     dde.grad.clear()
     assert jet.probe_streams(x, 1, second).key() == ((0,), ((0, 0),))
     dde.grad.clear()
-    x2 = torch.rand(16, 2).requires_grad_()
-    with pytest.raises(NotImplementedError):     # two inputs: third order is not compiled
-        jet.probe_streams(x2, 1, lambda x, y: dde.grad.jacobian(dde.grad.hessian(y, x, i=0, j=0), x, j=0))
+    x2 = torch.rand(16, 2).requires_grad_()      # two inputs: everything to third order (gPINN on Burgers)
+    u_xxx = lambda x, y: dde.grad.jacobian(dde.grad.hessian(y, x, i=0, j=0), x, j=0)
+    assert jet.probe_streams(x2, 1, u_xxx).key() == jet.JetSpec.two_direction_third(0, 1).key()
     dde.grad.clear()
+    burgers = lambda x, y: dde.grad.jacobian(y, x, j=1) + y * dde.grad.jacobian(y, x, j=0) - 0.01 * dde.grad.hessian(y, x, i=0, j=0)
+    assert jet.probe_streams(x2, 1, burgers).key() == ((1, 0), ((0, 0),)) or jet.probe_streams(x2, 1, burgers).n2 == 1
+    dde.grad.clear()
+    with pytest.raises(NotImplementedError):     # fourth order along two inputs is not compiled
+        jet.probe_streams(x2, 1, lambda x, y: dde.grad.hessian(dde.grad.hessian(y, x, i=0, j=0), x, i=0, j=0))
+    dde.grad.clear()
+    x3 = torch.rand(16, 3).requires_grad_()
+    with pytest.raises(NotImplementedError):     # three inputs: third order is not compiled
+        jet.probe_streams(x3, 1, lambda x, y: dde.grad.jacobian(dde.grad.hessian(y, x, i=0, j=0), x, j=0))
+    dde.grad.clear()
+
+
+@pytest.mark.parametrize("act", ["tanh", "sin", "sigmoid"])
+def test_two_input_nets_go_to_third_order(act):
+    """Pattern P_2_3 = {u, a, b, aa, ab, bb, aaa, aab, abb, bbb} (gPINN on second-order PDEs in (x, t);
+    algorithm/gPINN.py:45-48): every third derivative reached by differentiating a hessian column once more, and
+    the parameter gradient of a residual built from them, against NESTED torch.autograd in float64."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import jet
+
+    dde.config.set_default_float("float32")
+    torch.manual_seed(0)
+    net = dde.nn.FNN([2, 20, 20, 2], act, "Glorot normal")
+    x = (torch.rand(40, 2) * 2 - 1).requires_grad_()
+    with net.jet_scope(jet.JetSpec.two_direction_third(0, 1)):
+        y = net(x)
+    uxx = dde.grad.hessian(y, x, component=1, i=0, j=0)
+    uxt = dde.grad.hessian(y, x, component=1, i=0, j=1)
+    utt = dde.grad.hessian(y, x, component=1, i=1, j=1)
+    r = (dde.grad.jacobian(uxx, x, j=0) + 2 * dde.grad.jacobian(uxx, x, j=1) + 3 * dde.grad.jacobian(uxt, x, j=1)
+         + 4 * dde.grad.jacobian(utt, x, j=1) + 0.5 * dde.grad.jacobian(uxt, x, j=0) + uxx * y[:, :1])
+    dde.grad.clear()
+    net.zero_grad()
+    (r ** 2).mean().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double()
+    xr = x.detach().double().requires_grad_()
+    ps = [p.detach().double().requires_grad_() for p in net.parameters()]
+    f = {"tanh": torch.tanh, "sin": torch.sin, "sigmoid": torch.sigmoid}[act]
+    h = xr
+    for i in range(0, len(ps) - 2, 2):
+        h = f(h @ ps[i].t() + ps[i + 1])
+    yr = h @ ps[-2].t() + ps[-1]
+    G = lambda t: torch.autograd.grad(t.sum(), xr, create_graph=True)[0]
+    d1 = G(yr[:, 1:])
+    dx, dt = G(d1[:, 0:1]), G(d1[:, 1:2])
+    dxx, dxt, dtt = G(dx[:, 0:1]), G(dx[:, 1:2]), G(dt[:, 1:2])
+    rr = dxx[:, 0:1] + 2 * dxx[:, 1:2] + 3 * dxt[:, 1:2] + 4 * dtt[:, 1:2] + 0.5 * dxt[:, 0:1] + dx[:, 0:1] * yr[:, :1]
+    gr = torch.cat([t.reshape(-1) for t in torch.autograd.grad((rr ** 2).mean(), ps)])
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(r.detach().double(), rr.detach()) < 1e-5
+    assert rel(g, gr) < 1e-5

@@ -182,6 +182,8 @@ ALGORITHMS = {
         A.cases.Beltrami_flow(NumDomain=60, layer_size=[4, 16, 16, 4]), max_iter=2, causally_sampling=True),
     "gPINN": lambda A: A.algorithm.gPINN(A.cases.A_Simple_ODE()),
     "gPINN_second_order_1d": lambda A: A.algorithm.gPINN(A.cases.Poisson_1D_Dirichlet()),   # third-order jets
+    "gPINN_burgers": lambda A: A.algorithm.gPINN(A.cases.Burgers(**_SMALL)),    # the reference's own gPINN example
+    "gPINN_heat": lambda A: A.algorithm.gPINN(A.cases.Heat(NumDomain=150)),     # soft BC / IC terms beside it
     "CausalPINN": lambda A: A.algorithm.CausalPINN(A.cases.AllenCahn(**_SMALL), t_num=4, num_per_t=50, iter=2,
                                                    warmup_iter=3),
     "FBPINN": lambda A: A.algorithm.FBPINN(A.cases.Harmonic_Oscillator_1D(NumDomain=200), segment=4, iter=1),
