@@ -265,6 +265,54 @@ class Disk(Geometry):
         return (self.radius * np.hstack([np.cos(theta), np.sin(theta)]) + self.center).astype(_real())
 
 
+class Sphere(Geometry):
+    """dde.geometry.Sphere (the ball of the reference's 3-D fractional Poisson case, cases/PDECases.py:2346).
+    Pseudo-random interior points: radius U^(1/3) times a normalised Gaussian direction, U drawn before the
+    directions; boundary points: normalised Gaussian directions."""
+    dim = 3
+
+    def __init__(self, center, radius):
+        self.center = np.array(center, dtype=_real())
+        self.radius = radius
+        self.bbox = (self.center - radius, self.center + radius)
+        self.diam = 2 * radius
+
+    def _distance(self, x):
+        return np.linalg.norm(x - self.center, axis=-1)
+
+    def inside(self, x):
+        return self._distance(x) <= self.radius
+
+    def on_boundary(self, x):
+        return np.isclose(self._distance(x), self.radius)
+
+    def boundary_normal(self, x):
+        v = x - self.center
+        l = np.linalg.norm(v, axis=-1, keepdims=True)
+        return v / l * np.isclose(l, self.radius)
+
+    def _directions(self, n, random, skip=0):
+        if random == "pseudo":
+            g = np.random.normal(size=(n, self.dim))
+        else:
+            from scipy import stats
+
+            g = stats.norm.ppf(sample(n, self.dim + skip, random)[:, skip:])
+        return g / np.linalg.norm(g, axis=1, keepdims=True)
+
+    def random_points(self, n, random="pseudo"):
+        if random == "pseudo":
+            u = np.random.rand(n, 1)
+            d = self._directions(n, random)
+        else:
+            u = sample(n, self.dim + 1, random)[:, 0:1]
+            d = self._directions(n, random, skip=1)
+        return (self.radius * u ** (1 / self.dim) * d + self.center).astype(_real())
+
+    def random_boundary_points(self, n, random="pseudo"):
+        return (self.radius * self._directions(n, random) + self.center).astype(_real())
+
+
 class Polygon(Geometry):
     """Simple polygon given by its vertices in order (either orientation; stored clockwise as DeepXDE does) --
     `dde.geometry.Polygon([[0, 0], [1, 0], [1, -1], [-1, -1], [-1, 1], [0, 1]])` is the L-shaped domain of

@@ -337,6 +337,55 @@ class Disk(Geometry):
         return (self.radius * X + self.center).astype(config.real(np))
 
 
+class Hypersphere(Geometry):
+    """[DeepXDE-upstream `geometry_nd.Hypersphere`, restated; parity unpinned against the absent package]: ball of
+    any dimension; 'pseudo' interior points are U^(1/dim) * normalised Gaussian vectors with U drawn first."""
+
+    def __init__(self, center, radius):
+        self.center = np.array(center, dtype=config.real(np))
+        self.radius = radius
+        super().__init__(len(center), (self.center - radius, self.center + radius), 2 * radius)
+        self._r2 = radius**2
+
+    def inside(self, x):
+        return np.linalg.norm(x - self.center, axis=-1) <= self.radius
+
+    def on_boundary(self, x):
+        return np.isclose(np.linalg.norm(x - self.center, axis=-1), self.radius)
+
+    def boundary_normal(self, x):
+        _n = x - self.center
+        l = np.linalg.norm(_n, axis=-1, keepdims=True)
+        return _n / l * np.isclose(l, self.radius)
+
+    def random_points(self, n, random="pseudo"):
+        if random == "pseudo":
+            U = np.random.rand(n, 1)
+            X = np.random.normal(size=(n, self.dim))
+        else:
+            from scipy import stats
+
+            rng = sample(n, self.dim + 1, random)
+            U, X = rng[:, 0:1], stats.norm.ppf(rng[:, 1:])
+        X = X / np.linalg.norm(X, axis=1, keepdims=True)
+        X = U ** (1 / self.dim) * X
+        return (self.radius * X + self.center).astype(config.real(np))
+
+    def random_boundary_points(self, n, random="pseudo"):
+        if random == "pseudo":
+            X = np.random.normal(size=(n, self.dim))
+        else:
+            from scipy import stats
+
+            X = stats.norm.ppf(sample(n, self.dim, random))
+        X = X / np.linalg.norm(X, axis=1, keepdims=True)
+        return (self.radius * X + self.center).astype(config.real(np))
+
+
+class Sphere(Hypersphere):
+    """Constructed by the reference at /root/reference/AI4XDE/cases/PDECases.py:2346 (`Sphere([0, 0, 0], 1)`)."""
+
+
 class Polygon(Geometry):
     """Simple polygon given by its vertices in order (either orientation; stored clockwise as DeepXDE does) --
     `dde.geometry.Polygon([[0, 0], [1, 0], [1, -1], [-1, -1], [-1, 1], [0, 1]])` is the L-shaped domain of

@@ -443,3 +443,36 @@ def test_two_input_nets_go_to_third_order(act):
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
     assert rel(r.detach().double(), rr.detach()) < 1e-5
     assert rel(g, gr) < 1e-5
+
+
+def test_sphere_geometry_product_and_oracle_agree():
+    """dde.geometry.Sphere (cases/PDECases.py:2346): interior / boundary sampling on the same NumPy stream gives the
+    same points in product and oracle; the points lie where they should; normals are outward unit vectors."""
+    import ai4xde_b200.dde as dde
+    from oracle import ddelite
+
+    for d in (dde, ddelite):
+        d.config.set_default_float("float64")
+    try:
+        got = []
+        for d in (dde, ddelite):
+            np.random.seed(7)
+            g = d.geometry.Sphere([0.5, -1.0, 2.0], 1.5)
+            got.append((g.random_points(500), g.random_boundary_points(200), g))
+        (pi, pb, gp), (oi, ob, go) = got
+        np.testing.assert_allclose(pi, oi, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(pb, ob, rtol=1e-13, atol=1e-13)
+        c = np.array([0.5, -1.0, 2.0])
+        assert gp.dim == go.dim == 3 and gp.inside(pi).all() and not gp.on_boundary(pi).any()
+        r = np.linalg.norm(pi - c, axis=1) / 1.5
+        assert 0.2 < np.mean(r ** 3) < 0.8 and abs(np.mean(r ** 3) - 0.5) < 0.06      # uniform in volume: r^3 ~ U(0, 1)
+        assert gp.on_boundary(pb).all() and go.on_boundary(pb).all()
+        n = gp.boundary_normal(pb)
+        np.testing.assert_allclose(n, (pb - c) / 1.5, atol=1e-12)
+        np.testing.assert_allclose(go.boundary_normal(pb), n, atol=1e-12)
+        assert np.all(gp.boundary_normal(pi) == 0)
+        assert gp.random_points(64, random="Hammersley").shape == (64, 3) and gp.inside(gp.random_points(64, random="Hammersley")).all()
+    finally:
+        for d in (dde, ddelite):
+            d.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
