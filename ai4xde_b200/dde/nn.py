@@ -697,6 +697,9 @@ class STMsFFN(NN):
         t_dim = d - 1
         xs, ts = [p for p in spec.dirs if p < t_dim], [p for p in spec.dirs if p == t_dim]
         need2 = set()
+        if spec.third is not None or spec.triples:
+            raise NotImplementedError("third- and higher-order derivatives of an STMsFFN are not in the fused path "
+                                      "(its space and time nets carry second-order jets)")
         for pa, pb in spec.pairs:
             if pa == jet.JetSpec.TRACE and pb == jet.JetSpec.TRACE:
                 need2 |= {(p, p) for p in spec.dirs}
