@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ax_jet_supported": (C.c_int, [C.POINTER(JetDesc)]),
     "ax_engine_supported": (C.c_int, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int]),
     "ax_stash_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64, C.c_int]),
+    "ax_stash_bytes_engine": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64, C.c_int, C.c_int]),
     "ax_forward_ws_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64]),
     "ax_backward_ws_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64]),
     "ax_jet_mlp_forward": (
@@ -88,6 +89,7 @@ _SIGNATURES = {
         [_P, _P, _P, C.c_int64, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, _P],
     ),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "ax_debug_fma_peak": (C.c_double, [_P, C.c_int32, C.c_int32, _P]),
 }
 
 _lib = None
@@ -189,6 +191,10 @@ def engine_supported(net, jet, engine):
     return bool(load().ax_engine_supported(C.byref(net), C.byref(jet), ENGINE[engine]))
 
 
+def stash_bytes(net, jet, ldn, keep_all, engine="auto"):
+    return int(load().ax_stash_bytes_engine(C.byref(net), C.byref(jet), int(ldn), int(bool(keep_all)), ENGINE[engine]))
+
+
 def launch_count():
     return int(load().ax_launch_count())
 
@@ -226,7 +232,7 @@ def jet_forward(net, jet, params, x_soa, n, keep_all, engine="auto"):
     C_out = net.widths[net.n_linear]
     dev = x_soa.device
     jets = torch.empty((net.n_nets, S, C_out, ldn), dtype=torch.float32, device=dev)
-    stash = _bytes_buf(lib.ax_stash_bytes(C.byref(net), C.byref(jet), ldn, int(keep_all)), dev)
+    stash = _bytes_buf(lib.ax_stash_bytes_engine(C.byref(net), C.byref(jet), ldn, int(keep_all), ENGINE[engine]), dev)
     wsb = lib.ax_forward_ws_bytes(C.byref(net), C.byref(jet), ldn)
     ws = _bytes_buf(wsb, dev)
     rc = lib.ax_jet_mlp_forward(
@@ -358,6 +364,30 @@ def debug_tc_wgrad(zbar, a):
     _check(lib.ax_debug_tc_wgrad(_ptr(zbar), _ptr(a), rows, H, _ptr(out), _ptr(ws), _stream()),
            "ax_debug_tc_wgrad")
     return out
+
+
+def measure_fp32_fma_peak(seconds=0.3):
+    """Measured FP32 FMA rate of this GPU in TFLOP/s (CUDA events around ax_debug_fma_peak, best of 3)."""
+    lib = load()
+    out = torch.zeros(1, device="cuda")
+    props = torch.cuda.get_device_properties(out.device)
+    blocks = props.multi_processor_count * 8
+    iters = 1 << 14
+    best = 0.0
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flops = lib.ax_debug_fma_peak(_ptr(out), blocks, iters, _stream())
+        e1.record()
+        torch.cuda.synchronize()
+        if flops <= 0:
+            raise NativeLibraryError("ax_debug_fma_peak failed")
+        ms = e0.elapsed_time(e1)
+        if rep > 0:
+            best = max(best, flops / (ms * 1e-3) / 1e12)
+        if ms * 1e-3 < seconds / 4:
+            iters = min(iters * 2, 1 << 20)
+    return best
 
 
 def gather_points(x_soa, idx):

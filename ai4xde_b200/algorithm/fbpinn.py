@@ -17,6 +17,7 @@ from .. import dde, jet
 from ..dde import backend as bkd
 from ..dde import gradients as grad
 from ..dde import config as dconfig
+from ..dde.model import _allreduce_grads
 from ..solver import PINNSolver
 
 
@@ -193,6 +194,9 @@ class FBPINN(PINNSolver):
             losses = torch.stack(losses)
             if loss_weights is not None:
                 losses = losses * torch.as_tensor(loss_weights, dtype=torch.float32, device=dev)
+            scale = model._dp_term_scale(losses, inputs)     # point-sharded ranks: exact global means
+            if scale is not None:
+                losses = losses * scale
             grad.clear()
             return outputs_, losses
 
@@ -208,6 +212,7 @@ class FBPINN(PINNSolver):
                 total_loss = torch.sum(losses)
                 model.opt.zero_grad()
                 total_loss.backward()
+                _allreduce_grads(list(model.net.parameters()))
                 model.last_total_loss = total_loss.detach()
                 return total_loss
 

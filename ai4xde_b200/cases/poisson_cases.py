@@ -90,3 +90,35 @@ class Poisson_1D_Fourier_Net(PoissonCase1D):
         bc = dde.icbc.DirichletBC(self.geomtime, self.sol, lambda _, on_boundary: on_boundary)
         return dde.data.PDE(self.geomtime, self.pde, bc, self.NumDomain, self.num_boundary,
                             train_distribution="pseudo", solution=self.sol, num_test=10000)
+
+
+def multiscale_fbpinn_case(NumDomain=1280, layer_size=(1, 64, 64, 64, 1), activation="tanh",
+                           initializer="Glorot uniform"):
+    """The parent case of BASELINE config 5: the 1-D multiscale Poisson problem (forcing and solution of
+    PoissonCases.py:469-476) on a dde.nn.FNN built by the BASE `gen_net` with `use_output_transform=True`, so that
+    FBPINN's sub-cases get their sigmoid window wired (FBPINN.py:35-42 -- with the reference's own
+    Poisson_1D_Fourier_Net the flag is set but its `gen_net` override never applies the transform, SURVEY.md
+    App. C #8 / #11).  FBPINN builds every sub-case with the CLASS defaults (FBPINN.py:42 `PDE()`), so the
+    requested point count and net shape are baked into a fresh class; returns an instance of it."""
+    nd, ls, act, ini = int(NumDomain), [int(w) for w in layer_size], activation, initializer
+
+    class Poisson_1D_Multiscale(PoissonCase1D):
+        def __init__(self, NumDomain=nd, layer_size=ls, activation=act, initializer=ini):
+            self.A, self.B = 2, 50
+            super().__init__(name="Poisson equation in 1D, multiscale forcing (FBPINN parent)", NumDomain=NumDomain,
+                             Interval=[0, 1], use_output_transform=True, layer_size=layer_size,
+                             activation=activation, initializer=initializer)
+
+        def func(self, x):
+            a, b = np.pi * self.A, np.pi * self.B
+            return -(a**2) * bkd.sin(a * x) - 0.1 * b**2 * bkd.sin(b * x)
+
+        def sol(self, x):
+            return np.sin(np.pi * self.A * x) + 0.1 * np.sin(np.pi * self.B * x)
+
+        def gen_data(self):
+            bc = dde.icbc.DirichletBC(self.geomtime, self.sol, lambda _, on_boundary: on_boundary)
+            return dde.data.PDE(self.geomtime, self.pde, bc, self.NumDomain, 2, train_distribution="pseudo",
+                                solution=self.sol, num_test=1000)
+
+    return Poisson_1D_Multiscale()

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "simt_kernels.cuh"
+#include "narrow.cuh"
 #include "tc_engine.cuh"
 
 namespace ax {
@@ -156,6 +157,22 @@ __global__ void k_reduce_partials(const float *__restrict__ partial, int64_t par
 
 static int jet_S(const ax_jet_desc *jet) { return 1 + jet->n1 + jet->n2; }
 
+// FP32 FMA micro-benchmark: 16 independent dependent-FMA chains per thread, `iters` rounds (the peak the FP32
+// engine's fractions are quoted against; bench.py times it with CUDA events)
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i) * 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 12345.678f) out[0] = s;   // keeps the chains alive without a store in the common case
+}
+
 }  // namespace ax
 
 using namespace ax;
@@ -237,6 +254,17 @@ size_t ax_stash_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ld
   return (size_t)net->n_nets * slots * jet_S(jet) * g.Hmax * ldn * sizeof(float);
 }
 
+static int resolve_engine(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine);
+
+size_t ax_stash_bytes_engine(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all, int engine) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  if (match_pattern(jet) < 0) return 0;
+  const int e = resolve_engine(g, net, jet, engine);
+  if (e == AX_ENGINE_TF32 && tc_supported(g, net, jet, e) && tc_bank_usable(g, net, keep_all)) return 0;
+  return ax_stash_bytes(net, jet, ldn, keep_all);
+}
+
 size_t ax_forward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
   NetGeom g;
   if (make_geom(net, &g)) return 0;
@@ -248,6 +276,10 @@ size_t ax_backward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int6
   if (make_geom(net, &g)) return 0;
   size_t a = simt_backward_ws_bytes(g, jet_S(jet), ldn, net->n_nets);
   size_t b = tc_backward_ws_bytes(g, net, jet, ldn);
+  if (narrow_supported(g, net, jet)) {
+    const size_t c = narrow_backward_ws_bytes(g, jet_S(jet), ldn, net->n_nets);
+    if (c > a) a = c;
+  }
   return a > b ? a : b;
 }
 
@@ -281,6 +313,8 @@ int ax_jet_mlp_forward(const ax_net_desc *net, const ax_jet_desc *jet, const flo
     }
     return tc_forward(g, a, engine);
   }
+  // narrow nets (hidden width 20 / 32): whole-net kernels, one thread per point (narrow.cuh)
+  if (narrow_supported(g, net, jet)) return narrow_forward(g, a);
   switch (id) {
 #define AX_CASE(ID, PAT) \
   case ID:               \
@@ -321,6 +355,7 @@ int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const fl
     }
     return tc_backward(g, a, engine);
   }
+  if (narrow_supported(g, net, jet)) return narrow_backward(g, a);
   switch (id) {
 #define AX_CASE(ID, PAT) \
   case ID:               \
@@ -330,6 +365,15 @@ int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const fl
   }
   set_error("unreachable pattern id %d", id);
   return 1;
+}
+
+// FP32 FMA peak probe: launches blocks x 256 threads x iters x 16 FMAs; returns the FLOP count (0 on error)
+double ax_debug_fma_peak(float *out, int32_t blocks, int32_t iters, void *stream) {
+  if (!out || blocks < 1 || iters < 1) return 0.0;
+  k_fma_peak<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 1e-4f);
+  if (cudaGetLastError() != cudaSuccess) return 0.0;
+  count_launch();
+  return 2.0 * 16.0 * 256.0 * (double)blocks * (double)iters;
 }
 
 // testing hook (tests/test_gpu_tc.py): tensor-core weight-gradient GEMM on caller-provided matrices.

@@ -754,7 +754,9 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
   float dw[CM][4], dbo[CM], dbh[4];
 #pragma unroll
   for (int c = 0; c < CM; ++c) {
-    wc[c] = c < C ? __ldg(reinterpret_cast<const float4 *>(Wout + (long long)c * H) + kq) : make_float4(0, 0, 0, 0);
+    // scalar loads: a net inside a [K][P] bank starts at any 4-byte boundary (P is odd for 1-[64]x3-1)
+    const float *wrow = Wout + (long long)c * H + 4 * kq;
+    wc[c] = c < C ? make_float4(__ldg(wrow), __ldg(wrow + 1), __ldg(wrow + 2), __ldg(wrow + 3)) : make_float4(0, 0, 0, 0);
     dbo[c] = 0.0f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) dw[c][u] = 0.0f;

@@ -54,36 +54,6 @@ struct ChainArgs {
   int num_tiles;
 };
 
-// activation jet with exp2/rcp special-function units: |error of a| ~ 1e-7 absolute, far below the TF32
-// rounding of the streams it feeds; s1 is formed from the stored a exactly as the adjoint re-forms it.
-template <class P, int ACT>
-__device__ __forceinline__ void jet_forward_fast(float (&z)[P::S], float (&A)[P::S]) {
-  float a, s1, s2;
-  if (ACT == AX_ACT_TANH) {
-    a = tanh_fast(z[0]);
-    s1 = fmaf(-a, a, 1.0f);
-    s2 = -2.0f * a * s1;
-  } else {
-    a = sigmoid_fast(z[0]);
-    s1 = a * (1.0f - a);
-    s2 = s1 * (1.0f - 2.0f * a);
-  }
-  A[0] = a;
-#pragma unroll
-  for (int j = 0; j < P::N1; ++j) A[1 + j] = s1 * z[1 + j];
-#pragma unroll
-  for (int q = 0; q < P::N2; ++q) {
-    if (P::pa(q) == kTracePair) {
-      float sq = 0.0f;
-#pragma unroll
-      for (int j = 0; j < P::N1; ++j) sq = fmaf(z[1 + j], z[1 + j], sq);
-      A[1 + P::N1 + q] = fmaf(s2, sq, s1 * z[1 + P::N1 + q]);
-    } else {
-      A[1 + P::N1 + q] = fmaf(s2 * z[1 + (P::pa(q) & 3)], z[1 + (P::pb(q) & 3)], s1 * z[1 + P::N1 + q]);
-    }
-  }
-}
-
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
@@ -551,6 +521,9 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
   const size_t layer_fl = (size_t)a.ldn * S * H;
   const int slots = a.keep_all ? g.L : 2;
   const JetDirs dirs = make_dirs(a.jet);
+  // forward-only evaluation of width-64 nets (residual probes, FBPINN's frozen subdomain nets): one launch for
+  // all nets, activations never leave the SM (tc_bank.cu)
+  if (H == 64 && tc_bank_usable(g, a.net, a.keep_all)) return tc_bank_forward(g, a);
   const size_t need = (size_t)(g.L - 1) * H * H * sizeof(float) * a.net->n_nets + (size_t)2 * S * a.ldn * sizeof(float);
   float *jets_part = (float *)a.ws + (size_t)(g.L - 1) * H * H * a.net->n_nets;
   if (a.ws_bytes < need || !a.ws) {

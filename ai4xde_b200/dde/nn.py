@@ -282,16 +282,24 @@ class FNN(NN):
 
 
 class _FusedBankForward(torch.autograd.Function):
-    """K nets, one launch.  Streams come back as (n, K*C); the reverse pass runs the fused backward
-    only for the `active` nets (FBPINN trains one subdomain net at a time,
-    /root/reference/AI4XDE/algorithm/FBPINN.py:112-119)."""
+    """K nets, one launch.  Streams come back as (n, K*C).  FBPINN trains one subdomain net at a time
+    (/root/reference/AI4XDE/algorithm/FBPINN.py:112-119), so the bank is evaluated forward-only -- on the
+    tensor-core engine a single launch in which no activation leaves the SM (csrc/tc_bank.cu) -- and only the
+    `active` nets are evaluated once more with their layers kept for the reverse pass: the stash holds
+    len(active) nets instead of K."""
 
     @staticmethod
     def forward(ctx, bank, x_soa, n, spec, engine, need_backward, active, *params):
-        jets, stash = _lib.jet_forward(bank.net_desc, spec.desc, bank.flat, x_soa, n,
-                                       keep_all=need_backward, engine=engine)
+        jets = bank.evaluate(spec, x_soa, n, engine)
+        stashes = []
+        if need_backward:
+            for k in active:
+                jk, stash = _lib.jet_forward(bank.single_desc, spec.desc, bank.flat[k : k + 1], x_soa, n,
+                                             keep_all=True, engine=engine)
+                jets[k] = jk[0]          # the streams the reverse pass is consistent with
+                stashes.append(stash)
         ctx.bank, ctx.spec, ctx.engine, ctx.n, ctx.active = bank, spec, engine, n, tuple(active)
-        ctx.x_soa, ctx.stash, ctx.kept = x_soa, stash, bool(need_backward)
+        ctx.x_soa, ctx.stashes, ctx.kept = x_soa, stashes, bool(need_backward)
         K, S, C = jets.shape[0], jets.shape[1], jets.shape[2]
         return tuple(jets[:, s, :, :n].permute(2, 0, 1).reshape(n, K * C) for s in range(S))
 
@@ -301,18 +309,16 @@ class _FusedBankForward(torch.autograd.Function):
         if not ctx.kept:
             raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
         bank, spec, n = ctx.bank, ctx.spec, ctx.n
-        K, C = bank.K, bank.layer_sizes[-1]
+        C = bank.layer_sizes[-1]
         ldn = ctx.x_soa.shape[1]
-        jets_bar = torch.zeros((K, spec.S, C, ldn), dtype=torch.float32, device=bank.flat.device)
-        for s, g in enumerate(gouts):
-            if g is not None:
-                jets_bar[:, s, :, :n] = g.reshape(n, K, C).permute(1, 2, 0)
-        per_net_stash = ctx.stash.numel() // K
         grads = []
-        for k in ctx.active:
+        for k, stash in zip(ctx.active, ctx.stashes):
+            jets_bar = torch.zeros((1, spec.S, C, ldn), dtype=torch.float32, device=bank.flat.device)
+            for s, g in enumerate(gouts):
+                if g is not None:
+                    jets_bar[0, s, :, :n] = g[:, k * C : (k + 1) * C].t()
             g_flat = _lib.jet_backward(bank.single_desc, spec.desc, bank.flat[k : k + 1], ctx.x_soa, n,
-                                       jets_bar[k : k + 1], ctx.stash[k * per_net_stash : (k + 1) * per_net_stash],
-                                       engine=ctx.engine)[0]
+                                       jets_bar, stash, engine=ctx.engine)[0]
             off = 0
             for shp in bank.shapes:
                 cnt = 1
@@ -320,7 +326,7 @@ class _FusedBankForward(torch.autograd.Function):
                     cnt *= d
                 grads.append(g_flat[off : off + cnt].view(shp))
                 off += cnt
-        ctx.stash = None
+        ctx.stashes = None
         return (None,) * 7 + tuple(grads)
 
 
@@ -345,6 +351,24 @@ class NetBank:
         for k, n_ in enumerate(self.nets):
             n_.adopt_storage(self.flat[k])
         self.shapes = [p.shape for p in first._param_list()]
+
+    def evaluate(self, spec, x_soa, n, engine, max_stash_bytes=4 << 30):
+        """Forward-only streams [K, S, C, ldn] of all K nets.  One launch sequence when the engine keeps no
+        stash (tensor-core engine, width 64) or its two-layer ping-pong stash is small; otherwise the nets go
+        in groups so that the scratch stays below `max_stash_bytes`."""
+        K, ldn = self.K, x_soa.shape[1]
+        per_net = max(_lib.stash_bytes(self.single_desc, spec.desc, ldn, False, engine), 1)
+        group = max(1, min(K, max_stash_bytes // per_net))
+        if group >= K:
+            return _lib.jet_forward(self.net_desc, spec.desc, self.flat, x_soa, n, keep_all=False, engine=engine)[0]
+        C = self.layer_sizes[-1]
+        jets = torch.empty((K, spec.S, C, ldn), dtype=torch.float32, device=x_soa.device)
+        for k0 in range(0, K, group):
+            k1 = min(K, k0 + group)
+            desc = _lib.make_net_desc(self.layer_sizes, self.nets[0].activation_name, n_nets=k1 - k0)
+            jets[k0:k1] = _lib.jet_forward(desc, spec.desc, self.flat[k0:k1], x_soa, n, keep_all=False,
+                                           engine=engine)[0]
+        return jets
 
     def _check_storage(self):
         base, P = self.flat.data_ptr(), self.flat.shape[1]

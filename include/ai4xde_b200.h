@@ -78,6 +78,11 @@ int ax_jet_supported(const ax_jet_desc *jet);
 int ax_engine_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engine);
 
 size_t ax_stash_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all_layers);
+/* as ax_stash_bytes for the engine the call will run on: forward-only evaluation (keep_all_layers = 0) of
+ * width-64 nets on the tensor-core engine keeps every activation on chip and needs no stash (0 is returned;
+ * pass any valid device pointer) */
+size_t ax_stash_bytes_engine(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all_layers,
+                             int engine);
 size_t ax_forward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
 size_t ax_backward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
 
@@ -206,6 +211,10 @@ int64_t ax_launch_count(void);
  */
 void ax_timing_enable(int on);
 int64_t ax_timing_report(char *h_buf, int64_t cap);
+
+/* measurement hook: blocks x 256 threads x iters x 16 independent FP32 FMAs; returns the FLOPs enqueued (the
+ * caller times the launch): the FP32-FMA peak the narrow-net kernels' fractions are quoted against. */
+double ax_debug_fma_peak(float *out, int32_t blocks, int32_t iters, void *stream);
 
 /* testing hook: dW[H][H] = zbar[rows][H]^T a[rows][H] on the tcgen05 weight-gradient path
  * (H in {64,128,256}); ws: at least 149*H*H floats. */

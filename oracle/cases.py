@@ -122,6 +122,58 @@ def fbpinn_window(x, lo, hi):
     return bkd.sigmoid(x - lo) * bkd.sigmoid(hi - x)
 
 
+def fbpinn_build(limits, points, state_dicts, layer_size, activation="tanh", initializer="Glorot uniform"):
+    """FBPINN on the 1-D multiscale Poisson problem (cfg5) as the reference wires it
+    (/root/reference/AI4XDE/algorithm/FBPINN.py:23-43, 107-110): for every subdomain (lo, hi) a sub-case with
+    geometry Interval(lo, hi), the parent's pde and Dirichlet condition on the SUBDOMAIN's ends, and a
+    dde.nn.FNN whose output transform is window(x) * y (the parent's own transform returns None,
+    cases/PDECases.py:93-94, so `y = y_parent` is skipped).  `points[k]` is sub-case k's train_x_all (boundary rows
+    first, as dde.data.PDE lays them out) and `state_dicts[k]` its weights: the caller hands over the product's,
+    so both sides see identical inputs.  Returns (datas, nets)."""
+    datas, nets = [], []
+    for (lo, hi), pts, sd in zip(limits, points, state_dicts):
+        geom = dde.geometry.Interval(lo, hi)
+        bc = dde.icbc.DirichletBC(geom, poisson1d_sol, lambda _, on_boundary: on_boundary)
+        data = dde.data.PDE(geom, poisson1d_pde, bc, 0, 0, anchors=np.asarray(pts), train_distribution="pseudo",
+                            solution=poisson1d_sol)
+        net = dde.nn.FNN(layer_size, activation, initializer)
+        net.load_state_dict({k: torch.as_tensor(np.asarray(v), dtype=dde.config.real(torch)) for k, v in sd.items()})
+        net.apply_output_transform((lambda l, h: (lambda x, y: fbpinn_window(x, l, h) * y))(lo, hi))
+        datas.append(data)
+        nets.append(net)
+    return datas, nets
+
+
+def fbpinn_step_outputs(datas, nets, k, loss_weights=None):
+    """One evaluation of sub-model k's patched closure (FBPINN.py:143-185): outputs = get_predict(inputs) =
+    the in-order sum over ALL sub-nets (FBPINN.py:196-204) on model k's batch, losses of model k's data,
+    gradient with respect to net k's parameters (the optimiser of model k holds only those, FBPINN.py:108-110)."""
+    model = dde.Model(datas[k], nets[k])
+    model.compile("adam", lr=1e-3, loss_weights=loss_weights)
+    for net in nets:
+        net.zero_grad()
+    x = torch.as_tensor(datas[k].train_x).requires_grad_()
+    result = None
+    for net in nets:
+        net.train()
+        y = net(x)
+        result = y if result is None else result + y
+    res = datas[k].pde(x, result)
+    losses = datas[k].losses_train(None, result, dde.losses.get("MSE"), x, model)
+    losses = torch.stack(losses)
+    if loss_weights is not None:
+        losses = losses * torch.as_tensor(loss_weights)
+    dde.grad.clear()
+    losses.sum().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in nets[k].parameters()])
+    return {
+        "outputs": result.detach().numpy(),
+        "residuals": [res.detach().numpy()],
+        "losses": losses.detach().numpy(),
+        "grad": g.numpy().copy(),
+    }
+
+
 # ---------------------------------------------------------------------------------------
 CONFIGS = {
     # name: (layer_size, activation, initializer, n_domain default)

@@ -91,3 +91,63 @@ def product_vs_oracle(cfg, n_domain, engine="fp32", seed=0, oracle_dtype="float6
         "model": model,
         "case": case,
     }
+
+
+def fbpinn_vs_oracle(segment, num_domain, engine="fp32", check=(0,), seed=0, layer_size=(1, 64, 64, 64, 1)):
+    """BASELINE config 5: FBPINN with `segment` windowed subdomain nets on the 1-D multiscale Poisson problem.
+    The product builds the decomposition (its own points and weights); the oracle twin
+    (oracle.cases.fbpinn_build: the reference's wiring restated on ddelite, float64) is handed the same points
+    and weights.  For every sub-model k in `check`: get_predict on model k's batch (the sum over ALL nets), the
+    per-term losses, the residual, and the gradient of net k -- with every other net's gradient untouched."""
+    from oracle import cases as oc, ddelite
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import algorithm
+    from ai4xde_b200.cases.poisson_cases import multiscale_fbpinn_case
+
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    dde.config.set_default_float("float32")
+    case = multiscale_fbpinn_case(NumDomain=num_domain, layer_size=layer_size)
+    solver = algorithm.FBPINN(case, segment=segment, iter=1)
+    limits = solver.domains.limits
+    points = [np.asarray(m.data.train_x_all, dtype=np.float64) for m in solver.model_list]
+    sds = [{k: v.detach().double().cpu().numpy() for k, v in m.net.state_dict().items()} for m in solver.model_list]
+    prev = ddelite.config.default_float()
+    ddelite.config.set_default_float("float64")
+    try:
+        datas, nets = oc.fbpinn_build(limits, points, sds, list(layer_size))
+        refs = {k: oc.fbpinn_step_outputs(datas, nets, k) for k in check}
+    finally:
+        ddelite.config.set_default_float(prev)
+        torch.set_default_dtype(torch.float32)
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+    out = {}
+    dde.config.set_engine(engine)
+    try:
+        for k in check:
+            model, pde = solver.model_list[k], solver.domains.pdeCase_list[k]
+            solver.compile(pde, model, "adam", lr=1e-3)
+            assert np.array_equal(np.asarray(model.data.train_x, dtype=np.float64), datas[k].train_x)
+            for m in solver.model_list:
+                m.net.zero_grad()
+            outs, losses = model.outputs_losses_train(model.data.train_x, None, None)
+            losses.sum().backward()
+            g = torch.cat([p.grad.reshape(-1) for p in model.net.parameters()]).double().cpu().numpy()
+            others = [p.grad for j, m in enumerate(solver.model_list) if j != k for p in m.net.parameters()]
+            x = torch.as_tensor(model.data.train_x, dtype=torch.float32, device=outs.device).requires_grad_()
+            res = pde.pde(x, solver.get_predict(x, param_grad=False))
+            dde.grad.clear()
+            out[k] = {
+                "out_rel": rel(outs.detach().double().cpu().numpy(), refs[k]["outputs"]),
+                "loss_rel": rel(losses.detach().double().cpu().numpy(), refs[k]["losses"]),
+                "res_rel": rel(res.detach().double().cpu().numpy(), refs[k]["residuals"][0]),
+                "grad_rel": rel(g, refs[k]["grad"]),
+                "others_untouched": all(t is None or float(t.abs().max()) == 0.0 for t in others),
+                "n_rows": len(model.data.train_x),
+            }
+    finally:
+        dde.config.set_engine("auto")
+    return out, solver

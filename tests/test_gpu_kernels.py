@@ -57,6 +57,19 @@ CASES = [
     ([2, 64, 64, 64, 1], "tanh", "2o3", 1001, 2),
     ([2, 48, 32, 2], "sin", "2o3", 333, 1),
     ([3, 40, 40, 1], "sigmoid", "2o3r", 130, 1),
+    # narrow nets (hidden width 20 / 32): the whole-net one-thread-per-point kernels (csrc/narrow.cuh) -- every
+    # chunking they are compiled with (forward OC = 20 / 4 / 32 / 16, backward KC = 4 / 8), ragged tails, several
+    # nets per launch, 1..4 inputs / outputs, all three activations
+    ([2, 20, 20, 20, 1], "tanh", "2t", 100003, 1),
+    ([2, 20, 20, 20, 20, 3], "sin", "2d", 4099, 1),
+    ([2, 20, 20, 1], "sigmoid", "2f", 1500, 2),
+    ([2, 32, 32, 32, 1], "tanh", "2a", 70001, 1),       # the reference's default net (cases/PDECases.py:8-20)
+    ([2, 32, 32, 32, 32, 32, 32, 1], "tanh", "2t", 3000, 1),
+    ([1, 32, 32, 32, 2], "sin", "1d", 129, 3),
+    ([3, 32, 32, 4], "tanh", "2", 127, 1),
+    ([4, 20, 20, 20, 2], "tanh", "1", 6000, 1),
+    ([1, 20, 20, 20, 1], "tanh", "1d", 128, 64),        # FBPINN-style bank of narrow nets
+    ([2, 32, 32, 32, 1], "tanh", "v", 5000, 1),
     # large point sets (many point tiles per output block, ragged tails)
     ([2, 150, 150, 150, 1], "sin", "2t", 40001, 1),
     ([2, 64, 64, 3], "tanh", "2a", 38000, 2),

@@ -68,7 +68,13 @@ def test_tf32_engine_matches_double(widths, act, spec, n):
     for s in range(js.S):
         assert _rel(jets[0, s, :, :n].double(), ref[0, s, :, :n]) < TF32_JET_TOL, f"stream {s}"
     jets2, _ = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=False, engine="tf32")
-    assert torch.equal(jets2[..., :n], jets[..., :n])
+    if widths[1] == 64:
+        # forward-only evaluation of width-64 nets is the whole-net kernel (csrc/tc_bank.cu): another summation
+        # order and a TF32-rounded value stream, so it is held to the double, not to the layer-by-layer kernels
+        for s in range(js.S):
+            assert _rel(jets2[0, s, :, :n].double(), ref[0, s, :, :n]) < TF32_JET_TOL, f"bank stream {s}"
+    else:
+        assert torch.equal(jets2[..., :n], jets[..., :n])
     jb = torch.randn(jets.shape, generator=gen).to(dev)
     jb[..., n:] = 0
     grad = _lib.jet_backward(net, js.desc, params, xs, n, jb, stash, engine="tf32")
@@ -80,6 +86,40 @@ def test_tf32_engine_matches_double(widths, act, spec, n):
             off += cnt
     grad2 = _lib.jet_backward(net, js.desc, params, xs, n, jb, stash, engine="tf32")
     assert torch.equal(grad, grad2)  # deterministic two-level reduction
+
+
+@pytest.mark.parametrize("widths,act,spec,n,k", [
+    ([1, 64, 64, 64, 1], "tanh", ((0,), ((0, 0),)), 5000, 64),          # config 5: 64 subdomain nets, S = 3
+    ([1, 64, 64, 64, 1], "tanh", ((0,), ((0, 0),)), 128, 3),            # exactly one tile per net
+    ([1, 64, 64, 64, 1], "tanh", ((0,), ((0, 0),)), 1, 2),              # one point
+    ([2, 64, 64, 64, 64, 1], "tanh", ((1, 0), ((0, 0),)), 100000, 1),   # config 2 residual probe, S = 4
+    ([2, 64, 64, 1], "tanh", ((), ()), 777, 5),                          # value only, one GEMM layer
+    ([2, 64, 64, 64, 3], "sigmoid", ((0, 1), ((0, 0), (1, 1))), 1037, 2),            # S = 5, three outputs
+    ([2, 64, 64, 64, 64, 64, 64, 2], "tanh", ((0, 1), ((0, 0), (0, 1), (1, 1))), 300, 2),   # S = 6, six hidden layers
+    ([3, 64, 64, 64, 1], "tanh", ((0, 1), ((15, 15),)), 4099, 4),       # Laplacian stream, three inputs
+])
+def test_bank_forward_kernel_matches_double(widths, act, spec, n, k):
+    """csrc/tc_bank.cu: K nets x all layers in one launch, activations on chip.  Against the float64 double,
+    net by net; bit-identical when repeated; K nets in one launch == the same nets launched one at a time."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    js = JetSpec(*spec)
+    net = _lib.make_net_desc(widths, act, n_nets=k)
+    one = _lib.make_net_desc(widths, act, n_nets=1)
+    assert _lib.engine_supported(net, js.desc, "tf32")
+    assert _lib.stash_bytes(net, js.desc, _lib.pad32(n), False, "tf32") == 0
+    params = _glorot_params(widths, gen, k).to(dev)
+    x = (torch.rand((n, widths[0]), generator=gen) * 2 - 1).to(dev)
+    xs = to_soa(x)
+    jets, _ = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=False, engine="tf32")
+    again, _ = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=False, engine="tf32")
+    assert torch.equal(jets[..., :n], again[..., :n])
+    ref, _ = td.jet_forward(net, js.desc, params.double(), xs.double(), n, False)
+    for s in range(js.S):      # relative to the stream's largest entry over the bank (as for one net)
+        assert _rel(jets[:, s, :, :n].double(), ref[:, s, :, :n]) < TF32_JET_TOL, f"stream {s}"
+    for j in sorted({0, k - 1}):
+        single, _ = _lib.jet_forward(one, js.desc, params[j:j + 1].contiguous(), xs, n, keep_all=False, engine="tf32")
+        assert torch.equal(single[0, ..., :n], jets[j, ..., :n])
 
 
 def test_tf32_engine_refuses_what_it_cannot_do():

@@ -248,6 +248,22 @@ def test_fbpinn_bank_matches_sum_of_nets():
     assert moved[1] > 0 and moved[0] == 0 and moved[2] == 0 and moved[3] == 0
 
 
+def test_fbpinn_windowed_bank_matches_oracle_restatement(monkeypatch):
+    """BASELINE config 5 at a small size on the kernel double: the product's FBPINN (weight bank, forward-only
+    evaluation of all nets + a kept evaluation of the active one, vectorised window sum) against the oracle's
+    restatement of the reference wiring, which tests/test_oracle_pins.py pins to the unmodified reference class."""
+    import _taylor_double as td
+    from parity_util import fbpinn_vs_oracle
+
+    td.install(monkeypatch)
+    out, solver = fbpinn_vs_oracle(8, 40, engine="fp32", check=(0, 3, 7), layer_size=(1, 16, 16, 1))
+    assert solver.bank.K == 8
+    for k, r in out.items():
+        assert r["others_untouched"], k
+        assert r["out_rel"] < 1e-5 and r["loss_rel"] < 1e-5, (k, r)
+        assert r["res_rel"] < 5e-5 and r["grad_rel"] < 5e-5, (k, r)   # float32 double, forcing ~ (50 pi)^2
+
+
 @pytest.mark.parametrize("d_in,act", [(2, "tanh"), (3, "sin")])
 def test_stmsffn_product_matches_oracle(d_in, act):
     """dde.nn.STMsFFN of the fused path (K_x space nets and K_t time nets through the kernel double, last
