@@ -61,6 +61,13 @@ _SIGNATURES = {
         [C.POINTER(NetDesc), C.POINTER(JetDesc), _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P,
          C.c_size_t, C.c_int, _P],
     ),
+    "ax_fbpinn_window_supported": (C.c_int, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int]),
+    "ax_fbpinn_window_ws_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64]),
+    "ax_fbpinn_window_forward": (
+        C.c_int,
+        [C.POINTER(NetDesc), C.POINTER(JetDesc), _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int32, _P, _P,
+         C.c_size_t, C.c_int, _P],
+    ),
     "ax_resample_ws_bytes": (C.c_size_t, [C.c_int64]),
     "ax_pairwise_sum_f32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "ax_pairwise_sum_f64": (C.c_int, [_P, C.c_int64, _P, _P, C.c_size_t, _P]),
@@ -258,6 +265,27 @@ def jet_backward(net, jet, params, x_soa, n, jets_bar, stash, engine="auto"):
     )
     _check(rc, "ax_jet_mlp_backward")
     return grad
+
+
+def fbpinn_window_supported(net, jet, engine):
+    return bool(load().ax_fbpinn_window_supported(C.byref(net), C.byref(jet), ENGINE[engine]))
+
+
+def fbpinn_window_forward(net, jet, params, x_soa, n, win_lo, win_hi, net_list, engine="auto"):
+    """Streams [S, ldn] of sum_k sigmoid(x - lo_k) sigmoid(hi_k - x) N_k(x) over the nets in `net_list`
+    (int32 device tensor of ids into the [K, P] bank), one launch (csrc/tc_bank.cu)."""
+    lib = load()
+    _need_cuda(params, x_soa, win_lo, win_hi, net_list)
+    ldn = x_soa.shape[1]
+    S = 1 + jet.n1 + jet.n2
+    out = torch.empty((S, ldn), dtype=torch.float32, device=x_soa.device)
+    wsb = lib.ax_fbpinn_window_ws_bytes(C.byref(net), C.byref(jet), ldn)
+    ws = _bytes_buf(wsb, x_soa.device)
+    rc = lib.ax_fbpinn_window_forward(C.byref(net), C.byref(jet), _ptr(params), _ptr(x_soa), int(n), int(ldn),
+                                      _ptr(win_lo), _ptr(win_hi), _ptr(net_list), int(net_list.numel()), _ptr(out),
+                                      _ptr(ws), int(wsb), ENGINE[engine], _stream())
+    _check(rc, "ax_fbpinn_window_forward")
+    return out
 
 
 # ---- resampling ---------------------------------------------------------------------------

@@ -13,7 +13,7 @@ being trained."""
 import numpy as np
 import torch
 
-from .. import dde, jet
+from .. import _lib, dde, jet
 from ..dde import backend as bkd
 from ..dde import gradients as grad
 from ..dde import config as dconfig
@@ -143,6 +143,7 @@ class FBPINN(PINNSolver):
         self._lims = (torch.as_tensor(lims[:, 0], device=dev)[None, :], torch.as_tensor(lims[:, 1], device=dev)[None, :])
         parent_cls = type(self.PDECase)
         self._parent_transform = (lambda xx, yy: parent_cls.output_transform(self.PDECase, xx, yy)) if self._wired else None
+        self._window_linear = False
         try:
             g = torch.Generator().manual_seed(0)
             lo, hi = float(lims[:, 0].min()), float(lims[:, 1].max())
@@ -151,10 +152,64 @@ class FBPINN(PINNSolver):
             a, b = self._combine_loop(x, y), self._combine_vectorised(x, y)
             if a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-6):
                 self._combine = self._combine_vectorised
+            # is the wired transform exactly  window(x) * y  (the parent's own transform returns None)?  Then the sum
+            # over the nets that are not being trained is  sum_k w_k(x) N_k(x): one kernel launch (csrc/tc_bank.cu)
+            if self._wired and C == 1 and self.bank.layer_sizes[0] == 1:
+                w = torch.sigmoid(x - self._lims[0]) * torch.sigmoid(self._lims[1] - x)
+                self._window_linear = bool(torch.allclose(a, (w * y).sum(dim=1, keepdim=True), rtol=1e-5, atol=1e-6))
         except Exception:
             self._combine = self._combine_loop
+        self._net_lists = {}
+
+    def _frozen_list(self, active):
+        key = tuple(active)
+        hit = self._net_lists.get(key)
+        if hit is None:
+            ids = [k for k in range(self.bank.K) if k not in key]
+            hit = torch.tensor(ids, dtype=torch.int32, device=dconfig.device())
+            self._net_lists[key] = hit
+        return hit
+
+    def _predict_fused(self, input, active, spec, x_soa, param_grad):
+        """sum_k window_k(x) N_k(x) with the frozen nets (all but `active`) summed inside ONE kernel launch -- the
+        K per-net streams never reach HBM -- and the nets being trained evaluated by their own dde.nn.FNN forward
+        (layers kept for the reverse pass, output transform = their window) and added on top.  None if this
+        decomposition / engine / stream pattern is not served by that kernel."""
+        if not getattr(self, "_window_linear", False) or not input.is_cuda:
+            return None
+        wants_jets = input.requires_grad and torch.is_grad_enabled()
+        if not wants_jets:
+            spec = jet.JetSpec.value_only()
+        elif spec is None:
+            spec = jet.JetSpec.full(input.shape[1])
+        engine = dconfig.engine()
+        if not _lib.fbpinn_window_supported(self.bank.net_desc, spec.desc, engine):
+            return None
+        self.bank._check_storage()
+        active = [] if (active is None or not param_grad or not torch.is_grad_enabled()) else list(active)
+        n = input.shape[0]
+        if x_soa is None or x_soa.shape[1] < n:
+            x_soa = jet.to_soa(input.detach().to(torch.float32))
+        lo, hi = self._lims
+        streams = _lib.fbpinn_window_forward(self.bank.net_desc, spec.desc, self.bank.flat, x_soa, n,
+                                             lo.reshape(-1).contiguous(), hi.reshape(-1).contiguous(),
+                                             self._frozen_list(active), engine=engine)
+        parts = tuple(streams[s, :n].unsqueeze(1) for s in range(spec.S))
+        if wants_jets:
+            y = jet.make_leaf(input, spec, parts)
+            grad.register(y, jet.JetOutput(input, spec, parts))
+        else:
+            y = parts[0].clone()
+        for k in active:
+            net = self.model_list[k].net
+            with net.jet_scope(spec, x_soa, param_grad=True):
+                y = y + net(input)
+        return y
 
     def get_predict(self, input, active=None, spec=None, x_soa=None, param_grad=True):
+        y = self._predict_fused(input, active, spec, x_soa, param_grad)
+        if y is not None:
+            return y
         y_all = self.bank.forward_all(input, x_soa=x_soa, spec=spec, active=active, param_grad=param_grad)
         return self._combine(input, y_all)
 

@@ -376,6 +376,45 @@ double ax_debug_fma_peak(float *out, int32_t blocks, int32_t iters, void *stream
   return 2.0 * 16.0 * 256.0 * (double)blocks * (double)iters;
 }
 
+// ---- FBPINN: windowed sum over subdomain nets, one launch (csrc/tc_bank.cu) -----------------------------
+int ax_fbpinn_window_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  if (match_pattern(jet) < 0) return 0;
+  const int e = resolve_engine(g, net, jet, engine);
+  return (e == AX_ENGINE_TF32 && tc_supported(g, net, jet, e) && tc_bank_window_usable(g, net, jet)) ? 1 : 0;
+}
+
+size_t ax_fbpinn_window_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  return tc_bank_ws_bytes(g, net->n_nets, jet_S(jet), ldn, 1);
+}
+
+int ax_fbpinn_window_forward(const ax_net_desc *net, const ax_jet_desc *jet, const float *params, const float *x_soa,
+                             int64_t n, int64_t ldn, const float *win_lo, const float *win_hi,
+                             const int32_t *net_list, int32_t n_list, float *out, void *ws, size_t ws_bytes,
+                             int engine, void *stream) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 1;
+  if (check_jet(net, jet) < 0) return 1;
+  if (!ax_fbpinn_window_supported(net, jet, engine)) {
+    set_error("windowed bank forward needs the tensor-core engine, width-64 nets with one input and one output, "
+              "and the value or value/first/second-derivative pattern");
+    return 1;
+  }
+  if (ldn < n || (ldn % 32) != 0 || n <= 0) {
+    set_error("ldn = %lld must be a multiple of 32 and >= n = %lld > 0", (long long)ldn, (long long)n);
+    return 1;
+  }
+  if (!params || !x_soa || !win_lo || !win_hi || !out || !ws || n_list < 0 || n_list > net->n_nets) {
+    set_error("null device pointer or bad net list (%d of %d nets)", n_list, net->n_nets);
+    return 1;
+  }
+  FwdArgs a{net, jet, params, x_soa, n, ldn, nullptr, nullptr, 0, ws, ws_bytes, (cudaStream_t)stream};
+  return tc_bank_window_forward(g, a, win_lo, win_hi, net_list, n_list, out);
+}
+
 // testing hook (tests/test_gpu_tc.py): tensor-core weight-gradient GEMM on caller-provided matrices.
 // ws needs (SM count + 1) * H * H floats.
 int ax_debug_tc_wgrad(const float *zbar, const float *a, int64_t rows, int32_t H, float *out, float *ws,

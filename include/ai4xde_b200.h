@@ -111,6 +111,22 @@ int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const fl
                         const float *stash, float *grad_params, void *ws, size_t ws_bytes,
                         int engine, void *stream);
 
+/*
+ * FBPINN's sum over subdomain nets (algorithm/FBPINN.py:196-204 `get_predict`) with each net's sigmoid window
+ * (FBPINN.py:35-50: y_k = sigmoid(x - lo_k) * sigmoid(hi_k - x) * N_k(x)) in ONE launch for the nets in
+ * `net_list` (device int32 ids into the bank; NULL = all n_list first nets):
+ *   out[s][p] = stream s (value, d/dx, d2/dx2 -- the jet's pattern) of  sum_k y_k  at point p,    out: [S][ldn]
+ * The per-net streams never reach HBM.  One input, one output, hidden width 64, tensor-core engine
+ * (ax_fbpinn_window_supported answers 1); the nets FBPINN is not training are frozen, so this is a forward-only
+ * entry: the net being trained is evaluated by ax_jet_mlp_forward / backward and added by the caller.
+ */
+int ax_fbpinn_window_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engine);
+size_t ax_fbpinn_window_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn);
+int ax_fbpinn_window_forward(const ax_net_desc *net, const ax_jet_desc *jet, const float *params, const float *x_soa,
+                             int64_t n, int64_t ldn, const float *win_lo, const float *win_hi,
+                             const int32_t *net_list, int32_t n_list, float *out, void *ws, size_t ws_bytes,
+                             int engine, void *stream);
+
 /* ---- residual-driven resampling, device resident ------------------------------------- */
 
 /* scratch for the resampling entry points below (covers all of them for n elements) */

@@ -122,6 +122,52 @@ def test_bank_forward_kernel_matches_double(widths, act, spec, n, k):
         assert torch.equal(single[0, ..., :n], jets[j, ..., :n])
 
 
+@pytest.mark.parametrize("k,n,skip,spec", [
+    (64, 5000, (29,), ((0,), ((0, 0),))),        # config 5: all nets but the one being trained; net chunks over grid.y
+    (64, 70001, (), ((0,), ((0, 0),))),          # more tile groups than SMs: one chunk, ragged last group
+    (3, 1, (0, 2), ((0,), ((0, 0),))),           # one point, one net left
+    (8, 1000, (), ((), ())),                     # value only (evaluation under no_grad)
+    (5, 300, (0, 1, 2, 3, 4), ((0,), ((0, 0),))),  # empty list -> zeros
+])
+def test_fbpinn_window_sum_kernel_matches_double(k, n, skip, spec):
+    """ax_fbpinn_window_forward: sum_k sigmoid(x - lo_k) sigmoid(hi_k - x) N_k(x) with its first and second
+    x-derivative, nets summed inside the launch (/root/reference/AI4XDE/algorithm/FBPINN.py:35-50, 196-204), against
+    float64: per-net streams from the double, window derivatives by autograd."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    js = JetSpec(*spec)
+    widths = [1, 64, 64, 64, 1]
+    net = _lib.make_net_desc(widths, "tanh", n_nets=k)
+    assert _lib.fbpinn_window_supported(net, js.desc, "tf32")
+    assert not _lib.fbpinn_window_supported(net, js.desc, "fp32")
+    params = _glorot_params(widths, gen, k).to(dev)
+    x = torch.rand((n, 1), generator=gen).to(dev)
+    xs = to_soa(x)
+    edges = torch.linspace(0, 1, k + 1)
+    lo = (edges[:-1] - 0.1 / k).clamp_min(0).to(dev)
+    hi = (edges[1:] + 0.1 / k).clamp_max(1).to(dev)
+    ids = [j for j in range(k) if j not in skip]
+    lst = torch.tensor(ids, dtype=torch.int32, device=dev)
+    out = _lib.fbpinn_window_forward(net, js.desc, params, xs, n, lo, hi, lst, engine="tf32")
+    again = _lib.fbpinn_window_forward(net, js.desc, params, xs, n, lo, hi, lst, engine="tf32")
+    assert torch.equal(out[:, :n], again[:, :n])
+    ref, _ = td.jet_forward(net, js.desc, params.double(), xs.double(), n, False)      # [k, S, 1, ldn]
+    xd = x.double().requires_grad_()
+    w = torch.sigmoid(xd - lo.double()[None, :]) * torch.sigmoid(hi.double()[None, :] - xd)    # (n, k)
+    w1 = torch.stack([torch.autograd.grad(w[:, j].sum(), xd, create_graph=True)[0][:, 0] for j in range(k)], dim=1)
+    w2 = torch.stack([torch.autograd.grad(w1[:, j].sum(), xd, retain_graph=True)[0][:, 0] for j in range(k)], dim=1)
+    N = [ref[:, s, 0, :n].t() for s in range(js.S)]                                      # each (n, k)
+    want = [(w * N[0])[:, ids].sum(dim=1)]
+    if js.S == 3:
+        want.append((w1 * N[0] + w * N[1])[:, ids].sum(dim=1))
+        want.append((w2 * N[0] + 2 * w1 * N[1] + w * N[2])[:, ids].sum(dim=1))
+    for s in range(js.S):
+        if not ids:
+            assert float(out[s, :n].abs().max()) == 0.0
+        else:
+            assert _rel(out[s, :n].double(), want[s].detach()) < TF32_JET_TOL, f"stream {s}"
+
+
 def test_tf32_engine_refuses_what_it_cannot_do():
     net = _lib.make_net_desc([2, 150, 150, 1], "tanh")
     js = JetSpec((0, 1), ((0, 0), (1, 1)))
