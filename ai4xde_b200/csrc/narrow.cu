@@ -25,16 +25,19 @@ bool narrow_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_des
   if (g.widths[0] > 4 || g.widths[g.L + 1] > 4) return false;
   const int id = match_pattern(jet);
   if (id < 0 || !(H == 20 ? narrow_pattern_h20(id) : narrow_pattern_h32(id))) return false;
-  // shared memory of the backward kernel: weights + one gradient row per warp
-  const size_t smem = (size_t)(H * 4 + (g.L - 1) * H * H + 4 * H + (kNarrowBwdThreads / 32) * g.P) * sizeof(float);
+  // shared memory of the backward kernel: weights + the threads' exchange columns + one gradient row per warp
+  const int S = 1 + jet->n1 + jet->n2;
+  const size_t smem = (size_t)(H * 4 + (g.L - 1) * H * H + 4 * H + 4 + S * H * kNarrowThreads +
+                               (kNarrowThreads / 32) * g.P) * sizeof(float);
   (void)net;
   return smem <= 200 * 1024;
 }
 
 size_t narrow_backward_ws_bytes(const NetGeom &g, int S, int64_t ldn, int n_nets) {
-  const int H = g.widths[1];
-  const size_t rows_max = (size_t)narrow_grid_x(1 << 30, n_nets, kNarrowBwdPerSm) * (kNarrowBwdThreads / 32);
-  return ((size_t)2 * n_nets * S * H * ldn + (size_t)n_nets * rows_max * g.P) * sizeof(float);
+  (void)S;
+  (void)ldn;
+  const size_t rows_max = (size_t)narrow_grid_x(1 << 30, n_nets, kNarrowBwdPerSm) * (kNarrowThreads / 32);
+  return (size_t)n_nets * rows_max * g.P * sizeof(float);
 }
 
 int narrow_forward(const NetGeom &g, const FwdArgs &a) {

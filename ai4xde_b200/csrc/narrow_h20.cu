@@ -16,7 +16,7 @@ bool narrow_pattern_h20(int id) {
 
 int narrow_forward_h20(const NetGeom &g, const FwdArgs &a, int id) {
 #define AX_FWD(ID, PAT) \
-  if (id == ID) return narrow_launch_fwd<PAT, 20, (PAT::S <= 5 ? 20 : 4)>(g, a);
+  if (id == ID) return narrow_launch_fwd<PAT, 20>(g, a);
   AX_NARROW20(AX_FWD)
 #undef AX_FWD
   set_error("narrow kernels: stream pattern %d not compiled for width 20", id);

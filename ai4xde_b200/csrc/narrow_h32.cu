@@ -16,7 +16,7 @@ bool narrow_pattern_h32(int id) {
 
 int narrow_forward_h32(const NetGeom &g, const FwdArgs &a, int id) {
 #define AX_FWD(ID, PAT) \
-  if (id == ID) return narrow_launch_fwd<PAT, 32, (PAT::S <= 3 ? 32 : 16)>(g, a);
+  if (id == ID) return narrow_launch_fwd<PAT, 32>(g, a);
   AX_NARROW32(AX_FWD)
 #undef AX_FWD
   set_error("narrow kernels: stream pattern %d not compiled for width 32", id);

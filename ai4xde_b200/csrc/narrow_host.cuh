@@ -39,7 +39,7 @@ static inline void narrow_fill_args(const NetGeom &g, const ax_net_desc *net, co
   }
 }
 
-template <class P, int H, int OC>
+template <class P, int H>
 static int narrow_launch_fwd(const NetGeom &g, const FwdArgs &a) {
   constexpr int S = P::S;
   const int K = a.net->n_nets;
@@ -53,12 +53,12 @@ static int narrow_launch_fwd(const NetGeom &g, const FwdArgs &a) {
   na.stash = a.stash;
   na.layer_stride = (long long)S * H * a.ldn;
   na.keep_all = a.keep_all;
-  na.stash_net_stride = na.layer_stride * (a.keep_all ? g.L : (g.L < 2 ? g.L : 2));
-  na.tiles = (int)((a.n + kNarrowFwdThreads - 1) / kNarrowFwdThreads);
-  const size_t smem = (size_t)narrow_fwd_smem_floats<H>(g.L) * sizeof(float);
+  na.stash_net_stride = na.layer_stride * (a.keep_all ? g.L : (g.L < 2 ? g.L : 2));   // written only when kept
+  na.tiles = (int)((a.n + kNarrowThreads - 1) / kNarrowThreads);
+  const size_t smem = (size_t)(((narrow_fwd_weight_floats<H>(g.L) + 3) & ~3) + narrow_exchange_floats<S, H>()) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
-    AX_CUDA_OK(cudaFuncSetAttribute(k_narrow_fwd<P, H, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AX_CUDA_OK(cudaFuncSetAttribute(k_narrow_fwd<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   dim3 grid((unsigned)narrow_grid_x(na.tiles, K, 4), (unsigned)K);
@@ -66,7 +66,7 @@ static int narrow_launch_fwd(const NetGeom &g, const FwdArgs &a) {
     double mac = (double)g.widths[0] * H + (double)S * (g.L - 1) * H * H + (double)S * H * na.C;
     KernelTimer t("narrow_fwd", a.stream, 2.0 * mac * (double)a.n * K,
                   4.0 * ((double)g.widths[0] + S * na.C + (a.keep_all ? (double)S * H * g.L : 0.0)) * (double)a.n * K);
-    k_narrow_fwd<P, H, OC><<<grid, kNarrowFwdThreads, smem, a.stream>>>(na);
+    k_narrow_fwd<P, H><<<grid, kNarrowThreads, smem, a.stream>>>(na);
   }
   AX_LAUNCH_OK();
   return 0;
@@ -87,17 +87,17 @@ static int narrow_launch_bwd(const NetGeom &g, const BwdArgs &a) {
   na.layer_stride = (long long)S * H * a.ldn;
   na.keep_all = 1;
   na.stash_net_stride = na.layer_stride * g.L;
-  na.tiles = (int)((a.n + kNarrowBwdThreads - 1) / kNarrowBwdThreads);
+  na.tiles = (int)((a.n + kNarrowThreads - 1) / kNarrowThreads);
   const int gx = narrow_grid_x(na.tiles, K, kNarrowBwdPerSm);
-  const int rows = gx * (kNarrowBwdThreads / 32);
+  const int rows = gx * (kNarrowThreads / 32);
   const size_t need = narrow_backward_ws_bytes(g, S, a.ldn, K);
   if (!a.ws || a.ws_bytes < need) {
     set_error("backward workspace too small: %zu < %zu", a.ws_bytes, need);
     return 1;
   }
-  na.zbuf = (float *)a.ws;
-  na.partial = na.zbuf + (size_t)2 * K * na.layer_stride;
-  const size_t smem = ((size_t)narrow_bwd_weight_floats<H>(g.L) + (size_t)(kNarrowBwdThreads / 32) * g.P) * sizeof(float);
+  na.partial = (float *)a.ws;
+  const size_t smem = ((size_t)((narrow_bwd_weight_floats<H>(g.L) + 3) & ~3) + narrow_exchange_floats<S, H>() +
+                       (size_t)(kNarrowThreads / 32) * g.P) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
     AX_CUDA_OK(cudaFuncSetAttribute(k_narrow_bwd<P, H, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -108,7 +108,7 @@ static int narrow_launch_bwd(const NetGeom &g, const BwdArgs &a) {
     double mac = (double)g.widths[0] * H + (double)S * (g.L - 1) * H * H + (double)S * H * na.C;
     KernelTimer t("narrow_bwd", a.stream, 4.0 * mac * (double)a.n * K,
                   4.0 * ((double)g.widths[0] + S * na.C + (double)S * H * g.L) * (double)a.n * K);
-    k_narrow_bwd<P, H, KC><<<grid, kNarrowBwdThreads, smem, a.stream>>>(na);
+    k_narrow_bwd<P, H, KC><<<grid, kNarrowThreads, smem, a.stream>>>(na);
   }
   AX_LAUNCH_OK();
   dim3 rg((unsigned)((g.P + 255) / 256), (unsigned)K);

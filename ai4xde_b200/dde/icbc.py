@@ -12,20 +12,22 @@ from . import config, gradients as grad
 
 
 class _DeviceValues:
-    """func(X[beg:end]) -> device tensor, cached per (X identity, beg, end)."""
+    """func(X[beg:end]) -> device tensor, cached per (X, beg, end).  The entry holds X itself and compares with
+    `is`: an id() alone could be recycled by a later array of the same shape and serve stale targets."""
 
     def __init__(self, func):
         self.func = func
+        self._X = None
         self._key = None
         self._val = None
 
     def __call__(self, X, beg, end):
-        key = (id(X), X.shape, beg, end)
-        if key != self._key:
+        key = (X.shape, beg, end)
+        if X is not self._X or key != self._key:
             v = self.func(X[beg:end])
             self._val = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v,
                                         dtype=config.real(torch), device=config.device())
-            self._key = key
+            self._X, self._key = X, key
         return self._val
 
 

@@ -102,6 +102,8 @@ class DeviceLBFGS(torch.optim.Optimizer):
         use_graph = self._graph_ok(closure)
         if not use_graph or key != self._graph_key:
             self._graph, self._graph_key, self._seen = None, key, 0
+        # a captured iteration replays kernels on this batch's device pointers: own it while the graph lives
+        self._graph_batch = getattr(closure, "graph_batch", None) if use_graph else None
         # first evaluation of this call, eagerly; detached at once -- a live autograd graph would pin its
         # AccumulateGrad nodes to this stream and invalidate a later capture
         first = self._iterate(closure, 1).detach()

@@ -63,10 +63,11 @@ class _DeviceBatch:
     """Device-resident mirror of one host point array: AoS tensor for the case's `pde` code,
     SoA copy for the kernels."""
 
-    __slots__ = ("host", "aos", "soa")
+    __slots__ = ("host", "aos", "soa", "version")
 
-    def __init__(self, host):
+    def __init__(self, host, version=None):
         self.host = host
+        self.version = version
         dev = config.device()
         if torch.is_tensor(host):
             t = host.to(device=dev, dtype=torch.float32, non_blocking=True)
@@ -98,11 +99,30 @@ class Model:
         self.last_total_loss = None  # device scalar of the most recent closure evaluation
 
     # ---- device mirror -----------------------------------------------------------------------
+    def _owns(self, inputs):
+        """Is `inputs` one of the point arrays this framework builds and replaces as a whole (dde/data.py makes a
+        NEW array and bumps `data.version` on every mutation)?  Only those are mirrored across calls."""
+        d, ts = self.data, self.train_state
+        for holder, names in ((d, ("train_x", "test_x", "train_x_all")), (ts, ("X_train", "X_test"))):
+            for name in names:
+                if getattr(holder, name, None) is inputs:
+                    return True
+        return False
+
     def device_batch(self, inputs):
-        for b in self._batches:
-            if b.host is inputs:
+        """Device mirror of a host point array.  Framework-owned arrays are cached by identity AND data version
+        (true LRU, four entries, the entry keeps the host array alive so its id cannot be recycled); anything else
+        -- an array a user hands to `predict`, which may be a buffer they refill in place -- is uploaded on every
+        call, as DeepXDE does, and never displaces a cached training batch."""
+        if not self._owns(inputs):
+            return _DeviceBatch(inputs)
+        version = getattr(self.data, "version", None)
+        for i, b in enumerate(self._batches):
+            if b.host is inputs and b.version == version:
+                self._batches.append(self._batches.pop(i))
                 return b
-        b = _DeviceBatch(inputs)
+        self._batches = [b for b in self._batches if b.host is not inputs]
+        b = _DeviceBatch(inputs, version)
         self._batches.append(b)
         if len(self._batches) > 4:
             self._batches.pop(0)
@@ -186,23 +206,28 @@ class Model:
             and self.outputs_losses_train.__qualname__.startswith("Model.compile")
         )
         key = (id(inputs), getattr(self.data, "version", None), id(self.opt), id(self.data.pde))
+        eligible = eligible and self._owns(inputs)   # foreign arrays are re-uploaded per call: nothing stable to capture
         if not eligible:
-            st.update(key=None, seen=0, graph=None)
+            st.update(key=None, seen=0, graph=None, batch=None)
             return False
         if st["key"] != key:
-            st.update(key=key, seen=0, graph=None, holder=inputs)
+            # the graph bakes in the device pointers of this batch: keep the batch itself (not only the host
+            # array) alive for as long as the graph may be replayed
+            st.update(key=key, seen=0, graph=None, holder=inputs, batch=self.device_batch(inputs))
         if st["graph"] is not None:
             st["graph"].replay()
             return True
         st["seen"] += 1
         if st["seen"] <= 3:
             return False                      # eager warm-up (also runs the stream-set probe, BC uploads)
+        stepped = False
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 self.opt.step(closure)        # THIS call's step, eagerly, on a side stream (capture warm-up)
             torch.cuda.current_stream().wait_stream(side)
+            stepped = True
             g = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(g):         # records the next steps; nothing executes here
@@ -215,7 +240,7 @@ class Model:
             warnings.warn(f"ai4xde_b200: CUDA-graph capture of the train step failed ({e}); running eagerly")
             config.set_cuda_graphs(False)
             torch.cuda.synchronize()
-            return False
+            return stepped      # the side-stream warm-up WAS this call's step: do not step twice
 
     # ---- data parallel -----------------------------------------------------------------------
     def _dp_term_scale(self, losses, inputs):
@@ -313,8 +338,9 @@ class Model:
                 return
             if targets is None and auxiliary_vars is None and hasattr(inputs, "__len__"):
                 # lets DeviceLBFGS decide whether its per-iteration sequence may be replayed from a CUDA graph
-                closure.graph_rows = len(inputs)
+                closure.graph_rows = len(inputs) if self._owns(inputs) else None
                 closure.graph_key = (id(inputs), getattr(self.data, "version", None), id(self.data.pde))
+                closure.graph_batch = self.device_batch(inputs)   # kept alive by the optimiser's graph
             self.opt.step(closure)
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()
