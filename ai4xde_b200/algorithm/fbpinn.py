@@ -214,8 +214,10 @@ class FBPINN(PINNSolver):
         return self._combine(input, y_all)
 
     def _spec_for(self, model, batch, targets, loss_fn, losses_fn):
-        key = (id(model.data), id(model.data.pde))
-        if key not in self._specs:
+        key = self.model_list.index(model)
+        owners = (model.data, model.data.pde)
+        hit = self._specs.get(key)
+        if hit is None or hit[0][0] is not owners[0] or hit[0][1] is not owners[1]:
             x = batch.aos.detach().requires_grad_()
             C, K = self.bank.layer_sizes[-1], self.bank.K
 
@@ -224,8 +226,8 @@ class FBPINN(PINNSolver):
                 grad.clear()
                 return out
 
-            self._specs[key] = jet.probe_streams(x, K * C, fn)
-        return self._specs[key]
+            self._specs[key] = (owners, jet.probe_streams(x, K * C, fn))
+        return self._specs[key][1]
 
     # ---- per-model closures (FBPINN.py:125-194) ------------------------------------------------
     def compile(self, pde, model, optimizer, lr=None, loss="MSE", metrics=None, decay=None,

@@ -65,7 +65,9 @@ class R3Sampling(PINNSolver):
         else:
             def gated(x, y, ex):
                 out = inner(x, y, ex)
-                w = self.causal_weight(bkd.to_numpy(x), tensor=True)
+                # one weight per ROW: (n,) -> (n, 1) (an (n, 1) residual times an (n,) weight would broadcast to
+                # (n, n); the reference's in-place `res_i *= causal_weight` raises on that shape instead)
+                w = self.causal_weight(bkd.to_numpy(x), tensor=True).reshape(-1, 1)
                 return [r * w for r in (out if isinstance(out, list) else [out])]
         PDECase.set_pde(gated)
 

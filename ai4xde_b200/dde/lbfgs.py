@@ -59,8 +59,17 @@ class DeviceLBFGS(torch.optim.Optimizer):
                           for p in self._params])
 
     def _iterate(self, closure, begin):
+        import torch.distributed as dist
+
         g = self.param_groups[0]
         loss = closure()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # point-sharded ranks: the closure's loss is this rank's share (terms scaled so that the MEAN over ranks
+            # is the global loss, dde/model.py:_dp_term_scale).  Every stopping test of the iteration kernel that
+            # looks at the loss must see the same number on every rank, or one rank stops updating alone.
+            loss = loss.detach().clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+            loss /= dist.get_world_size()
         flat_g = self._flat_grad()
         alias = self._flat_alias()
         x = alias

@@ -136,8 +136,15 @@ class Model:
         return self.net.layer_sizes[-1]
 
     def spec_for_losses(self, batch, targets, loss_fn, losses_fn):
-        key = ("losses", id(self.data), id(self.data.pde), len(self.data.bcs))
-        spec = self._specs.get(key)
+        # the entry keeps data, pde and every BC alive and is matched with `is`: an id() recycled after
+        # `set_pde`, or a swapped BC list of the same length, must not serve a stale stream set
+        key = ("losses",)
+        owners = (self.data, self.data.pde, losses_fn.__func__ if hasattr(losses_fn, "__func__") else losses_fn) \
+            + tuple(self.data.bcs)
+        hit = self._specs.get(key)
+        spec = None
+        if hit is not None and len(hit[0]) == len(owners) and all(a is b for a, b in zip(hit[0], owners)):
+            spec = hit[1]
         if spec is None:
             x = batch.aos.detach().requires_grad_()
 
@@ -148,8 +155,9 @@ class Model:
                 grad.clear()
                 return out
 
-            spec = jet.probe_streams(x, self._n_out(), fn, feature=getattr(self.net, "_input_transform", None))
-            self._specs[key] = spec
+            spec = jet.probe_streams(x, self._n_out(), fn, feature=getattr(self.net, "_input_transform", None),
+                                     variables=self.external_trainable_variables)
+            self._specs[key] = (owners, spec)
             if Model.verbose:
                 print(f"[ai4xde_b200] streams for training losses: {spec}")
         return spec
@@ -168,7 +176,8 @@ class Model:
             grad.clear()
             return out
 
-        spec = jet.probe_streams(x, self._n_out(), fn, feature=getattr(self.net, "_input_transform", None))
+        spec = jet.probe_streams(x, self._n_out(), fn, feature=getattr(self.net, "_input_transform", None),
+                                 variables=self.external_trainable_variables)
         self._specs[key] = (operator, spec)
         if Model.verbose:
             print(f"[ai4xde_b200] streams for operator {getattr(operator, '__name__', operator)}: {spec}")

@@ -21,6 +21,16 @@ set_LBFGS_options()
 config = types.SimpleNamespace(set_LBFGS_options=set_LBFGS_options, LBFGS_options=LBFGS_options)
 
 
+def lbfgs_factory(params, **kw):
+    """The L-BFGS of the fused path: one kernel launch per iteration on the flat parameter vector, no
+    per-iteration host sync (dde/lbfgs.py, csrc/lbfgs.cu).  There is no PyTorch / CPU fallback: DeviceLBFGS raises
+    on parameters that are not CUDA tensors (the `not gpu` host-logic tests replace this factory together with the
+    kernels by their plain-PyTorch doubles)."""
+    from .lbfgs import DeviceLBFGS
+
+    return DeviceLBFGS(params, **kw)
+
+
 def is_external_optimizer(name):
     return name in ("L-BFGS", "L-BFGS-B")
 
@@ -34,13 +44,7 @@ def get(params, optimizer, learning_rate=None, decay=None, weight_decay=0):
         kw = dict(lr=1, max_iter=LBFGS_options["iter_per_step"], max_eval=LBFGS_options["fun_per_step"],
                   tolerance_grad=LBFGS_options["gtol"], tolerance_change=LBFGS_options["ftol"],
                   history_size=LBFGS_options["maxcor"])
-        params = list(params)
-        if params and all(p.is_cuda for p in params):
-            from .lbfgs import DeviceLBFGS     # one kernel launch per iteration, no per-iteration host sync
-
-            optim = DeviceLBFGS(params, **kw)
-        else:                                  # host-logic tests on CPU tensors (the kernels are doubled there)
-            optim = torch.optim.LBFGS(params, line_search_fn=None, **kw)
+        optim = lbfgs_factory(list(params), **kw)
     else:
         if learning_rate is None:
             raise ValueError("No learning rate for {}.".format(optimizer))

@@ -328,7 +328,31 @@ def probe_spec(d):
     return JetSpec.two_direction_third(0, 1) if d == 2 else JetSpec.full(d)
 
 
-def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
+class _ProbeRecord:
+    """Stands in for JetOutput during the discovery dry run: notes every derivative the caller asks of the RAW
+    network output through dde.grad.jacobian / hessian and answers None, so the request is then served by
+    autograd over the probe leaf as usual.  A stream that was asked for by name is carried even if the loss
+    happened not to depend on it numerically during the dry run (`dde.Variable(0.0) * u_xx`, a curriculum weight
+    that starts at zero): dropping it would make that derivative silently zero for the rest of the run."""
+
+    def __init__(self, x, d):
+        self.x, self.d = x, d
+        self.firsts, self.seconds = set(), set()
+
+    def first(self, comp, dim):
+        self.firsts.add(int(dim))
+        return None
+
+    def first_all(self, comp):
+        self.firsts.update(range(self.d))
+        return None
+
+    def second(self, comp, dim_i, dim_j):
+        self.seconds.add(tuple(sorted((int(dim_i), int(dim_j)))))
+        return None
+
+
+def probe_streams(x, n_out, fn, allow_trace=True, feature=None, variables=()):
     """Find which derivative streams `fn(x, y)` really uses.
 
     With a feature transform (`net.apply_feature_transform(f)`) the kernels differentiate w.r.t. the
@@ -337,9 +361,28 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
 
     fn receives the input tensor and a stand-in network output whose value / first / second
     derivative streams are independent random tensors, and must return the tensors that the
-    training loss (or the predict operator) is built from.  A stream is needed iff the result
-    has a non-zero gradient w.r.t. it.  Returns JetSpec.covering(...).  No kernel is involved.
+    training loss (or the predict operator) is built from.  A stream is needed if the result
+    has a non-zero gradient w.r.t. it, or if the caller asked dde.grad.jacobian / hessian for it by name on
+    the raw network output (see _ProbeRecord).  `variables` are the external trainable variables
+    (`dde.Variable`s of inverse problems): entries that are exactly zero are set to 0.5 for the duration of the
+    dry run, so a term they multiply is not mistaken for an absent one.
+    Returns JetSpec.covering(...).  No kernel is involved.
     """
+    saved = []
+    for v in variables or ():
+        if torch.is_tensor(v) and bool((v.detach() == 0).any()):
+            saved.append((v, v.detach().clone()))
+            with torch.no_grad():
+                v.copy_(torch.where(v == 0, torch.full_like(v, 0.5), v))
+    try:
+        return _probe_streams(x, n_out, fn, allow_trace, feature)
+    finally:
+        with torch.no_grad():
+            for v, old in saved:
+                v.copy_(old)
+
+
+def _probe_streams(x, n_out, fn, allow_trace, feature):
     n = x.shape[0]
     with torch.enable_grad():
         leaf_in = x if feature is None else feature(x)
@@ -354,8 +397,12 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
     gen.manual_seed(1234)
     mk = lambda: torch.randn((n, n_out), dtype=x.dtype, device=x.device, generator=gen).requires_grad_()
     streams = [mk() for _ in range(full.S)]
+    from .dde import gradients as grad_mod  # local import: jet <-> dde.gradients
+
+    asked = _ProbeRecord(leaf_in, d)
     with torch.enable_grad():
         y = make_leaf(leaf_in, full, streams)
+        grad_mod.register(y, asked)
         outs = fn(x, y)
         if not isinstance(outs, (list, tuple)):
             outs = [outs]
@@ -368,10 +415,10 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
         if total is None:
             return JetSpec.value_only()
         grads = torch.autograd.grad(total, streams[1:], allow_unused=True, retain_graph=True)
-    need1, need2 = [], []
+    need1, need2 = sorted(asked.firsts), sorted(asked.seconds)
     for j in range(full.n1):
         g = grads[j]
-        if g is not None and bool((g != 0).any()):
+        if g is not None and bool((g != 0).any()) and full.dirs[j] not in need1:
             need1.append(full.dirs[j])
     order = 2
     for q, (a, b) in enumerate(full.pairs):
@@ -381,8 +428,8 @@ def probe_streams(x, n_out, fn, allow_trace=True, feature=None):
                 order = max(order, 3 if q == full.third else 4)
             elif q in full.triples.values():
                 order = max(order, 3)
-            else:
-                need2.append((full.dirs[a], full.dirs[b]))
+            elif tuple(sorted((full.dirs[a], full.dirs[b]))) not in need2:
+                need2.append(tuple(sorted((full.dirs[a], full.dirs[b]))))
     if order > 2:
         return JetSpec.covering(full.dirs if full.triples else (need1 or [full.dirs[0]]), need2, order=order)
     cover = JetSpec.covering(need1, need2)

@@ -232,7 +232,7 @@ def run_ours(args):
     ms_step = ms / args.steps
     value = world * n_pts * args.steps / (ms * 1e-3)
     # streams actually carried (the dry run adopts the Laplacian pattern for Helmholtz: S = 4)
-    specs = [v for k, v in model._specs.items() if k[0] == "losses"]
+    specs = [v[1] for k, v in model._specs.items() if k[0] == "losses"]
     s_run = specs[0].S if specs else S
     f_train = 3 * 2 * (P1 + s_run * PREST)
 

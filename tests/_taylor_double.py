@@ -105,12 +105,20 @@ def jet_backward(net, jet, params, x_soa, n, jets_bar, stash, engine="auto"):
     return torch.stack(grads)
 
 
+def torch_lbfgs(params, **kw):
+    """Stand-in for the device L-BFGS on CPU tensors: the optimiser it follows statement by statement."""
+    return torch.optim.LBFGS(params, line_search_fn=None, **kw)
+
+
 def install(monkeypatch=None):
-    """Route the product's kernel calls to this double (CPU host-logic tests only)."""
+    """Route the product's kernel calls (jet kernels, device L-BFGS) to doubles (CPU host-logic tests only)."""
     from ai4xde_b200 import _lib
+    from ai4xde_b200.dde import optimizers
 
     if monkeypatch is not None:
         monkeypatch.setattr(_lib, "jet_forward", jet_forward)
         monkeypatch.setattr(_lib, "jet_backward", jet_backward)
+        monkeypatch.setattr(optimizers, "lbfgs_factory", torch_lbfgs)
     else:
         _lib.jet_forward, _lib.jet_backward = jet_forward, jet_backward
+        optimizers.lbfgs_factory = torch_lbfgs

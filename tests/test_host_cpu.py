@@ -104,7 +104,7 @@ def test_stream_discovery():
         m = dde.Model(case.data, case.net)
         m.compile("adam", lr=1e-3, loss_weights=lw)
         m.outputs_losses_train(case.data.train_x, None, None)
-        return [v for k, v in m._specs.items() if k[0] == "losses"][0]
+        return [v[1] for k, v in m._specs.items() if k[0] == "losses"][0]
 
     np.random.seed(0)
     s = spec_of(pc.Burgers(NumDomain=20, layer_size=[2, 8, 1]))
@@ -246,6 +246,56 @@ def test_fbpinn_bank_matches_sum_of_nets():
     model.train(iterations=2)
     moved = (solver.bank.flat - before).abs().sum(dim=1)
     assert moved[1] > 0 and moved[0] == 0 and moved[2] == 0 and moved[3] == 0
+
+
+def test_stream_discovery_keeps_terms_whose_coefficient_is_zero_at_probe_time():
+    """Advisor finding (round 1): a derivative that is structurally present but multiplied by zero during the dry
+    run (`dde.Variable(0.0) * u_xx` of an inverse problem) must stay in the carried stream set -- otherwise it is
+    silently zero for the rest of the run and the coefficient can never learn."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import jet
+
+    x = torch.rand(16, 2).requires_grad_()
+    c = dde.Variable(0.0)
+
+    def raw(xx, y):          # asked by name on the raw network output
+        r = dde.grad.jacobian(y, xx, i=0, j=1) - c * dde.grad.hessian(y, xx, i=0, j=0)
+        dde.grad.clear()
+        return r
+
+    spec = jet.probe_streams(x, 1, raw)
+    assert (0, 0) in spec.second_of_dims and 1 in spec.first_of_dim
+
+    def transformed(xx, y):  # behind an output transform the request reaches autograd only
+        yt = xx[:, 0:1] * y
+        r = dde.grad.jacobian(yt, xx, i=0, j=1) - c * dde.grad.hessian(yt, xx, i=0, j=0)
+        dde.grad.clear()
+        return r
+
+    assert (0, 0) not in jet.probe_streams(x, 1, transformed).second_of_dims          # the hazard, without the list
+    spec2 = jet.probe_streams(x, 1, transformed, variables=[c])                       # dde.Model passes the list
+    assert (0, 0) in spec2.second_of_dims and float(c) == 0.0                         # ... and the value is restored
+
+
+def test_stream_set_cache_is_not_fooled_by_a_new_pde_or_bc_list(monkeypatch):
+    import _taylor_double as td
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    td.install(monkeypatch)
+    dde.config.set_default_float("float32")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = pc.Heat(NumDomain=40, layer_size=[2, 8, 8, 1])
+    model = dde.Model(case.data, case.net)
+    case.compile(model, "adam", lr=1e-3)
+    model.outputs_losses_train(case.data.train_x, None, None)
+    first = model._specs[("losses",)][1]
+    assert first.n2 == 1                                     # u_t and u_xx
+    case.set_pde(lambda x, y: dde.grad.jacobian(y, x, i=0, j=1) + dde.grad.hessian(y, x, i=1, j=1))
+    model.data = case.data
+    model.outputs_losses_train(case.data.train_x, None, None)
+    assert model._specs[("losses",)][1] is not first and (1, 1) in model._specs[("losses",)][1].second_of_dims
 
 
 def test_fbpinn_windowed_bank_matches_oracle_restatement(monkeypatch):
