@@ -131,19 +131,13 @@ __global__ void __launch_bounds__(kNarrowThreads) k_narrow_fwd(const NarrowArgs 
 #pragma unroll
       for (int o = 0; o < H; ++o) {
         const float4 w = *reinterpret_cast<const float4 *>(sW0 + o * 4);
-        const float wv[4] = {w.x, w.y, w.z, w.w};
         float st[S], A[S];
-        float z0 = sb0[o];
-#pragma unroll
-        for (int d = 0; d < 4; ++d) z0 = fmaf(wv[d], xv[d], z0);
+        const float z0 = fmaf(w.w, xv[3], fmaf(w.z, xv[2], fmaf(w.y, xv[1], fmaf(w.x, xv[0], sb0[o]))));
         st[0] = stash_slot0(a.act0, z0);
+        // d z / d x_dir = W0[unit][dir]: an indexed shared-memory read (a select chain over a register copy of the
+        // row is turned into a local-memory array by the compiler)
 #pragma unroll
-        for (int j = 0; j < P::N1; ++j) {
-          float t = 0.0f;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) t = (a.dirs.d[j] == d) ? wv[d] : t;
-          st[1 + j] = t;
-        }
+        for (int j = 0; j < P::N1; ++j) st[1 + j] = sW0[o * 4 + a.dirs.d[j]];
 #pragma unroll
         for (int q = 0; q < P::N2; ++q) st[1 + P::N1 + q] = 0.0f;
         if (wr) {

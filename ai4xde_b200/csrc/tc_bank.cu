@@ -87,8 +87,10 @@ static __global__ void k_tc_bank_sum_chunks(const float *__restrict__ part, int 
 
 __device__ __forceinline__ float sigmoid_acc(float t) { return 1.0f / (1.0f + expf(-t)); }
 
+// 576 threads x 112 registers = 63 K of the 64 K register file (ptxas settles on 96 under __launch_bounds__ alone
+// and spills into the epilogue's hot loops: ncu attributed 26 % of the stall samples to LDL, profiles/r02_bank_ncu.md)
 template <class P, int ACT, int NT, bool WINDOW>
-__global__ void __launch_bounds__(kBankThreads, 1)
+__global__ void __maxnreg__(112)
 k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
   constexpr int S = P::S;
   using G = BankGeom<S, NT>;
@@ -98,7 +100,9 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
   static_assert(!WINDOW || S <= 3, "window mode carries value / first / second derivative along one input");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an OFFSET into the shared array (not a round trip through uintptr_t): the compiler keeps
+  // the shared address space and emits LDS / STS for the parameter block instead of generic loads
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t *img = smem;                                  // NT operand images
   uint8_t *ring = smem + NT * G::IMG_BYTES;
   float *prm = (float *)(ring + NW * kBankWBytes);      // two parameter blocks (double-buffered over nets)
@@ -270,16 +274,12 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 w = *reinterpret_cast<const float4 *>(sw0 + (u0 + i) * 4);
-            const float wv[4] = {w.x, w.y, w.z, w.w};
             float z[S], A[S];
             z[0] = fmaf(w.w, xv[3], fmaf(w.z, xv[2], fmaf(w.y, xv[1], fmaf(w.x, xv[0], sb[u0 + i]))));
+            // d z / d x_dir = W0[unit][dir]: an indexed shared-memory read (a select chain over a register copy of the
+            // row is turned into a local-memory array by the compiler)
 #pragma unroll
-            for (int j = 0; j < P::N1; ++j) {
-              float tt = 0.0f;
-#pragma unroll
-              for (int d = 0; d < 4; ++d) tt = (g.dirs.d[j] == d) ? wv[d] : tt;
-              z[1 + j] = tt;
-            }
+            for (int j = 0; j < P::N1; ++j) z[1 + j] = sw0[(u0 + i) * 4 + g.dirs.d[j]];
 #pragma unroll
             for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
             jet_forward_fast<P, ACT>(z, A);

@@ -31,7 +31,14 @@ P1 = 2 * H
 PREST = (L - 1) * H * H + H * 1
 F_FWD = 2 * (P1 + S * PREST)      # 3 280 384 FLOP / point   
 F_TRAIN = 3 * F_FWD               # 9 841 152 FLOP / point
-WORKLOAD = "cfg4: Helmholtz 2D, FNN 2-[256]x6-1 tanh, 2^20 pts/GPU + 80 bdry, loss_weights [1,100], Adam"
+WORKLOADS = {
+    "cfg4": "cfg4: Helmholtz 2D, FNN 2-[256]x6-1 tanh, 2^20 pts/GPU + 80 bdry, loss_weights [1,100], Adam",
+    "cfg5": "cfg5: FBPINN, 1D multiscale Poisson, 64 windowed subdomain nets 1-[64]x3-1 tanh batched per launch, "
+            "2^20 pts of the sub-model being trained sharded over the GPUs (+2 bdry), Adam on the active net",
+}
+WORKLOAD = WORKLOADS["cfg4"]
+K5, H5, L5, S5 = 64, 64, 3, 3
+F_FWD5 = 2 * (1 * H5 + S5 * ((L5 - 1) * H5 * H5 + H5))     # 49 664 FLOP per net and point
 
 
 def parse():
@@ -40,7 +47,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=2**20, help="collocation points per GPU")
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS),
+                    help="cfg4 (default): the configuration the metric is quoted on; cfg5: FBPINN K = 64 (strong split)")
+    ap.add_argument("--points", type=int, default=2**20,
+                    help="collocation points per GPU (cfg4) / in total, split over the GPUs (cfg5)")
     ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tf32"])
     ap.add_argument("--cpu-points", type=int, default=2**14, help="points per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -97,7 +107,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(points, steps, warmup, threads_list=None):
+def cpu_reference_run(points, steps, warmup, threads_list=None, workload="cfg4"):
     """Time the oracle's train step (ddelite + autograd, float64 -- the reference default,
     /root/reference/AI4XDE/solver/PDESolver.py:6) on host cores.  Returns best over thread counts."""
     import numpy as np
@@ -112,17 +122,39 @@ def cpu_reference_run(points, steps, warmup, threads_list=None):
     try:
         np.random.seed(0)
         torch.manual_seed(0)
-        data, net, _ = oc.build("cfg4", points)
-        model = ddelite.Model(data, net)
-        model.compile("adam", lr=1e-3, loss_weights=oc.LOSS_WEIGHTS["cfg4"])
-        X = data.train_x
+        if workload == "cfg5":
+            # the reference's FBPINN closure of one sub-model (algorithm/FBPINN.py:143-185): all 64 nets evaluated
+            # on the batch, autograd jets through the sum, gradient of the active net, Adam on it
+            limits = oc.fbpinn_subdomains(0.0, 1.0, K5)
+            ls = [1] + [H5] * L5 + [1]
+            k = K5 // 2
+            pts, sds = [], []
+            for (lo, hi) in limits:
+                pts.append(np.vstack(([[lo], [hi]], np.random.uniform(lo, hi, (points, 1)))))
+                net0 = ddelite.nn.FNN(ls, "tanh", "Glorot uniform")
+                sds.append({n_: v.detach().numpy() for n_, v in net0.state_dict().items()})
+            datas, nets = oc.fbpinn_build(limits, pts, sds, ls)
+            opt = torch.optim.Adam(nets[k].parameters(), lr=1e-3)
+
+            def step():
+                oc.fbpinn_step_outputs(datas, nets, k)
+                opt.step()
+
+            what = f"oracle FBPINN closure (64 nets, ddelite+autograd, float64) + Adam on {points} pts of sub-model {k}"
+        else:
+            data, net, _ = oc.build("cfg4", points)
+            model = ddelite.Model(data, net)
+            model.compile("adam", lr=1e-3, loss_weights=oc.LOSS_WEIGHTS["cfg4"])
+            X = data.train_x
+            step = lambda: model.train_step(X, None, None)
+            what = f"oracle (ddelite+autograd, float64) train step on {points} pts of the cfg4 net"
         for th in threads_list:
             torch.set_num_threads(th)
             for _ in range(warmup):
-                model.train_step(X, None, None)
+                step()
             t0 = time.perf_counter()
             for _ in range(steps):
-                model.train_step(X, None, None)
+                step()
             dt = (time.perf_counter() - t0) / steps
             if best is None or dt < best[0]:
                 best = (dt, th)
@@ -131,23 +163,28 @@ def cpu_reference_run(points, steps, warmup, threads_list=None):
         torch.set_default_dtype(torch.float32)
     dt, th = best
     return {"value": points / dt, "unit": "points/s", "cores": th, "kind": "port",
-            "sample": f"oracle (ddelite+autograd, float64) train step on {points} pts of the cfg4 net, "
-                      f"{steps} steps after {warmup} warm-up, best of threads {threads_list} "
+            "sample": f"{what}, {steps} steps after {warmup} warm-up, best of threads {threads_list} "
                       f"(os.cpu_count()={cores})",
             "ms_per_step": dt * 1e3}
+
+
+def cpu_sample_points(args):
+    return args.cpu_points if args.workload == "cfg4" else min(args.cpu_points, 2048)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.cpu_points, max(1, args.steps), max(1, args.warmup))
+    pts = cpu_sample_points(args)
+    r = cpu_reference_run(pts, max(1, args.steps), max(1, args.warmup), workload=args.workload)
     line = {
         "impl": "reference", "metric": "train collocation points/sec (residual+backward)",
         "value": r["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak" if args.workload == "cfg4" else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_points_per_step": args.cpu_points},
+        "config": {"workload": WORKLOADS[args.workload], "sample_points_per_step": pts},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,7 +192,70 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measure_peaks(torch, _lib):
+    """FP32-FMA and TF32 tensor peaks of THIS GPU, measured in this run (SURVEY.md 8d "peaks to divide by"):
+    the library's FMA probe kernel, and torch.matmul 8192^3 with TF32 allowed (a library GEMM, used only as the
+    yardstick) -- best of 5 after a warm-up, CUDA events."""
+    out = {"fp32_fma_tflops": _lib.measure_fp32_fma_peak()}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device="cuda")
+        b = torch.randn((8192, 8192), device="cuda")
+        torch.matmul(a, b)
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * 8192**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out["tf32_tflops"] = best
+        del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
+def build_cfg4(args, rank, world):
+    import numpy as np
+    import torch
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases
+
+    n = args.points
+    np.random.seed(1234 + rank)     # each rank owns its own 2^20 points (weak scaling)
+    torch.manual_seed(0)            # identical weights on every rank
+    case = cases.Helmholtz(NumDomain=n, layer_size=[2] + [H] * L + [1], activation="tanh",
+                           honor_num_domain=True)
+    model = dde.Model(case.data, case.net)
+    case.compile(model, "adam", lr=1e-3)
+    return {"model": model, "X": case.data.train_x, "n_pts": case.data.train_x_all.shape[0], "scaling": "weak"}
+
+
+def build_cfg5(args, rank, world):
+    import numpy as np
+    import torch
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import algorithm
+    from ai4xde_b200.cases.poisson_cases import multiscale_fbpinn_case
+
+    dde.config.set_default_float("float32")
+    n = args.points // world         # strong split: 2^20 points of the sub-model in total
+    np.random.seed(0)
+    torch.manual_seed(0)             # identical decomposition and weights on every rank
+    solver = algorithm.FBPINN(multiscale_fbpinn_case(NumDomain=256), segment=K5, iter=1)
+    k = K5 // 2
+    model, pde = solver.model_list[k], solver.domains.pdeCase_list[k]
+    lo, hi = solver.domains.limits[k]
+    rng = np.random.RandomState(1234 + rank)   # each rank owns its own share of the sub-model's points
+    model.data.replace_with_anchors(rng.uniform(lo, hi, (n, 1)).astype(np.float32))
+    solver.compile(pde, model, "adam", lr=1e-3)
+    return {"model": model, "X": model.data.train_x, "n_pts": n, "scaling": "strong", "solver": solver}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -186,24 +286,20 @@ def run_ours(args):
     import warnings
     warnings.simplefilter("ignore")
     import ai4xde_b200.dde as dde
-    from ai4xde_b200 import _lib, cases
+    from ai4xde_b200 import _lib
 
     dde.config.set_engine(args.engine)
-    n = args.points
-    np.random.seed(1234 + rank)     # each rank owns its own 2^20 points (weak scaling)
-    torch.manual_seed(0)            # identical weights on every rank
-    case = cases.Helmholtz(NumDomain=n, layer_size=[2] + [H] * L + [1], activation="tanh",
-                           honor_num_domain=True)
-    model = dde.Model(case.data, case.net)
-    case.compile(model, "adam", lr=1e-3)
-    X = case.data.train_x                       # (80 bc rows + 80 + n, 2) host float64
+    wl = (build_cfg4 if args.workload == "cfg4" else build_cfg5)(args, rank, world)
+    model, X, n_pts = wl["model"], wl["X"], wl["n_pts"]
     rows = X.shape[0]
-    n_pts = case.data.train_x_all.shape[0]      # points counted by the metric (no BC duplicates)
+    weak = wl["scaling"] == "weak"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    peaks_run = measure_peaks(torch, _lib) if rank == 0 else None
 
     # ---- device-resident arm ------------------------------------------------------------------
     clocks = ClockSampler(local)
@@ -231,14 +327,20 @@ def run_ours(args):
     ms = float(t.item())
     ms_step = ms / args.steps
     value = world * n_pts * args.steps / (ms * 1e-3)
-    # streams actually carried (the dry run adopts the Laplacian pattern for Helmholtz: S = 4)
-    specs = [v[1] for k, v in model._specs.items() if k[0] == "losses"]
-    s_run = specs[0].S if specs else S
-    f_train = 3 * 2 * (P1 + s_run * PREST)
+    if args.workload == "cfg4":
+        # streams actually carried (the dry run adopts the Laplacian pattern for Helmholtz: S = 4)
+        specs = [v[1] for k, v in model._specs.items() if k[0] == "losses"]
+        s_run = specs[0].S if specs else S
+        f_train = 3 * 2 * (P1 + s_run * PREST)
+    else:
+        # the reference's schedule (algorithm/FBPINN.py:112-119): forward of all K nets, reverse pass through the one
+        # being trained -> (K + 2) * F_fwd per point
+        s_run = S5
+        f_train = (K5 + 2) * F_FWD5
 
     # ---- end-to-end arm: host buffers in, loss out, every step ----------------------------------
     host = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).pin_memory()
-    views = [host.view_as(host) for _ in range(args.steps + args.warmup)]   # distinct objects -> no device cache hit
+    views = [host.view_as(host) for _ in range(args.steps + args.warmup)]   # distinct objects -> re-uploaded per step
     # every step's loss is read back to pinned host memory; the read of step i is consumed (event wait + float())
     # while step i+1 is already queued -- the usual asynchronous logging pattern -- and the last one before the
     # closing event, so all K device->host reads complete inside the timed region.
@@ -280,10 +382,8 @@ def run_ours(args):
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
-        bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense = half the bf16 rate)" if peaks \
-            else "fallback 1.4 PFLOP/s bf16 sustained / 2"
-        tf32_peak = bf16 / 2.0
+        tf32_peak = peaks_run["tf32_tflops"]
+        peak_src = "measured in this run: torch.matmul 8192^3, allow_tf32, best of 5 (CUDA events)"
         dom = max(kern.items(), key=lambda kv: kv[1]["ms"]) if kern else None
         roofline = None
         if dom is not None:
@@ -292,15 +392,15 @@ def run_ours(args):
             sec = k["ms"] * 1e-3
             tflops = k["flops"] / sec / 1e12 if sec > 0 else 0.0
             gbs = k["bytes"] / sec / 1e9 if sec > 0 else 0.0
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-            if os.path.exists(tpath):
-                per_pt = json.load(open(tpath))["dram_bytes_per_point"].get(name)
-                if per_pt is not None:
-                    traffic = per_pt * n_pts
-            # the layer GEMMs stream S*H*4 bytes per point and layer through HBM: ncu shows DRAM at
-            # 70-80 % of peak and the tensor pipe at 25-45 % => the dominant kernel is HBM-bound; its
-            # tensor-pipe rate is reported alongside.
+            traffic, traffic_src = None, None
+            for tfile in ("r02_traffic.json", "r01_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", tfile)
+                if traffic is None and os.path.exists(tpath):
+                    per_pt = json.load(open(tpath))["dram_bytes_per_point"].get(name)
+                    if per_pt is not None:
+                        traffic = per_pt * n_pts
+                        traffic_src = f"replayed from profiles/{tfile} (ncu --set full dram__bytes per point of this kernel, " \
+                                      f"captured separately; not measured in this run)"
             # which roof the dominant kernel sits closer to decides the reported bound
             hbm_bound = (gbs / hbm_peak) >= (tflops / tf32_peak)
             roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": name,
@@ -308,7 +408,7 @@ def run_ours(args):
                         "peak": hbm_peak if hbm_bound else tf32_peak,
                         "unit": "GB/s" if hbm_bound else "TFLOP/s",
                         "frac": (gbs / hbm_peak) if hbm_bound else (tflops / tf32_peak),
-                        "traffic": traffic,
+                        "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": ("MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6650 GB/s")
                         if hbm_bound else peak_src,
                         "algorithmic_bytes_per_launch": k["bytes"] / max(1, k["launches"]),
@@ -323,19 +423,27 @@ def run_ours(args):
                                     for kk, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(args.cpu_points, 5, 1)   # ~10 s of host work: 3 thread counts x 6 steps
+            r = cpu_reference_run(cpu_sample_points(args), 5 if args.workload == "cfg4" else 2, 1, workload=args.workload)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        config = {"workload": WORKLOADS[args.workload], "points_per_gpu": n_pts, "rows_per_step": rows,
+                  "engine": args.engine, "parallelism": f"dp{world}", "streams": s_run, "flop_per_point": f_train}
+        if args.workload == "cfg4":
+            config["l2"] = "working set (per-layer jet stash, GBs) far exceeds the 126 MB L2; no flush needed"
+            config["flop_per_point_S5"] = F_TRAIN
+        else:
+            config["l2"] = ("per step the kernels stream 64 nets x 34 KB of weights from L2 by design; the only HBM-sized "
+                            "buffers (active net's stash, 100s of MB) exceed the 126 MB L2; no flush needed")
+            config["nets"] = K5
+            config["net_evals_per_s"] = value * K5
         line = {
             "metric": "train collocation points/sec (residual+backward)", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "f32" if args.engine == "fp32" else "tf32/f32-accumulate (f32 first/last layer)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_gpu": n_pts, "rows_per_step": rows, "engine": args.engine,
-                       "l2": "working set (per-layer jet stash, GBs) far exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world}", "streams": s_run, "flop_per_point": f_train,
-                       "flop_per_point_S5": F_TRAIN},
+            "config": config,
             "clocks": clk,
+            "peaks_measured_in_run": peaks_run,
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
