@@ -90,6 +90,11 @@ _SIGNATURES = {
         [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P],
     ),
     "ax_gather_points": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
+    "ax_uniform_box_points": (
+        C.c_int,
+        [_P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64,
+         C.c_uint64, _P],
+    ),
     "ax_lbfgs_ws_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
     "ax_lbfgs_iterate": (
         C.c_int,
@@ -416,6 +421,17 @@ def measure_fp32_fma_peak(seconds=0.3):
         if ms * 1e-3 < seconds / 4:
             iters = min(iters * 2, 1 << 20)
     return best
+
+
+def uniform_box_points(x_soa, first, m, lo, hi, seed, offset):
+    """Fill columns [first, first + m) of the SoA point buffer with Philox uniforms in the box [lo, hi)."""
+    lib = load()
+    _need_cuda(x_soa)
+    d, ldn = x_soa.shape
+    lo_a = (C.c_float * d)(*[float(v) for v in lo])
+    hi_a = (C.c_float * d)(*[float(v) for v in hi])
+    _check(lib.ax_uniform_box_points(_ptr(x_soa), d, ldn, int(first), int(m), lo_a, hi_a, int(seed) & (2**64 - 1),
+                                     int(offset) & (2**64 - 1), _stream()), "ax_uniform_box_points")
 
 
 def gather_points(x_soa, idx):

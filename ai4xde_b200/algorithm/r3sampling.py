@@ -11,8 +11,9 @@ residual, closure`) keep the reference's names.  Deviations, both listed in SURV
     residual (a loop variable is rebound, R3Sampling.py:43-44); that no-op is kept.  The causal gate on
     the sampling side (R3Sampling.py:80-82) runs in NumPy as in the reference."""
 import numpy as np
+import torch
 
-from .. import dde, resample
+from .. import _lib, dde, resample
 from ..dde import backend as bkd
 from ..solver import PINNSolver
 
@@ -33,8 +34,28 @@ class _CausalGate:
         self.gamma += self.beta_lr * np.exp(-self.tol * gated_mean)
 
 
+def _box_limits(geom):
+    """(lo, hi) of an axis-aligned box geometry (Interval, Rectangle / Hypercube, or one of them x TimeDomain), else
+    None: what the device-side uniform sampler can fill."""
+    G = dde.geometry
+    if isinstance(geom, G.GeometryXTime):
+        inner = _box_limits(geom.geometry)
+        if inner is None:
+            return None
+        return (list(inner[0]) + [float(geom.timedomain.t0)], list(inner[1]) + [float(geom.timedomain.t1)])
+    if isinstance(geom, G.Interval):
+        return ([float(geom.l)], [float(geom.r)])
+    if isinstance(geom, G.Hypercube):
+        return ([float(v) for v in geom.xmin], [float(v) for v in geom.xmax])
+    return None
+
+
 class R3Sampling(PINNSolver):
-    def __init__(self, PDECase, max_iter=100, causally_sampling=False, beta_lr=0.001, tol=20):
+    def __init__(self, PDECase, max_iter=100, causally_sampling=False, beta_lr=0.001, tol=20, device_rng=False,
+                 device_seed=0):
+        # [ext] device_rng: refill from the library's Philox box sampler instead of NumPy's stream (performance
+        # mode: the whole round stays on the device; the default keeps the reference's NumPy stream bit for bit)
+        self.device_rng, self.device_seed, self._rng_offset = bool(device_rng), int(device_seed), 0
         dde.optimizers.config.set_LBFGS_options(maxiter=1000)
         self._gate = _CausalGate(beta_lr=beta_lr, tol=tol)
         self.max_iter = max_iter
@@ -83,18 +104,63 @@ class R3Sampling(PINNSolver):
         """One retain / refill round; returns the boolean keep mask over the old population.
         New population = [fresh uniform points ; retained points] (R3Sampling.py:92-98)."""
         data, X = self.PDECase.data, self.PDECase.data.train_x_all
+        if not self.causally_sampling and resample._world()[2] == 1 and torch.cuda.is_available():
+            return self._resample_on_device(data, X)
         if self.causally_sampling:
             res = self.residual(X, True)
             keep = res > np.mean(res)
         else:
             # sharded population: global threshold (all-gather of the block residuals), local retain / refill
-            retain = resample.r3_retain_sharded if resample._world()[2] > 1 else resample.r3_retain
-            keep = retain(self.model, X, self.PDECase.pde)[0]
+            keep = resample.r3_retain_sharded(self.model, X, self.PDECase.pde)[0]
         kept = X[np.where(keep)]
-        data.replace_with_anchors(kept)
         released = len(X) - len(kept)
         if released > 0:
-            data.add_anchors(self.PDECase.geomtime.random_points(released))
+            data.set_train_x_all(np.vstack((self.PDECase.geomtime.random_points(released), kept)))
+        else:
+            data.replace_with_anchors(kept)
+        return keep
+
+    def _resample_on_device(self, data, X):
+        """The round without leaving the device: residual probe, NumPy-order threshold, ordered compaction of the
+        retained points to the END of a fresh SoA buffer (`ax_r3_retain`), refill of its FRONT -- from NumPy's
+        stream on the host in parity mode (one upload of the released share), from the Philox box sampler in the
+        kernel library with `device_rng=True` -- and the result registered as the device mirror of the new
+        `train_x_all` / `train_x`, so the next train step uploads nothing.  The host arrays the reference API
+        exposes are rebuilt once (`set_train_x_all`): exactly, from the float64 originals, when the host float is
+        float64 (parity with the reference's `X[np.where(res > mean)]`); by one device-to-host copy otherwise."""
+        from ..dde import config as dconfig
+
+        model, geom = self.model, self.PDECase.geomtime
+        res, n = resample.residual_matrix(model, X, self.PDECase.pde)
+        batch = model.device_batch(X)
+        x_out, n_keep_dev, thr, res_sum = _lib.r3_retain(res, batch.soa, n, place_at_end=True)
+        keep_dev = res_sum > thr
+        n_keep = int(n_keep_dev.item())
+        released = n - n_keep
+        box = _box_limits(geom) if self.device_rng else None
+        new_host = None
+        if released > 0:
+            if box is not None:
+                _lib.uniform_box_points(x_out, 0, released, box[0], box[1], self.device_seed, self._rng_offset)
+                self._rng_offset += released
+            else:
+                new_host = geom.random_points(released)
+                x_out[:, :released] = torch.as_tensor(np.ascontiguousarray(new_host, dtype=np.float32)).to(
+                    x_out.device, non_blocking=True).t()
+        aos = x_out[:, :n].t().contiguous()
+        keep = keep_dev.cpu().numpy()
+        if box is not None or dconfig.real(np) == np.float32:
+            host_all = aos.cpu().numpy()                   # the device values ARE the points
+        else:
+            kept = X[np.where(keep)]                       # float64 originals, as the reference keeps them
+            host_all = kept if new_host is None else np.vstack((new_host, kept))
+        data.set_train_x_all(host_all)
+        # device mirrors of the new host arrays: nothing to upload at the next step
+        model.adopt_device_batch(data.train_x_all, aos, soa=x_out)
+        n_bc = int(sum(data.num_bcs)) if data.num_bcs else 0
+        if data.train_x is not data.train_x_all:
+            bc_dev = torch.as_tensor(np.ascontiguousarray(data.train_x[:n_bc], dtype=np.float32)).to(aos.device)
+            model.adopt_device_batch(data.train_x, torch.cat((bc_dev, aos), dim=0) if n_bc else aos)
         return keep
 
     def closure(self):

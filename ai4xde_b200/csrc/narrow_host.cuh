@@ -23,7 +23,7 @@ static inline int narrow_grid_x(int tiles, int K, int per_sm) {
   if (gx > tiles) gx = tiles;
   return gx < 1 ? 1 : gx;
 }
-constexpr int kNarrowBwdPerSm = 2;
+constexpr int kNarrowBwdPerSm = 3;   // upper bound used for the workspace; width 20 runs 3 CTAs per SM, width 32 two
 
 static inline void narrow_fill_args(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, NarrowArgs *na) {
   na->P = g.P;
@@ -88,7 +88,7 @@ static int narrow_launch_bwd(const NetGeom &g, const BwdArgs &a) {
   na.keep_all = 1;
   na.stash_net_stride = na.layer_stride * g.L;
   na.tiles = (int)((a.n + kNarrowThreads - 1) / kNarrowThreads);
-  const int gx = narrow_grid_x(na.tiles, K, kNarrowBwdPerSm);
+  const int gx = narrow_grid_x(na.tiles, K, H <= 20 ? 3 : 2);   // resident CTAs per SM (registers: 168 / 255 per thread)
   const int rows = gx * (kNarrowThreads / 32);
   const size_t need = narrow_backward_ws_bytes(g, S, a.ldn, K);
   if (!a.ws || a.ws_bytes < need) {

@@ -397,6 +397,44 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 using namespace ax;
 
+// ---------------------------------------------------------------------------------------
+// counter-based uniform points in a box (performance mode of the resamplers' refill / candidate draws):
+// Philox4x32-10 (Salmon et al., SC'11), key = seed, counter = (point index / 4-group, stream offset).  One call
+// of the generator yields 4 words = the coordinates of one point (d <= 4): the value of point i depends only on
+// (seed, offset, i), not on the launch geometry.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+struct BoxLimits {
+  float lo[4], span[4];
+};
+
+__global__ void k_uniform_box(float *__restrict__ x, int d, int64_t ldn, int64_t first, int64_t m, BoxLimits box,
+                              uint64_t seed, uint64_t offset) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint64_t ctr = offset + (uint64_t)i;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5851F42Du, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int k = 0; k < d; ++k) {
+    const float u = (float)(c[k] >> 8) * (1.0f / 16777216.0f);   // [0, 1) on a 2^-24 grid
+    x[(int64_t)k * ldn + first + i] = fmaf(u, box.span[k], box.lo[k]);
+  }
+}
+
 extern "C" {
 
 size_t ax_resample_ws_bytes(int64_t n) {
@@ -545,6 +583,25 @@ int ax_r3_retain(const float *res, int32_t n_res, int64_t ldr, const float *x_so
   if (pairwise_sum_impl<float>(res_sum_out, n, thr_out, (float)n, L.heap, L.heap_bytes, st)) return 1;
   return ax_r3_retain_thr(res_sum_out, thr_out, x_soa, d, n, ldn, x_out, ldn_out, place_at_end, n_keep_out, ws,
                           ws_bytes, stream);
+}
+
+int ax_uniform_box_points(float *x_soa, int32_t d, int64_t ldn, int64_t first, int64_t m, const float *h_lo,
+                          const float *h_hi, uint64_t seed, uint64_t offset, void *stream) {
+  if (m <= 0) return 0;
+  if (d < 1 || d > 4 || !x_soa || !h_lo || !h_hi || first < 0 || first + m > ldn) {
+    set_error("uniform_box_points: d = %d must be in [1, 4] and [first, first + m) inside ldn", d);
+    return 1;
+  }
+  BoxLimits box;
+  for (int k = 0; k < 4; ++k) {
+    box.lo[k] = k < d ? h_lo[k] : 0.0f;
+    box.span[k] = k < d ? h_hi[k] - h_lo[k] : 0.0f;
+  }
+  const int bs = 256;
+  k_uniform_box<<<(unsigned)((m + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(x_soa, d, ldn, first, m, box, seed,
+                                                                               offset);
+  AX_LAUNCH_OK();
+  return 0;
 }
 
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,

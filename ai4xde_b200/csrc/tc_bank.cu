@@ -87,10 +87,12 @@ static __global__ void k_tc_bank_sum_chunks(const float *__restrict__ part, int 
 
 __device__ __forceinline__ float sigmoid_acc(float t) { return 1.0f / (1.0f + expf(-t)); }
 
-// 576 threads x 112 registers = 63 K of the 64 K register file (ptxas settles on 96 under __launch_bounds__ alone
-// and spills into the epilogue's hot loops: ncu attributed 26 % of the stall samples to LDL, profiles/r02_bank_ncu.md)
+// 18 warps put 5 on one scheduler partition: 16 K registers / (5 x 32) caps a thread at 96 registers (a launch with
+// 112 is refused).  ncu of the first version attributed 26 % of its stall samples to LDL -- a select chain over a
+// register copy of the W0 row that the compiler had turned into a local-memory array, not spills; with that gone the
+// kernel fits 96 registers with a handful of spilled bytes (profiles/r02_bank_v2_ncu_full.md).
 template <class P, int ACT, int NT, bool WINDOW>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kBankThreads, 1)
 k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
   constexpr int S = P::S;
   using G = BankGeom<S, NT>;

@@ -26,8 +26,11 @@ class Data:
 
 
 class PDE(Data):
+    uses_targets = False   # the PDE / BC losses never read `targets`: dde.Model does not upload train_y per step
+
     def __init__(self, geometry, pde, bcs, num_domain=0, num_boundary=0, train_distribution="Hammersley",
                  anchors=None, exclusions=None, solution=None, num_test=None, auxiliary_var_function=None):
+        self._train_y, self._train_y_stale = None, False
         self.geom = geometry
         self.pde = pde
         self.bcs = bcs if isinstance(bcs, (list, tuple)) else [bcs]
@@ -74,8 +77,22 @@ class PDE(Data):
         return out
 
     # ---- point bookkeeping (host) ------------------------------------------------------------
+    @property
+    def train_y(self):
+        """`soln(train_x)` as DeepXDE keeps it -- evaluated on first use after the point set changed, not on every
+        anchor update (an R3 round updates twice; on 2^20 points the reference solution costs ~30 ms each time and no
+        loss term reads it)."""
+        if self._train_y_stale:
+            self._train_y = self.soln(self.train_x) if (self.soln and self.train_x is not None) else None
+            self._train_y_stale = False
+        return self._train_y
+
+    @train_y.setter
+    def train_y(self, value):
+        self._train_y, self._train_y_stale = value, False
+
     def _refresh_targets(self):
-        self.train_y = self.soln(self.train_x) if self.soln else None
+        self._train_y, self._train_y_stale = None, bool(self.soln)
         if self.auxiliary_var_fn is not None:
             self.train_aux_vars = self.auxiliary_var_fn(self.train_x).astype(config.real(np))
         self.version += 1
@@ -86,7 +103,7 @@ class PDE(Data):
         self._refresh_targets()
 
     def train_next_batch(self, batch_size=None):
-        if self.train_x is None and self.train_y is None and self.train_aux_vars is None:
+        if self.train_x is None and self.train_aux_vars is None:
             self.train_x_all = self.train_points()
             self.bc_points()
             self.train_x = np.vstack((self.train_x_bc, self.train_x_all)) if self.bcs else self.train_x_all
@@ -117,6 +134,14 @@ class PDE(Data):
 
     def replace_with_anchors(self, anchors):
         self.anchors = anchors.astype(config.real(np))
+        self.train_x_all = self.anchors
+        self._assemble()
+
+    def set_train_x_all(self, points):
+        """`replace_with_anchors(kept)` followed by `add_anchors(new)` (/root/reference/AI4XDE/algorithm/
+        R3Sampling.py:95-98) leaves `anchors == train_x_all == vstack(new, kept)`: this sets that state from the
+        already assembled array with ONE rebuild of `train_x` instead of two."""
+        self.anchors = np.ascontiguousarray(points, dtype=config.real(np))
         self.train_x_all = self.anchors
         self._assemble()
 
@@ -187,7 +212,7 @@ class IDE(PDE):
         self._refresh_targets()
 
     def train_next_batch(self, batch_size=None):
-        if self.train_x is None and self.train_y is None and self.train_aux_vars is None:
+        if self.train_x is None and self.train_aux_vars is None:
             self.train_x_all = self.train_points()
             self._assemble()
         return self.train_x, self.train_y, self.train_aux_vars

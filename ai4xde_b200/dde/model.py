@@ -131,6 +131,19 @@ class Model:
     def drop_device_batches(self):
         self._batches.clear()
 
+    def adopt_device_batch(self, host, aos, soa=None):
+        """Register device tensors that ALREADY hold `host` (a framework-owned point array assembled on the device by
+        a resampling round) as its mirror, so the next step does not upload it again."""
+        b = _DeviceBatch.__new__(_DeviceBatch)
+        b.host, b.version = host, getattr(self.data, "version", None)
+        b.aos = aos
+        b.soa = soa if soa is not None else jet.to_soa(aos)
+        self._batches = [c for c in self._batches if c.host is not host]
+        self._batches.append(b)
+        if len(self._batches) > 4:
+            self._batches.pop(0)
+        return b
+
     # ---- stream-set discovery ----------------------------------------------------------------
     def _n_out(self):
         return self.net.layer_sizes[-1]
@@ -304,6 +317,8 @@ class Model:
                 self.net.auxiliary_vars = torch.as_tensor(auxiliary_vars, dtype=torch.float32, device=config.device())
             self.net.train(mode=training)
             batch = self.device_batch(inputs)
+            if targets is not None and not getattr(self.data, "uses_targets", True):
+                targets = None      # dde.data.PDE never reads them: no per-step upload of soln(train_x)
             if targets is not None:
                 targets = torch.as_tensor(targets, dtype=torch.float32, device=config.device())
             spec = self.spec_for_losses(batch, targets, loss_fn, losses_fn)

@@ -212,6 +212,16 @@ int ax_lbfgs_iterate(float *x, const float *g, const float *loss, int64_t n_para
                      ax_lbfgs_state *state, int32_t history, float lr, float tol_grad, float tol_change,
                      int32_t begin_step, void *stream);
 
+/*
+ * Uniform points in an axis-aligned box, generated on the device: x_soa[k][first + i] = lo_k + (hi_k - lo_k) u,
+ * u in [0, 1) from Philox4x32-10 keyed by `seed` at counter `offset + i` (d <= 4 coordinates per counter).
+ * Performance-mode stand-in for geomtime.random_points(m) of algorithm/R3Sampling.py:97 and RAD.py:25 on
+ * Interval / Rectangle / Interval x TimeDomain geometries (the parity mode keeps NumPy's stream on the host).
+ * h_lo / h_hi are HOST arrays of d floats.
+ */
+int ax_uniform_box_points(float *x_soa, int32_t d, int64_t ldn, int64_t first, int64_t m, const float *h_lo,
+                          const float *h_hi, uint64_t seed, uint64_t offset, void *stream);
+
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
                      float *x_out, int64_t ldn_out, void *stream);
