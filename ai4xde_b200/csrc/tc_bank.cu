@@ -87,6 +87,11 @@ static __global__ void k_tc_bank_sum_chunks(const float *__restrict__ part, int 
 
 __device__ __forceinline__ float sigmoid_acc(float t) { return 1.0f / (1.0f + expf(-t)); }
 
+// Round-to-nearest TF32 for a value that ONLY the tensor core will read: kind::tf32 ignores the low 13 mantissa bits
+// of its operands, so adding half a TF32 ulp to the bit pattern is the whole rounding (the mask of to_tf32 is what the
+// hardware does anyway) -- one integer add instead of two instructions per operand value.
+__device__ __forceinline__ float tf32_round_for_mma(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
 // 18 warps put 5 on one scheduler partition: 16 K registers / (5 x 32) caps a thread at 96 registers (a launch with
 // 112 is refused).  ncu of the first version attributed 26 % of its stall samples to LDL -- a select chain over a
 // register copy of the W0 row that the compiler had turned into a local-memory array, not spills; with that gone the
@@ -286,7 +291,7 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
             for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
             jet_forward_fast<P, ACT>(z, A);
 #pragma unroll
-            for (int s = 0; s < S; ++s) v[s][i] = to_tf32(A[s]);
+            for (int s = 0; s < S; ++s) v[s][i] = tf32_round_for_mma(A[s]);
           }
           store_image(t, v);
           signal_image(t);
@@ -311,7 +316,7 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
                 z[0] += bl[i];
                 jet_forward_fast<P, ACT>(z, A);
 #pragma unroll
-                for (int s = 0; s < S; ++s) v[s][i] = to_tf32(A[s]);
+                for (int s = 0; s < S; ++s) v[s][i] = tf32_round_for_mma(A[s]);
               }
               store_image(t, v);
               signal_image(t);

@@ -348,13 +348,22 @@ class Model:
         trainable = list(self.net.parameters()) + self.external_trainable_variables
         self.opt, self.lr_scheduler = optimizers.get(trainable, self.opt_name, learning_rate=lr, decay=decay)
 
+        flat_grad = _bind_flat_grad(trainable)   # data parallel only: every p.grad a view of ONE buffer
+
         def train_step(inputs, targets, auxiliary_vars):
             def closure():
                 losses = outputs_losses_train(inputs, targets, auxiliary_vars)[1]
                 total_loss = torch.sum(losses)
-                self.opt.zero_grad()
-                total_loss.backward()
-                _allreduce_grads(trainable)
+                if flat_grad is not None and all(p.grad is not None and p.grad.data_ptr() == q for p, q in flat_grad[1]):
+                    # point-sharded ranks: autograd accumulates into the views, ONE collective on the flat buffer
+                    # (no torch.cat, no copy-back); the mean over ranks of the scaled local losses is the global loss
+                    flat_grad[0].zero_()
+                    total_loss.backward()
+                    _allreduce_flat(flat_grad[0])
+                else:
+                    self.opt.zero_grad()
+                    total_loss.backward()
+                    _allreduce_grads(trainable)
                 self.last_total_loss = total_loss.detach()
                 return total_loss
 
@@ -388,7 +397,15 @@ class Model:
         own = getattr(fn, "__qualname__", "").startswith("Model.compile")
         outs = self._outputs_losses_eval(training, inputs, targets, auxiliary_vars) if own else fn(
             inputs, targets, auxiliary_vars)
-        return utils.to_numpy(outs[0]), utils.to_numpy(outs[1])
+        losses = outs[1]
+        dist, world = _dist_world()
+        if dist is not None and torch.is_tensor(losses) and losses.is_cuda:
+            # point-sharded ranks: every rank logs the GLOBAL per-term losses (mean over ranks of the count-scaled
+            # local terms), not its own share
+            losses = losses.detach().clone()
+            dist.all_reduce(losses, op=dist.ReduceOp.SUM)
+            losses /= world
+        return utils.to_numpy(outs[0]), utils.to_numpy(losses)
 
     def _train_step(self, inputs, targets, auxiliary_vars):
         self.train_step(inputs, targets, auxiliary_vars)
@@ -515,6 +532,42 @@ class Model:
         ckpt = torch.load(save_path, map_location=device or config.device())
         self.net.load_state_dict(ckpt["model_state_dict"])
         self.opt.load_state_dict(ckpt["optimizer_state_dict"])
+
+
+def _dist_world():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_world_size()
+    return None, 1
+
+
+def _bind_flat_grad(params):
+    """Data parallel: make every parameter's .grad a view of ONE float32 buffer, so that the gradient exchange is a
+    single all-reduce of that buffer.  Returns (buffer, [(param, data_ptr of its view)]) or None (single process,
+    or parameters that are not float32 tensors of one CUDA device)."""
+    dist, world = _dist_world()
+    params = [p for p in params if p.requires_grad]
+    if dist is None or not params:
+        return None
+    dev = params[0].device
+    if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in params):
+        return None
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    views, off = [], 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        views.append((p, p.grad.data_ptr()))
+        off += p.numel()
+    return flat, views
+
+
+def _allreduce_flat(flat):
+    dist, world = _dist_world()
+    if dist is None:
+        return
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
 
 
 def _allreduce_grads(params):
