@@ -100,6 +100,10 @@ _SIGNATURES = {
         C.c_int,
         [_P, _P, _P, C.c_int64, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, _P],
     ),
+    "ax_adam_step": (
+        C.c_int,
+        [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P],
+    ),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "ax_debug_fma_peak": (C.c_double, [_P, C.c_int32, C.c_int32, _P]),
 }
@@ -385,6 +389,15 @@ def lbfgs_iterate(x, g, loss, ws, state, history, lr, tol_grad, tol_change, begi
     rc = lib.ax_lbfgs_iterate(_ptr(x), _ptr(g), _ptr(loss), x.numel(), _ptr(ws), _ptr(state), int(history),
                               float(lr), float(tol_grad), float(tol_change), int(begin_step), _stream())
     _check(rc, "ax_lbfgs_iterate")
+
+
+def adam_step(params, grad, exp_avg, exp_avg_sq, state, lr, beta1, beta2, eps, weight_decay=0.0):
+    """One Adam update of the flat float32 parameter vector, in place (csrc/adam.cu)."""
+    lib = load()
+    _need_cuda(params, grad, exp_avg, exp_avg_sq, state)
+    rc = lib.ax_adam_step(_ptr(params), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), _ptr(state),
+                          float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), _stream())
+    _check(rc, "ax_adam_step")
 
 
 def debug_tc_wgrad(zbar, a):

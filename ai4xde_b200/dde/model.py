@@ -221,7 +221,7 @@ class Model:
             and not optimizers.is_external_optimizer(self.opt_name)
             and self.lr_scheduler is None
             and targets is None and auxiliary_vars is None
-            and isinstance(self.opt, (torch.optim.Adam, torch.optim.AdamW))
+            and (isinstance(self.opt, (torch.optim.Adam, torch.optim.AdamW)) or getattr(self.opt, "capturable", False))
             and self.opt.defaults.get("capturable", False)
             and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
             and self.train_step.__qualname__.startswith("Model.compile")

@@ -52,10 +52,18 @@ def get(params, optimizer, learning_rate=None, decay=None, weight_decay=0):
                  "adamw": torch.optim.AdamW}
         if optimizer not in table:
             raise NotImplementedError(f"{optimizer} to be implemented for backend pytorch.")
+        params = list(params)
         kw = {}
-        if optimizer in ("adam", "adamw") and all(p.is_cuda for p in params):
+        optim = None
+        if optimizer == "adam" and params and all(p.is_cuda for p in params):
+            from .adam import FlatAdam, flat_alias
+
+            if flat_alias(params) is not None:    # dde.nn.FNN: one kernel launch per step on the flat buffer
+                optim = FlatAdam(params, lr=learning_rate, weight_decay=weight_decay)
+        if optimizer in ("adam", "adamw") and params and all(p.is_cuda for p in params):
             kw["capturable"] = True   # step counters on the device: the whole step can live in a CUDA graph
-        optim = table[optimizer](params, lr=learning_rate, weight_decay=weight_decay, **kw)
+        if optim is None:
+            optim = table[optimizer](params, lr=learning_rate, weight_decay=weight_decay, **kw)
     sched = None
     if decay is not None:
         if decay[0] == "step":

@@ -222,6 +222,14 @@ int ax_lbfgs_iterate(float *x, const float *g, const float *loss, int64_t n_para
 int ax_uniform_box_points(float *x_soa, int32_t d, int64_t ldn, int64_t first, int64_t m, const float *h_lo,
                           const float *h_hi, uint64_t seed, uint64_t offset, void *stream);
 
+/*
+ * Adam on the flat parameter vector in one launch: torch.optim.Adam(params, lr, betas, eps, weight_decay).step as
+ * DeepXDE's PyTorch backend builds it for the first phase of every train_step (solver/PDESolver.py:79-81).
+ * state: device int32[2], zeroed to start ([0] = step counter, [1] = scratch); exp_avg / exp_avg_sq: n floats, zeroed.
+ */
+int ax_adam_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int32_t *state,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, void *stream);
+
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
                      float *x_out, int64_t ldn_out, void *stream);

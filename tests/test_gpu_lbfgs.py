@@ -147,3 +147,40 @@ def test_lbfgs_iteration_kernel_matches_two_loop_reference(P, m):
         assert err < 5e-3, (it, err)
         xr = x_new                     # follow the device iterate: the check is per launch, not of accumulated drift
     assert int(st[0]) == 3 * m // 2 + 4 and int(st[1]) == min(m, 3 * m // 2 + 3)
+
+
+def test_flat_adam_follows_torch_adam():
+    """csrc/adam.cu (one launch per step on the flat parameter buffer of a dde.nn.FNN) against torch.optim.Adam on
+    a copy of the same parameters fed the same gradients: 200 steps, parameters within 2e-6 absolute (float32
+    rounding of two orderings of the same formula); dde.optimizers hands it out for FNN parameters."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200.dde.adam import FlatAdam
+
+    dde.config.set_default_float("float32")
+    torch.manual_seed(0)
+    net = dde.nn.FNN([2, 20, 20, 1], "tanh", "Glorot normal")
+    opt, _ = dde.optimizers.get(list(net.parameters()), "adam", learning_rate=1e-3)
+    assert isinstance(opt, FlatAdam)
+    ref_params = [p.detach().clone().requires_grad_() for p in net.parameters()]
+    ref = torch.optim.Adam(ref_params, lr=1e-3)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(200):
+        opt.zero_grad()
+        ref.zero_grad()
+        for p, q in zip(net.parameters(), ref_params):
+            g = torch.randn(p.shape, device="cuda", generator=gen) * (1.0 + it % 7)
+            p.grad.copy_(g)            # the views of the flat gradient buffer
+            q.grad = g.clone()
+        opt.step()
+        ref.step()
+    for p, q in zip(net.parameters(), ref_params):
+        assert float((p.detach() - q.detach()).abs().max()) < 2e-6
+    assert int(opt.state[opt._params[0]]["step_dev"][0]) == 200
+    # gradients that autograd puts into tensors of their own are gathered, not lost
+    opt.zero_grad()
+    before = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    after = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    assert bool(((before - after).abs() > 0).all())
