@@ -68,6 +68,8 @@ _SIGNATURES = {
         [C.POINTER(NetDesc), C.POINTER(JetDesc), _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int32, _P, _P,
          C.c_size_t, C.c_int, _P],
     ),
+    "ax_resample_set_fast": (None, [C.c_int]),
+    "ax_resample_get_fast": (C.c_int, []),
     "ax_resample_ws_bytes": (C.c_size_t, [C.c_int64]),
     "ax_pairwise_sum_f32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "ax_pairwise_sum_f64": (C.c_int, [_P, C.c_int64, _P, _P, C.c_size_t, _P]),
@@ -298,6 +300,15 @@ def fbpinn_window_forward(net, jet, params, x_soa, n, win_lo, win_hi, net_list, 
 
 
 # ---- resampling ---------------------------------------------------------------------------
+def resample_set_fast(on):
+    """Parallel float64 sum / cumsum in the RAD selection instead of NumPy's sequential order (see the header)."""
+    load().ax_resample_set_fast(int(bool(on)))
+
+
+def resample_get_fast():
+    return bool(load().ax_resample_get_fast())
+
+
 def resample_ws(n, device):
     nbytes = load().ax_resample_ws_bytes(int(n))
     return _bytes_buf(nbytes, device), int(nbytes)

@@ -8,7 +8,9 @@ from ..solver import PINNSolver
 
 
 class RAD(PINNSolver):
-    def __init__(self, PDECase, iter=100, k=1, c=1, warmup_iter=1000):
+    def __init__(self, PDECase, iter=100, k=1, c=1, warmup_iter=1000, fast=False):
+        # [ext] fast: parallel float64 sum / cumsum in the selection instead of NumPy's sequential order
+        self.fast = bool(fast)
         dde.optimizers.config.set_LBFGS_options(maxiter=1000)
         super().__init__(name=f"RAD_k_{k}_c_{c}", PDECase=PDECase)
         self.iter, self.k, self.c, self.warmup_iter = iter, k, c, warmup_iter
@@ -18,7 +20,7 @@ class RAD(PINNSolver):
         _, rank, world = resample._world()
         if world == 1:
             X = case.geomtime.random_points(case.NumDomain * 10)
-            ids = resample.rad_select(self.model, X, case.pde, case.NumDomain, k=self.k, c=self.c)
+            ids = resample.rad_select(self.model, X, case.pde, case.NumDomain, k=self.k, c=self.c, fast=self.fast)
             case.data.replace_with_anchors(X[ids])
             return ids
         # point-sharded run: NumDomain is this rank's share.  Every rank draws the SAME

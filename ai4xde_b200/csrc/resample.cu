@@ -391,6 +391,106 @@ __global__ void k_gather(const float *__restrict__ x, int d, int64_t ldn, const 
   for (int c = 0; c < d; ++c) x_out[(int64_t)c * ldn_out + j] = x[(int64_t)c * ldn + i];
 }
 
+// ---------------------------------------------------------------------------------------
+// fast mode: parallel float64 sum / inclusive scan (reduce-then-scan, three launches), bit-reproducible run to run
+// but NOT in NumPy's sequential rounding order -- the selected index sets agree with the parity mode unless a uniform
+// falls within one rounding of a cdf boundary (tests hold them equal on the reference fixtures).  A single-pass
+// decoupled look-back scan would save two launches but associates the block prefixes in an order that depends on
+// timing, i.e. its float64 roundings are not reproducible; at these sizes (<= a few M candidates) the launches are
+// noise next to the residual probe.
+// ---------------------------------------------------------------------------------------
+constexpr int kFsBlock = 1024, kFsItems = 4;
+
+__device__ __forceinline__ double fs_block_inclusive(double t, double *wsum, double *block_total) {
+  // inclusive scan of one value per thread over the block (warp shuffles, then the 32 warp totals)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double inc = t;
+  for (int o = 1; o < 32; o <<= 1) {
+    const double v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  double woff = 0.0, tot = 0.0;
+  for (int w = 0; w < kFsBlock / 32; ++w) {
+    if (w < warp) woff += wsum[w];
+    tot += wsum[w];
+  }
+  *block_total = tot;
+  return woff + inc;
+}
+
+__global__ void __launch_bounds__(kFsBlock) k_fs_block_sums(const double *__restrict__ a, int64_t n,
+                                                            double *__restrict__ bsum) {
+  __shared__ double wsum[32];
+  const int64_t i0 = ((int64_t)blockIdx.x * kFsBlock + threadIdx.x) * kFsItems;
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < kFsItems; ++k)
+    if (i0 + k < n) t += a[i0 + k];
+  double tot;
+  fs_block_inclusive(t, wsum, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+// single CTA: exclusive scan of the block sums in place, grand total to out[0]
+__global__ void __launch_bounds__(kFsBlock) k_fs_scan_sums(double *__restrict__ bsum, int nblocks,
+                                                           double *__restrict__ out) {
+  __shared__ double wsum[32];
+  __shared__ double carry_s;
+  if (threadIdx.x == 0) carry_s = 0.0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nblocks; b0 += kFsBlock) {
+    const int b = b0 + threadIdx.x;
+    const double v = b < nblocks ? bsum[b] : 0.0;
+    double tot;
+    const double inc = fs_block_inclusive(v, wsum, &tot);
+    const double carry = carry_s;
+    if (b < nblocks) bsum[b] = carry + (inc - v);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = carry_s;
+}
+
+__global__ void __launch_bounds__(kFsBlock) k_fs_block_scan(const double *__restrict__ a, int64_t n,
+                                                            const double *__restrict__ boff,
+                                                            double *__restrict__ cdf) {
+  __shared__ double wsum[32];
+  const int64_t i0 = ((int64_t)blockIdx.x * kFsBlock + threadIdx.x) * kFsItems;
+  double v[kFsItems], t = 0.0;
+#pragma unroll
+  for (int k = 0; k < kFsItems; ++k) {
+    v[k] = (i0 + k < n) ? a[i0 + k] : 0.0;
+    t += v[k];
+  }
+  double tot;
+  double run = boff[blockIdx.x] + (fs_block_inclusive(t, wsum, &tot) - t);
+#pragma unroll
+  for (int k = 0; k < kFsItems; ++k) {
+    run += v[k];
+    if (i0 + k < n) cdf[i0 + k] = run;
+  }
+}
+
+static int g_resample_fast = 0;
+
+// cdf may alias a; cdf == nullptr: total only.  scratch: >= nblocks doubles.
+static int fast_sum_scan(const double *a, int64_t n, double *cdf, double *total, double *scratch, cudaStream_t st) {
+  const int per = kFsBlock * kFsItems;
+  const int nblocks = (int)((n + per - 1) / per);
+  k_fs_block_sums<<<nblocks, kFsBlock, 0, st>>>(a, n, scratch);
+  AX_LAUNCH_OK();
+  k_fs_scan_sums<<<1, kFsBlock, 0, st>>>(scratch, nblocks, total);
+  AX_LAUNCH_OK();
+  if (cdf) {
+    k_fs_block_scan<<<nblocks, kFsBlock, 0, st>>>(a, n, scratch, cdf);
+    AX_LAUNCH_OK();
+  }
+  return 0;
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace ax
@@ -487,6 +587,14 @@ static int carve(void *ws, size_t ws_bytes, int64_t n, WsLayout *L) {
   return 0;
 }
 
+// block sums of the fast scan: the draw-index scratch is idle while the cdf is formed (a few scalars for tiny n)
+static double *fast_scratch(const WsLayout &L, int64_t n) {
+  return n > 6 * kFsBlock * kFsItems ? (double *)L.idx : L.scalars + 2;   // <= 6 block sums fit the scalar slots
+}
+
+void ax_resample_set_fast(int on) { g_resample_fast = on != 0; }
+int ax_resample_get_fast(void) { return g_resample_fast; }
+
 int ax_rad_probabilities(const float *res, int32_t n_res, int64_t ldr, int64_t n, double k, double c,
                          double *p_out, void *ws, size_t ws_bytes, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -501,8 +609,12 @@ int ax_rad_probabilities(const float *res, int32_t n_res, int64_t ldr, int64_t n
   if (pairwise_sum_impl<double>(L.arr, n, L.scalars, (double)n, L.heap, L.heap_bytes, st)) return 1;
   k_rad_err<<<nb, bs, 0, st>>>(L.arr, n, L.scalars, c);
   AX_LAUNCH_OK();
-  k_seq_chain<0><<<1, 1024, 0, st>>>(L.arr, n, nullptr, L.scalars + 1);
-  AX_LAUNCH_OK();
+  if (g_resample_fast) {
+    if (fast_sum_scan(L.arr, n, nullptr, L.scalars + 1, fast_scratch(L, n), st)) return 1;
+  } else {
+    k_seq_chain<0><<<1, 1024, 0, st>>>(L.arr, n, nullptr, L.scalars + 1);
+    AX_LAUNCH_OK();
+  }
   k_div_scalar<<<nb, bs, 0, st>>>(L.arr, n, L.scalars + 1, p_out);
   AX_LAUNCH_OK();
   return 0;
@@ -526,8 +638,12 @@ int ax_choice_round(double *p, int64_t n, const double *u, int64_t n_draw, int64
     k_fill_i32<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(L.first, n, INT_MAX);
     AX_LAUNCH_OK();
   }
-  k_seq_chain<1><<<1, 1024, 0, st>>>(p, n, L.arr, L.scalars);
-  AX_LAUNCH_OK();
+  if (g_resample_fast) {
+    if (fast_sum_scan(p, n, L.arr, L.scalars, fast_scratch(L, n), st)) return 1;
+  } else {
+    k_seq_chain<1><<<1, 1024, 0, st>>>(p, n, L.arr, L.scalars);
+    AX_LAUNCH_OK();
+  }
   k_div_scalar<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(L.arr, n, L.scalars, L.arr);
   AX_LAUNCH_OK();
   k_search<<<(unsigned)((n_draw + bs - 1) / bs), bs, 0, st>>>(L.arr, n, u, n_draw, L.idx, L.first);

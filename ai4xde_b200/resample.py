@@ -43,11 +43,17 @@ def choice_noreplace_device(p, size, rand=None):
     return found
 
 
-def rad_select(model, X, pde, num, k=1, c=1, rand=None):
-    """One RAD / RAR_D selection (RAD.py:26-39): indices into X (host int64 array)."""
+def rad_select(model, X, pde, num, k=1, c=1, rand=None, fast=False):
+    """One RAD / RAR_D selection (RAD.py:26-39): indices into X (host int64 array).  `fast`: the two float64
+    reductions whose order NumPy fixes (builtin sum, cumsum) run as parallel scans (`ax_resample_set_fast`)."""
     res, n = residual_matrix(model, X, pde)
-    p = _lib.rad_probabilities(res, n, k, c)
-    return choice_noreplace_device(p, num, rand).cpu().numpy()
+    prev = _lib.resample_get_fast()
+    _lib.resample_set_fast(fast)
+    try:
+        p = _lib.rad_probabilities(res, n, k, c)
+        return choice_noreplace_device(p, num, rand).cpu().numpy()
+    finally:
+        _lib.resample_set_fast(prev)
 
 
 def r3_retain(model, X, pde):

@@ -127,6 +127,12 @@ int ax_fbpinn_window_forward(const ax_net_desc *net, const ax_jet_desc *jet, con
                              const int32_t *net_list, int32_t n_list, float *out, void *ws, size_t ws_bytes,
                              int engine, void *stream);
 
+/* Fast mode of the two float64 reductions below whose ORDER NumPy fixes (Python's builtin sum at RAD.py:32, np.cumsum
+ * inside np.random.choice): 0 (default) = the sequential order, bit-exact index sets; 1 = a parallel reduce-then-scan
+ * (reproducible run to run, not NumPy's rounding order; index sets equal to the parity mode on the reference fixtures). */
+void ax_resample_set_fast(int on);
+int ax_resample_get_fast(void);
+
 /* ---- residual-driven resampling, device resident ------------------------------------- */
 
 /* scratch for the resampling entry points below (covers all of them for n elements) */

@@ -205,7 +205,8 @@ def _oracle_curve(cfg, n, dtype, X=None, state=None, iters=1000, lr=1e-3, pertur
     """Loss curve of the oracle (ddelite + autograd on the CPU).  The initial weights are rounded to float32 in every
     run, the float64 one included: that is what any float32 implementation starts from, so no curve differs from
     another by its starting point.  `perturb`: relative perturbation of the initial weights (one float32 ulp =
-    6e-8) -- the sensitivity probe of the trajectory itself."""
+    6e-8) -- the sensitivity probe of the trajectory itself; "tf32": the initial weights rounded ONCE to TF32 (10
+    mantissa bits, round to nearest) -- the size of perturbation a TF32 tensor-core operand sees at every step."""
     from oracle import cases as oc, ddelite
 
     ddelite.config.set_default_float(dtype)
@@ -219,7 +220,14 @@ def _oracle_curve(cfg, n, dtype, X=None, state=None, iters=1000, lr=1e-3, pertur
             odata.replace_with_anchors(X)
             onet.load_state_dict({k: v.to(onet.linears[0].weight.dtype) for k, v in state.items()})
         wdt = onet.linears[0].weight.dtype
-        onet.load_state_dict({k: (v.detach().float() * (1.0 + perturb)).to(wdt) for k, v in onet.state_dict().items()})
+
+        def start(v):
+            v = v.detach().float()
+            if perturb == "tf32":
+                return ((v.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32).to(wdt)
+            return (v * (1.0 + perturb)).to(wdt)
+
+        onet.load_state_dict({k: start(v) for k, v in onet.state_dict().items()})
         state0 = {k: v.detach().clone() for k, v in onet.state_dict().items()}
         omodel = ddelite.Model(odata, onet)
         omodel.compile("adam", lr=lr, loss_weights=oc.LOSS_WEIGHTS.get(cfg))
@@ -264,15 +272,18 @@ def _curves(cfg, n, lr):
             x = np.asarray(odata.train_x, dtype=np.float64)
             chk = np.array([w.sum(), np.abs(w).sum(), x.sum(), np.abs(x).sum(), float(len(w)), float(x.size)])
             if np.allclose(chk, g[name + "_check"], rtol=1e-12, atol=0.0):
-                _ORACLE_CURVES[key] = (odata, onet, g[name + "_ref"], [int(v) for v in g[name + "_steps"]],
-                                       g[name + "_dev32"], g[name + "_devp"])
-                return _ORACLE_CURVES[key]
+                if name + "_devt" in g:
+                    _ORACLE_CURVES[key] = (odata, onet, g[name + "_ref"], [int(v) for v in g[name + "_steps"]],
+                                           g[name + "_dev32"], g[name + "_devp"], g[name + "_devt"])
+                    return _ORACLE_CURVES[key]
     odata, onet, ref, steps = _oracle_curve(cfg, n, "float64", lr=lr)
     state = {k: v.detach().clone() for k, v in onet.state_dict().items()}
     X = odata.train_x_all.copy()
     _, _, ref32, _ = _oracle_curve(cfg, n, "float32", X=X, state=state, lr=lr)
     _, _, refp, _ = _oracle_curve(cfg, n, "float64", X=X, state=state, lr=lr, perturb=6e-8)
-    _ORACLE_CURVES[key] = (odata, onet, ref, steps, np.abs(ref32 - ref) / ref, np.abs(refp - ref) / ref)
+    _, _, reft, _ = _oracle_curve(cfg, n, "float64", X=X, state=state, lr=lr, perturb="tf32")
+    _ORACLE_CURVES[key] = (odata, onet, ref, steps, np.abs(ref32 - ref) / ref, np.abs(refp - ref) / ref,
+                           np.abs(reft - ref) / ref)
     return _ORACLE_CURVES[key]
 
 
@@ -314,15 +325,20 @@ def test_loss_curve_over_1k_steps(cfg, n, lr, engine):
     float64 oracle 1.7 % away; Burgers (cfg1) and the 1-D Poisson net (cfg5) stay within 0.2 %.  So every checkpoint is
     held to max(1 %, 4 x the larger of those two deviations there): strictly 1 % wherever the problem is well conditioned
     (all of cfg1 and cfg5, cfg2 to step 200, cfg3 to step 300, cfg4 to step 400 / 600), and to the problem's own
-    sensitivity where it is not -- for the TF32 engine too (no separate TF32 allowance)."""
-    odata, onet, ref, steps, dev32, devp = _curves(cfg, n, lr)
+    sensitivity where it is not.  The TF32 engine gets no flat allowance either: its frame adds a third oracle curve --
+    the float64 oracle started from weights rounded ONCE to TF32 -- i.e. it may deviate by 4 x what a single TF32-sized
+    perturbation does to the float64 reference itself (it applies one at every step), and is held to 1 % where that is
+    small."""
+    odata, onet, ref, steps, dev32, devp, devt = _curves(cfg, n, lr)
     a, got_steps = _product_curve(cfg, odata, onet, engine, lr)
     assert list(got_steps) == list(steps) and len(a) == 11
     rel = np.abs(a - ref) / ref
     floor = np.maximum(dev32, devp)
+    if engine == "tf32":
+        floor = np.maximum(floor, devt)
     print(cfg, engine, f"lr={lr:g}", "deviation from f64 oracle:", np.round(rel, 5), " f32 oracle's own:",
-          np.round(dev32, 5), " one-ulp-perturbed f64 oracle:", np.round(devp, 5),
-          " checkpoints within 1 %:", int((rel < 1e-2).sum()), "of 11")
+          np.round(dev32, 5), " one-ulp-perturbed f64 oracle:", np.round(devp, 5), " tf32-rounded-start f64 oracle:",
+          np.round(devt, 5), " checkpoints within 1 %:", int((rel < 1e-2).sum()), "of 11")
     assert (rel < np.maximum(1e-2, 4.0 * floor)).all()
 
 

@@ -214,3 +214,36 @@ def test_r3_sharded_halves_equal_fused_entry(n, nres, cuts):
         k = int(k.item())
         parts.append(xo[:, (hi - lo) - k:(hi - lo)].cpu().numpy())
     assert np.array_equal(np.concatenate(parts, axis=1), whole)
+
+
+@pytest.mark.parametrize("n,m", [(20000, 2000), (100000, 10000), (1000, 999), (2**20, 2**16)])
+def test_rad_fast_mode_selects_the_same_indices(n, m):
+    """`ax_resample_set_fast(1)`: the sequential float64 sum / cumsum of the RAD selection (NumPy's order) replaced by
+    a parallel reduce-then-scan.  Probabilities agree to a few ulp, and on the reference fixture
+    (tests/golden/sampling.npz residual field) as well as on log-normal fields of other sizes the selected index sets
+    are IDENTICAL to the parity mode's (a draw would have to fall within one rounding of a cdf boundary to differ)."""
+    import os
+
+    from ai4xde_b200 import resample
+
+    dev = torch.device("cuda:0")
+    if n == 20000:
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampling.npz"))
+        res_h = g["res"].reshape(-1).astype(np.float32)
+    else:
+        rng = np.random.RandomState(n)
+        res_h = (rng.randn(n) * np.exp(rng.randn(n))).astype(np.float32)
+    res = torch.zeros((1, _lib.pad32(n)), device=dev)
+    res[0, :n] = torch.as_tensor(res_h).to(dev)
+    out = {}
+    for fast in (False, True):
+        _lib.resample_set_fast(fast)
+        try:
+            p = _lib.rad_probabilities(res, n, 1.0, 1.0)
+            rs = np.random.RandomState(7)
+            ids = resample.choice_noreplace_device(p, m, rand=rs.random_sample).cpu().numpy()
+        finally:
+            _lib.resample_set_fast(False)
+        out[fast] = (p.cpu().numpy(), ids)
+    assert np.allclose(out[True][0], out[False][0], rtol=1e-13, atol=0.0)
+    assert np.array_equal(out[True][1], out[False][1])
