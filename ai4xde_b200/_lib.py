@@ -47,6 +47,7 @@ _SIGNATURES = {
     "ax_param_count": (C.c_int64, [C.POINTER(NetDesc)]),
     "ax_jet_supported": (C.c_int, [C.POINTER(JetDesc)]),
     "ax_engine_supported": (C.c_int, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int]),
+    "ax_narrow_supported": (C.c_int, [C.POINTER(NetDesc), C.POINTER(JetDesc)]),
     "ax_stash_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64, C.c_int]),
     "ax_stash_bytes_engine": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64, C.c_int, C.c_int]),
     "ax_forward_ws_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.POINTER(JetDesc), C.c_int64]),
@@ -211,6 +212,10 @@ def engine_supported(net, jet, engine):
 
 def stash_bytes(net, jet, ldn, keep_all, engine="auto"):
     return int(load().ax_stash_bytes_engine(C.byref(net), C.byref(jet), int(ldn), int(bool(keep_all)), ENGINE[engine]))
+
+
+def narrow_supported(net, jet):
+    return bool(load().ax_narrow_supported(C.byref(net), C.byref(jet)))
 
 
 def launch_count():

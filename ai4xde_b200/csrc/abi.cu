@@ -247,6 +247,14 @@ int ax_engine_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engi
   return engine == AX_ENGINE_AUTO ? 1 : 0;
 }
 
+// 1 if the FP32 engine serves this net / pattern with the whole-net narrow kernels (hidden width 20 / 32)
+int ax_narrow_supported(const ax_net_desc *net, const ax_jet_desc *jet) {
+  NetGeom g;
+  if (make_geom(net, &g)) return 0;
+  if (match_pattern(jet) < 0) return 0;
+  return narrow_supported(g, net, jet) ? 1 : 0;
+}
+
 size_t ax_stash_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all) {
   NetGeom g;
   if (make_geom(net, &g)) return 0;

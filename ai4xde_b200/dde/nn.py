@@ -42,6 +42,9 @@ class _FusedForward(torch.autograd.Function):
             pad = None
         if pad is not None and not _lib.engine_supported(pad.desc, spec.desc, "tf32"):
             pad = None                       # stream pattern outside the tensor-core engine: nothing to gain
+        if pad is None and engine in ("fp32", "auto") and net._narrow_pad is not None \
+                and _lib.narrow_supported(net._narrow_pad.desc, spec.desc):
+            pad = net._narrow_pad
         if pad is not None:
             flat = pad.widen(flat)
         desc = net.net_desc if pad is None else pad.desc
@@ -118,6 +121,22 @@ class _TensorCorePad:
         pad.auto_ok = h > 64    # narrower nets stay on FP32 FMA unless the caller asks for engine 'tf32'
         return pad
 
+    @staticmethod
+    def plan_narrow(layer_sizes, activation):
+        """Uniform hidden widths below 32 other than 20 / 32 (the reference has 2-[30]x6-1, cases/PDECases.py:1320):
+        the zero-padded image on 20 or 32 units runs on the whole-net narrow FP32 kernels (csrc/narrow.cuh) instead
+        of layer by layer.  Same function, same real-parameter gradients (a padded unit's activation -- 0, or 0.5
+        for sigmoid -- only ever meets zero outgoing weights)."""
+        hidden = layer_sizes[1:-1]
+        if activation not in ("tanh", "sin", "sigmoid") or len(hidden) < 1 or len(set(hidden)) != 1:
+            return None
+        if layer_sizes[0] > 4 or layer_sizes[-1] > 4:
+            return None
+        h = hidden[0]
+        if h >= 32 or h == 20 or h < 4:
+            return None
+        return _TensorCorePad(layer_sizes, activation, 20 if h < 20 else 32)
+
     def widen(self, flat):
         if self._image is None or self._image.device != flat.device:
             self._image = torch.zeros((1, self.count), dtype=torch.float32, device=flat.device)
@@ -168,6 +187,7 @@ class FNN(NN):
         self.activation_name = activation
         self.net_desc = _lib.make_net_desc(self.layer_sizes, activation)
         self._tc_pad = _TensorCorePad.plan(self.layer_sizes, activation)
+        self._narrow_pad = _TensorCorePad.plan_narrow(self.layer_sizes, activation)
         init = _INIT[kernel_initializer]
         self.linears = torch.nn.ModuleList()
         for i in range(1, len(self.layer_sizes)):

@@ -77,6 +77,10 @@ int ax_jet_supported(const ax_jet_desc *jet);
 /* 1 if the tensor-core engine can run this net (sm_100a tcgen05 path), else 0 */
 int ax_engine_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engine);
 
+/* 1 if the FP32 engine runs this net / pattern on the whole-net one-thread-per-point kernels (uniform hidden width
+ * 20 or 32, <= 4 inputs / outputs; csrc/narrow.cuh) rather than layer by layer */
+int ax_narrow_supported(const ax_net_desc *net, const ax_jet_desc *jet);
+
 size_t ax_stash_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn, int keep_all_layers);
 /* as ax_stash_bytes for the engine the call will run on: forward-only evaluation (keep_all_layers = 0) of
  * width-64 nets on the tensor-core engine keeps every activation on chip and needs no stash (0 is returned;

@@ -247,3 +247,50 @@ def test_rad_fast_mode_selects_the_same_indices(n, m):
         out[fast] = (p.cpu().numpy(), ids)
     assert np.allclose(out[True][0], out[False][0], rtol=1e-13, atol=0.0)
     assert np.array_equal(out[True][1], out[False][1])
+
+
+@pytest.mark.parametrize("widths,act", [([2, 30, 30, 30, 30, 30, 30, 1], "tanh"), ([2, 10, 10, 2], "sigmoid"),
+                                        ([1, 24, 24, 24, 1], "sin")])
+def test_fnn_below_width_32_rides_the_narrow_kernels_padded(widths, act):
+    """dde.nn.FNN with a uniform hidden width below 32 other than 20 / 32 (the reference's Diffusion_reaction net is
+    2-[30]x6-1, cases/PDECases.py:1320) is evaluated on its zero-padded 20- / 32-wide image by the whole-net narrow
+    kernels (the timing hooks name them); value, residual and the real parameters' gradients equal a float64 autograd
+    evaluation of the unpadded net to 1e-5."""
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float32")
+    dde.config.set_engine("fp32")
+    try:
+        torch.manual_seed(3)
+        net = dde.nn.FNN(widths, act, "Glorot normal")
+        d = widths[0]
+        x = (torch.rand((4099, d)) * 2 - 1).to("cuda").requires_grad_()
+        _lib.timing_report()
+        _lib.timing_enable(True)
+        y = net(x)
+        r = dde.grad.hessian(y, x, component=0 if widths[-1] > 1 else None, i=0, j=0) + dde.grad.jacobian(y, x, i=0, j=d - 1) + y[:, :1] ** 2
+        dde.grad.clear()
+        net.zero_grad()
+        (r ** 2).mean().backward()
+        _lib.timing_enable(False)
+        names = set(_lib.timing_report())
+        assert {"narrow_fwd", "narrow_bwd"} <= names, names
+        g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu()
+    finally:
+        _lib.timing_enable(False)
+        dde.config.set_engine("auto")
+    # float64 autograd on the plain module chain
+    f = {"tanh": torch.tanh, "sin": torch.sin, "sigmoid": torch.sigmoid}[act]
+    ps = [p.detach().double().cpu().requires_grad_() for p in net.parameters()]
+    xd = x.detach().double().cpu().requires_grad_()
+    h = xd
+    for i in range(0, len(ps) - 2, 2):
+        h = f(h @ ps[i].t() + ps[i + 1])
+    yd = h @ ps[-2].t() + ps[-1]
+    d1 = torch.autograd.grad(yd[:, 0].sum(), xd, create_graph=True)[0]
+    d2 = torch.autograd.grad(d1[:, 0].sum(), xd, create_graph=True)[0]
+    rd = d2[:, 0:1] + d1[:, d - 1:d] + yd[:, :1] ** 2
+    gd = torch.cat([t.reshape(-1) for t in torch.autograd.grad((rd ** 2).mean(), ps)])
+    assert _rel(y.detach().double().cpu(), yd.detach()) < 1e-5
+    assert _rel(r.detach().double().cpu(), rd.detach()) < 1e-5
+    assert _rel(g, gd) < 2e-5
