@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libai4xde_b200.so")
 
 MAX_LINEAR, MAX_FIRST, MAX_SECOND = 16, 4, 10
 ACT = {"tanh": 0, "sin": 1, "sigmoid": 2}
-ENGINE = {"auto": 0, "fp32": 1, "tf32": 2, "tf32x3": 3}
+ENGINE = {"auto": 0, "fp32": 1, "tf32": 2}
 
 
 class NetDesc(C.Structure):

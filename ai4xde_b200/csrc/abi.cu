@@ -243,7 +243,7 @@ int ax_engine_supported(const ax_net_desc *net, const ax_jet_desc *jet, int engi
   if (make_geom(net, &g)) return 0;
   if (match_pattern(jet) < 0) return 0;
   if (engine == AX_ENGINE_FP32) return 1;
-  if (engine == AX_ENGINE_TF32 || engine == AX_ENGINE_TF32X3) return tc_supported(g, net, jet, engine) ? 1 : 0;
+  if (engine == AX_ENGINE_TF32) return tc_supported(g, net, jet, engine) ? 1 : 0;
   return engine == AX_ENGINE_AUTO ? 1 : 0;
 }
 
@@ -314,7 +314,11 @@ int ax_jet_mlp_forward(const ax_net_desc *net, const ax_jet_desc *jet, const flo
   }
   FwdArgs a{net, jet, params, x_soa, n, ldn, jets, stash, keep_all_layers, ws, ws_bytes, (cudaStream_t)stream};
   engine = resolve_engine(g, net, jet, engine);
-  if (engine == AX_ENGINE_TF32 || engine == AX_ENGINE_TF32X3) {
+  if (engine != AX_ENGINE_FP32 && engine != AX_ENGINE_TF32) {
+    set_error("unknown engine %d (AX_ENGINE_AUTO / FP32 / TF32)", engine);
+    return 1;
+  }
+  if (engine == AX_ENGINE_TF32) {
     if (!tc_supported(g, net, jet, engine)) {
       set_error("tensor-core engine does not support this net/jet (hidden widths must be equal and a multiple of 64)");
       return 1;
@@ -356,7 +360,11 @@ int ax_jet_mlp_backward(const ax_net_desc *net, const ax_jet_desc *jet, const fl
   }
   BwdArgs a{net, jet, params, x_soa, n, ldn, jets_bar, stash, grad_params, ws, ws_bytes, (cudaStream_t)stream};
   engine = resolve_engine(g, net, jet, engine);
-  if (engine == AX_ENGINE_TF32 || engine == AX_ENGINE_TF32X3) {
+  if (engine != AX_ENGINE_FP32 && engine != AX_ENGINE_TF32) {
+    set_error("unknown engine %d (AX_ENGINE_AUTO / FP32 / TF32)", engine);
+    return 1;
+  }
+  if (engine == AX_ENGINE_TF32) {
     if (!tc_supported(g, net, jet, engine)) {
       set_error("tensor-core engine does not support this net/jet");
       return 1;

@@ -45,9 +45,8 @@ def default_float():
 
 
 def set_engine(name):
-    """'auto' | 'fp32' | 'tf32' -- arithmetic engine of the jet kernels ('tf32x3' is a reserved name: the
-    library refuses it, see include/ai4xde_b200.h)."""
-    if name not in ("auto", "fp32", "tf32", "tf32x3"):
+    """'auto' | 'fp32' | 'tf32' -- arithmetic engine of the jet kernels (include/ai4xde_b200.h)."""
+    if name not in ("auto", "fp32", "tf32"):
         raise ValueError(name)
     _state["engine"] = name
 

@@ -35,10 +35,10 @@ extern "C" {
 #define AX_MAX_SECOND 10
 
 enum { AX_ACT_TANH = 0, AX_ACT_SIN = 1, AX_ACT_SIGMOID = 2 };
-/* arithmetic engines: FP32 FMA (any width) or tcgen05 tensor cores (hidden width 64 / 128 / 256).
- * AX_ENGINE_TF32X3 (3-pass split TF32) is RESERVED: no kernel implements it, ax_engine_supported() answers 0
- * for it and the compute entry points return an error -- never a silent substitute. */
-enum { AX_ENGINE_AUTO = 0, AX_ENGINE_FP32 = 1, AX_ENGINE_TF32 = 2, AX_ENGINE_TF32X3 = 3 };
+/* arithmetic engines: FP32 FMA (any width; whole-net kernels for hidden widths 20 / 32) or tcgen05 tensor cores,
+ * TF32 operands with FP32 accumulation (hidden width 64 / 128 / 256).  An engine that cannot run a request makes the
+ * compute entry points return an error -- never a silent substitute. */
+enum { AX_ENGINE_AUTO = 0, AX_ENGINE_FP32 = 1, AX_ENGINE_TF32 = 2 };
 
 /* dde.nn.FNN(layer_size, activation, initializer): cases/PDECases.py:38-42 */
 typedef struct ax_net_desc {

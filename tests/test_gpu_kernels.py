@@ -267,7 +267,10 @@ def test_fnn_below_width_32_rides_the_narrow_kernels_padded(widths, act):
         x = (torch.rand((4099, d)) * 2 - 1).to("cuda").requires_grad_()
         _lib.timing_report()
         _lib.timing_enable(True)
-        y = net(x)
+        # the streams this residual needs (what dde.Model's dry run would find): u, u_x0, u_x(d-1), u_x0x0
+        spec = JetSpec((0,), ((0, 0),)) if d == 1 else JetSpec((0, d - 1), ((0, 0),))
+        with net.jet_scope(spec=spec):
+            y = net(x)
         r = dde.grad.hessian(y, x, component=0 if widths[-1] > 1 else None, i=0, j=0) + dde.grad.jacobian(y, x, i=0, j=d - 1) + y[:, :1] ** 2
         dde.grad.clear()
         net.zero_grad()
