@@ -106,6 +106,34 @@ def heat_pde(x, y):
     return dy_t - a * dy_xx
 
 
+# ---- gPINN: gradient-enhanced residual  (/root/reference/AI4XDE/algorithm/gPINN.py:31-50)
+def gpinn_pde(pde):
+    """[res_0 .. res_{m-1}, d res_0/d x_0, d res_0/d x_1, ..., d res_{m-1}/d x_{d-1}] for a 2-argument pde."""
+
+    def g_pde(x, y):
+        res = pde(x, y)
+        res = list(res) if isinstance(res, (list, tuple)) else [res]
+        out = list(res)
+        for r in res:
+            for j in range(x.shape[1]):
+                out.append(dde.grad.jacobian(r, x, j=j))
+        return out
+
+    return g_pde
+
+
+def gpinn_burgers_build(points, state_dict, layer_size):
+    """The reference's own gPINN example (algorithm/gPINN.py:77-81): hard-constraint Burgers (PDECases.py:1059-1125:
+    TimePDE without BCs, output transform :1124-1125) with the gradient-enhanced residual.  Returns (data, net)."""
+    gt = dde.geometry.GeometryXTime(dde.geometry.Interval(-1, 1), dde.geometry.TimeDomain(0, 1))
+    data = dde.data.TimePDE(gt, gpinn_pde(burgers_pde), [], num_domain=0, anchors=np.asarray(points),
+                            train_distribution="pseudo")
+    net = dde.nn.FNN(layer_size, "tanh", "Glorot normal")
+    net.load_state_dict({k: torch.as_tensor(np.asarray(v), dtype=dde.config.real(torch)) for k, v in state_dict.items()})
+    net.apply_output_transform(burgers_output_transform)
+    return data, net
+
+
 # ---- FBPINN window and subdomains  (/root/reference/AI4XDE/algorithm/FBPINN.py:45-79)
 def fbpinn_subdomains(l, r, segment, overlap=0.1):
     x_list = np.linspace(l, r, segment + 1)

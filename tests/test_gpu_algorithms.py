@@ -444,3 +444,39 @@ def test_gpinn_on_burgers_third_order_on_device(monkeypatch):
     l_ref, g_ref = evaluate()
     np.testing.assert_allclose(l_dev, l_ref, rtol=2e-4)
     assert np.abs(g_dev - g_ref).max() / np.abs(g_ref).max() < 2e-4
+
+
+def test_gpinn_on_burgers_matches_the_oracle():
+    """gPINN on the hard-constraint Burgers case against the ORACLE (float64 ddelite restatement of the reference's
+    gradient-enhanced residual, pinned to the unmodified reference class by tests/golden/gpinn_burgers.npz): the three
+    loss terms (residual, d/dx residual, d/dt residual -- third-order derivatives of the network through the output
+    transform) and their parameter gradient, same points, same weights.  FP32 kernels (width 20: the third-order pattern
+    runs layer by layer).  Stated bound 2e-4 of the largest entry: the d/dx term sums third derivatives of magnitude
+    ~1e3 in float32 (measured and printed)."""
+    dde = _setup()
+    from ai4xde_b200 import algorithm, cases
+    from oracle import cases as oc, ddelite
+
+    np.random.seed(5)
+    torch.manual_seed(5)
+    case = cases.Burgers(NumDomain=2540, layer_size=[2] + [20] * 3 + [1])
+    solver = algorithm.gPINN(case)
+    case.compile(solver.model, "adam", lr=1e-3)
+    X, y, aux = case.data.train_next_batch()
+    _, losses = solver.model.outputs_losses_train(X, y, aux)
+    case.net.zero_grad()
+    losses.sum().backward()
+    l_dev = losses.detach().double().cpu().numpy()
+    g_dev = torch.cat([p.grad.reshape(-1) for p in case.net.parameters()]).double().cpu().numpy()
+    ddelite.config.set_default_float("float64")
+    try:
+        sd = {k: v.detach().double().cpu().numpy() for k, v in case.net.state_dict().items()}
+        odata, onet = oc.gpinn_burgers_build(np.asarray(case.data.train_x_all, dtype=np.float64), sd, [2, 20, 20, 20, 1])
+        ref = oc.train_step_outputs(odata, onet, None)
+    finally:
+        ddelite.config.set_default_float("float32")
+        torch.set_default_dtype(torch.float32)
+    l_err = np.abs(l_dev - ref["losses"]).max() / np.abs(ref["losses"]).max()
+    g_err = np.abs(g_dev - ref["grad"]).max() / np.abs(ref["grad"]).max()
+    print("gPINN Burgers vs oracle: losses", l_dev, ref["losses"], f"rel {l_err:.2e}; gradient rel {g_err:.2e}")
+    assert l_dev.shape == (3,) and l_err < 2e-4 and g_err < 2e-4

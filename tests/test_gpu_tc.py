@@ -1,7 +1,9 @@
 """GPU parity of the tcgen05 (TF32) engine.  Bounds are looser than the FP32 engine's 1e-5 and are
 STATED here: TF32 keeps 10 mantissa bits (operands rounded to nearest, FP32 accumulate), so with
 Glorot-scale weights the jets and gradients agree with the float64 Taylor-mode double to a few
-1e-3 relative (of the largest entry), growing with depth."""
+1e-3 relative (of the largest entry), growing with depth.  Measured on the B200 (round 2, printed by the tests with
+`-s`): jets 0.5e-3 (one GEMM layer) .. 6.5e-3 (2-[64]x4-1, three GEMM layers) .. 4.8e-3 (five), gradients 0.5..3.6e-3.
+The bounds are within 3x of those: jets 3e-3 per GEMM layer (at most 1e-2), gradients 1e-2."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +16,13 @@ from parity_util import product_vs_oracle
 pytestmark = pytest.mark.gpu
 
 TF32_JET_TOL = 1e-2
-TF32_GRAD_TOL = 2e-2
+TF32_GRAD_TOL = 1e-2
+
+
+def jet_tol(widths):
+    """3e-3 per tensor-core GEMM layer (hidden layers - 1), at most TF32_JET_TOL"""
+    return min(TF32_JET_TOL, 3e-3 * max(1, len(widths) - 3))
+
 
 
 def _glorot_params(widths, gen, k=1):
@@ -65,8 +73,9 @@ def test_tf32_engine_matches_double(widths, act, spec, n):
     xs = to_soa(x)
     jets, stash = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=True, engine="tf32")
     ref, _ = td.jet_forward(net, js.desc, params.double(), xs.double(), n, True)
+    jet_errs = [_rel(jets[0, s, :, :n].double(), ref[0, s, :, :n]) for s in range(js.S)]
     for s in range(js.S):
-        assert _rel(jets[0, s, :, :n].double(), ref[0, s, :, :n]) < TF32_JET_TOL, f"stream {s}"
+        assert jet_errs[s] < jet_tol(widths), f"stream {s}"
     jets2, _ = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=False, engine="tf32")
     if widths[1] == 64:
         # forward-only evaluation of width-64 nets is the whole-net kernel (csrc/tc_bank.cu): another summation
@@ -80,10 +89,13 @@ def test_tf32_engine_matches_double(widths, act, spec, n):
     grad = _lib.jet_backward(net, js.desc, params, xs, n, jb, stash, engine="tf32")
     gref = td.jet_backward(net, js.desc, params.double(), xs.double(), n, jb.double(), None)
     off = 0
+    grad_errs = []
     for i, o in zip(widths[:-1], widths[1:]):
         for cnt in (i * o, o):
-            assert _rel(grad[0, off:off + cnt].double(), gref[0, off:off + cnt]) < TF32_GRAD_TOL, f"param block at {off}"
+            grad_errs.append(_rel(grad[0, off:off + cnt].double(), gref[0, off:off + cnt]))
+            assert grad_errs[-1] < TF32_GRAD_TOL, f"param block at {off}"
             off += cnt
+    print(f"MEASURED tf32 {widths} {act} S={js.S} n={n}: jets {max(jet_errs):.2e} grads {max(grad_errs):.2e}")
     grad2 = _lib.jet_backward(net, js.desc, params, xs, n, jb, stash, engine="tf32")
     assert torch.equal(grad, grad2)  # deterministic two-level reduction
 
@@ -193,12 +205,13 @@ def test_tc_wgrad_kernel(H):
 
 
 # Product-level parity on the BASELINE configs whose nets the tensor-core engine serves.
-# Stated TF32 bounds (relative to the largest reference entry).
+# Stated TF32 bounds (relative to the largest reference entry), each within 3x of what the B200 measures (round 2:
+# cfg2 loss 4e-5 / grad 5.1e-3 / res 3e-4; cfg3 9e-5 / 5e-4 / 7.3e-3; cfg4 1e-4 / 1.6e-3 / 3.6e-4; cfg5 1e-7 / 2.9e-3 / 1e-5).
 TF32_CFG_TOL = {
-    "cfg2": dict(loss=2e-3, grad=1e-2, res=5e-3),
-    "cfg3": dict(loss=5e-3, grad=2e-2, res=1e-2),
-    "cfg4": dict(loss=5e-3, grad=2e-2, res=1e-2),
-    "cfg5": dict(loss=5e-3, grad=2e-2, res=1e-2),
+    "cfg2": dict(loss=2e-4, grad=1.5e-2, res=1e-3),
+    "cfg3": dict(loss=3e-4, grad=1.5e-3, res=2e-2),
+    "cfg4": dict(loss=3e-4, grad=5e-3, res=1.1e-3),
+    "cfg5": dict(loss=1e-5, grad=9e-3, res=4e-5),
 }
 
 
