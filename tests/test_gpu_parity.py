@@ -20,9 +20,14 @@ FP32_TOL = {
 }
 
 
-@pytest.mark.parametrize("cfg,n", [("cfg1", 2540), ("cfg2", 10000), ("cfg3", 4096), ("cfg4", 4096), ("cfg5", 4096)])
+@pytest.mark.parametrize("cfg,n", [("cfg1", 2540), ("cfg2", 10000), ("cfg3", 16384), ("cfg4", 16384), ("cfg5", 16384)])
 def test_fp32_engine_matches_oracle(cfg, n):
+    """cfg1 / cfg2 at their BASELINE sizes; cfg3 / cfg4 / cfg5 on 2^14 points (the float64 CPU oracle differentiates
+    the 2-[256]x6-1 net twice by autograd: seconds at this size), several tiles and ragged tails per kernel launch.  The
+    full 2^20 + 80 rows of cfg4 are covered by tests/test_gpu_tc.py::test_cfg4_full_size_properties (tile independence, shard
+    additivity, exact linearity, a 2048-point subset against the double)."""
     r = product_vs_oracle(cfg, n, engine="fp32")
+    print(cfg, n, {k: f"{v:.2e}" for k, v in r.items() if k.endswith("_rel")})
     tol = FP32_TOL[cfg]
     assert r["loss_rel"] < tol["loss"], r
     assert r["grad_rel"] < tol["grad"], r
