@@ -269,8 +269,10 @@ size_t ax_stash_bytes_engine(const ax_net_desc *net, const ax_jet_desc *jet, int
   if (make_geom(net, &g)) return 0;
   if (match_pattern(jet) < 0) return 0;
   const int e = resolve_engine(g, net, jet, engine);
-  if (e == AX_ENGINE_TF32 && tc_supported(g, net, jet, e) && tc_bank_usable(g, net, keep_all)) return 0;
-  return ax_stash_bytes(net, jet, ldn, keep_all);
+  const bool tc = e == AX_ENGINE_TF32 && tc_supported(g, net, jet, e);
+  if (tc && net->activation != AX_ACT_SIN && tc_bank_usable(g, net, keep_all)) return 0;
+  // tensor-core engine, sin: a second stash of the same size holds the pre-activation streams (tc_common.cuh)
+  return ax_stash_bytes(net, jet, ldn, keep_all) * ((tc && net->activation == AX_ACT_SIN && keep_all) ? 2 : 1);
 }
 
 size_t ax_forward_ws_bytes(const ax_net_desc *net, const ax_jet_desc *jet, int64_t ldn) {

@@ -417,7 +417,7 @@ bool tc_bank_usable(const NetGeom &g, const ax_net_desc *net, int keep_all) {
     const char *e = getenv("AX_TC_BANK");
     g_use_bank = (e && e[0] == '0') ? 0 : 1;
   }
-  (void)net;
+  if (net->activation != AX_ACT_TANH && net->activation != AX_ACT_SIGMOID) return false;   // compiled activations
   return g_use_bank && !keep_all && g.widths[1] == 64 && g.L >= 2 && g.L <= kBankMaxL;
 }
 

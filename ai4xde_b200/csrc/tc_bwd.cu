@@ -266,7 +266,7 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
               z[s] = r[pp * S + s];
               a[s] = cur[pp * S + s];
             }
-            jet_adjoint_A<P>(g.act, a, z, w);
+            jet_adjoint_any<P>(g.act, a, z, w);
             dbsum += w[0];
             if (fuse_first) {
               dw0a = fmaf(w[0], xc[2 * pp], dw0a);
@@ -543,7 +543,7 @@ k_tc_bwd1(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CU
               z[s_] = r[pp * S + s_];
               a[s_] = cur[pp * S + s_];
             }
-            jet_adjoint_A<P>(g.act, a, z, w);
+            jet_adjoint_any<P>(g.act, a, z, w);
             dbsum += w[0];
             if (fuse_first) {
               dw0a = fmaf(w[0], xc[2 * pp], dw0a);
@@ -739,10 +739,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CU
 // A thread owns FOUR consecutive units (128-bit loads and stores: a (p,s) row of H floats is one or two
 // warp instructions) and every 256/(H/4)-th point of the block's range; the row groups are combined in a
 // fixed order through shared memory.  partial layout per block: [C*H | C | H]
-template <class P, int CM>
+template <class P, int CM, bool ZFORM>
 __global__ void __launch_bounds__(256, 2)
 k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar,
-              const float *__restrict__ actL, int H, int C, long long n, long long ldn,
+              const float *__restrict__ actL, const float *__restrict__ zL, int H, int C, long long n, long long ldn,
               int pts_per_block, float *__restrict__ gout, float *__restrict__ partial, int act) {
   constexpr int S = P::S;
   constexpr int U = (S * CM <= 4) ? 4 : (S <= 4) ? 2 : 1;   // points in flight per thread (U*S 128-bit loads outstanding)
@@ -786,6 +786,11 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
       const long long p = pb + (long long)u * PR;
       if (p >= p_end) break;
       float zq[S][4];
+      float4 Zr[S];   // sin: PRE-activation streams of the last hidden layer (the adjoint's argument)
+      if (ZFORM) {
+#pragma unroll
+        for (int s_ = 0; s_ < S; ++s_) Zr[s_] = __ldg(reinterpret_cast<const float4 *>(zL + (p * S + s_) * H) + kq);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float a_[S], ab[S], zb[S];
@@ -802,7 +807,14 @@ k_tc_last_bwd(const float *__restrict__ Wout, const float *__restrict__ jets_bar
           }
           ab[s_] = acc;
         }
-        jet_adjoint_A<P>(act, a_, ab, zb);
+        if (ZFORM) {
+          float z_[S];
+#pragma unroll
+          for (int s_ = 0; s_ < S; ++s_) z_[s_] = e == 0 ? Zr[s_].x : e == 1 ? Zr[s_].y : e == 2 ? Zr[s_].z : Zr[s_].w;
+          jet_adjoint_Z_sin<P>(z_, ab, zb);
+        } else {
+          jet_adjoint_A<P>(act, a_, ab, zb);
+        }
         dbh[e] += zb[0];
 #pragma unroll
         for (int s_ = 0; s_ < S; ++s_) zq[s_][e] = to_tf32(zb[s_]);
@@ -1044,9 +1056,13 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
   for (int net = 0; net < a.net->n_nets; ++net) {
     const float *prm = a.params + (long long)net * g.P;
     float *grad = a.grad + (long long)net * g.P;
-    const float *stash = a.stash + (size_t)net * L * layer_fl;
+    // sin nets keep two stashes per net: [L layers of post-activation streams][L layers of pre-activation streams]
+    const bool zform = act == AX_ACT_SIN;
+    const float *stash = a.stash + (size_t)net * L * layer_fl * (zform ? 2 : 1);
     const float *jbar = a.jets_bar + (size_t)net * S * C * a.ldn;
     auto slot = [&](int l) { return stash + (size_t)l * layer_fl; };
+    // what the adjoint of hidden layer l reads
+    auto aslot = [&](int l) { return stash + (size_t)(zform ? L + l : l) * layer_fl; };
     for (int l = 1; l < L; ++l) {
       k_tc_round_copy<<<(H * H + 255) / 256, 256, 0, a.stream>>>(prm + g.w_off[l], w.wround + (size_t)(l - 1) * H * H,
                                                                 H, H, 1);
@@ -1063,12 +1079,15 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       const int nb = (int)((a.n + ppb - 1) / ppb);
       {
         KernelTimer t("tc_last_bwd", a.stream, 4.0 * S * H * C * (double)a.n, 8.0 * S * H * (double)a.n);
-        if (C == 1)
-          k_tc_last_bwd<P, 1><<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn,
-                                                        (int)ppb, w.g[cur], w.partial, act);
-        else
-          k_tc_last_bwd<P, 4><<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), H, C, a.n, a.ldn,
-                                                        (int)ppb, w.g[cur], w.partial, act);
+        auto launch = [&](auto kern) {
+          kern<<<nb, 256, 0, a.stream>>>(prm + g.w_off[L], jbar, slot(L - 1), aslot(L - 1), H, C, a.n, a.ldn, (int)ppb,
+                                         w.g[cur], w.partial, act);
+        };
+        if (C == 1) {
+          if (zform) launch(k_tc_last_bwd<P, 1, true>); else launch(k_tc_last_bwd<P, 1, false>);
+        } else {
+          if (zform) launch(k_tc_last_bwd<P, 4, true>); else launch(k_tc_last_bwd<P, 4, false>);
+        }
       }
       AX_LAUNCH_OK();
       const long long stride = (long long)C * H + C + H;
@@ -1079,7 +1098,7 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       if (g_use_fused_bwd && BwdTileOf<S>::PT > 0 && (H != 256 || g_use_pair)) {
         // fused: zbar_{l-1} = adjoint(W_l^T zbar_l)  and  dW_l = zbar_l^T A_{l-1}  in one pass over the tile
         GemmArgs ga{};
-        ga.stash_in = slot(l - 1);
+        ga.stash_in = aslot(l - 1);
         ga.out = w.g[cur ^ 1];
         ga.db_partial = dbpart;
         if (l == 1 && fuse_first) {
@@ -1116,7 +1135,7 @@ static int tc_backward_impl(const NetGeom &g, const BwdArgs &a) {
       if (reduce_to(w.partial, (long long)H * H, 0, wg_grid, (long long)H * H, grad + g.w_off[l], a.stream)) return 1;
       // zbar_{l-1} = adjoint(W_l^T zbar_l)
       GemmArgs ga{};
-      ga.stash_in = slot(l - 1);
+      ga.stash_in = aslot(l - 1);
       ga.out = w.g[cur ^ 1];
       ga.db_partial = dbpart;
       if (l == 1 && fuse_first) {

@@ -141,6 +141,17 @@ __device__ __forceinline__ float tanh_fast(float z) {
 __device__ __forceinline__ float sigmoid_fast(float z) {
   return rcp_approx(1.0f + ex2_approx(z * -1.4426950408889634f));
 }
+// sine and cosine on the special-function unit after one Cody-Waite step to [-pi, pi] (2 pi split into its
+// FP32 rounding and the remainder): |error| ~ 5e-7 absolute for any |z| < 1e5, the same rounding class as
+// tanh_fast.  Forward and adjoint call THIS function on the same stored pre-activation, so the gradient is
+// the gradient of the function that was evaluated.
+__device__ __forceinline__ void sincos_fast(float z, float *s, float *c) {
+  const float k = rintf(z * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, z);
+  r = fmaf(k, 1.7484555e-7f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
 
 // ---- warp-uniform issue: the WHOLE MMA warp runs the loop (so ptxas keeps descriptors and addresses in
 // uniform registers) and one elected lane's predicate guards the tcgen05 instructions.  Issuing from inside
@@ -239,7 +250,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 // =========================================================================================
 // pointwise jet math on POST-activation streams
 // =========================================================================================
-// tanh / sigmoid only (sin needs the pre-activation; the FP32 engine serves it).
+// tanh / sigmoid: the adjoint is expressed in these streams (jet_adjoint_A).  sin: the post-activation streams
+// are still what the next layer multiplies, but its adjoint needs the PRE-activation streams (z_j = a_j / cos z
+// is lost where cos z -> 0), which the forward kernels write to a second stash (GemmArgs::zout) -- see
+// jet_adjoint_any.
 template <class P>
 __device__ __forceinline__ void jet_forward_A(int act, float (&z)[P::S], float (&A)[P::S]) {
   float a, s1, s2;
@@ -247,6 +261,9 @@ __device__ __forceinline__ void jet_forward_A(int act, float (&z)[P::S], float (
     a = tanh_fast(z[0]);
     s1 = fmaf(-a, a, 1.0f);
     s2 = -2.0f * a * s1;
+  } else if (act == AX_ACT_SIN) {
+    sincos_fast(z[0], &a, &s1);
+    s2 = -a;
   } else {
     a = sigmoid_fast(z[0]);
     s1 = a * (1.0f - a);
@@ -346,6 +363,54 @@ __device__ __forceinline__ void jet_adjoint_A(int act, const float (&A)[P::S], c
   zb[0] = z0b;
 }
 
+// sin: adjoint from the stored PRE-activation streams Z (s1 = cos z, s2 = -sin z, s3 = -cos z):
+//   zbar_q = s1 abar_q ;  zbar_a += s2 z_b abar_q ;  zbar_j += s1 abar_j ;
+//   zbar_0 = s1 abar_0 + sum_j s2 z_j abar_j + sum_q (s3 z_a z_b + s2 z_q) abar_q
+template <class P>
+__device__ __forceinline__ void jet_adjoint_Z_sin(const float (&Z)[P::S], const float (&ab)[P::S],
+                                                  float (&zb)[P::S]) {
+  float a, c;
+  sincos_fast(Z[0], &a, &c);
+  float z0b = c * ab[0];
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) {
+    zb[1 + j] = c * ab[1 + j];
+    z0b = fmaf(-a * Z[1 + j], ab[1 + j], z0b);
+  }
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q) {
+    const float zq = Z[1 + P::N1 + q];
+    const float g = ab[1 + P::N1 + q];
+    zb[1 + P::N1 + q] = c * g;
+    if (P::pa(q) == kTracePair) {
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < P::N1; ++j) {
+        sq = fmaf(Z[1 + j], Z[1 + j], sq);
+        zb[1 + j] = fmaf(-2.0f * a * Z[1 + j], g, zb[1 + j]);
+      }
+      z0b = fmaf(-fmaf(c, sq, a * zq), g, z0b);
+    } else {
+      const float za = Z[1 + (P::pa(q) & 3)], zc = Z[1 + (P::pb(q) & 3)];
+      zb[1 + (P::pa(q) & 3)] = fmaf(-a * zc, g, zb[1 + (P::pa(q) & 3)]);
+      zb[1 + (P::pb(q) & 3)] = fmaf(-a * za, g, zb[1 + (P::pb(q) & 3)]);
+      z0b = fmaf(-fmaf(c * za, zc, a * zq), g, z0b);
+    }
+  }
+  zb[0] = z0b;
+}
+
+// what the backward kernels call: `st` = the layer's stash rows -- post-activation streams for tanh / sigmoid,
+// pre-activation streams (the Z stash) for sin
+template <class P>
+__device__ __forceinline__ void jet_adjoint_any(int act, const float (&st)[P::S], const float (&ab)[P::S],
+                                                float (&zb)[P::S]) {
+  if (act == AX_ACT_SIN)
+    jet_adjoint_Z_sin<P>(st, ab, zb);
+  else
+    jet_adjoint_A<P>(act, st, ab, zb);
+}
+
 // =========================================================================================
 // tile geometry
 // =========================================================================================
@@ -362,8 +427,9 @@ constexpr int kEpiWarps = 8;
 
 struct GemmArgs {
   const float *bias;      // fwd: bias of this layer [H]
-  const float *stash_in;  // dgrad: POST-activation streams of the destination layer [rows][H]
+  const float *stash_in;  // dgrad: stash rows of the destination layer [rows][H] (sin: its PRE-activation streams)
   float *out;             // fwd: act of this layer; dgrad: zbar of the previous layer  [rows][H]
+  float *zout;            // fwd, sin nets with the layers kept: PRE-activation streams of this layer [rows][H]
   float *db_partial;      // dgrad: [grid][H] per-CTA sums of zbar_0 (bias gradient of the dest layer)
   // dgrad into the FIRST hidden layer: zbar_0 is consumed on the spot -- dW0[o][d] = sum_p zbar_0 x_d +
   // sum_j [dir_j == d] zbar_j accumulates in registers and `out` is never written (saves S*H*4 B/point
@@ -557,6 +623,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
               float *dst = outp + (p * S) * H + o;
               if (MODE == 0) {
                 z[0] += (h == 0) ? bias[0] : bias[NH - 1];
+                if (g.zout != nullptr) {
+                  float *zd = g.zout + (p * S) * H + o;
+#pragma unroll
+                  for (int s = 0; s < S; ++s) zd[(long long)s * H] = z[s];
+                }
                 jet_forward_A<P>(g.act, z, w);
                 dst[0] = w[0];
 #pragma unroll
@@ -565,7 +636,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
                 float a[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) a[s] = cur[pp * S + s];
-                jet_adjoint_A<P>(g.act, a, z, w);
+                jet_adjoint_any<P>(g.act, a, z, w);
                 dba += w[0];
                 if (fuse_first) {
 #pragma unroll
@@ -828,6 +899,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
       const bool full_tile = (p0 + PT <= g.n);
       const float *sbase = (MODE == 1) ? stash_in + (p0 * S) * H + o : nullptr;
       float *obase = outp + (p0 * S) * H + o;
+      float *zbase = (MODE == 0 && g.zout != nullptr) ? g.zout + (p0 * S) * H + o : nullptr;
       float st[MODE == 1 ? 8 * S : 1];
       float xs[MODE == 1 ? 16 : 1];   // x of the next group's points (fused first-layer gradient, d_in <= 2)
       auto prefetch = [&](int grp) {
@@ -893,6 +965,11 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
             for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
             if (MODE == 0) {
               z[0] += bias;
+              if (zbase != nullptr) {
+                float *zp = zbase + grp * GSTRIDE;
+#pragma unroll
+                for (int s = 0; s < S; ++s) zp[(pp * S + s) * H] = z[s];
+              }
               jet_forward_A<P>(g.act, z, w);
 #pragma unroll
               for (int s = 1; s < S; ++s) w[s] = to_tf32(w[s]);
@@ -908,7 +985,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
               float a[S];
 #pragma unroll
               for (int s = 0; s < S; ++s) a[s] = cur[pp * S + s];
-              jet_adjoint_A<P>(g.act, a, z, w);
+              jet_adjoint_any<P>(g.act, a, z, w);
               dbsum += w[0];
               if (fuse_first) {
                 dw0a = fmaf(w[0], xc[2 * pp], dw0a);

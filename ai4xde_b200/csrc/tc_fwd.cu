@@ -362,8 +362,8 @@ k_tc_fwd_chain(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 template <class P>
 __global__ void __launch_bounds__(256)
 k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float *__restrict__ x,
-           int d_in, JetDirs dirs, int H, long long n, long long ldn, float *__restrict__ act0, int act,
-           int pts_per_block) {
+           int d_in, JetDirs dirs, int H, long long n, long long ldn, float *__restrict__ act0,
+           float *__restrict__ z0out, int act, int pts_per_block) {
   constexpr int S = P::S;
   const int HQ = H >> 2, PR = 256 / HQ;
   const int kq = threadIdx.x % HQ, pr = threadIdx.x / HQ;
@@ -384,7 +384,7 @@ k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float
     float xv[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d) xv[d] = d < d_in ? __ldg(x + (long long)d * ldn + p) : 0.0f;
-    float out[S][4];
+    float out[S][4], zo[S][4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float z[S], A[S];
@@ -395,6 +395,8 @@ k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float
       for (int j = 0; j < P::N1; ++j) z[1 + j] = wd[e][j];
 #pragma unroll
       for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
+#pragma unroll
+      for (int s_ = 0; s_ < S; ++s_) zo[s_][e] = z[s_];
       jet_forward_A<P>(act, z, A);
       out[0][e] = A[0];
 #pragma unroll
@@ -403,6 +405,11 @@ k_tc_first(const float *__restrict__ W, const float *__restrict__ b, const float
 #pragma unroll
     for (int s_ = 0; s_ < S; ++s_)
       reinterpret_cast<float4 *>(act0 + (p * S + s_) * H)[kq] = make_float4(out[s_][0], out[s_][1], out[s_][2], out[s_][3]);
+    if (z0out != nullptr) {   // sin nets with the layers kept: the adjoint reads the pre-activation streams
+#pragma unroll
+      for (int s_ = 0; s_ < S; ++s_)
+        reinterpret_cast<float4 *>(z0out + (p * S + s_) * H)[kq] = make_float4(zo[s_][0], zo[s_][1], zo[s_][2], zo[s_][3]);
+    }
   }
 }
 
@@ -494,7 +501,7 @@ static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id =
 
 bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
   if (engine != AX_ENGINE_TF32) return false;
-  if (net->activation != AX_ACT_TANH && net->activation != AX_ACT_SIGMOID) return false;
+  if (net->activation != AX_ACT_TANH && net->activation != AX_ACT_SIGMOID && net->activation != AX_ACT_SIN) return false;
   if (net->first_activation > 0 && net->first_activation - 1 != net->activation) return false;   // FP32 engine
   if (g.L < 2) return false;
   const int H = g.widths[1];
@@ -523,7 +530,9 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
   const JetDirs dirs = make_dirs(a.jet);
   // forward-only evaluation of width-64 nets (residual probes, FBPINN's frozen subdomain nets): one launch for
   // all nets, activations never leave the SM (tc_bank.cu)
-  if (H == 64 && tc_bank_usable(g, a.net, a.keep_all)) return tc_bank_forward(g, a);
+  if (H == 64 && act != AX_ACT_SIN && tc_bank_usable(g, a.net, a.keep_all)) return tc_bank_forward(g, a);
+  // sin nets whose layers are kept write a second stash behind the first: the pre-activation streams
+  const bool zform = (act == AX_ACT_SIN) && a.keep_all;
   const size_t need = (size_t)(g.L - 1) * H * H * sizeof(float) * a.net->n_nets + (size_t)2 * S * a.ldn * sizeof(float);
   float *jets_part = (float *)a.ws + (size_t)(g.L - 1) * H * H * a.net->n_nets;
   if (a.ws_bytes < need || !a.ws) {
@@ -532,16 +541,17 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
   }
   for (int net = 0; net < a.net->n_nets; ++net) {
     const float *prm = a.params + (long long)net * g.P;
-    float *stash = a.stash + (size_t)net * slots * layer_fl;
+    float *stash = a.stash + (size_t)net * slots * layer_fl * (zform ? 2 : 1);
     float *wr = (float *)a.ws + (size_t)net * (g.L - 1) * H * H;
     float *jets = a.jets + (size_t)net * S * C * a.ldn;
     auto slot = [&](int l) { return stash + (size_t)(a.keep_all ? l : (l & 1)) * layer_fl; };
+    auto zslot = [&](int l) { return zform ? stash + (size_t)(slots + l) * layer_fl : (float *)nullptr; };
     for (int l = 1; l < g.L; ++l) {
       k_tc_round_copy<<<(H * H + 255) / 256, 256, 0, a.stream>>>(prm + g.w_off[l], wr + (size_t)(l - 1) * H * H, H,
                                                                 H, 0);
       AX_LAUNCH_OK();
     }
-    if (H == 256 && g_use_pair && g_use_chain && d_in <= 4) {
+    if (H == 256 && g_use_pair && g_use_chain && d_in <= 4 && act != AX_ACT_SIN) {
       // whole hidden stack in one launch: activations stay in the SM pair, only the stash goes to HBM
       using G = ChainGeom<S>;
       ChainArgs ca{};
@@ -582,7 +592,7 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       KernelTimer t("tc_first_layer", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
       const int ppb = 256;   // points per block
       k_tc_first<P><<<(unsigned)((a.n + ppb - 1) / ppb), 256, 0, a.stream>>>(prm + g.w_off[0], prm + g.b_off[0], a.x,
-                                                                            d_in, dirs, H, a.n, a.ldn, slot(0), act, ppb);
+                                                                            d_in, dirs, H, a.n, a.ldn, slot(0), zslot(0), act, ppb);
     }
     AX_LAUNCH_OK();
     // the output layer rides in the last hidden layer's epilogue when that kernel can carry it (CTA pair,
@@ -592,6 +602,7 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       GemmArgs ga{};
       ga.bias = prm + g.b_off[l];
       ga.out = slot(l);
+      ga.zout = zslot(l);
       ga.n = a.n;
       ga.num_tiles = (int)((a.n + PT - 1) / PT);
       ga.act = act;

@@ -84,7 +84,7 @@ class _FusedForward(torch.autograd.Function):
 class _TensorCorePad:
     """Zero-padded image of an FNN whose uniform hidden width H lies strictly between the widths the tcgen05
     engine is compiled for (64 / 128 / 256): the same function on the next compiled width.  Padded units see
-    zero incoming weights and bias (pre-activation 0, derivative streams 0) and feed zero outgoing weights, so
+    zero incoming weights and bias (pre-activation 0, derivative streams 0; sin(0) = 0) and feed zero outgoing weights, so
     value, jets and the gradient of every real parameter are unchanged; the gradients of padded entries are
     dropped.  One scatter per evaluation builds the image from the flat master buffer, one gather brings the
     gradient back.  Used under engine 'auto' for widths above 64 and under an explicit 'tf32' also for widths
@@ -110,7 +110,7 @@ class _TensorCorePad:
     @staticmethod
     def plan(layer_sizes, activation):
         hidden = layer_sizes[1:-1]
-        if activation not in ("tanh", "sigmoid") or len(hidden) < 2 or len(set(hidden)) != 1:
+        if activation not in ("tanh", "sin", "sigmoid") or len(hidden) < 2 or len(set(hidden)) != 1:
             return None
         if layer_sizes[0] > 4 or layer_sizes[-1] > 4:
             return None

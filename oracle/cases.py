@@ -210,6 +210,8 @@ CONFIGS = {
     "cfg3": ([2] + [128] * 5 + [3], "tanh", "Glorot normal", 2**18),
     "cfg4": ([2] + [256] * 6 + [1], "tanh", "Glorot uniform", 2**20),
     "cfg5": ([1] + [64] * 3 + [1], "tanh", "Glorot uniform", 2**20),
+    # the reference's own Helmholtz defaults (cases/PDECases.py:513-515): 2-[150]x3-1, sin
+    "cfg4_sin": ([2] + [150] * 3 + [1], "sin", "Glorot uniform", 2**18),
 }
 
 
@@ -249,7 +251,7 @@ def build(cfg, num_domain=None, layer_size=None, activation=None):
                                                 component=comp))
         data = dde.data.PDE(geom, pde, bcs, nd, 200, train_distribution="pseudo")
         net = dde.nn.FNN(layer_size, activation, init)
-    elif cfg == "cfg4":
+    elif cfg in ("cfg4", "cfg4_sin"):
         geom = dde.geometry.Rectangle([0, 0], [1, 1])
         pde = helmholtz_pde
         bc = dde.icbc.DirichletBC(geom, lambda x: 0, lambda _, on_boundary: on_boundary)
@@ -267,7 +269,7 @@ def build(cfg, num_domain=None, layer_size=None, activation=None):
     return data, net, pde
 
 
-LOSS_WEIGHTS = {"cfg4": [1, 100]}
+LOSS_WEIGHTS = {"cfg4": [1, 100], "cfg4_sin": [1, 100]}
 
 
 def train_step_outputs(data, net, loss_weights=None):

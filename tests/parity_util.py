@@ -25,8 +25,9 @@ def build_product(cfg, odata, onet, soft=True):
         case = pc.NS_Flow_in_LidDriven_Cavity(NumDomain=1, layer_size=ls, train_distribution="pseudo")
         data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=odata.train_x_all,
                             train_distribution="pseudo")
-    elif cfg == "cfg4":
-        case = pc.Helmholtz(NumDomain=1, layer_size=ls, activation="tanh", honor_num_domain=True)
+    elif cfg in ("cfg4", "cfg4_sin"):
+        case = pc.Helmholtz(NumDomain=1, layer_size=ls, activation="sin" if cfg == "cfg4_sin" else "tanh",
+                            honor_num_domain=True)
         data = dde.data.PDE(case.geomtime, case.pde, case.data.bcs, 0, 0, anchors=odata.train_x_all,
                             train_distribution="pseudo", solution=case.sol)
     elif cfg == "cfg5":

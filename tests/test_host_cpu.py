@@ -357,11 +357,12 @@ def test_stmsffn_product_matches_oracle(d_in, act):
         assert rel(g[k], tr) < 1e-5, k
 
 
-@pytest.mark.parametrize("ls,act", [([2, 100, 100, 100, 2], "tanh"), ([3, 150, 150, 1], "sigmoid"), ([2, 70, 70, 70, 70, 1], "tanh")])
+@pytest.mark.parametrize("ls,act", [([2, 100, 100, 100, 2], "tanh"), ([3, 150, 150, 1], "sigmoid"), ([2, 70, 70, 70, 70, 1], "tanh"),
+                                    ([2, 150, 150, 150, 1], "sin")])
 def test_tensor_core_padding_is_the_same_function(ls, act):
     """An FNN whose hidden width lies between the tensor-core engine's compiled widths is evaluated on a
     zero-padded image (engine 'auto'): value, residual and the gradient of every real parameter equal the
-    unpadded evaluation (engine 'fp32'); widths the engine is compiled for, narrow nets and sin nets get no image."""
+    unpadded evaluation (engine 'fp32'); widths the engine is compiled for and narrow nets get no image."""
     import ai4xde_b200.dde as dde
 
     dde.config.set_default_float("float32")
@@ -388,7 +389,8 @@ def test_tensor_core_padding_is_the_same_function(ls, act):
         assert dde.nn.FNN(other, "tanh", "Glorot normal")._tc_pad is None
     narrow = dde.nn.FNN([2, 50, 50, 50, 3], "tanh", "Glorot normal")._tc_pad     # only on an explicit 'tf32'
     assert narrow is not None and narrow.desc.widths[1] == 64 and not narrow.auto_ok
-    assert dde.nn.FNN([2, 100, 100, 1], "sin", "Glorot normal")._tc_pad is None
+    sin_net = dde.nn.FNN([2, 100, 100, 1], "sin", "Glorot normal")._tc_pad     # the wave nets of the reference
+    assert sin_net is not None and sin_net.desc.widths[1] == 128 and sin_net.auto_ok
 
 
 @pytest.mark.parametrize("act", ["tanh", "sin", "sigmoid"])
