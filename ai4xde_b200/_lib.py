@@ -38,6 +38,17 @@ class JetDesc(C.Structure):
 
 
 _P = C.c_void_p
+
+
+class ResidualProgram(C.Structure):
+    _fields_ = [
+        ("code", _P), ("segments", _P), ("consts", _P), ("aux", _P), ("aux_meta", _P), ("scalars", _P),
+        ("term_scale", _P),
+        ("n_instr", C.c_int32), ("n_seg", C.c_int32), ("n_reg", C.c_int32), ("n_terms", C.c_int32),
+        ("n_streams", C.c_int32), ("n_const", C.c_int32),
+    ]
+
+
 _SIGNATURES = {
     "ax_version": (C.c_int, []),
     "ax_last_error": (C.c_char_p, []),
@@ -107,6 +118,9 @@ _SIGNATURES = {
         C.c_int,
         [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P],
     ),
+    "ax_residual_ws_bytes": (C.c_size_t, [C.POINTER(ResidualProgram), C.c_int64]),
+    "ax_residual_forward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "ax_residual_backward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "ax_debug_fma_peak": (C.c_double, [_P, C.c_int32, C.c_int32, _P]),
 }
@@ -281,6 +295,65 @@ def jet_backward(net, jet, params, x_soa, n, jets_bar, stash, engine="auto"):
     )
     _check(rc, "ax_jet_mlp_backward")
     return grad
+
+
+class ResidualTables:
+    """Device tables of one residual.Program (code, segments, constants, array / scalar pointers, term scales) and
+    the C struct that points at them.  Holds every tensor the program reads, so nothing it points at can be freed."""
+
+    def __init__(self, program, device):
+        import numpy as np
+
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32).reshape(-1), device=device)
+        code, segs, off = [], [], 0
+        for beg, end, c in program.segments:
+            code.append(c)
+            segs.append((beg, end, off, off + len(c)))
+            off += len(c)
+        self.code = i32(np.concatenate(code, axis=0))
+        self.segments = i32(np.array(segs))
+        self.consts = torch.as_tensor(program.consts, dtype=torch.float32, device=device)
+        self.term_scale = torch.as_tensor(program.scale, dtype=torch.float32, device=device)
+        self.aux = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t, _ in program.aux]
+        self.scalars = [t.detach() for t in program.scalars]
+        for t in self.scalars:
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise NativeLibraryError("residual program scalars must be float32 CUDA tensors")
+        ptrs = lambda ts: torch.tensor([t.data_ptr() for t in ts] or [0], dtype=torch.int64, device=device)
+        self.aux_ptr, self.scalar_ptr = ptrs(self.aux), ptrs(self.scalars)
+        self.aux_meta = i32(np.array([(first, t.shape[1]) for t, (_, first) in zip(self.aux, program.aux)] or [(0, 1)]))
+        self.n_terms, self.n_streams = program.n_terms, program.S * program.C
+        self.struct = ResidualProgram(
+            _ptr(self.code), _ptr(self.segments), _ptr(self.consts), _ptr(self.aux_ptr), _ptr(self.aux_meta),
+            _ptr(self.scalar_ptr), _ptr(self.term_scale), off, len(segs), program.n_reg, program.n_terms,
+            self.n_streams, int(self.consts.numel()))
+
+
+def residual_forward(tables, x_soa, jets, n):
+    """per-term losses [T] of a residual program (csrc/residual_vm.cu); jets [1, S, C, ldn]"""
+    lib = load()
+    _need_cuda(x_soa, jets)
+    ldn = x_soa.shape[1]
+    losses = torch.empty(tables.n_terms, dtype=torch.float32, device=x_soa.device)
+    wsb = lib.ax_residual_ws_bytes(C.byref(tables.struct), int(n))
+    ws = _bytes_buf(wsb, x_soa.device)
+    rc = lib.ax_residual_forward(C.byref(tables.struct), _ptr(x_soa), _ptr(jets), int(n), int(ldn), _ptr(losses),
+                                 _ptr(ws), int(wsb), _stream())
+    _check(rc, "ax_residual_forward")
+    return losses
+
+
+def residual_backward(tables, x_soa, jets, n, term_grads):
+    """jets_bar [1, S, C, ldn] = sum_t term_grads[t] * d losses[t] / d jets"""
+    lib = load()
+    term_grads = term_grads.to(torch.float32).contiguous()
+    _need_cuda(x_soa, jets, term_grads)
+    ldn = x_soa.shape[1]
+    jets_bar = torch.empty_like(jets)
+    rc = lib.ax_residual_backward(C.byref(tables.struct), _ptr(x_soa), _ptr(jets), int(n), int(ldn),
+                                  _ptr(term_grads), _ptr(jets_bar), _stream())
+    _check(rc, "ax_residual_backward")
+    return jets_bar
 
 
 def fbpinn_window_supported(net, jet, engine):

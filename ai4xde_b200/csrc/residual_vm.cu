@@ -1,0 +1,321 @@
+// residual_vm.cu -- residual programs: the case's pde / BC / loss algebra, traced on the host
+// (ai4xde_b200/residual.py), interpreted per collocation point.  One thread owns one point; the program (a few
+// dozen register instructions) and the register file live in shared memory ([register][thread]: conflict-free,
+// every thread reads the same instruction word).  Forward: per-term loss sums (fixed-order block tree, per-block
+// partials, fixed-order final sum: bit-reproducible).  Reverse: the forward is recomputed, adjoints run down the
+// program and land in jets_bar[s][c][p] -- the layout ax_jet_mlp_backward reads -- so a train step's loss side
+// is three launches instead of a few hundred tensor kernels.  HBM traffic: x + jets read, jets_bar written
+// (8 + 8*S*C bytes per point): noise next to the MLP kernels.
+#include "common.cuh"
+
+namespace ax {
+
+enum {
+  R_LOADX = 0, R_LOADJ, R_LOADA, R_LOADS, R_CONST, R_ADD, R_SUB, R_MUL, R_DIV, R_NEG, R_SIN, R_COS, R_EXP, R_TANH,
+  R_LOG, R_SQRT, R_ABS, R_SIGN, R_POW, R_SUMT
+};
+
+struct ResView {
+  const int4 *code;
+  const int4 *seg;            // row_begin, row_end, code_begin, code_end
+  const float *consts;
+  const float *const *aux;    // row-major [rows][ncol] arrays
+  const int2 *aux_meta;       // first row, ncol
+  const float *const *scalars;
+  const float *term_scale;
+  int n_instr, n_seg, n_reg, n_terms, n_streams, n_const;
+};
+
+__device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.0f) - (v < 0.0f)); }
+
+// one forward sweep of code [cb, ce) for point p; R = this thread's register column (stride T)
+template <bool ZERO_ADJ>
+__device__ __forceinline__ void res_forward(const int4 *code, int cb, int ce, const float *consts, const ResView &pv,
+                                            const float *x, const float *jets, long long p, long long ldn, float *R,
+                                            float *A, float *tacc, int T) {
+  for (int pc = cb; pc < ce; ++pc) {
+    const int4 in = code[pc];
+    float v;
+    switch (in.x) {
+      case R_LOADX: v = __ldg(x + (long long)in.z * ldn + p); break;
+      case R_LOADJ: v = __ldg(jets + (long long)in.z * ldn + p); break;
+      case R_LOADA: {
+        const int2 m = pv.aux_meta[in.z];
+        v = __ldg(pv.aux[in.z] + (p - m.x) * m.y + in.w);
+        break;
+      }
+      case R_LOADS: v = __ldg(pv.scalars[in.z]); break;
+      case R_CONST: v = consts[in.z]; break;
+      case R_ADD: v = R[in.z * T] + R[in.w * T]; break;
+      case R_SUB: v = R[in.z * T] - R[in.w * T]; break;
+      case R_MUL: v = R[in.z * T] * R[in.w * T]; break;
+      case R_DIV: v = R[in.z * T] / R[in.w * T]; break;
+      case R_NEG: v = -R[in.z * T]; break;
+      case R_SIN: v = sinf(R[in.z * T]); break;
+      case R_COS: v = cosf(R[in.z * T]); break;
+      case R_EXP: v = expf(R[in.z * T]); break;
+      case R_TANH: v = tanhf(R[in.z * T]); break;
+      case R_LOG: v = logf(R[in.z * T]); break;
+      case R_SQRT: v = sqrtf(R[in.z * T]); break;
+      case R_ABS: v = fabsf(R[in.z * T]); break;
+      case R_SIGN: v = sgnf(R[in.z * T]); break;
+      case R_POW: v = powf(R[in.z * T], consts[in.w]); break;
+      default:   // R_SUMT: term in.y += register in.z
+        if (!ZERO_ADJ) tacc[in.y * T] += R[in.z * T];
+        continue;
+    }
+    R[in.y * T] = v;
+    if (ZERO_ADJ) A[in.y * T] = 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_residual_fwd(ResView pv, const float *__restrict__ x, const float *__restrict__ jets, long long n, long long ldn,
+               float *__restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  int4 *code = reinterpret_cast<int4 *>(res_smem);
+  int4 *seg = code + pv.n_instr;
+  float *consts = reinterpret_cast<float *>(seg + pv.n_seg);
+  float *regs = consts + pv.n_const;
+  float *tacc = regs + (size_t)pv.n_reg * T;
+  for (int i = tid; i < pv.n_instr; i += T) code[i] = pv.code[i];
+  for (int i = tid; i < pv.n_seg; i += T) seg[i] = pv.seg[i];
+  for (int i = tid; i < pv.n_const; i += T) consts[i] = pv.consts[i];
+  for (int t = 0; t < pv.n_terms; ++t) tacc[t * T + tid] = 0.0f;
+  __syncthreads();
+  for (long long base = (long long)blockIdx.x * T; base < n; base += (long long)gridDim.x * T) {
+    const long long p = base + tid;
+    if (p < n) {
+      for (int s = 0; s < pv.n_seg; ++s) {
+        const int4 sg = seg[s];
+        if (p >= sg.x && p < sg.y)
+          res_forward<false>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, regs + tid, nullptr, tacc + tid, T);
+      }
+    }
+  }
+  // fixed-order tree over the block's threads, every term at once
+  for (int stride = T >> 1; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if (tid < stride)
+      for (int t = 0; t < pv.n_terms; ++t) tacc[t * T + tid] += tacc[t * T + tid + stride];
+  }
+  if (tid == 0)
+    for (int t = 0; t < pv.n_terms; ++t) partial[(long long)blockIdx.x * pv.n_terms + t] = tacc[t * T];
+}
+
+// losses[t] = scale[t] * sum over blocks (fixed order: thread i takes blocks i, i + 256, ...; then a tree)
+__global__ void __launch_bounds__(256)
+k_residual_reduce(const float *__restrict__ partial, int nblocks, int n_terms, const float *__restrict__ scale,
+                  float *__restrict__ losses) {
+  __shared__ float red[256];
+  const int t = blockIdx.x;
+  float s = 0.0f;
+  for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(long long)b * n_terms + t];
+  red[threadIdx.x] = s;
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if (threadIdx.x < stride) red[threadIdx.x] += red[threadIdx.x + stride];
+  }
+  if (threadIdx.x == 0) losses[t] = red[0] * scale[t];
+}
+
+__global__ void __launch_bounds__(128)
+k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict__ jets, long long n, long long ldn,
+               const float *__restrict__ term_grads, float *__restrict__ jets_bar) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  int4 *code = reinterpret_cast<int4 *>(res_smem);
+  int4 *seg = code + pv.n_instr;
+  float *consts = reinterpret_cast<float *>(seg + pv.n_seg);
+  float *tg = consts + pv.n_const;
+  float *regs = tg + pv.n_terms;
+  float *adj = regs + (size_t)pv.n_reg * T;
+  float *jb = adj + (size_t)pv.n_reg * T;
+  for (int i = tid; i < pv.n_instr; i += T) code[i] = pv.code[i];
+  for (int i = tid; i < pv.n_seg; i += T) seg[i] = pv.seg[i];
+  for (int i = tid; i < pv.n_const; i += T) consts[i] = pv.consts[i];
+  for (int i = tid; i < pv.n_terms; i += T) tg[i] = term_grads[i] * pv.term_scale[i];
+  __syncthreads();
+  float *R = regs + tid, *A = adj + tid, *J = jb + tid;
+  for (long long base = (long long)blockIdx.x * T; base < ldn; base += (long long)gridDim.x * T) {
+    const long long p = base + tid;
+    if (p >= ldn) continue;
+    for (int i = 0; i < pv.n_streams; ++i) J[i * T] = 0.0f;
+    if (p < n) {
+      for (int s = 0; s < pv.n_seg; ++s) {
+        const int4 sg = seg[s];
+        if (p < sg.x || p >= sg.y) continue;
+        res_forward<true>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, R, A, nullptr, T);
+        for (int pc = sg.w - 1; pc >= sg.z; --pc) {
+          const int4 in = code[pc];
+          if (in.x == R_SUMT) {
+            A[in.z * T] += tg[in.y];
+            continue;
+          }
+          const float d = A[in.y * T];
+          if (d == 0.0f) continue;          // nothing flows through this value (also keeps 0 * inf out)
+          switch (in.x) {
+            case R_LOADJ: J[in.z * T] += d; break;
+            case R_ADD: A[in.z * T] += d; A[in.w * T] += d; break;
+            case R_SUB: A[in.z * T] += d; A[in.w * T] -= d; break;
+            case R_MUL: {
+              const float a = R[in.z * T], b = R[in.w * T];
+              A[in.z * T] += d * b;
+              A[in.w * T] += d * a;
+              break;
+            }
+            case R_DIV: {
+              const float q = d / R[in.w * T];
+              A[in.z * T] += q;
+              A[in.w * T] -= q * R[in.y * T];
+              break;
+            }
+            case R_NEG: A[in.z * T] -= d; break;
+            case R_SIN: A[in.z * T] += d * cosf(R[in.z * T]); break;
+            case R_COS: A[in.z * T] -= d * sinf(R[in.z * T]); break;
+            case R_EXP: A[in.z * T] += d * R[in.y * T]; break;
+            case R_TANH: { const float v = R[in.y * T]; A[in.z * T] += d * (1.0f - v * v); break; }
+            case R_LOG: A[in.z * T] += d / R[in.z * T]; break;
+            case R_SQRT: A[in.z * T] += 0.5f * d / R[in.y * T]; break;
+            case R_ABS: A[in.z * T] += d * sgnf(R[in.z * T]); break;
+            case R_POW: { const float e = consts[in.w]; A[in.z * T] += d * e * powf(R[in.z * T], e - 1.0f); break; }
+            default: break;   // loads of x / arrays / scalars / constants, sign: no adjoint wanted
+          }
+        }
+      }
+    }
+    for (int i = 0; i < pv.n_streams; ++i) jets_bar[(long long)i * ldn + p] = J[i * T];
+  }
+}
+
+static int res_blocks(long long rows, int threads) {
+  long long b = (rows + threads - 1) / threads;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+static int res_check(const ax_residual_program *pg) {
+  if (!pg || !pg->code || !pg->segments || !pg->consts || !pg->term_scale) {
+    set_error("residual program: null table");
+    return 1;
+  }
+  if (pg->n_instr < 1 || pg->n_instr > 4096 || pg->n_seg < 1 || pg->n_seg > 256 || pg->n_reg < 1 || pg->n_reg > 380 ||
+      pg->n_terms < 1 || pg->n_terms > 64 || pg->n_streams < 1 || pg->n_streams > 64 || pg->n_const < 1 ||
+      pg->n_const > 1024) {
+    set_error("residual program: sizes out of range (instr %d, seg %d, reg %d, terms %d, streams %d, consts %d)",
+              pg->n_instr, pg->n_seg, pg->n_reg, pg->n_terms, pg->n_streams, pg->n_const);
+    return 1;
+  }
+  return 0;
+}
+
+static ResView res_view(const ax_residual_program *pg) {
+  ResView v;
+  v.code = reinterpret_cast<const int4 *>(pg->code);
+  v.seg = reinterpret_cast<const int4 *>(pg->segments);
+  v.consts = pg->consts;
+  v.aux = reinterpret_cast<const float *const *>(pg->aux);
+  v.aux_meta = reinterpret_cast<const int2 *>(pg->aux_meta);
+  v.scalars = reinterpret_cast<const float *const *>(pg->scalars);
+  v.term_scale = pg->term_scale;
+  v.n_instr = pg->n_instr;
+  v.n_seg = pg->n_seg;
+  v.n_reg = pg->n_reg;
+  v.n_terms = pg->n_terms;
+  v.n_streams = pg->n_streams;
+  v.n_const = pg->n_const;
+  return v;
+}
+
+// threads per block: the largest of 128 / 64 / 32 whose register file fits in shared memory
+static int res_threads(const ax_residual_program *pg, bool bwd, size_t *smem) {
+  const size_t fixed = (size_t)(pg->n_instr + pg->n_seg) * 16 + (size_t)(pg->n_const + pg->n_terms) * 4;
+  for (int t = 128; t >= 32; t >>= 1) {
+    const size_t per = bwd ? (size_t)(2 * pg->n_reg + pg->n_streams) : (size_t)(pg->n_reg + pg->n_terms);
+    const size_t need = fixed + per * t * 4;
+    if (need <= 200 * 1024) {
+      *smem = need;
+      return t;
+    }
+  }
+  return 0;
+}
+
+}  // namespace ax
+
+using namespace ax;
+
+extern "C" {
+
+size_t ax_residual_ws_bytes(const ax_residual_program *prog, int64_t n) {
+  if (res_check(prog)) return 0;
+  return (size_t)res_blocks(n, 32) * prog->n_terms * sizeof(float);
+}
+
+int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
+                        float *losses, void *ws, size_t ws_bytes, void *stream) {
+  if (res_check(prog)) return 1;
+  if (!x_soa || !jets || !losses || !ws || n < 1 || ldn < n) {
+    set_error("residual forward: null pointer or bad sizes (n = %lld, ldn = %lld)", (long long)n, (long long)ldn);
+    return 1;
+  }
+  size_t smem = 0;
+  const int threads = res_threads(prog, false, &smem);
+  if (!threads) {
+    set_error("residual program does not fit in shared memory");
+    return 1;
+  }
+  const int blocks = res_blocks(n, threads);
+  if (ws_bytes < (size_t)blocks * prog->n_terms * sizeof(float)) {
+    set_error("residual forward: workspace too small");
+    return 1;
+  }
+  static size_t attr = 0;
+  if (smem > attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_residual_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr = 200 * 1024;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    KernelTimer t("residual_fwd", st, 0.0, (8.0 + 4.0 * prog->n_streams) * (double)n);
+    k_residual_fwd<<<blocks, threads, smem, st>>>(res_view(prog), x_soa, jets, n, ldn, (float *)ws);
+  }
+  AX_LAUNCH_OK();
+  k_residual_reduce<<<prog->n_terms, 256, 0, st>>>((const float *)ws, blocks, prog->n_terms, prog->term_scale, losses);
+  AX_LAUNCH_OK();
+  return 0;
+}
+
+int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
+                         const float *term_grads, float *jets_bar, void *stream) {
+  if (res_check(prog)) return 1;
+  if (!x_soa || !jets || !term_grads || !jets_bar || n < 1 || ldn < n) {
+    set_error("residual backward: null pointer or bad sizes (n = %lld, ldn = %lld)", (long long)n, (long long)ldn);
+    return 1;
+  }
+  size_t smem = 0;
+  const int threads = res_threads(prog, true, &smem);
+  if (!threads) {
+    set_error("residual program does not fit in shared memory");
+    return 1;
+  }
+  static size_t attr = 0;
+  if (smem > attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_residual_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr = 200 * 1024;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    KernelTimer t("residual_bwd", st, 0.0, (8.0 + 8.0 * prog->n_streams) * (double)n);
+    k_residual_bwd<<<res_blocks(ldn, threads), threads, smem, st>>>(res_view(prog), x_soa, jets, n, ldn, term_grads,
+                                                                  jets_bar);
+  }
+  AX_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -68,6 +68,17 @@ def cuda_graphs():
     return _state["graphs"], _state["graph_max_rows"]
 
 
+def set_residual_programs(on):
+    """True (default): the loss side of a train step -- pde / BC algebra, per-term reductions, their reverse pass --
+    runs as one traced program per point (ai4xde_b200/residual.py) whenever the case's code can be traced and the
+    program reproduces the autograd path on the live batch; False: always torch.autograd over the jet leaves."""
+    _state["residual_programs"] = bool(on)
+
+
+def residual_programs():
+    return _state.get("residual_programs", True)
+
+
 def device():
     return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 

@@ -11,6 +11,8 @@ module.  Two routes:
 """
 import torch
 
+from .. import residual as _residual
+
 _records = {}  # id(y) -> (y, JetOutput): alive until clear()
 
 
@@ -93,6 +95,8 @@ _jacobians, _hessians = {}, {}
 
 
 def jacobian(ys, xs, i=0, j=None):
+    if isinstance(ys, _residual.Sym):       # the loss code is being traced into a residual program
+        return _residual.jacobian(ys, xs, i=i, j=j)
     key = (id(ys), id(xs))
     J = _jacobians.get(key)
     if J is None or J.ys is not ys or J.xs is not xs:
@@ -101,6 +105,8 @@ def jacobian(ys, xs, i=0, j=None):
 
 
 def hessian(ys, xs, component=None, i=0, j=0, grad_y=None):
+    if isinstance(ys, _residual.Sym):
+        return _residual.hessian(ys, xs, component=component, i=i, j=j, grad_y=grad_y)
     key = (id(ys), id(xs), component)
     H = _hessians.get(key)
     if H is None or H.y is not ys or H.xs is not xs:

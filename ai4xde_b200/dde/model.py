@@ -13,7 +13,7 @@ import os
 import numpy as np
 import torch
 
-from .. import jet
+from .. import _lib, jet, residual
 from . import config, gradients as grad, losses as losses_module, metrics as metrics_module
 from . import optimizers, utils
 from .callbacks import CallbackList
@@ -95,6 +95,8 @@ class Model:
         self.outputs = self.outputs_losses_train = self.outputs_losses_test = self.train_step = None
         self._batches = []      # small LRU of _DeviceBatch
         self._specs = {}        # stream sets by use
+        self._residual = {}     # traced loss programs by use: (owners, key, tables or None, note)
+        self._residual_epoch = 0
         self._weights_dev = None
         self.last_total_loss = None  # device scalar of the most recent closure evaluation
 
@@ -204,6 +206,68 @@ class Model:
             return operator(x, y, self.net.auxiliary_vars)
         raise ValueError("operator must take 2 or 3 arguments")
 
+    # ---- traced loss programs (ai4xde_b200/residual.py) -------------------------------------------
+    def residual_program_note(self, use="train"):
+        """Why the loss side of `use` runs (or does not run) as a traced program -- for logs and tests."""
+        hit = self._residual.get(use)
+        return None if hit is None else hit[3]
+
+    def _residual_tables(self, use, batch, spec, loss_fn, losses_fn, autograd_losses):
+        """Device tables of the loss code traced into a residual program, or None when it stays on autograd.
+        Traced once per (data, pde, BCs, point-set version, stream set, output transform, compile / train call);
+        adopted only if, on this very batch, its per-term losses and the parameter gradient of their sum reproduce
+        `autograd_losses()` -- the ordinary path over the jet leaves."""
+        net = self.net
+        from .nn import FNN, _FusedLosses
+
+        if not config.residual_programs() or type(net) is not FNN or net._input_transform is not None \
+                or net.regularizer is not None or self.external_trainable_variables or net.auxiliary_vars is not None:
+            return None
+        owners = (self.data, self.data.pde, losses_fn.__func__ if hasattr(losses_fn, "__func__") else losses_fn,
+                  net._output_transform, loss_fn if not isinstance(loss_fn, (list, tuple)) else tuple(loss_fn)) \
+            + tuple(getattr(self.data, "bcs", ()))
+        n_rows = int(batch.aos.shape[0])
+        key = (getattr(self.data, "version", None), n_rows, spec.key(), self._residual_epoch, batch.host is self.data.train_x)
+        hit = self._residual.get(use)
+        if hit is not None and hit[1] == key and len(hit[0]) == len(owners) and all(a is b for a, b in zip(hit[0], owners)):
+            return hit[2]
+        tables, note = None, ""
+        try:
+            def fn(xs, ys):
+                out = losses_fn(None, ys, loss_fn, xs, self)
+                grad.clear()
+                return out
+
+            prog = residual.trace(fn, spec, n_rows, net.layer_sizes[0], net.layer_sizes[-1],
+                                  output_transform=net._output_transform)
+            tables = _lib.ResidualTables(prog, batch.aos.device)
+            note = prog.describe()
+        except residual.Unsupported as e:
+            note = f"autograd path: {e}"
+        finally:
+            grad.clear()
+        if tables is not None:
+            # adoption check on the live batch: same losses, same parameter gradient as the autograd path
+            params = [p for p in net._param_list() if p.requires_grad]
+            with torch.enable_grad():
+                ref = autograd_losses()
+                g_ref = torch.autograd.grad(ref.sum(), params, allow_unused=True)
+                got = _FusedLosses.apply(net, tables, batch.soa, n_rows, spec, config.engine(), True, *net._param_list())
+                g_got = torch.autograd.grad(got.sum(), params, allow_unused=True)
+            scale = float(ref.detach().abs().max().clamp_min(1e-30))
+            bad = float((got.detach() - ref.detach()).abs().max()) > 1e-4 * scale or got.shape != ref.shape
+            for a, b in zip(g_got, g_ref):
+                if (a is None) != (b is None):
+                    bad = True
+                elif a is not None:
+                    bad = bad or float((a - b).abs().max()) > 1e-3 * float(b.abs().max().clamp_min(1e-30))
+            if bad or not bool(torch.isfinite(got).all()):
+                tables, note = None, f"autograd path: traced program ({note}) did not reproduce it on the live batch"
+        self._residual[use] = (owners, key, tables, note)
+        if Model.verbose:
+            print(f"[ai4xde_b200] loss side of {use}: {note}")
+        return tables
+
     # ---- CUDA-graph replay of the small-problem step -------------------------------------------
     def _graphed_step(self, inputs, targets, auxiliary_vars, closure):
         """Launch-bound regime (cfg1 is ~60 MFLOP per step): after three eager
@@ -294,6 +358,7 @@ class Model:
     def compile(self, optimizer, lr=None, loss="MSE", metrics=None, decay=None, loss_weights=None,
                 external_trainable_variables=None):
         self.opt_name = optimizer
+        self._residual_epoch += 1
         loss_fn = losses_module.get(loss)
         self.loss_weights = loss_weights
         self._weights_dev = None
@@ -311,7 +376,8 @@ class Model:
                 with self.net.jet_scope(jet.JetSpec.value_only(), batch.soa, param_grad=False):
                     return self.net(batch.aos)
 
-        def outputs_losses(training, inputs, targets, auxiliary_vars, losses_fn, param_grad=True):
+        def outputs_losses(training, inputs, targets, auxiliary_vars, losses_fn, param_grad=True, fused=False,
+                           raw=False):
             self.net.auxiliary_vars = None
             if auxiliary_vars is not None:
                 self.net.auxiliary_vars = torch.as_tensor(auxiliary_vars, dtype=torch.float32, device=config.device())
@@ -322,13 +388,31 @@ class Model:
             if targets is not None:
                 targets = torch.as_tensor(targets, dtype=torch.float32, device=config.device())
             spec = self.spec_for_losses(batch, targets, loss_fn, losses_fn)
-            x = batch.aos.detach().requires_grad_()
-            with self.net.jet_scope(spec, batch.soa, param_grad=param_grad):
-                outputs_ = self.net(x)
-            losses = losses_fn(targets, outputs_, loss_fn, x, self)
-            if not isinstance(losses, list):
-                losses = [losses]
-            losses = torch.stack(losses)
+            tables = None
+            if fused and param_grad and targets is None and auxiliary_vars is None and torch.is_grad_enabled():
+                # the caller wants the losses only (train closure): network + loss side as two fused stages
+                tables = self._residual_tables(
+                    "train" if training else "test", batch, spec, loss_fn, losses_fn,
+                    lambda: outputs_losses(training, inputs, targets, auxiliary_vars, losses_fn, raw=True)[1])
+            if tables is not None:
+                from .nn import _FusedLosses
+
+                params = self.net._param_list()
+                need_bwd = any(p.requires_grad for p in params)
+                outputs_ = None
+                losses = _FusedLosses.apply(self.net, tables, batch.soa, int(batch.aos.shape[0]), spec, config.engine(),
+                                            need_bwd, *params)
+            else:
+                x = batch.aos.detach().requires_grad_()
+                with self.net.jet_scope(spec, batch.soa, param_grad=param_grad):
+                    outputs_ = self.net(x)
+                losses = losses_fn(targets, outputs_, loss_fn, x, self)
+                if not isinstance(losses, list):
+                    losses = [losses]
+                losses = torch.stack(losses)
+            if raw:
+                grad.clear()
+                return outputs_, losses
             if self.loss_weights is not None:
                 if self._weights_dev is None:
                     self._weights_dev = torch.as_tensor(self.loss_weights, dtype=torch.float32, device=losses.device)
@@ -352,7 +436,7 @@ class Model:
 
         def train_step(inputs, targets, auxiliary_vars):
             def closure():
-                losses = outputs_losses_train(inputs, targets, auxiliary_vars)[1]
+                losses = outputs_losses(True, inputs, targets, auxiliary_vars, self.data.losses_train, fused=True)[1]
                 total_loss = torch.sum(losses)
                 if flat_grad is not None and all(p.grad is not None and p.grad.data_ptr() == q for p, q in flat_grad[1]):
                     # point-sharded ranks: autograd accumulates into the views, ONE collective on the flat buffer
@@ -415,6 +499,7 @@ class Model:
         if iterations is None and epochs is not None:
             iterations = epochs
         self.batch_size = batch_size
+        self._residual_epoch += 1     # Python-level constants of the pde / BC code are re-read once per train() call
         self.callbacks = CallbackList(callbacks=callbacks)
         self.callbacks.set_model(self)
         if disregard_previous_best:

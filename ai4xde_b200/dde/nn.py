@@ -31,24 +31,48 @@ class _JetScope:
         self.spec, self.x_soa, self.param_grad, self.probe_streams = spec, x_soa, param_grad, probe_streams
 
 
+def _launch_forward(net, x_soa, n, spec, engine, need_backward):
+    """Engine / padded-image choice and the forward kernel sequence of one FNN evaluation.
+    -> (jets [1, S, C, ldn], stash, desc, pad, flat parameter image the kernels ran on)"""
+    flat = net.flat_params()
+    pad = net._tc_pad
+    if pad is not None and not (engine == "tf32" or (engine == "auto" and pad.auto_ok)):
+        pad = None
+    if pad is not None and not _lib.engine_supported(pad.desc, spec.desc, "tf32"):
+        pad = None                       # stream pattern outside the tensor-core engine: nothing to gain
+    if pad is None and engine in ("fp32", "auto") and net._narrow_pad is not None \
+            and _lib.narrow_supported(net._narrow_pad.desc, spec.desc):
+        pad = net._narrow_pad
+    if pad is not None:
+        flat = pad.widen(flat)
+    desc = net.net_desc if pad is None else pad.desc
+    jets, stash = _lib.jet_forward(desc, spec.desc, flat, x_soa, n, keep_all=need_backward, engine=engine)
+    return jets, stash, desc, pad, flat
+
+
+def _launch_backward(ctx, jets_bar):
+    """Backward kernel sequence -> the per-parameter gradient views (order of ctx.shapes)."""
+    g_flat = _lib.jet_backward(ctx.desc, ctx.spec.desc, ctx.flat, ctx.x_soa, ctx.n, jets_bar, ctx.stash,
+                               engine=ctx.engine)[0]
+    if ctx.pad is not None:
+        g_flat = ctx.pad.narrow(g_flat)
+    ctx.stash = None
+    outs, off = [], 0
+    for shp in ctx.shapes:
+        cnt = 1
+        for d in shp:
+            cnt *= d
+        outs.append(g_flat[off : off + cnt].view(shp))
+        off += cnt
+    return tuple(outs)
+
+
 class _FusedForward(torch.autograd.Function):
     """Routes the flat-buffer gradient of jet.JetMLP back to the per-layer nn.Parameters."""
 
     @staticmethod
     def forward(ctx, net, x_soa, n, spec, engine, need_backward, *params):
-        flat = net.flat_params()
-        pad = net._tc_pad
-        if pad is not None and not (engine == "tf32" or (engine == "auto" and pad.auto_ok)):
-            pad = None
-        if pad is not None and not _lib.engine_supported(pad.desc, spec.desc, "tf32"):
-            pad = None                       # stream pattern outside the tensor-core engine: nothing to gain
-        if pad is None and engine in ("fp32", "auto") and net._narrow_pad is not None \
-                and _lib.narrow_supported(net._narrow_pad.desc, spec.desc):
-            pad = net._narrow_pad
-        if pad is not None:
-            flat = pad.widen(flat)
-        desc = net.net_desc if pad is None else pad.desc
-        jets, stash = _lib.jet_forward(desc, spec.desc, flat, x_soa, n, keep_all=need_backward, engine=engine)
+        jets, stash, desc, pad, flat = _launch_forward(net, x_soa, n, spec, engine, need_backward)
         ctx.net, ctx.spec, ctx.engine, ctx.n, ctx.desc, ctx.pad = net, spec, engine, n, desc, pad
         ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = x_soa, stash, bool(need_backward), flat
         ctx.shapes = [p.shape for p in params]
@@ -66,19 +90,31 @@ class _FusedForward(torch.autograd.Function):
         for s, g in enumerate(gouts):
             if g is not None:
                 jets_bar[0, s, :, :n] = g.t()
-        g_flat = _lib.jet_backward(ctx.desc, spec.desc, ctx.flat, ctx.x_soa, n, jets_bar, ctx.stash,
-                                   engine=ctx.engine)[0]
-        if ctx.pad is not None:
-            g_flat = ctx.pad.narrow(g_flat)
-        ctx.stash = None
-        outs, off = [], 0
-        for shp in ctx.shapes:
-            cnt = 1
-            for d in shp:
-                cnt *= d
-            outs.append(g_flat[off : off + cnt].view(shp))
-            off += cnt
-        return (None, None, None, None, None, None) + tuple(outs)
+        return (None, None, None, None, None, None) + _launch_backward(ctx, jets_bar)
+
+
+class _FusedLosses(torch.autograd.Function):
+    """Network AND loss side of a train step without a tensor-level graph in between: jet kernels -> residual
+    program (per-term losses) ; backward: residual program in reverse (jets_bar) -> backward kernels.
+    `tables`: _lib.ResidualTables of the traced loss code (ai4xde_b200/residual.py)."""
+
+    @staticmethod
+    def forward(ctx, net, tables, x_soa, n, spec, engine, need_backward, *params):
+        jets, stash, desc, pad, flat = _launch_forward(net, x_soa, n, spec, engine, need_backward)
+        ctx.spec, ctx.engine, ctx.n, ctx.desc, ctx.pad = spec, engine, n, desc, pad
+        ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = x_soa, stash, bool(need_backward), flat
+        ctx.shapes = [p.shape for p in params]
+        ctx.tables, ctx.jets = tables, (jets if need_backward else None)
+        return _lib.residual_forward(tables, x_soa, jets, n)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_losses):
+        if not ctx.kept:
+            raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
+        jets_bar = _lib.residual_backward(ctx.tables, ctx.x_soa, ctx.jets, ctx.n, g_losses)
+        ctx.jets = None
+        return (None, None, None, None, None, None, None) + _launch_backward(ctx, jets_bar)
 
 
 class _TensorCorePad:

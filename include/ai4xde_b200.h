@@ -240,6 +240,41 @@ int ax_uniform_box_points(float *x_soa, int32_t d, int64_t ldn, int64_t first, i
 int ax_adam_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int32_t *state,
                  float lr, float beta1, float beta2, float eps, float weight_decay, void *stream);
 
+/*
+ * Residual programs: the loss side of a train step -- the case's `pde(x, y)` algebra (cases/PDECases.py:1087-1094,
+ * :538-550 ...), every `bc.error` slice and the mean-squared reduction per term (deepxde data.PDE.losses, called from
+ * solver/PDESolver.py:79-85 through model.train) -- as ONE interpreted program per collocation point instead of a few
+ * hundred tensor kernels.  The host traces the case's own Python code once (ai4xde_b200/residual.py) and hands over:
+ *   code      [n_instr][4] int32  = opcode, destination register, operand a, operand b
+ *             0 LOADX a=input dim | 1 LOADJ a=stream*d_out+component | 2 LOADA a=array, b=column | 3 LOADS a=scalar |
+ *             4 CONST a=index | 5 ADD 6 SUB 7 MUL 8 DIV (registers a, b) | 9 NEG 10 SIN 11 COS 12 EXP 13 TANH 14 LOG
+ *             15 SQRT 16 ABS 17 SIGN (register a) | 18 POW a=register, b=index of the constant exponent |
+ *             19 SUMT dst=term, a=register: term += register
+ *   segments  [n_seg][4] int32    = first row, end row, first instruction, end instruction: a point runs the segments
+ *             whose row range holds it (BC rows come first in train_x, then the residual rows)
+ *   aux       [n_aux] device pointers to row-major float arrays (BC target values, normals ...), aux_meta [n_aux][2]
+ *             = first row, columns; scalars: device pointers to single floats; term_scale[t]: 1 / count of term t.
+ * Forward: losses[t] = term_scale[t] * sum over the term's rows (fixed-order reduction, bit-reproducible; ws from
+ * ax_residual_ws_bytes).  Backward: jets_bar[s][c][p] = sum_t term_grads[t] * d losses[t] / d jets[s][c][p], rows
+ * n..ldn zeroed -- the argument ax_jet_mlp_backward takes.  jets as ax_jet_mlp_forward writes them, n_nets = 1.
+ */
+typedef struct ax_residual_program {
+  const int32_t *code;
+  const int32_t *segments;
+  const float *consts;
+  const void *const *aux;
+  const int32_t *aux_meta;
+  const void *const *scalars;
+  const float *term_scale;
+  int32_t n_instr, n_seg, n_reg, n_terms, n_streams, n_const;
+} ax_residual_program;
+
+size_t ax_residual_ws_bytes(const ax_residual_program *prog, int64_t n);
+int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
+                        float *losses, void *ws, size_t ws_bytes, void *stream);
+int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
+                         const float *term_grads, float *jets_bar, void *stream);
+
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
                      float *x_out, int64_t ldn_out, void *stream);

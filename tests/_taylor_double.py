@@ -105,6 +105,69 @@ def jet_backward(net, jet, params, x_soa, n, jets_bar, stash, engine="auto"):
     return torch.stack(grads)
 
 
+# ---- residual programs (ai4xde_b200/residual.py) interpreted in torch: tests only ------------------------------
+class ResidualTables:
+    """Stand-in for _lib.ResidualTables: keeps the lowered program itself."""
+
+    def __init__(self, program, device=None):
+        self.program = program
+        self.n_terms, self.n_streams = program.n_terms, program.S * program.C
+
+
+def _run_program(program, x_soa, jets, n):
+    """per-term losses of a lowered program, one vectorised sweep per row segment (differentiable w.r.t. jets)"""
+    from ai4xde_b200 import residual as R
+
+    flat = jets.reshape(-1, jets.shape[-1])          # [S * C, ldn]
+    sums = [torch.zeros((), dtype=jets.dtype) for _ in range(program.n_terms)]
+    un = {R.OP_SIN: torch.sin, R.OP_COS: torch.cos, R.OP_EXP: torch.exp, R.OP_TANH: torch.tanh, R.OP_LOG: torch.log,
+          R.OP_SQRT: torch.sqrt, R.OP_ABS: torch.abs, R.OP_SIGN: torch.sign, R.OP_NEG: torch.neg}
+    for beg, end, code in program.segments:
+        assert 0 <= beg < end <= n
+        reg = {}
+        for op, dst, a, b in code.tolist():
+            if op == R.OP_LOADX:
+                reg[dst] = x_soa[a, beg:end].to(jets.dtype)
+            elif op == R.OP_LOADJ:
+                reg[dst] = flat[a, beg:end]
+            elif op == R.OP_LOADA:
+                ten, first = program.aux[a]
+                reg[dst] = ten.to(jets.dtype)[beg - first : end - first, b]
+            elif op == R.OP_LOADS:
+                reg[dst] = program.scalars[a].to(jets.dtype).reshape(()).expand(end - beg)
+            elif op == R.OP_CONST:
+                reg[dst] = torch.full((end - beg,), float(program.consts[a]), dtype=jets.dtype)
+            elif op == R.OP_ADD:
+                reg[dst] = reg[a] + reg[b]
+            elif op == R.OP_SUB:
+                reg[dst] = reg[a] - reg[b]
+            elif op == R.OP_MUL:
+                reg[dst] = reg[a] * reg[b]
+            elif op == R.OP_DIV:
+                reg[dst] = reg[a] / reg[b]
+            elif op == R.OP_POW:
+                reg[dst] = reg[a] ** float(program.consts[b])
+            elif op == R.OP_SUMT:
+                sums[dst] = sums[dst] + reg[a].sum()
+            else:
+                reg[dst] = un[op](reg[a])
+    return torch.stack(sums) * torch.as_tensor(program.scale, dtype=jets.dtype)
+
+
+def residual_forward(tables, x_soa, jets, n):
+    with torch.no_grad():
+        return _run_program(tables.program, x_soa, jets, n).to(torch.float32)
+
+
+def residual_backward(tables, x_soa, jets, n, term_grads):
+    """reverse pass by torch.autograd over the interpreter (the kernel's hand-written adjoint rules are held to it)"""
+    j = jets.detach().clone().requires_grad_()
+    with torch.enable_grad():
+        tot = (_run_program(tables.program, x_soa, j, n) * term_grads.to(j.dtype)).sum()
+        (g,) = torch.autograd.grad(tot, j, allow_unused=True)
+    return torch.zeros_like(jets) if g is None else g
+
+
 def torch_lbfgs(params, **kw):
     """Stand-in for the device L-BFGS on CPU tensors: the optimiser it follows statement by statement."""
     return torch.optim.LBFGS(params, line_search_fn=None, **kw)
@@ -118,7 +181,11 @@ def install(monkeypatch=None):
     if monkeypatch is not None:
         monkeypatch.setattr(_lib, "jet_forward", jet_forward)
         monkeypatch.setattr(_lib, "jet_backward", jet_backward)
+        monkeypatch.setattr(_lib, "ResidualTables", ResidualTables)
+        monkeypatch.setattr(_lib, "residual_forward", residual_forward)
+        monkeypatch.setattr(_lib, "residual_backward", residual_backward)
         monkeypatch.setattr(optimizers, "lbfgs_factory", torch_lbfgs)
     else:
         _lib.jet_forward, _lib.jet_backward = jet_forward, jet_backward
+        _lib.ResidualTables, _lib.residual_forward, _lib.residual_backward = ResidualTables, residual_forward, residual_backward
         optimizers.lbfgs_factory = torch_lbfgs

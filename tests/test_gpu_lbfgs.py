@@ -84,15 +84,16 @@ def test_solver_lbfgs_phase_runs_on_the_device_optimiser():
     torch.manual_seed(0)
     dde.optimizers.set_LBFGS_options(maxiter=300)
     try:
-        case = cases.Burgers(NumDomain=1000, layer_size=[2] + [20] * 3 + [1])
+        # Heat (cases/PDECases.py: 2-[20]x3-1, soft IC / BC): L-BFGS as DeepXDE configures it (lr = 1, NO line search)
+        # converges from every seed tried.  On the hard-constraint Burgers it is chaotic -- a last-bit difference in
+        # the Adam weights decides between a final loss of 0.003 and an overflow, for torch.optim.LBFGS just the same
+        # (half of the seeds 0..3 end in NaN on either loss path) -- which makes a poor gate
+        case = cases.Heat(NumDomain=1000, layer_size=[2] + [20] * 3 + [1])
         s = solver.PINNSolver("pinn", case)
-        # a long enough Adam phase first: L-BFGS as DeepXDE configures it (lr = 1, NO line search) is chaotic
-        # when started far from a minimum -- after only 300 Adam steps a last-bit difference in the weights moves
-        # torch.optim.LBFGS's own final loss between 0.017 and 0.036, and some trajectories overflow
-        s.train_step(lr=1e-3, iterations=3000)
+        s.train_step(lr=1e-3, iterations=1000)
         assert isinstance(s.model.opt, DeviceLBFGS)
         lh = np.array(s.losshistory.loss_train).sum(1)
-        assert s.model.train_state.step > 3000 + 50                   # the L-BFGS phase really iterated
+        assert s.model.train_state.step > 1000 + 50                   # the L-BFGS phase really iterated
         assert np.isfinite(lh).all() and lh[-1] < 0.5 * lh[0]
     finally:
         dde.optimizers.set_LBFGS_options()

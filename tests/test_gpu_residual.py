@@ -1,0 +1,154 @@
+"""Residual programs on the GPU: the CUDA interpreter (csrc/residual_vm.cu) against the float64 torch
+interpreter of the same lowered program (tests/_taylor_double.py; its reverse pass is torch.autograd), and the
+train closure with traced programs against the train closure on torch.autograd over the jet leaves (which the
+parity tests pin to the oracle).  FP32 bound: 1e-5 of the largest entry."""
+import numpy as np
+import pytest
+import torch
+
+import _taylor_double as td
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _all_ops_code(x, y):
+    import ai4xde_b200.dde as dde
+
+    u = torch.sin(x[:, 0:1]) * y[:, 0:1] + torch.exp(-x[:, 1:2]) * torch.tanh(y[:, 1:2]) / (1.5 + torch.cos(x[:, 0:1] * x[:, 1:2]))
+    u = u + torch.sqrt(2.0 + (y[:, 0:1] * y[:, 1:2]) ** 2) - abs(y[:, 0:1]) ** 3 + torch.log(3.0 + u ** 2) + 2.0 ** x[:, 1:2]
+    r = dde.grad.jacobian(u, x, i=0, j=1) - 0.3 * dde.grad.hessian(u, x, i=0, j=0) + dde.grad.hessian(u, x, i=0, j=1) * u
+    v = dde.grad.hessian(y, x, component=1, i=1, j=1) / (1.0 + y[:, 0:1] ** 2)
+    return [torch.mean(torch.square(r)), torch.mean(abs(u[5:200])), torch.mean(torch.square(v[100:])), torch.sum(v * u)]
+
+
+@pytest.mark.parametrize("n", [1, 37, 1000, 300001])
+def test_interpreter_kernels_match_the_float64_interpreter(n):
+    """Every opcode, four terms over three row ranges, two network outputs, S = 6 streams; ragged sizes; repeated
+    launches bit-identical (fixed-order reductions)."""
+    from ai4xde_b200 import _lib, residual as R
+    from ai4xde_b200.jet import JetSpec
+
+    dev = torch.device("cuda:0")
+    spec = JetSpec.full(2)
+    code = _all_ops_code if n >= 256 else (lambda x, y: [torch.mean(torch.square(
+        torch.sin(x[:, 0:1]) * y[:, 0:1] - y[:, 1:2] ** 2 / (2.0 + torch.exp(x[:, 1:2]))))])
+    prog = R.trace(code, spec, n, 2, 2)
+    gen = torch.Generator().manual_seed(n)
+    ldn = _lib.pad32(n)
+    x = torch.zeros((2, ldn), dtype=torch.float64)
+    x[:, :n] = torch.rand((2, n), generator=gen, dtype=torch.float64)
+    jets = torch.zeros((1, spec.S, 2, ldn), dtype=torch.float64)
+    jets[..., :n] = torch.randn((1, spec.S, 2, n), generator=gen, dtype=torch.float64)
+    tg = torch.randn(prog.n_terms, generator=gen, dtype=torch.float64)
+    want = td._run_program(prog, x, jets, n)
+    want_bar = td.residual_backward(td.ResidualTables(prog), x, jets, n, tg)
+    tables = _lib.ResidualTables(prog, dev)
+    xs, js = x.float().to(dev), jets.float().to(dev)
+    got = _lib.residual_forward(tables, xs, js, n)
+    got_bar = _lib.residual_backward(tables, xs, js, n, tg.float().to(dev))
+    assert _rel(got.double().cpu(), want) < 1e-5, (got, want)
+    assert _rel(got_bar.double().cpu(), want_bar) < 1e-5
+    assert bool((got_bar[..., n:] == 0).all())
+    assert torch.equal(got, _lib.residual_forward(tables, xs, js, n))
+    assert torch.equal(got_bar, _lib.residual_backward(tables, xs, js, n, tg.float().to(dev)))
+    print(f"n={n}: {prog.describe()}; losses rel {_rel(got.double().cpu(), want):.2e}, jets_bar rel {_rel(got_bar.double().cpu(), want_bar):.2e}")
+
+
+def _closure_loss_and_grad(model, fused):
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_residual_programs(fused)
+    dde.config.set_cuda_graphs(False)
+    try:
+        model.net.zero_grad()
+        seen = {}
+        orig = model.opt.step
+        model.opt.step = lambda closure: seen.__setitem__("loss", closure())
+        try:
+            model.train_step(model.data.train_x, None, None)
+        finally:
+            model.opt.step = orig
+        g = torch.cat([p.grad.reshape(-1) for p in model.net.parameters()]).clone()
+        return seen["loss"].detach().clone(), g
+    finally:
+        dde.config.set_residual_programs(True)
+        dde.config.set_cuda_graphs("auto")
+
+
+def _case(name):
+    from ai4xde_b200 import cases as pc
+
+    np.random.seed(3)
+    torch.manual_seed(3)
+    if name == "cfg1":
+        return pc.Burgers(NumDomain=2540, layer_size=[2] + [20] * 3 + [1], soft_constraints=True), None, "fp32"
+    if name == "burgers_hard":
+        return pc.Burgers(NumDomain=2540, layer_size=[2] + [20] * 3 + [1]), None, "fp32"
+    if name == "cfg2":
+        return pc.AllenCahn(NumDomain=10000, layer_size=[2] + [64] * 4 + [1]), None, "fp32"
+    if name == "cfg3":
+        return pc.NS_Flow_in_LidDriven_Cavity(NumDomain=2 ** 14, layer_size=[2] + [128] * 5 + [3]), None, "tf32"
+    if name == "cfg4":
+        return pc.Helmholtz(NumDomain=2 ** 15, layer_size=[2] + [256] * 6 + [1], activation="tanh",
+                            honor_num_domain=True), [1, 100], "tf32"
+    if name == "cfg4_sin":
+        return pc.Helmholtz(NumDomain=2 ** 14, honor_num_domain=True), [1, 100], "auto"   # 2-[150]x3-1 sin
+    if name == "cfg5":
+        return pc.Poisson_1D_Fourier_Net(NumDomain=2 ** 14, layer_size=[1] + [64] * 3 + [1]), None, "fp32"
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "burgers_hard", "cfg2", "cfg3", "cfg4", "cfg4_sin", "cfg5"])
+def test_train_closure_on_the_traced_program_matches_autograd(name):
+    """BASELINE configs (and the hard-constraint / sin variants the reference defaults to): total loss and flat
+    parameter gradient of the train closure, traced program vs autograd over the jet leaves, same kernels below.
+    The MLP kernels are deterministic, so the only difference is float32 summation order in the loss algebra."""
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_default_float("float32")
+    case, lw, engine = _case(name)
+    dde.config.set_engine(engine)
+    try:
+        model = dde.Model(case.data, case.net)
+        model.compile("adam", lr=1e-3, loss_weights=lw)
+        l_ref, g_ref = _closure_loss_and_grad(model, fused=False)
+        l_fus, g_fus = _closure_loss_and_grad(model, fused=True)
+        note = model.residual_program_note()
+        assert note is not None and not note.startswith("autograd path"), note
+        l2, g2 = _closure_loss_and_grad(model, fused=True)
+        assert torch.equal(l_fus, l2) and torch.equal(g_fus, g2)      # bit-reproducible
+    finally:
+        dde.config.set_engine("auto")
+    print(f"{name}: {note}; loss rel {abs(float(l_fus) - float(l_ref)) / abs(float(l_ref)):.2e}, grad rel {_rel(g_fus, g_ref):.2e}")
+    assert abs(float(l_fus) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
+    assert _rel(g_fus, g_ref) < 1e-5
+
+
+def test_training_with_programs_follows_the_autograd_trajectory():
+    """200 Adam steps of cfg1 (CUDA-graph replay active): loss history with traced programs == without, to float32
+    summation-order noise."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    dde.config.set_default_float("float32")
+    hist = {}
+    for fused in (False, True):
+        np.random.seed(0)
+        torch.manual_seed(0)
+        dde.config.set_residual_programs(fused)
+        try:
+            case = pc.Burgers(NumDomain=2540, layer_size=[2] + [20] * 3 + [1], soft_constraints=True)
+            model = dde.Model(case.data, case.net)
+            model.compile("adam", lr=1e-3)
+            lh, _ = model.train(iterations=200, display_every=50)
+            hist[fused] = np.array([np.sum(l) for l in lh.loss_train])
+            if fused:
+                assert not model.residual_program_note().startswith("autograd path")
+        finally:
+            dde.config.set_residual_programs(True)
+    print(hist)
+    assert np.allclose(hist[True], hist[False], rtol=2e-3)

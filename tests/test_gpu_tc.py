@@ -197,8 +197,10 @@ def test_tf32_engine_refuses_what_it_cannot_do():
     with pytest.raises(_lib.NativeLibraryError):
         _lib.jet_forward(net, js.desc, torch.zeros((1, _lib.param_count(net)), device=dev),
                          torch.zeros((2, 32), device=dev), 8, True, engine="tf32")
-    sin_net = _lib.make_net_desc([2, 128, 128, 1], "sin")
-    assert not _lib.engine_supported(sin_net, js.desc, "tf32")   # served by the FP32 engine
+    fourier = _lib.make_net_desc([2, 128, 128, 1], "tanh", first_activation="sin")
+    assert not _lib.engine_supported(fourier, js.desc, "tf32")   # Fourier first layers: served by the FP32 engine
+    third = JetSpec.two_direction_third(0, 1)
+    assert not _lib.engine_supported(_lib.make_net_desc([2, 128, 128, 1], "sin"), third.desc, "tf32")
 
 
 @pytest.mark.parametrize("H", [64, 128, 256])

@@ -1,0 +1,171 @@
+"""Residual programs (ai4xde_b200/residual.py) on the CPU: the case's own pde / BC / loss code traced into a
+register program must give the losses and parameter gradients of the ordinary autograd path.  The kernels are
+replaced by the plain-PyTorch doubles (tests/_taylor_double.py: Taylor-mode network, program interpreter with
+torch.autograd as its reverse pass); the CUDA interpreter is held to the same double in tests/test_gpu_residual.py."""
+import numpy as np
+import pytest
+import torch
+
+import _taylor_double as td
+
+
+@pytest.fixture(autouse=True)
+def _doubles(monkeypatch):
+    import ai4xde_b200.dde as dde
+
+    monkeypatch.setattr(dde.config, "device", lambda: torch.device("cpu"))
+    td.install(monkeypatch)
+    dde.config.set_default_float("float32")
+    yield
+    dde.config.set_residual_programs(True)
+
+
+def _losses_and_grad(model, fused):
+    import ai4xde_b200.dde as dde
+
+    dde.config.set_residual_programs(fused)
+    model.net.zero_grad()
+    X = model.data.train_x
+    seen = {}
+    orig = model.opt.step
+
+    def step(closure):            # evaluate the train closure once, without moving the weights
+        seen["loss"] = closure()
+
+    model.opt.step = step
+    try:
+        model.train_step(X, None, None)
+    finally:
+        model.opt.step = orig
+    g = torch.cat([p.grad.reshape(-1) for p in model.net.parameters()]).clone()
+    return float(seen["loss"]), g
+
+
+def _case(name):
+    from ai4xde_b200 import cases as pc
+
+    np.random.seed(3)
+    torch.manual_seed(3)
+    if name == "burgers_soft":
+        return pc.Burgers(NumDomain=300, layer_size=[2, 12, 12, 1], soft_constraints=True), None
+    if name == "burgers_hard":
+        return pc.Burgers(NumDomain=300, layer_size=[2, 12, 12, 1]), None
+    if name == "allencahn":
+        return pc.AllenCahn(NumDomain=300, layer_size=[2, 12, 12, 1]), None
+    if name == "ns_cavity":
+        return pc.NS_Flow_in_LidDriven_Cavity(NumDomain=200, layer_size=[2, 12, 12, 3]), None
+    if name == "helmholtz":
+        return pc.Helmholtz(NumDomain=256, layer_size=[2, 12, 12, 1], activation="sin", honor_num_domain=True), [1, 100]
+    if name == "poisson1d":
+        return pc.Poisson_1D_Fourier_Net(NumDomain=200, layer_size=[1, 12, 12, 1]), None
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["burgers_soft", "burgers_hard", "allencahn", "ns_cavity", "helmholtz", "poisson1d"])
+def test_traced_program_reproduces_the_autograd_path(name):
+    """BASELINE cases P1..P5 (+ the hard-constraint Burgers: output transform inside net.forward): the train
+    closure on the traced program == the train closure on torch.autograd over the jet leaves."""
+    import ai4xde_b200.dde as dde
+
+    case, lw = _case(name)
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3, loss_weights=lw)
+    l_ref, g_ref = _losses_and_grad(model, fused=False)
+    l_fus, g_fus = _losses_and_grad(model, fused=True)
+    note = model.residual_program_note()
+    assert note is not None and not note.startswith("autograd path"), note
+    assert abs(l_fus - l_ref) <= 2e-5 * abs(l_ref), (l_fus, l_ref)
+    assert float((g_fus - g_ref).abs().max()) <= 2e-4 * float(g_ref.abs().max()), note
+    print(name, note)
+
+
+def test_symbolic_derivatives_match_autograd():
+    """Graph.diff against torch.autograd on a transform that mixes every supported operation."""
+    from ai4xde_b200 import residual as R
+    from ai4xde_b200.jet import JetSpec
+
+    spec = JetSpec.full(2)
+
+    def loss_code(x, y):
+        u = torch.sin(x[:, 0:1]) * y + torch.exp(-x[:, 1:2]) * torch.tanh(y) / (1.5 + torch.cos(x[:, 0:1] * x[:, 1:2]))
+        u = u + torch.sqrt(2.0 + y * y) - abs(y) ** 3 + torch.log(3.0 + u ** 2) + 2.0 ** x[:, 1:2]
+        import ai4xde_b200.dde as dde
+
+        r = dde.grad.jacobian(u, x, i=0, j=1) - 0.3 * dde.grad.hessian(u, x, i=0, j=0) \
+            + dde.grad.hessian(u, x, i=0, j=1) * u
+        return [torch.mean(torch.square(r)), torch.mean(abs(u[5:20]))]
+
+    n = 40
+    prog = R.trace(loss_code, spec, n, 2, 1)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand((n, 2), generator=gen, dtype=torch.float64)
+    jets = torch.randn((1, spec.S, 1, n), generator=gen, dtype=torch.float64)
+    got = td._run_program(prog, x.t().contiguous(), jets, n)
+    # the same code on torch tensors, the "network" being a quadratic form with exactly these jets at each point
+    xt = x.clone().requires_grad_()
+    from ai4xde_b200 import jet as J
+
+    streams = [jets[0, s, :, :].t().clone() for s in range(spec.S)]
+    y = J.make_leaf(xt, spec, streams)
+    import ai4xde_b200.dde as dde
+
+    dde.grad.register(y, J.JetOutput(xt, spec, streams))
+    want = torch.stack(loss_code(xt, y))
+    dde.grad.clear()
+    assert torch.allclose(got, want.detach(), rtol=1e-10, atol=1e-12), (got, want)
+
+
+@pytest.mark.parametrize("what", ["detach", "row_gather", "trainable", "matmul"])
+def test_untraceable_code_stays_on_autograd(what):
+    """Code a program cannot express is refused by the tracer -- the step still runs, on the autograd path."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = pc.Burgers(NumDomain=100, layer_size=[2, 8, 8, 1], soft_constraints=True)
+    base = case.data.pde
+    coef = torch.tensor(0.5, requires_grad=True)
+
+    def pde(x, y):
+        r = base(x, y)
+        if what == "detach":
+            return r * y.detach()
+        if what == "row_gather":
+            return r[torch.arange(len(r))]
+        if what == "trainable":
+            return r * coef
+        return torch.matmul(r.t(), r)
+
+    case.data.pde = pde
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3)
+    if what == "matmul":
+        return            # shape-changing code: not a point-wise residual at all; nothing to run
+    loss, g = _losses_and_grad(model, fused=True)
+    assert np.isfinite(loss) and bool(torch.isfinite(g).all())
+    note = model.residual_program_note()
+    assert note is None or note.startswith("autograd path"), note
+
+
+def test_program_is_retraced_when_the_point_set_changes():
+    """BC target arrays are baked per point-set version: after add_anchors the program is traced again."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = pc.Burgers(NumDomain=100, layer_size=[2, 8, 8, 1], soft_constraints=True)
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3)
+    _losses_and_grad(model, fused=True)
+    first = model._residual["train"][2]
+    assert first is not None
+    _losses_and_grad(model, fused=True)
+    assert model._residual["train"][2] is first
+    case.data.add_anchors(np.random.rand(17, 2).astype(np.float32))
+    l_fus, g_fus = _losses_and_grad(model, fused=True)
+    assert model._residual["train"][2] is not first and model._residual["train"][2] is not None
+    l_ref, g_ref = _losses_and_grad(model, fused=False)
+    assert abs(l_fus - l_ref) <= 2e-5 * abs(l_ref)
+    assert float((g_fus - g_ref).abs().max()) <= 2e-4 * float(g_ref.abs().max())
