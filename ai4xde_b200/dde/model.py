@@ -458,7 +458,14 @@ class Model:
                 closure.graph_rows = len(inputs) if self._owns(inputs) else None
                 closure.graph_key = (id(inputs), getattr(self.data, "version", None), id(self.data.pde))
                 closure.graph_batch = self.device_batch(inputs)   # kept alive by the optimiser's graph
-            self.opt.step(closure)
+            scope = None
+            if optimizers.is_external_optimizer(self.opt_name) and config.engine() == "auto":
+                # second-order phase: FP32-accurate gradients where they are affordable (config.set_lbfgs_engine)
+                mode, max_rows = config.lbfgs_engine()
+                if mode == "fp32" and hasattr(inputs, "__len__") and len(inputs) <= max_rows:
+                    scope = "fp32"
+            with config.engine_scope(scope):
+                self.opt.step(closure)
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()
 
