@@ -74,6 +74,17 @@ def product_vs_oracle(cfg, n_domain, engine="fp32", seed=0, oracle_dtype="float6
         case.net.zero_grad()
         losses.sum().backward()
         g = torch.cat([p.grad.reshape(-1) for p in case.net.parameters()]).double().cpu().numpy()
+        # the train closure as model.train runs it: network kernels + the loss side as a traced residual program
+        # (ai4xde_b200/residual.py), evaluated once without moving the weights
+        case.net.zero_grad()
+        seen, step = {}, model.opt.step
+        model.opt.step = lambda closure: seen.__setitem__("loss", closure())
+        try:
+            model.train_step(case.data.train_x, None, None)
+        finally:
+            model.opt.step = step
+        g_closure = torch.cat([p.grad.reshape(-1) for p in case.net.parameters()]).double().cpu().numpy()
+        l_closure = float(seen["loss"])
     finally:
         dde.config.set_engine("auto")
 
@@ -86,6 +97,9 @@ def product_vs_oracle(cfg, n_domain, engine="fp32", seed=0, oracle_dtype="float6
         "grad_rel": rel(g, ref["grad"]),
         "res_rel": res_rel,
         "out_rel": rel(outs.detach().double().cpu().numpy(), ref["outputs"]),
+        "closure_loss_rel": abs(l_closure - float(np.sum(ref["losses"]))) / abs(float(np.sum(ref["losses"]))),
+        "closure_grad_rel": rel(g_closure, ref["grad"]),
+        "program": model.residual_program_note(),
         "n_rows": len(case.data.train_x),
         "losses": losses.detach().cpu().numpy(),
         "ref_losses": ref["losses"],

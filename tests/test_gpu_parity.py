@@ -32,6 +32,9 @@ def test_fp32_engine_matches_oracle(cfg, n):
     assert r["loss_rel"] < tol["loss"], r
     assert r["grad_rel"] < tol["grad"], r
     assert r["res_rel"] < tol["res"], r
+    # the same step through the train closure, its loss side running as a traced residual program
+    assert r["program"] is not None and not r["program"].startswith("autograd path"), r["program"]
+    assert r["closure_loss_rel"] < tol["loss"] and r["closure_grad_rel"] < tol["grad"], r
 
 
 @pytest.mark.parametrize("engine,width,tol", [("fp32", 32, 2e-5), ("tf32", 64, 2e-2)])
