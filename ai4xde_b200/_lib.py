@@ -121,6 +121,7 @@ _SIGNATURES = {
     "ax_residual_ws_bytes": (C.c_size_t, [C.POINTER(ResidualProgram), C.c_int64]),
     "ax_residual_forward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
     "ax_residual_backward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "ax_residual_eval": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "ax_debug_fma_peak": (C.c_double, [_P, C.c_int32, C.c_int32, _P]),
 }
@@ -313,7 +314,7 @@ class ResidualTables:
         self.code = i32(np.concatenate(code, axis=0))
         self.segments = i32(np.array(segs))
         self.consts = torch.as_tensor(program.consts, dtype=torch.float32, device=device)
-        self.term_scale = torch.as_tensor(program.scale, dtype=torch.float32, device=device)
+        self.term_scale = torch.as_tensor(program.scale if len(program.scale) else [0.0], dtype=torch.float32, device=device)
         self.aux = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t, _ in program.aux]
         self.scalars = [t.detach() for t in program.scalars]
         for t in self.scalars:
@@ -341,6 +342,17 @@ def residual_forward(tables, x_soa, jets, n):
                                  _ptr(ws), int(wsb), _stream())
     _check(rc, "ax_residual_forward")
     return losses
+
+
+def residual_eval(tables, x_soa, jets, n, n_cols):
+    """point-wise outputs [n_cols, ldn] of an operator program (rows n..ldn are left untouched: zero them if read)"""
+    lib = load()
+    _need_cuda(x_soa, jets)
+    ldn = x_soa.shape[1]
+    out = torch.zeros((n_cols, ldn), dtype=torch.float32, device=x_soa.device)
+    rc = lib.ax_residual_eval(C.byref(tables.struct), _ptr(x_soa), _ptr(jets), int(n), int(ldn), _ptr(out), _stream())
+    _check(rc, "ax_residual_eval")
+    return out
 
 
 def residual_backward(tables, x_soa, jets, n, term_grads):

@@ -6,7 +6,9 @@ from ..solver import PINNSolver
 
 
 class RAR_D(PINNSolver):
-    def __init__(self, PDECase, iter=100, k=2, c=0):
+    def __init__(self, PDECase, iter=100, k=2, c=0, device_rng=False, device_seed=0):
+        # [ext] device_rng: the whole round on the device (see RAD)
+        self.device_rng, self.device_seed, self._rng_offset = bool(device_rng), int(device_seed), 0
         dde.optimizers.config.set_LBFGS_options(maxiter=1000)
         super().__init__(name=f"RAR_D_k_{k}_c_{c}", PDECase=PDECase)
         self.iter, self.k, self.c = iter, k, c
@@ -15,6 +17,12 @@ class RAR_D(PINNSolver):
     def resample(self):
         case = self.PDECase
         _, rank, world = resample._world()
+        if world == 1 and self.device_rng:
+            from .rad import device_round
+
+            done = device_round(self, case, self.num_candidates, case.NumDomain // 100, replace=False)
+            if done is not None:
+                return done
         if world == 1:
             X = case.geomtime.random_points(self.num_candidates)
             ids = resample.rad_select(self.model, X, case.pde, case.NumDomain // 100, k=self.k, c=self.c)

@@ -12,8 +12,9 @@ namespace ax {
 
 enum {
   R_LOADX = 0, R_LOADJ, R_LOADA, R_LOADS, R_CONST, R_ADD, R_SUB, R_MUL, R_DIV, R_NEG, R_SIN, R_COS, R_EXP, R_TANH,
-  R_LOG, R_SQRT, R_ABS, R_SIGN, R_POW, R_SUMT
+  R_LOG, R_SQRT, R_ABS, R_SIGN, R_POW, R_SUMT, R_STORE
 };
+enum { RES_SUM = 0, RES_ADJ = 1, RES_EVAL = 2 };   // what a forward sweep is for
 
 struct ResView {
   const int4 *code;
@@ -29,10 +30,12 @@ struct ResView {
 __device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.0f) - (v < 0.0f)); }
 
 // one forward sweep of code [cb, ce) for point p; R = this thread's register column (stride T)
-template <bool ZERO_ADJ>
+// MODE RES_SUM: `sink` = this thread's term accumulators (stride T); RES_ADJ: adjoint registers A are zeroed as the
+// values are written; RES_EVAL: `sink` = output matrix [columns][ldn], R_STORE writes column in.y at point p
+template <int MODE>
 __device__ __forceinline__ void res_forward(const int4 *code, int cb, int ce, const float *consts, const ResView &pv,
                                             const float *x, const float *jets, long long p, long long ldn, float *R,
-                                            float *A, float *tacc, int T) {
+                                            float *A, float *sink, int T) {
   for (int pc = cb; pc < ce; ++pc) {
     const int4 in = code[pc];
     float v;
@@ -60,12 +63,15 @@ __device__ __forceinline__ void res_forward(const int4 *code, int cb, int ce, co
       case R_ABS: v = fabsf(R[in.z * T]); break;
       case R_SIGN: v = sgnf(R[in.z * T]); break;
       case R_POW: v = powf(R[in.z * T], consts[in.w]); break;
+      case R_STORE:
+        if (MODE == RES_EVAL) sink[(long long)in.y * ldn + p] = R[in.z * T];
+        continue;
       default:   // R_SUMT: term in.y += register in.z
-        if (!ZERO_ADJ) tacc[in.y * T] += R[in.z * T];
+        if (MODE == RES_SUM) sink[in.y * T] += R[in.z * T];
         continue;
     }
     R[in.y * T] = v;
-    if (ZERO_ADJ) A[in.y * T] = 0.0f;
+    if (MODE == RES_ADJ) A[in.y * T] = 0.0f;
   }
 }
 
@@ -90,7 +96,7 @@ k_residual_fwd(ResView pv, const float *__restrict__ x, const float *__restrict_
       for (int s = 0; s < pv.n_seg; ++s) {
         const int4 sg = seg[s];
         if (p >= sg.x && p < sg.y)
-          res_forward<false>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, regs + tid, nullptr, tacc + tid, T);
+          res_forward<RES_SUM>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, regs + tid, nullptr, tacc + tid, T);
       }
     }
   }
@@ -120,6 +126,31 @@ k_residual_reduce(const float *__restrict__ partial, int nblocks, int n_terms, c
   if (threadIdx.x == 0) losses[t] = red[0] * scale[t];
 }
 
+// operator evaluation (model.predict(x, operator=pde): the residual probe of RAD / RAR_D / R3): out[column][p]
+__global__ void __launch_bounds__(128)
+k_residual_eval(ResView pv, const float *__restrict__ x, const float *__restrict__ jets, long long n, long long ldn,
+                float *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  int4 *code = reinterpret_cast<int4 *>(res_smem);
+  int4 *seg = code + pv.n_instr;
+  float *consts = reinterpret_cast<float *>(seg + pv.n_seg);
+  float *regs = consts + pv.n_const;
+  for (int i = tid; i < pv.n_instr; i += T) code[i] = pv.code[i];
+  for (int i = tid; i < pv.n_seg; i += T) seg[i] = pv.seg[i];
+  for (int i = tid; i < pv.n_const; i += T) consts[i] = pv.consts[i];
+  __syncthreads();
+  for (long long base = (long long)blockIdx.x * T; base < n; base += (long long)gridDim.x * T) {
+    const long long p = base + tid;
+    if (p >= n) continue;
+    for (int s = 0; s < pv.n_seg; ++s) {
+      const int4 sg = seg[s];
+      if (p >= sg.x && p < sg.y)
+        res_forward<RES_EVAL>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, regs + tid, nullptr, out, T);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict__ jets, long long n, long long ldn,
                const float *__restrict__ term_grads, float *__restrict__ jets_bar) {
@@ -146,13 +177,14 @@ k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict_
       for (int s = 0; s < pv.n_seg; ++s) {
         const int4 sg = seg[s];
         if (p < sg.x || p >= sg.y) continue;
-        res_forward<true>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, R, A, nullptr, T);
+        res_forward<RES_ADJ>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, R, A, nullptr, T);
         for (int pc = sg.w - 1; pc >= sg.z; --pc) {
           const int4 in = code[pc];
           if (in.x == R_SUMT) {
             A[in.z * T] += tg[in.y];
             continue;
           }
+          if (in.x == R_STORE) continue;
           const float d = A[in.y * T];
           if (d == 0.0f) continue;          // nothing flows through this value (also keeps 0 * inf out)
           switch (in.x) {
@@ -204,7 +236,7 @@ static int res_check(const ax_residual_program *pg) {
     return 1;
   }
   if (pg->n_instr < 1 || pg->n_instr > 4096 || pg->n_seg < 1 || pg->n_seg > 256 || pg->n_reg < 1 || pg->n_reg > 380 ||
-      pg->n_terms < 1 || pg->n_terms > 64 || pg->n_streams < 1 || pg->n_streams > 64 || pg->n_const < 1 ||
+      pg->n_terms < 0 || pg->n_terms > 64 || pg->n_streams < 1 || pg->n_streams > 64 || pg->n_const < 1 ||
       pg->n_const > 1024) {
     set_error("residual program: sizes out of range (instr %d, seg %d, reg %d, terms %d, streams %d, consts %d)",
               pg->n_instr, pg->n_seg, pg->n_reg, pg->n_terms, pg->n_streams, pg->n_const);
@@ -259,6 +291,10 @@ size_t ax_residual_ws_bytes(const ax_residual_program *prog, int64_t n) {
 int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
                         float *losses, void *ws, size_t ws_bytes, void *stream) {
   if (res_check(prog)) return 1;
+  if (prog->n_terms < 1) {
+    set_error("residual forward: the program has no loss terms (an operator program: ax_residual_eval)");
+    return 1;
+  }
   if (!x_soa || !jets || !losses || !ws || n < 1 || ldn < n) {
     set_error("residual forward: null pointer or bad sizes (n = %lld, ldn = %lld)", (long long)n, (long long)ldn);
     return 1;
@@ -290,9 +326,40 @@ int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, con
   return 0;
 }
 
+int ax_residual_eval(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
+                     float *out, void *stream) {
+  if (res_check(prog)) return 1;
+  if (!x_soa || !jets || !out || n < 1 || ldn < n) {
+    set_error("residual eval: null pointer or bad sizes (n = %lld, ldn = %lld)", (long long)n, (long long)ldn);
+    return 1;
+  }
+  size_t smem = 0;
+  const int threads = res_threads(prog, false, &smem);
+  if (!threads) {
+    set_error("residual program does not fit in shared memory");
+    return 1;
+  }
+  static size_t attr = 0;
+  if (smem > attr) {
+    AX_CUDA_OK(cudaFuncSetAttribute(k_residual_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr = 200 * 1024;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    KernelTimer t("residual_eval", st, 0.0, (8.0 + 4.0 * prog->n_streams) * (double)n);
+    k_residual_eval<<<res_blocks(n, threads), threads, smem, st>>>(res_view(prog), x_soa, jets, n, ldn, out);
+  }
+  AX_LAUNCH_OK();
+  return 0;
+}
+
 int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
                          const float *term_grads, float *jets_bar, void *stream) {
   if (res_check(prog)) return 1;
+  if (prog->n_terms < 1) {
+    set_error("residual backward: the program has no loss terms");
+    return 1;
+  }
   if (!x_soa || !jets || !term_grads || !jets_bar || n < 1 || ldn < n) {
     set_error("residual backward: null pointer or bad sizes (n = %lld, ldn = %lld)", (long long)n, (long long)ldn);
     return 1;

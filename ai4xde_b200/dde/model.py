@@ -76,6 +76,14 @@ class _DeviceBatch:
         self.aos = t
         self.soa = jet.to_soa(t)
 
+    @classmethod
+    def on_device(cls, aos, soa=None, host=None, version=None):
+        """A batch whose points were produced on the device (resampling rounds): nothing to upload."""
+        b = cls.__new__(cls)
+        b.host, b.version, b.aos = host, version, aos
+        b.soa = soa if soa is not None else jet.to_soa(aos)
+        return b
+
 
 class Model:
     verbose = int(os.environ.get("AI4XDE_B200_VERBOSE", "0"))
@@ -208,7 +216,11 @@ class Model:
 
     # ---- traced loss programs (ai4xde_b200/residual.py) -------------------------------------------
     def residual_program_note(self, use="train"):
-        """Why the loss side of `use` runs (or does not run) as a traced program -- for logs and tests."""
+        """Why the loss side of `use` ("train", "test", or "operator": the most recent operator program) runs -- or
+        does not run -- as a traced program; for logs and tests."""
+        if use == "operator":
+            keys = [k for k in self._residual if isinstance(k, tuple) and k[0] == "operator"]
+            return self._residual[keys[-1]][3] if keys else None
         hit = self._residual.get(use)
         return None if hit is None else hit[3]
 
@@ -267,6 +279,66 @@ class Model:
         if Model.verbose:
             print(f"[ai4xde_b200] loss side of {use}: {note}")
         return tables
+
+    def _operator_program(self, batch, spec, operator, autograd_eval):
+        """(tables, column counts, list?) of `operator` traced into a program that STORES its outputs, or None.
+        Same eligibility, tracing and adoption check (against `autograd_eval()`, the ordinary path, on this batch)
+        as the train-step programs; one entry per (operator, number of rows)."""
+        net = self.net
+        from .nn import FNN
+
+        if not config.residual_programs() or type(net) is not FNN or net._input_transform is not None \
+                or net.auxiliary_vars is not None or utils.get_num_args(operator) != 2:
+            return None
+        n_rows = int(batch.aos.shape[0])
+        use = ("operator", id(operator), n_rows)
+        owners = (operator, net._output_transform)
+        key = (spec.key(), self._residual_epoch)
+        hit = self._residual.get(use)
+        if hit is not None and hit[1] == key and all(a is b for a, b in zip(hit[0], owners)):
+            return hit[2]
+        entry, note = None, ""
+        try:
+            prog, widths, as_list = residual.trace_operator(
+                lambda xs, ys: operator(xs, ys), spec, n_rows, net.layer_sizes[0], net.layer_sizes[-1],
+                output_transform=net._output_transform)
+            entry = (_lib.ResidualTables(prog, batch.aos.device), widths, as_list)
+            note = prog.describe()
+        except residual.Unsupported as e:
+            note = f"autograd path: {e}"
+        finally:
+            grad.clear()
+        if entry is not None:
+            ref = autograd_eval()
+            ref = list(ref) if isinstance(ref, (list, tuple)) else [ref]
+            got = self._run_operator_program(entry, batch, spec)
+            got = list(got) if isinstance(got, (list, tuple)) else [got]
+            bad = len(got) != len(ref)
+            for a, b in zip(got, ref):
+                bad = bad or a.shape != b.shape or not bool(torch.isfinite(a).all()) \
+                    or float((a - b).abs().max()) > 1e-4 * float(b.abs().max().clamp_min(1e-30))
+            if bad:
+                entry, note = None, f"autograd path: traced operator ({note}) did not reproduce it on the live batch"
+        for k in [k for k in self._residual if isinstance(k, tuple) and k[0] == "operator"][:-7]:
+            del self._residual[k]            # a handful of (operator, size) entries is all an algorithm uses
+        self._residual[use] = (owners, key, entry, note)
+        if Model.verbose:
+            print(f"[ai4xde_b200] operator {getattr(operator, '__name__', operator)} on {n_rows} rows: {note}")
+        return entry
+
+    def _run_operator_program(self, entry, batch, spec):
+        from .nn import _launch_forward
+
+        tables, widths, as_list = entry
+        n = int(batch.aos.shape[0])
+        with torch.no_grad():
+            jets = _launch_forward(self.net, batch.soa, n, spec, config.engine(), False)[0]
+            out = _lib.residual_eval(tables, batch.soa, jets, n, sum(widths))
+        cols, res = 0, []
+        for w in widths:
+            res.append(out[cols : cols + w, :n].t())       # (n, w) view; w = 1 for every reference pde
+            cols += w
+        return res if as_list else res[0]
 
     # ---- CUDA-graph replay of the small-problem step -------------------------------------------
     def _graphed_step(self, inputs, targets, auxiliary_vars, closure):
@@ -597,18 +669,27 @@ class Model:
         return y
 
     def predict_on_device(self, x, operator):
-        """`operator(x, net(x))` evaluated with forward-only jets; returns device tensor(s)."""
+        """`operator(x, net(x))` evaluated with forward-only jets; returns device tensor(s).  `x`: a host point array
+        or a _DeviceBatch that is already on the device (the on-device resampling rounds).  The operator runs as a
+        traced residual program (one launch after the jet kernels) whenever its code can be traced."""
         self.net.eval()
-        batch = self.device_batch(x)
+        batch = x if isinstance(x, _DeviceBatch) else self.device_batch(x)
         spec = self.spec_for_operator(batch, operator)
-        xt = batch.aos.detach().requires_grad_()
-        with self.net.jet_scope(spec, batch.soa, param_grad=False):
-            outputs = self.net(xt)
-        y = self._call_operator(operator, xt, outputs)
-        grad.clear()
-        if isinstance(y, (list, tuple)):
-            return [t.detach() for t in y]
-        return y.detach()
+
+        def autograd_eval():
+            xt = batch.aos.detach().requires_grad_()
+            with self.net.jet_scope(spec, batch.soa, param_grad=False):
+                outputs = self.net(xt)
+            y = self._call_operator(operator, xt, outputs)
+            grad.clear()
+            if isinstance(y, (list, tuple)):
+                return [t.detach() for t in y]
+            return y.detach()
+
+        entry = self._operator_program(batch, spec, operator, autograd_eval)
+        if entry is not None:
+            return self._run_operator_program(entry, batch, spec)
+        return autograd_eval()
 
     # ---- persistence -------------------------------------------------------------------------
     def state_dict(self):

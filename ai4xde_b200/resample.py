@@ -12,7 +12,8 @@ from . import _lib
 
 
 def residual_matrix(model, X, pde):
-    """|residual| inputs of the selectors: float32 device matrix [n_res, ldr] (zero padded)."""
+    """|residual| inputs of the selectors: float32 device matrix [n_res, ldr] (zero padded).  `X`: host point array,
+    or a device batch (dde/model.py:_DeviceBatch) when the candidates were generated on the device."""
     res = model.predict_on_device(X, pde)
     res = list(res) if isinstance(res, (list, tuple)) else [res]
     n = res[0].shape[0]
@@ -37,7 +38,10 @@ def choice_noreplace_device(p, size, rand=None):
     ws, wsb = _lib.resample_ws(n, dev)
     n_found = 0
     while n_found < size:
-        u = torch.as_tensor(rand(size - n_found), dtype=torch.float64).to(dev)
+        u = rand(size - n_found)          # NumPy's stream (parity) or a float64 CUDA tensor (device sampler)
+        if not torch.is_tensor(u):
+            u = torch.as_tensor(u, dtype=torch.float64)
+        u = u.to(device=dev, dtype=torch.float64)
         _lib.choice_round(p, u, found, n_found, n_found_dev, ws, wsb)
         n_found = int(n_found_dev.item())
     return found
@@ -54,6 +58,33 @@ def rad_select(model, X, pde, num, k=1, c=1, rand=None, fast=False):
         return choice_noreplace_device(p, num, rand).cpu().numpy()
     finally:
         _lib.resample_set_fast(prev)
+
+
+def rad_round_on_device(model, geom_box, pde, n_candidates, num, k, c, seed, offset):
+    """A whole RAD / RAR_D selection without the host in the data path ([ext], performance mode): candidates from
+    the library's Philox box sampler (`ax_uniform_box_points`), residual probe on them where they lie, probabilities
+    and the without-replacement draw with the parallel float64 scans (`ax_resample_set_fast`), uniforms of the draw
+    from torch's device generator, selected points gathered on the device (`ax_gather_points`).
+    Returns (indices into the candidate set [num] int64 CUDA, selected points SoA [d, pad32(num)], AoS [num, d])."""
+    from .dde.model import _DeviceBatch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d, ldc = len(geom_box[0]), _lib.pad32(n_candidates)
+    cand = torch.zeros((d, ldc), dtype=torch.float32, device=dev)
+    _lib.uniform_box_points(cand, 0, n_candidates, geom_box[0], geom_box[1], seed, offset)
+    batch = _DeviceBatch.on_device(cand[:, :n_candidates].t().contiguous(), cand)
+    res, n = residual_matrix(model, batch, pde)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed((int(seed) * 0x9E3779B1 + int(offset)) & 0x7FFFFFFFFFFFFFFF)
+    prev = _lib.resample_get_fast()
+    _lib.resample_set_fast(True)
+    try:
+        p = _lib.rad_probabilities(res, n, k, c)
+        ids = choice_noreplace_device(p, num, lambda m: torch.rand(m, dtype=torch.float64, device=dev, generator=gen))
+    finally:
+        _lib.resample_set_fast(prev)
+    sel = _lib.gather_points(cand, ids)
+    return ids, sel, sel[:, :num].t().contiguous()
 
 
 def r3_retain(model, X, pde):

@@ -31,7 +31,7 @@ class Unsupported(Exception):
 OP_LOADX, OP_LOADJ, OP_LOADA, OP_LOADS, OP_CONST = 0, 1, 2, 3, 4
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG = 5, 6, 7, 8, 9
 OP_SIN, OP_COS, OP_EXP, OP_TANH, OP_LOG, OP_SQRT, OP_ABS, OP_SIGN, OP_POW = 10, 11, 12, 13, 14, 15, 16, 17, 18
-OP_SUMT = 19
+OP_SUMT, OP_STORE = 19, 20
 _UNARY = {"sin": OP_SIN, "cos": OP_COS, "exp": OP_EXP, "tanh": OP_TANH, "log": OP_LOG, "sqrt": OP_SQRT,
           "abs": OP_ABS, "sign": OP_SIGN, "neg": OP_NEG}
 _BINARY = {"add": OP_ADD, "sub": OP_SUB, "mul": OP_MUL, "div": OP_DIV}
@@ -578,9 +578,14 @@ class Program:
     """A lowered residual program.  `segments`: (first row, end row, code [m, 4] int32 = op, dst, a, b); terms are
     numbered in the order the traced code produced them; `scale[t]` turns a term's row sum into its loss."""
 
-    def __init__(self, graph, spec, terms, n_rows):
-        if not terms or len(terms) > MAX_TERMS:
+    def __init__(self, graph, spec, terms, n_rows, outputs=None):
+        """`terms`: reduced loss terms (train step); `outputs`: point-wise columns over all rows to be STORED
+        (model.predict(x, operator=pde): the residual probe of RAD / RAR_D / R3) -- one of the two."""
+        if outputs is None and (not terms or len(terms) > MAX_TERMS):
             raise Unsupported(f"{len(terms)} loss terms")
+        self.n_outputs = 0 if outputs is None else len(outputs)
+        if outputs is not None and not 1 <= len(outputs) <= MAX_TERMS:
+            raise Unsupported(f"{len(outputs)} operator outputs")
         self.n_terms, self.n_rows = len(terms), int(n_rows)
         self.S, self.C, self.d_in = spec.S, graph.n_out, graph.n_in
         self.scale = np.array([t.scale for t in terms], dtype=np.float64)   # uploaded as float32
@@ -588,7 +593,9 @@ class Program:
         consts, cindex = [], {}
         by_win = {}
         for t, term in enumerate(terms):
-            by_win.setdefault(term.win, []).append((t, term.expr))
+            by_win.setdefault(term.win, []).append((OP_SUMT, t, term.expr))
+        for c, expr in enumerate(outputs or ()):
+            by_win.setdefault((0, int(n_rows)), []).append((OP_STORE, c, expr))
         self.segments, n_reg = [], 0
         for win in sorted(by_win):
             if win[0] < 0 or win[1] > n_rows or win[0] >= win[1]:
@@ -635,8 +642,8 @@ class Program:
             limit = sys.getrecursionlimit()
             sys.setrecursionlimit(max(limit, 20000))
             try:
-                for t, expr in by_win[win]:
-                    code.append((OP_SUMT, t, emit(expr), 0))
+                for sink, t, expr in by_win[win]:
+                    code.append((sink, t, emit(expr), 0))
             finally:
                 sys.setrecursionlimit(limit)
             n_reg = max(n_reg, len(reg))
@@ -652,7 +659,8 @@ class Program:
         self._device = None
 
     def describe(self):
-        return (f"{self.n_terms} terms, {len(self.segments)} row segments, {self.n_instr} instructions, "
+        what = f"{self.n_terms} terms" if not self.n_outputs else f"{self.n_outputs} output columns"
+        return (f"{what}, {len(self.segments)} row segments, {self.n_instr} instructions, "
                 f"{self.n_reg} registers, {len(self.aux)} arrays")
 
 
@@ -679,3 +687,32 @@ def trace(losses_fn, spec, n_rows, n_in, n_out, output_transform=None):
         if not isinstance(t, Term):
             raise Unsupported(f"loss term of type {type(t).__name__}")
     return Program(g, spec, list(terms), n_rows)
+
+
+def trace_operator(operator_fn, spec, n_rows, n_in, n_out, output_transform=None):
+    """`operator_fn(x, y)` -- the operator of model.predict(x, operator=...), usually the case's pde -- on symbolic
+    columns.  Returns (program that stores every output column, column counts of the tensors it returned, whether
+    it returned a list)."""
+    g = Graph(n_in, n_out)
+    x = Sym(g, [g.x(d) for d in range(n_in)], (0, n_rows))
+    x.is_input = True
+    y = Sym(g, [g.net(c) for c in range(n_out)], (0, n_rows))
+    if output_transform is not None:
+        y = output_transform(x, y)
+        if not isinstance(y, Sym) or y.vec or y.win != (0, n_rows):
+            raise Unsupported("output transform does not return one row per point")
+    try:
+        outs = operator_fn(x, y)
+    except Unsupported:
+        raise
+    except (TypeError, AttributeError, ValueError, IndexError, RuntimeError, NotImplementedError) as e:
+        raise Unsupported(f"{type(e).__name__}: {e}") from e
+    as_list = isinstance(outs, (list, tuple))
+    outs = list(outs) if as_list else [outs]
+    cols, widths = [], []
+    for o in outs:
+        if not isinstance(o, Sym) or o.vec or o.win != (0, n_rows):
+            raise Unsupported("operator output is not one row per point")
+        cols += o.cols
+        widths.append(len(o.cols))
+    return Program(g, spec, [], n_rows, outputs=cols), widths, as_list

@@ -67,6 +67,12 @@ def main():
     case = cases.AllenCahn(NumDomain=10000, layer_size=[2] + [64] * 4 + [1])
     solver = algorithm.RAD(case, iter=1, k=1, c=1, fast=True)
     out["rad_100k_candidates_fast_scan"] = dict(candidates=100000, selected=10000, **timed_rounds(solver))
+    dde.config.set_default_float("float32")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = cases.AllenCahn(NumDomain=10000, layer_size=[2] + [64] * 4 + [1])
+    solver = algorithm.RAD(case, iter=1, k=1, c=1, device_rng=True)
+    out["rad_100k_candidates_device_rng"] = dict(candidates=100000, selected=10000, **timed_rounds(solver))
     print(json.dumps(out, indent=1))
 
 

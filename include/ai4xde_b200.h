@@ -249,7 +249,7 @@ int ax_adam_step(float *params, const float *grad, float *exp_avg, float *exp_av
  *             0 LOADX a=input dim | 1 LOADJ a=stream*d_out+component | 2 LOADA a=array, b=column | 3 LOADS a=scalar |
  *             4 CONST a=index | 5 ADD 6 SUB 7 MUL 8 DIV (registers a, b) | 9 NEG 10 SIN 11 COS 12 EXP 13 TANH 14 LOG
  *             15 SQRT 16 ABS 17 SIGN (register a) | 18 POW a=register, b=index of the constant exponent |
- *             19 SUMT dst=term, a=register: term += register
+ *             19 SUMT dst=term, a=register: term += register | 20 STORE (ax_residual_eval only)
  *   segments  [n_seg][4] int32    = first row, end row, first instruction, end instruction: a point runs the segments
  *             whose row range holds it (BC rows come first in train_x, then the residual rows)
  *   aux       [n_aux] device pointers to row-major float arrays (BC target values, normals ...), aux_meta [n_aux][2]
@@ -274,6 +274,10 @@ int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, con
                         float *losses, void *ws, size_t ws_bytes, void *stream);
 int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
                          const float *term_grads, float *jets_bar, void *stream);
+/* the same interpreter for `model.predict(x, operator=pde)` (the residual probe of algorithm/RAD.py:26, RAR_D.py:24,
+ * R3Sampling.py:78): opcode 20 STORE dst=column, a=register writes out[column][p]; out is [columns][ldn]. */
+int ax_residual_eval(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
+                     float *out, void *stream);
 
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,

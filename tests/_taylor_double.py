@@ -149,9 +149,53 @@ def _run_program(program, x_soa, jets, n):
                 reg[dst] = reg[a] ** float(program.consts[b])
             elif op == R.OP_SUMT:
                 sums[dst] = sums[dst] + reg[a].sum()
+            elif op == R.OP_STORE:
+                pass
             else:
                 reg[dst] = un[op](reg[a])
     return torch.stack(sums) * torch.as_tensor(program.scale, dtype=jets.dtype)
+
+
+def residual_eval(tables, x_soa, jets, n, n_cols):
+    """operator programs (OP_STORE): out [n_cols, ldn]"""
+    from ai4xde_b200 import residual as R
+
+    program = tables.program
+    out = torch.zeros((n_cols, x_soa.shape[1]), dtype=torch.float32)
+    flat = jets.reshape(-1, jets.shape[-1]).double()
+    un = {R.OP_SIN: torch.sin, R.OP_COS: torch.cos, R.OP_EXP: torch.exp, R.OP_TANH: torch.tanh, R.OP_LOG: torch.log,
+          R.OP_SQRT: torch.sqrt, R.OP_ABS: torch.abs, R.OP_SIGN: torch.sign, R.OP_NEG: torch.neg}
+    for beg, end, code in program.segments:
+        reg = {}
+        for op, dst, a, b in code.tolist():
+            if op == R.OP_LOADX:
+                reg[dst] = x_soa[a, beg:end].double()
+            elif op == R.OP_LOADJ:
+                reg[dst] = flat[a, beg:end]
+            elif op == R.OP_LOADA:
+                ten, first = program.aux[a]
+                reg[dst] = ten.double()[beg - first : end - first, b]
+            elif op == R.OP_LOADS:
+                reg[dst] = program.scalars[a].double().reshape(()).expand(end - beg)
+            elif op == R.OP_CONST:
+                reg[dst] = torch.full((end - beg,), float(program.consts[a]), dtype=torch.float64)
+            elif op == R.OP_ADD:
+                reg[dst] = reg[a] + reg[b]
+            elif op == R.OP_SUB:
+                reg[dst] = reg[a] - reg[b]
+            elif op == R.OP_MUL:
+                reg[dst] = reg[a] * reg[b]
+            elif op == R.OP_DIV:
+                reg[dst] = reg[a] / reg[b]
+            elif op == R.OP_POW:
+                reg[dst] = reg[a] ** float(program.consts[b])
+            elif op == R.OP_STORE:
+                out[dst, beg:end] = reg[a].to(torch.float32)
+            elif op == R.OP_SUMT:
+                pass
+            else:
+                reg[dst] = un[op](reg[a])
+    return out
 
 
 def residual_forward(tables, x_soa, jets, n):
@@ -184,8 +228,10 @@ def install(monkeypatch=None):
         monkeypatch.setattr(_lib, "ResidualTables", ResidualTables)
         monkeypatch.setattr(_lib, "residual_forward", residual_forward)
         monkeypatch.setattr(_lib, "residual_backward", residual_backward)
+        monkeypatch.setattr(_lib, "residual_eval", residual_eval)
         monkeypatch.setattr(optimizers, "lbfgs_factory", torch_lbfgs)
     else:
         _lib.jet_forward, _lib.jet_backward = jet_forward, jet_backward
         _lib.ResidualTables, _lib.residual_forward, _lib.residual_backward = ResidualTables, residual_forward, residual_backward
+        _lib.residual_eval = residual_eval
         optimizers.lbfgs_factory = torch_lbfgs

@@ -40,6 +40,68 @@ def test_rad_round_equals_numpy_choice_on_device_residuals():
     assert len(np.unique(ids)) == case.NumDomain
 
 
+@pytest.mark.parametrize("algo", ["RAD", "RAR_D"])
+def test_rad_round_on_the_device_sampler(algo):
+    """[ext] device_rng: candidates from the Philox box sampler, draw uniforms from the device generator, gather on
+    the device.  Checked against a host replay of the same round: the candidates regenerated from (seed, offset), the
+    operator on them, the oracle's NumPy-order probabilities and NumPy's own inverse-CDF draw fed the same uniforms
+    (the device's parallel scan agrees with NumPy's sequential cumsum except possibly at ties: >= 99.9 % of the indices);
+    the selected points are exactly candidates[ids]; the new point sets have their device mirrors registered."""
+    dde = _setup()
+    dde.config.set_default_float("float32")
+    from ai4xde_b200 import _lib, algorithm, cases
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    if algo == "RAD":
+        case = cases.AllenCahn(NumDomain=2000, layer_size=[2] + [64] * 4 + [1])
+        solver = algorithm.RAD(case, iter=1, k=1, c=1, device_rng=True, device_seed=7)
+        n_cand, num = 20000, 2000
+    else:
+        case = cases.Burgers(NumDomain=1000, layer_size=[2, 20, 20, 20, 1])
+        solver = algorithm.RAR_D(case, iter=1, k=2, c=0, device_rng=True, device_seed=7)
+        n_cand, num = 100000, 10
+    case.compile(solver.model, "adam", lr=1e-3)
+    before = case.data.train_x_all.copy()
+    ids = solver.resample()
+    assert ids.shape == (num,) and len(np.unique(ids)) == num and ids.min() >= 0 and ids.max() < n_cand
+    # replay: same candidates, same residuals, NumPy's arithmetic
+    dev = torch.device("cuda:0")
+    cand = torch.zeros((2, _lib.pad32(n_cand)), device=dev)
+    _lib.uniform_box_points(cand, 0, n_cand, [-1.0, 0.0], [1.0, 1.0], 7, 0)
+    X = cand[:, :n_cand].t().contiguous().cpu().numpy()
+    assert X[:, 0].min() >= -1 and X[:, 0].max() < 1 and X[:, 1].min() >= 0 and X[:, 1].max() < 1
+    picked = X[ids]
+    new_all = picked if algo == "RAD" else np.vstack((picked, before))
+    assert np.array_equal(case.data.train_x_all, new_all)
+    res = np.abs(solver.model.predict(X, operator=case.pde)).astype(np.float64)
+    err = np.power(res, solver.k) / np.power(res, solver.k).mean() + solver.c
+    p = (err / sum(err))[:, 0]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed((7 * 0x9E3779B1 + 0) & 0x7FFFFFFFFFFFFFFF)
+    found, pp = [], p.copy()
+    while len(found) < num:                      # numpy.random.choice(replace=False, p) with the device's uniforms
+        u = torch.rand(num - len(found), dtype=torch.float64, device=dev, generator=gen).cpu().numpy()
+        if found:
+            pp[found] = 0
+        cdf = np.cumsum(pp)
+        cdf /= cdf[-1]
+        new = np.searchsorted(cdf, u, side="right")
+        _, first = np.unique(new, return_index=True)
+        new = new[np.sort(first)]
+        found += [int(i) for i in new if i not in set(found)][: num - len(found)]
+    agree = np.mean(np.asarray(found[:num]) == ids)
+    print(algo, "device round: agreement with the NumPy replay", agree)
+    assert agree >= 0.999
+    # device mirrors registered: the next step finds them, uploads nothing
+    m = solver.model
+    b = m.device_batch(case.data.train_x)
+    assert any(b is c for c in m._batches)
+    assert np.array_equal(b.aos.cpu().numpy(), case.data.train_x.astype(np.float32))
+    m.train_step(case.data.train_x, None, None)
+    assert np.isfinite(float(m.last_total_loss))
+
+
 def test_rar_d_round_adds_anchors():
     dde = _setup()
     from ai4xde_b200 import algorithm, cases

@@ -169,3 +169,31 @@ def test_program_is_retraced_when_the_point_set_changes():
     l_ref, g_ref = _losses_and_grad(model, fused=False)
     assert abs(l_fus - l_ref) <= 2e-5 * abs(l_ref)
     assert float((g_fus - g_ref).abs().max()) <= 2e-4 * float(g_ref.abs().max())
+
+
+@pytest.mark.parametrize("name", ["burgers_hard", "allencahn", "ns_cavity", "helmholtz"])
+def test_operator_programs_reproduce_predict(name):
+    """model.predict(X, operator=pde) -- the residual probe of RAD / RAR_D / R3 (algorithm/RAD.py:26) -- as a traced
+    program that stores the operator's columns == the operator run on tensors over the jet leaves."""
+    import ai4xde_b200.dde as dde
+
+    case, lw = _case(name)
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3, loss_weights=lw)
+    X = case.geomtime.random_points(333)
+    dde.config.set_residual_programs(False)
+    ref = model.predict(X, operator=case.pde)
+    dde.config.set_residual_programs(True)
+    got = model.predict(X, operator=case.pde)
+    note = model.residual_program_note("operator")
+    assert note is not None and not note.startswith("autograd path"), note
+    ref = ref if isinstance(ref, list) else [ref]
+    got = got if isinstance(got, list) else [got]
+    assert len(ref) == len(got)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max(), note
+    # another size: its own program; the first one stays cached
+    got2 = model.predict(X[:50], operator=case.pde)
+    got2 = got2 if isinstance(got2, list) else [got2]
+    assert np.abs(got2[0] - ref[0][:50]).max() <= 2e-5 * np.abs(ref[0]).max()
