@@ -122,6 +122,7 @@ _SIGNATURES = {
     "ax_residual_forward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
     "ax_residual_backward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "ax_residual_eval": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "ax_tc_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "ax_debug_fma_peak": (C.c_double, [_P, C.c_int32, C.c_int32, _P]),
 }
@@ -366,6 +367,11 @@ def residual_backward(tables, x_soa, jets, n, term_grads):
                                   _ptr(term_grads), _ptr(jets_bar), _stream())
     _check(rc, "ax_residual_backward")
     return jets_bar
+
+
+def tc_set_option(name, value):
+    """run-time switch of the tcgen05 engine ("l2chain", "l2chain_group", "l2chain_hints")"""
+    _check(load().ax_tc_set_option(name.encode(), int(value)), "ax_tc_set_option")
 
 
 def fbpinn_window_supported(net, jet, engine):

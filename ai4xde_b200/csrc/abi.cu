@@ -433,6 +433,11 @@ int ax_fbpinn_window_forward(const ax_net_desc *net, const ax_jet_desc *jet, con
   return tc_bank_window_forward(g, a, win_lo, win_hi, net_list, n_list, out);
 }
 
+// run-time switches of the tensor-core engine (defaults come from the environment): "l2chain" 0 / 1 -- every hidden
+// GEMM layer of an H = 256 forward in one launch chained through L2, or one launch per layer; "l2chain_group" tiles
+// per group; "l2chain_hints" L2 eviction hints on its TMA loads
+int ax_tc_set_option(const char *name, int32_t value) { return tc_set_option(name, value); }
+
 // testing hook (tests/test_gpu_tc.py): tensor-core weight-gradient GEMM on caller-provided matrices.
 // ws needs (SM count + 1) * H * H floats.
 int ax_debug_tc_wgrad(const float *zbar, const float *a, int64_t rows, int32_t H, float *out, float *ws,

@@ -16,5 +16,6 @@ size_t tc_bank_ws_bytes(const NetGeom &g, int n_nets, int S, int64_t ldn, int wi
 bool tc_bank_window_usable(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet);
 int tc_bank_window_forward(const NetGeom &g, const FwdArgs &a, const float *lo, const float *hi, const int *net_list,
                            int n_list, float *out);
+int tc_set_option(const char *name, int value);
 int tc_debug_wgrad(const float *zbar, const float *a, long long rows, int H, float *out, float *ws, cudaStream_t st);
 }  // namespace ax

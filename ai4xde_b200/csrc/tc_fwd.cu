@@ -18,6 +18,8 @@
 // Operands are staged by TMA (cp.async.bulk.tensor.3d, 128B swizzle) through an mbarrier ring;
 // one elected thread issues tcgen05.mma; four epilogue warps drain TMEM with tcgen05.ld.
 // Reference behaviour replaced: see simt_kernels.cuh (same math, FP32 engine).
+#include <string>
+
 #include "tc_common.cuh"
 
 namespace ax {
@@ -497,6 +499,382 @@ __global__ void k_tc_jets_combine(const float *__restrict__ part, const float *_
   jets[i] = (part[i] + part[(long long)S * ldn + i]) + (s_ == 0 ? __ldg(bout) : 0.0f);
 }
 
+// =========================================================================================
+// kernel A3: all hidden GEMM layers of the forward in ONE launch, chained through L2 (H = 256, CTA pair).
+// The layer-by-layer kernel (k_tc_gemm2) is HBM-bound: every layer writes its S*H*4 bytes per point and the next
+// launch reads them back from HBM, because a whole layer (4 GB at 2^20 points) is far larger than L2.  Here a cluster
+// walks GROUPS of G consecutive tiles through the layers -- work items ordered (group, layer, tile in group) -- so the
+// streams a tile wrote for layer l are read back for layer l + 1 a few items later, out of L2: HBM sees the stash
+// writes (which the backward needs anyway) and the first layer's read, nothing else.  Inside an item the kernel IS
+// k_tc_gemm2<fwd> (TMA ring -> tcgen05.mma cta_group::2 -> epilogue out of two TMEM accumulators); what is new is the
+// hand-off: the 16 epilogue warps of the pair release a finished tile to both TMA producers through a cluster-scope
+// mbarrier (generic-proxy stores -> fence.proxy.async -> arrive.release.cluster; the producer acquires, fences, and
+// only then lets the async proxy read those rows).  With G >= 3 the producer's wait is always already satisfied:
+// it runs at most ~1.75 items ahead of the epilogue (6-stage ring + double-buffered accumulator).
+// Unlike the smem-mediated chain above, two to three tiles are in flight per cluster, so the tensor pipe, the TMA ring
+// and the epilogue overlap exactly as in the layer-by-layer kernel.
+// =========================================================================================
+constexpr int kL2MaxG = 8;
+constexpr int kL2EpiWarps = 16;                        // four warps per TMEM lane quarter: the epilogue is latency-bound
+constexpr int kL2Threads = 32 * (2 + kL2EpiWarps);
+constexpr int kL2Subs = kL2EpiWarps / 4;
+
+struct L2ChainArgs {
+  const float *bias[AX_MAX_LINEAR];   // bias of GEMM layer l
+  float *out[AX_MAX_LINEAR];          // post-activation streams written by layer l (nullptr: not stored)
+  float *zout[AX_MAX_LINEAR];         // sin nets with the layers kept: pre-activation streams of layer l, or nullptr
+  int in_row[AX_MAX_LINEAR];          // first row, in the stacked stash map, of the slot layer l READS
+  int L;                              // hidden layers: GEMM layers are 1 .. L-1
+  int G;                              // tiles per group (<= kL2MaxG)
+  int hints;                          // L2 eviction hints on the TMA loads (AX_TC_L2CHAIN_HINTS)
+  long long n;
+  int num_tiles;
+  int act;
+  const float *wout;                  // fused output layer on l == L-1 (see GemmArgs), or nullptr
+  float *jets_part;
+  long long ldn;
+};
+
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait_acq_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_acq_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// ONE cluster-scope release fence, then relaxed arrivals on the barrier of both CTAs (two release-arrives would each
+// wait for the warp's stores to be acknowledged)
+__device__ __forceinline__ void mbar_arrive_both_after_release(uint64_t *bar) {
+  asm volatile(
+      "{\n\t.reg .b32 r0, r1;\n\t"
+      "fence.acq_rel.cluster;\n\t"
+      "mapa.shared::cluster.u32 r0, %0, 0;\n\t"
+      "mapa.shared::cluster.u32 r1, %0, 1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [r0];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [r1];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+// L2 eviction hints for the TMA loads of this kernel: a tile's input rows are dead for L2 once read (the backward
+// reads the stash from HBM much later), so they go first when the freshly written rows of the NEXT layer need room;
+// the weights are the only data every cluster keeps re-reading.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_3d_2sm_hint_p(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0,
+                                                       int c1, int c2, uint64_t policy, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5}], [%2], %7;\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(issue), "l"(policy)
+      : "memory");
+}
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kL2Threads, 1)
+k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_act,
+            const __grid_constant__ L2ChainArgs g) {
+  constexpr int S = P::S, H = 256;
+  constexpr int PT = TileOf<S>::PT, N = TileOf<S>::N, NHALF = N / 2;
+  constexpr int KB = H / 32;
+  constexpr int W_BYTES = 128 * 128, IN_BYTES = NHALF * 128;
+  constexpr int STAGE_BYTES = W_BYTES + ((IN_BYTES + 1023) / 1024) * 1024;
+  constexpr int NSTAGE = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
+  constexpr uint32_t IDESC = make_idesc_m256(N);
+  constexpr int G8 = PT / 8;
+  static_assert(NHALF % 8 == 0, "row halves must be whole swizzle atoms");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = (uint64_t *)(smem + NSTAGE * STAGE_BYTES);
+  uint64_t *empty = full + NSTAGE;
+  uint64_t *tmem_full = empty + NSTAGE;   // [2]
+  uint64_t *tmem_empty = tmem_full + 2;   // [2]
+  uint64_t *tile_done = tmem_empty + 2;   // [kL2MaxG]: tile j of the current group finished a layer (pair-wide)
+  uint32_t *tmem_slot = (uint32_t *)(tile_done + kL2MaxG);
+  float *jacc = reinterpret_cast<float *>(tmem_slot + 4);   // [2 items][G8][4 quarters][32] (fused output layer)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int G = g.G, L = g.L;
+  const int num_groups = (g.num_tiles + G - 1) / G;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 2 * kL2EpiWarps);
+    }
+    for (int j = 0; j < kL2MaxG; ++j) mbar_init(&tile_done[j], 2 * kL2EpiWarps);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs; whole warp, one elected lane issues) ----
+    const uint32_t issue = elect_one();
+    const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
+    uint32_t stage = 0, phase = 0;
+    uint32_t done_par = 0;   // bit j: parity of tile_done[j] the next wait looks for (one toggle per completed wait)
+    for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      for (int l = 1; l < L; ++l) {
+        for (int j = 0; j < G; ++j) {
+          const int tile = grp * G + j;
+          if (tile >= g.num_tiles) break;
+          if (l >= 2) {
+            // the rows this item reads were written by the pair's epilogue warps one layer ago
+            mbar_wait_acq_cluster(&tile_done[j], (done_par >> j) & 1u);
+            done_par ^= 1u << j;
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+          }
+          const int row0 = g.in_row[l] + tile * N + (int)rank * NHALF;
+          const int wrow = (l - 1) * H + (int)rank * 128;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t *sw = smem + stage * STAGE_BYTES;
+            mbar_expect_tx_p(&full[stage], 2 * (W_BYTES + IN_BYTES), rank == 0 ? issue : 0u);
+            const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
+            if (g.hints) {
+              tma_load_3d_2sm_hint_p(&map_w, leader_bar, sw, 0, wrow, kb, pol_w, issue);
+              tma_load_3d_2sm_hint_p(&map_act, leader_bar, sw + W_BYTES, 0, row0, kb, pol_a, issue);
+            } else {
+              tma_load_3d_2sm_p(&map_w, leader_bar, sw, 0, wrow, kb, issue);
+              tma_load_3d_2sm_p(&map_act, leader_bar, sw + W_BYTES, 0, row0, kb, issue);
+            }
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only; whole warp, one elected lane issues) ----
+    if (rank == 0) {
+      const uint32_t issue = elect_one();
+      uint32_t stage = 0, phase = 0, it = 0;
+      const uint64_t d_w = make_desc(smem_u32(smem), 16, 1024);
+      const uint64_t d_in = make_desc(smem_u32(smem) + W_BYTES, 16, 1024);
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+        for (int l = 1; l < L; ++l) {
+          for (int j = 0; j < G; ++j) {
+            if (grp * G + j >= g.num_tiles) break;
+            const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+            ++it;
+            mbar_wait(&tmem_empty[b], bphase ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_tf32_2sm_p(tmem_base + b * 256, d_w + so + ((ks * 32) >> 4), d_in + so + ((ks * 32) >> 4), IDESC,
+                                (kb | ks) != 0 ? 1u : 0u, issue);
+              umma_commit_2sm_p(&empty[stage], issue);
+              if (++stage == NSTAGE) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            umma_commit_2sm_p(&tmem_full[b], issue);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 units) --------
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    constexpr int MY_ITEMS = (G8 + kL2Subs - 1) / kL2Subs;
+    static_assert(G8 >= kL2Subs, "every epilogue warp needs a group of its own (it arrives once per item)");
+    constexpr int GSTRIDE = 8 * S * H;
+    const int o = (int)rank * 128 + q * 32 + lane;
+    constexpr bool kCanFuseOut = (8 * S == 32);
+    const float wout_o = (kCanFuseOut && g.wout != nullptr) ? __ldg(g.wout + o) : 0.0f;
+    uint32_t it = 0;
+    for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      for (int l = 1; l < L; ++l) {
+        const float bias = __ldg(g.bias[l] + o);
+        float *const outl = g.out[l];
+        float *const zoutl = g.zout[l];
+        const bool fuse_out = kCanFuseOut && (g.wout != nullptr) && (l == L - 1);
+        for (int j = 0; j < G; ++j) {
+          const int tile = grp * G + j;
+          if (tile >= g.num_tiles) break;
+          const uint32_t b = it & 1, bphase = (it >> 1) & 1;
+          const long long p0 = (long long)tile * PT;
+          const bool full_tile = (p0 + PT <= g.n);
+          float *obase = outl != nullptr ? outl + (p0 * S) * H + o : nullptr;
+          float *zbase = zoutl != nullptr ? zoutl + (p0 * S) * H + o : nullptr;
+          mbar_wait(&tmem_full[b], bphase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int k = 0; k < MY_ITEMS; ++k) {
+            const int g8 = sub + kL2Subs * k;
+            if (g8 >= G8) break;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * 256 + g8 * 8 * S;
+            float r[8 * S];
+            tmem_ld_cols<8 * S>(taddr, r);
+            tmem_ld_wait();
+            if (g8 + kL2Subs >= G8) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cta(&tmem_empty[b], 0);
+            }
+            const int valid = full_tile ? 8 : (int)((g.n - p0 - g8 * 8) < 8 ? (g.n - p0 - g8 * 8) : 8);
+            float t[kCanFuseOut ? 32 : 1];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              if (full_tile || pp < valid) {
+                float z[S], w[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
+                z[0] += bias;
+                if (zbase != nullptr) {
+                  float *zp = zbase + g8 * GSTRIDE;
+#pragma unroll
+                  for (int s = 0; s < S; ++s) zp[(pp * S + s) * H] = z[s];
+                }
+                jet_forward_A<P>(g.act, z, w);
+#pragma unroll
+                for (int s = 1; s < S; ++s) w[s] = to_tf32(w[s]);
+                if (obase != nullptr) {
+                  float *op = obase + g8 * GSTRIDE;
+#pragma unroll
+                  for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = w[s];
+                }
+                if (kCanFuseOut && fuse_out) {
+#pragma unroll
+                  for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = wout_o * w[s];
+                }
+              } else if (kCanFuseOut && fuse_out) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = 0.0f;
+              }
+            }
+            if (kCanFuseOut && fuse_out) {
+#pragma unroll
+              for (int step = 16; step >= 1; step >>= 1) {
+                const bool up = (lane & step) != 0;
+#pragma unroll
+                for (int i = 0; i < step; ++i) {
+                  const float send = up ? t[i] : t[i + step];
+                  const float keep = up ? t[i + step] : t[i];
+                  t[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                }
+              }
+              jacc[(((it & 1) * G8 + g8) * 4 + q) * 32 + lane] = t[0];
+            }
+          }
+          if (l < L - 1) {
+            // release the tile to the pair's TMA producers: the warp's rows are written (generic proxy, ordered before
+            // lane 0 by the warp barrier); lane 0 fences towards the async proxy and release-arrives, once per warp, on
+            // the barrier of BOTH CTAs.  (A per-lane `fence.proxy.async` over all state spaces here cost 13 % of the
+            // kernel's stall samples: MEMBAR + CCTL.IVALL + ERRBAR + FENCE.VIEW.ASYNC in every thread.)  The producer
+            // fences once more on its side after the acquire.
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+              mbar_arrive_both_after_release(&tile_done[j]);
+            }
+          }
+          if (kCanFuseOut && fuse_out) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kL2EpiWarps) : "memory");
+            const int e = (sub * 4 + q) * 32 + lane;
+            if (e < G8 * 32) {
+              const int g8 = e >> 5, v = e & 31;
+              const float *ja = jacc + (((it & 1) * G8 + g8) * 4) * 32 + v;
+              const float sum = (ja[0] + ja[32]) + (ja[64] + ja[96]);
+              const long long p = p0 + g8 * 8 + v / S;
+              if (p < g.n) g.jets_part[((long long)rank * S + (v % S)) * g.ldn + p] = sum;
+            }
+          }
+          ++it;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// AX_TC_L2CHAIN=0: layer-by-layer forward launches (k_tc_gemm2) instead of the L2-chained kernel; AX_TC_L2CHAIN_G:
+// tiles per group (default 3)
+static int g_l2chain = -1, g_l2chain_G = 0, g_l2chain_hints = -1;
+static bool l2chain_on() {
+  if (g_l2chain < 0) {
+    const char *e = getenv("AX_TC_L2CHAIN");
+    g_l2chain = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_l2chain != 0;
+}
+static int l2chain_group() {
+  if (!g_l2chain_G) {
+    const char *e = getenv("AX_TC_L2CHAIN_G");
+    g_l2chain_G = e ? atoi(e) : 2;
+    if (g_l2chain_G < 1) g_l2chain_G = 1;
+    if (g_l2chain_G > kL2MaxG) g_l2chain_G = kL2MaxG;
+  }
+  return g_l2chain_G;
+}
+static int l2chain_hints() {
+  if (g_l2chain_hints < 0) {
+    const char *e = getenv("AX_TC_L2CHAIN_HINTS");
+    g_l2chain_hints = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_l2chain_hints;
+}
+// run-time switches of the tensor-core forward (tests compare the chained kernel with the layer-by-layer one bit for bit)
+int tc_set_option(const char *name, int value) {
+  const std::string n(name ? name : "");
+  if (n == "l2chain") g_l2chain = value != 0;
+  else if (n == "l2chain_group") g_l2chain_G = value < 1 ? 1 : (value > kL2MaxG ? kL2MaxG : value);
+  else if (n == "l2chain_hints") g_l2chain_hints = value != 0;
+  else {
+    set_error("unknown tensor-core option '%s' (l2chain, l2chain_group, l2chain_hints)", n.c_str());
+    return 1;
+  }
+  return 0;
+}
+
 static bool pattern_in_tc(int id) { return id == 0 || id == 2 || id == 3 || id == 4 || id == 5 || id == 6 || id == 13; }
 
 bool tc_supported(const NetGeom &g, const ax_net_desc *net, const ax_jet_desc *jet, int engine) {
@@ -551,7 +929,65 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
                                                                 H, 0);
       AX_LAUNCH_OK();
     }
-    if (H == 256 && g_use_pair && g_use_chain && d_in <= 4 && act != AX_ACT_SIN) {
+    if (H == 256 && g_use_pair && l2chain_on() && g.L >= 3 && !(g_use_chain && d_in <= 4 && act != AX_ACT_SIN)) {
+      // layer 0 as its own launch, then every hidden GEMM layer in ONE launch chained through L2 (k_tc_fwd_l2)
+      {
+        KernelTimer t("tc_first_layer", a.stream, 2.0 * d_in * H * (double)a.n, 4.0 * S * H * (double)a.n);
+        const int ppb = 256;
+        k_tc_first<P><<<(unsigned)((a.n + ppb - 1) / ppb), 256, 0, a.stream>>>(prm + g.w_off[0], prm + g.b_off[0], a.x,
+                                                                              d_in, dirs, H, a.n, a.ldn, slot(0), zslot(0), act, ppb);
+      }
+      AX_LAUNCH_OK();
+      const bool fuse_out = g_use_fuse_out && C == 1 && 8 * S == 32;
+      L2ChainArgs la{};
+      const long long slot_rows = (long long)a.ldn * S;
+      for (int l = 1; l < g.L; ++l) {
+        la.bias[l] = prm + g.b_off[l];
+        la.out[l] = slot(l);
+        la.zout[l] = zslot(l);
+        la.in_row[l] = (int)((a.keep_all ? (l - 1) : ((l - 1) & 1)) * slot_rows);
+      }
+      if (fuse_out && !a.keep_all) la.out[g.L - 1] = nullptr;
+      la.L = g.L;
+      la.G = l2chain_group();
+      la.hints = l2chain_hints();
+      la.n = a.n;
+      la.num_tiles = (int)((a.n + PT - 1) / PT);
+      la.act = act;
+      la.ldn = a.ldn;
+      if (fuse_out) {
+        la.wout = prm + g.w_off[g.L];
+        la.jets_part = jets_part;
+      }
+      constexpr int N_ = TileOf<S>::N, NHALF_ = N_ / 2;
+      constexpr int STAGE_BYTES_ = 128 * 128 + ((NHALF_ * 128 + 1023) / 1024) * 1024;
+      constexpr int NSTAGE_ = (196 * 1024 / STAGE_BYTES_) > 8 ? 8 : (196 * 1024 / STAGE_BYTES_);
+      const size_t smem = (size_t)NSTAGE_ * STAGE_BYTES_ + 1024 + 512 + 2 * 8 * 4 * 32 * sizeof(float);
+      CUtensorMap mw, ma;
+      if (make_map(&mw, wr, (long long)(g.L - 1) * H, H, 128, 1)) return 1;
+      if (make_map(&ma, stash, (long long)slots * slot_rows, H, NHALF_, 1)) return 1;
+      static bool attr = false;
+      if (!attr) {
+        AX_CUDA_OK(cudaFuncSetAttribute(k_tc_fwd_l2<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+      }
+      int clusters = sm_count() / 2;
+      const int groups = (la.num_tiles + la.G - 1) / la.G;
+      if (groups < clusters) clusters = groups;
+      {
+        KernelTimer t("tc_fwd_l2chain", a.stream, 2.0 * S * H * (double)H * (double)a.n * (g.L - 1),
+                      4.0 * S * H * (double)a.n * (a.keep_all ? g.L : 1.0));
+        k_tc_fwd_l2<P><<<2 * clusters, kL2Threads, smem, a.stream>>>(mw, ma, la);
+      }
+      AX_LAUNCH_OK();
+      if (fuse_out) {
+        const long long cnt = (long long)S * a.ldn;
+        k_tc_jets_combine<<<(unsigned)((cnt + 255) / 256), 256, 0, a.stream>>>(jets_part, prm + g.b_off[g.L], S, a.n, a.ldn,
+                                                                             jets);
+        AX_LAUNCH_OK();
+        continue;
+      }
+    } else if (H == 256 && g_use_pair && g_use_chain && d_in <= 4 && act != AX_ACT_SIN) {
       // whole hidden stack in one launch: activations stay in the SM pair, only the stash goes to HBM
       using G = ChainGeom<S>;
       ChainArgs ca{};

@@ -279,6 +279,10 @@ int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, co
 int ax_residual_eval(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
                      float *out, void *stream);
 
+/* run-time switches of the tcgen05 engine, e.g. ("l2chain", 0) = one launch per hidden layer instead of the L2-chained
+ * forward kernel; results are bit-identical either way.  Returns non-zero for an unknown name. */
+int ax_tc_set_option(const char *name, int32_t value);
+
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
 int ax_gather_points(const float *x_soa, int32_t d, int64_t ldn, const int64_t *idx, int64_t m,
                      float *x_out, int64_t ldn_out, void *stream);

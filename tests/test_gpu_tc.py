@@ -256,6 +256,48 @@ def test_reference_default_helmholtz_sin_net_on_the_tensor_cores():
     assert f["loss_rel"] < 1e-5 and f["grad_rel"] < 1e-5 and f["res_rel"] < 1e-5, f
 
 
+@pytest.mark.parametrize("widths,act,spec,n,keep", [
+    ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((15, 15),)), 200003, True),      # cfg4 as trained: 5 chained layers
+    ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((15, 15),)), 200003, False),     # residual probe: ping-pong slots
+    ([2, 256, 256, 256, 1], "sin", ((0, 1), ((15, 15),)), 70001, True),             # second stash written on the way
+    ([3, 256, 256, 256, 256, 2], "sigmoid", ((0, 1), ((0, 0), (1, 1))), 30011, True),   # S = 5: 48-point tiles, no fused output
+    ([2, 256, 256, 256, 1], "tanh", ((), ()), 9999, True),                          # S = 1: 256-point tiles
+    ([2, 256, 256, 256, 256, 1], "tanh", ((0, 1), ((15, 15),)), 100, True),         # fewer tiles than clusters
+])
+def test_l2_chained_forward_is_bit_identical_to_the_layer_launches(widths, act, spec, n, keep):
+    """csrc/tc_fwd.cu k_tc_fwd_l2: all hidden GEMM layers in one launch, a tile's streams handed from layer to layer
+    through L2 (epilogue -> release-arrive -> TMA producer).  Same MMAs, same epilogue arithmetic: jets AND every
+    stash layer must equal the one-launch-per-layer path bit for bit, for every group size, five times in a row (a
+    lost hand-off would read rows that are not written yet)."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    js = JetSpec(*spec)
+    net = _lib.make_net_desc(widths, act)
+    params = _glorot_params(widths, gen).to(dev)
+    xs = to_soa((torch.rand((n, widths[0]), generator=gen) * 2 - 1).to(dev))
+    try:
+        _lib.tc_set_option("l2chain", 0)
+        jets0, stash0 = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=keep, engine="tf32")
+        H, S, ldn = widths[1], js.S, xs.shape[1]
+        rows = n * S * H                                  # written part of a stash layer: [(p, s)][unit], p < n
+        layer = ldn * S * H
+        L = len(widths) - 2
+        n_layers = L * (2 if act == "sin" else 1) if keep else 0
+        s0 = stash0.view(torch.float32)
+        for G in (1, 2, 3, 5, 8):
+            _lib.tc_set_option("l2chain", 1)
+            _lib.tc_set_option("l2chain_group", G)
+            for rep in range(5 if G == 2 else 2):
+                jets1, stash1 = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=keep, engine="tf32")
+                assert torch.equal(jets1[..., :n], jets0[..., :n]), (G, rep)
+                s1 = stash1.view(torch.float32)
+                for l in range(n_layers):
+                    assert torch.equal(s1[l * layer : l * layer + rows], s0[l * layer : l * layer + rows]), (G, rep, l)
+    finally:
+        _lib.tc_set_option("l2chain", 1)
+        _lib.tc_set_option("l2chain_group", 2)
+
+
 def test_cfg4_full_size_properties():
     """BASELINE cfg4 at its full size (2^20 + 80 rows, 2-[256]x6-1 tanh, Laplacian stream pattern) through
     size-independent properties: (i) every point's jets do not depend on which tile / launch it rode in
