@@ -45,7 +45,7 @@ class ResidualProgram(C.Structure):
         ("code", _P), ("segments", _P), ("consts", _P), ("aux", _P), ("aux_meta", _P), ("scalars", _P),
         ("term_scale", _P),
         ("n_instr", C.c_int32), ("n_seg", C.c_int32), ("n_reg", C.c_int32), ("n_terms", C.c_int32),
-        ("n_streams", C.c_int32), ("n_const", C.c_int32),
+        ("n_streams", C.c_int32), ("n_const", C.c_int32), ("n_scalars", C.c_int32),
     ]
 
 
@@ -120,7 +120,8 @@ _SIGNATURES = {
     ),
     "ax_residual_ws_bytes": (C.c_size_t, [C.POINTER(ResidualProgram), C.c_int64]),
     "ax_residual_forward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
-    "ax_residual_backward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "ax_residual_backward": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P,
+                                       C.c_size_t, _P]),
     "ax_residual_eval": (C.c_int, [C.POINTER(ResidualProgram), _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "ax_tc_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "ax_debug_tc_wgrad": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
@@ -317,7 +318,7 @@ class ResidualTables:
         self.consts = torch.as_tensor(program.consts, dtype=torch.float32, device=device)
         self.term_scale = torch.as_tensor(program.scale if len(program.scale) else [0.0], dtype=torch.float32, device=device)
         self.aux = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t, _ in program.aux]
-        self.scalars = [t.detach() for t in program.scalars]
+        self.scalars = list(program.scalars)       # read through their storage at every step (never copied)
         for t in self.scalars:
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise NativeLibraryError("residual program scalars must be float32 CUDA tensors")
@@ -328,7 +329,8 @@ class ResidualTables:
         self.struct = ResidualProgram(
             _ptr(self.code), _ptr(self.segments), _ptr(self.consts), _ptr(self.aux_ptr), _ptr(self.aux_meta),
             _ptr(self.scalar_ptr), _ptr(self.term_scale), off, len(segs), program.n_reg, program.n_terms,
-            self.n_streams, int(self.consts.numel()))
+            self.n_streams, int(self.consts.numel()), len(self.scalars))
+        self.n_scalars, self.scalar_grad = len(self.scalars), list(program.scalar_grad)
 
 
 def residual_forward(tables, x_soa, jets, n):
@@ -357,16 +359,23 @@ def residual_eval(tables, x_soa, jets, n, n_cols):
 
 
 def residual_backward(tables, x_soa, jets, n, term_grads):
-    """jets_bar [1, S, C, ldn] = sum_t term_grads[t] * d losses[t] / d jets"""
+    """(jets_bar [1, S, C, ldn] = sum_t term_grads[t] * d losses[t] / d jets, gradients w.r.t. the program's run-time
+    scalars [n_scalars] or None when none of them is trainable)"""
     lib = load()
     term_grads = term_grads.to(torch.float32).contiguous()
     _need_cuda(x_soa, jets, term_grads)
     ldn = x_soa.shape[1]
     jets_bar = torch.empty_like(jets)
+    sgrad = ws = None
+    wsb = 0
+    if tables.scalar_grad:
+        sgrad = torch.empty(tables.n_scalars, dtype=torch.float32, device=x_soa.device)
+        wsb = lib.ax_residual_ws_bytes(C.byref(tables.struct), int(ldn))
+        ws = _bytes_buf(wsb, x_soa.device)
     rc = lib.ax_residual_backward(C.byref(tables.struct), _ptr(x_soa), _ptr(jets), int(n), int(ldn),
-                                  _ptr(term_grads), _ptr(jets_bar), _stream())
+                                  _ptr(term_grads), _ptr(jets_bar), _ptr(sgrad), _ptr(ws), int(wsb), _stream())
     _check(rc, "ax_residual_backward")
-    return jets_bar
+    return jets_bar, sgrad
 
 
 def tc_set_option(name, value):

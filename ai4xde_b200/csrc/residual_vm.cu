@@ -24,7 +24,7 @@ struct ResView {
   const int2 *aux_meta;       // first row, ncol
   const float *const *scalars;
   const float *term_scale;
-  int n_instr, n_seg, n_reg, n_terms, n_streams, n_const;
+  int n_instr, n_seg, n_reg, n_terms, n_streams, n_const, n_scalars;
 };
 
 __device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.0f) - (v < 0.0f)); }
@@ -123,7 +123,7 @@ k_residual_reduce(const float *__restrict__ partial, int nblocks, int n_terms, c
     __syncthreads();
     if (threadIdx.x < stride) red[threadIdx.x] += red[threadIdx.x + stride];
   }
-  if (threadIdx.x == 0) losses[t] = red[0] * scale[t];
+  if (threadIdx.x == 0) losses[t] = scale ? red[0] * scale[t] : red[0];
 }
 
 // operator evaluation (model.predict(x, operator=pde): the residual probe of RAD / RAR_D / R3): out[column][p]
@@ -153,7 +153,7 @@ k_residual_eval(ResView pv, const float *__restrict__ x, const float *__restrict
 
 __global__ void __launch_bounds__(128)
 k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict__ jets, long long n, long long ldn,
-               const float *__restrict__ term_grads, float *__restrict__ jets_bar) {
+               const float *__restrict__ term_grads, float *__restrict__ jets_bar, float *__restrict__ spartial) {
   extern __shared__ __align__(16) unsigned char res_smem[];
   const int T = blockDim.x, tid = threadIdx.x;
   int4 *code = reinterpret_cast<int4 *>(res_smem);
@@ -163,10 +163,14 @@ k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict_
   float *regs = tg + pv.n_terms;
   float *adj = regs + (size_t)pv.n_reg * T;
   float *jb = adj + (size_t)pv.n_reg * T;
+  float *sacc = jb + (size_t)pv.n_streams * T;     // [n_scalars][T]: d loss / d scalar, this thread's share
+  const bool want_scalars = spartial != nullptr;
   for (int i = tid; i < pv.n_instr; i += T) code[i] = pv.code[i];
   for (int i = tid; i < pv.n_seg; i += T) seg[i] = pv.seg[i];
   for (int i = tid; i < pv.n_const; i += T) consts[i] = pv.consts[i];
   for (int i = tid; i < pv.n_terms; i += T) tg[i] = term_grads[i] * pv.term_scale[i];
+  if (want_scalars)
+    for (int k = 0; k < pv.n_scalars; ++k) sacc[k * T + tid] = 0.0f;
   __syncthreads();
   float *R = regs + tid, *A = adj + tid, *J = jb + tid;
   for (long long base = (long long)blockIdx.x * T; base < ldn; base += (long long)gridDim.x * T) {
@@ -189,6 +193,7 @@ k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict_
           if (d == 0.0f) continue;          // nothing flows through this value (also keeps 0 * inf out)
           switch (in.x) {
             case R_LOADJ: J[in.z * T] += d; break;
+            case R_LOADS: if (want_scalars) sacc[in.z * T + tid] += d; break;
             case R_ADD: A[in.z * T] += d; A[in.w * T] += d; break;
             case R_SUB: A[in.z * T] += d; A[in.w * T] -= d; break;
             case R_MUL: {
@@ -219,6 +224,16 @@ k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict_
     }
     for (int i = 0; i < pv.n_streams; ++i) jets_bar[(long long)i * ldn + p] = J[i * T];
   }
+  if (want_scalars) {
+    // trainable scalars: fixed-order tree over the block, per-block partials (summed by k_residual_reduce)
+    for (int stride = T >> 1; stride >= 1; stride >>= 1) {
+      __syncthreads();
+      if (tid < stride)
+        for (int k = 0; k < pv.n_scalars; ++k) sacc[k * T + tid] += sacc[k * T + tid + stride];
+    }
+    if (tid == 0)
+      for (int k = 0; k < pv.n_scalars; ++k) spartial[(long long)blockIdx.x * pv.n_scalars + k] = sacc[k * T];
+  }
 }
 
 static int res_blocks(long long rows, int threads) {
@@ -237,7 +252,7 @@ static int res_check(const ax_residual_program *pg) {
   }
   if (pg->n_instr < 1 || pg->n_instr > 4096 || pg->n_seg < 1 || pg->n_seg > 256 || pg->n_reg < 1 || pg->n_reg > 380 ||
       pg->n_terms < 0 || pg->n_terms > 64 || pg->n_streams < 1 || pg->n_streams > 64 || pg->n_const < 1 ||
-      pg->n_const > 1024) {
+      pg->n_const > 1024 || pg->n_scalars < 0 || pg->n_scalars > 64) {
     set_error("residual program: sizes out of range (instr %d, seg %d, reg %d, terms %d, streams %d, consts %d)",
               pg->n_instr, pg->n_seg, pg->n_reg, pg->n_terms, pg->n_streams, pg->n_const);
     return 1;
@@ -260,6 +275,7 @@ static ResView res_view(const ax_residual_program *pg) {
   v.n_terms = pg->n_terms;
   v.n_streams = pg->n_streams;
   v.n_const = pg->n_const;
+  v.n_scalars = pg->n_scalars;
   return v;
 }
 
@@ -267,7 +283,7 @@ static ResView res_view(const ax_residual_program *pg) {
 static int res_threads(const ax_residual_program *pg, bool bwd, size_t *smem) {
   const size_t fixed = (size_t)(pg->n_instr + pg->n_seg) * 16 + (size_t)(pg->n_const + pg->n_terms) * 4;
   for (int t = 128; t >= 32; t >>= 1) {
-    const size_t per = bwd ? (size_t)(2 * pg->n_reg + pg->n_streams) : (size_t)(pg->n_reg + pg->n_terms);
+    const size_t per = bwd ? (size_t)(2 * pg->n_reg + pg->n_streams + pg->n_scalars) : (size_t)(pg->n_reg + pg->n_terms);
     const size_t need = fixed + per * t * 4;
     if (need <= 200 * 1024) {
       *smem = need;
@@ -285,7 +301,8 @@ extern "C" {
 
 size_t ax_residual_ws_bytes(const ax_residual_program *prog, int64_t n) {
   if (res_check(prog)) return 0;
-  return (size_t)res_blocks(n, 32) * prog->n_terms * sizeof(float);
+  const int most = prog->n_terms > prog->n_scalars ? prog->n_terms : prog->n_scalars;
+  return (size_t)res_blocks(n + 32, 32) * (most > 0 ? most : 1) * sizeof(float);
 }
 
 int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
@@ -354,7 +371,8 @@ int ax_residual_eval(const ax_residual_program *prog, const float *x_soa, const 
 }
 
 int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
-                         const float *term_grads, float *jets_bar, void *stream) {
+                         const float *term_grads, float *jets_bar, float *scalar_grads, void *ws, size_t ws_bytes,
+                         void *stream) {
   if (res_check(prog)) return 1;
   if (prog->n_terms < 1) {
     set_error("residual backward: the program has no loss terms");
@@ -378,8 +396,18 @@ int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, co
   cudaStream_t st = (cudaStream_t)stream;
   {
     KernelTimer t("residual_bwd", st, 0.0, (8.0 + 8.0 * prog->n_streams) * (double)n);
-    k_residual_bwd<<<res_blocks(ldn, threads), threads, smem, st>>>(res_view(prog), x_soa, jets, n, ldn, term_grads,
-                                                                  jets_bar);
+    const int blocks = res_blocks(ldn, threads);
+    const bool want = scalar_grads != nullptr && prog->n_scalars > 0;
+    if (want && (!ws || ws_bytes < (size_t)blocks * prog->n_scalars * sizeof(float))) {
+      set_error("residual backward: workspace too small for the scalar gradients");
+      return 1;
+    }
+    k_residual_bwd<<<blocks, threads, smem, st>>>(res_view(prog), x_soa, jets, n, ldn, term_grads, jets_bar,
+                                                  want ? (float *)ws : nullptr);
+    if (want) {
+      AX_LAUNCH_OK();
+      k_residual_reduce<<<prog->n_scalars, 256, 0, st>>>((const float *)ws, blocks, prog->n_scalars, nullptr, scalar_grads);
+    }
   }
   AX_LAUNCH_OK();
   return 0;

@@ -35,8 +35,12 @@ def reshape(t, shape):
 
 
 def Variable(initial_value, dtype=None):
-    return _torch.tensor(initial_value, dtype=dtype or config.real(_torch), device=config.device(),
-                         requires_grad=True)
+    """A trainable scalar of an inverse problem (cases/InverseCases.py:61-63): an ordinary leaf tensor for autograd and
+    the optimiser, and recognised by the residual-program tracer (ai4xde_b200/residual.py:VariableTensor)."""
+    from ..residual import VariableTensor
+
+    data = _torch.tensor(initial_value, dtype=dtype or config.real(_torch), device=config.device())
+    return VariableTensor.make(data)
 
 
 def as_tensor(data, dtype=None):

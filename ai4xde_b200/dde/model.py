@@ -233,7 +233,7 @@ class Model:
         from .nn import FNN, _FusedLosses
 
         if not config.residual_programs() or type(net) is not FNN or net._input_transform is not None \
-                or net.regularizer is not None or self.external_trainable_variables or net.auxiliary_vars is not None:
+                or net.regularizer is not None or net.auxiliary_vars is not None:
             return None
         owners = (self.data, self.data.pde, losses_fn.__func__ if hasattr(losses_fn, "__func__") else losses_fn,
                   net._output_transform, loss_fn if not isinstance(loss_fn, (list, tuple)) else tuple(loss_fn)) \
@@ -254,17 +254,25 @@ class Model:
                                   output_transform=net._output_transform)
             tables = _lib.ResidualTables(prog, batch.aos.device)
             note = prog.describe()
-        except residual.Unsupported as e:
-            note = f"autograd path: {e}"
+            # the trainable scalars the program reads must be exactly variables this model optimises
+            tables.variables = [prog.scalars[k] for k in prog.scalar_grad]
+            for v in tables.variables:
+                if not any(v is w for w in self.external_trainable_variables):
+                    raise residual.Unsupported("a dde.Variable that is not in external_trainable_variables")
+            if tables.variables:
+                note += f", {len(tables.variables)} trainable variables"
+        except (residual.Unsupported, _lib.NativeLibraryError) as e:
+            tables, note = None, f"autograd path: {e}"
         finally:
             grad.clear()
         if tables is not None:
-            # adoption check on the live batch: same losses, same parameter gradient as the autograd path
-            params = [p for p in net._param_list() if p.requires_grad]
+            # adoption check on the live batch: same losses, same parameter (and variable) gradient as the autograd path
+            params = [p for p in net._param_list() if p.requires_grad] + list(tables.variables)
             with torch.enable_grad():
                 ref = autograd_losses()
                 g_ref = torch.autograd.grad(ref.sum(), params, allow_unused=True)
-                got = _FusedLosses.apply(net, tables, batch.soa, n_rows, spec, config.engine(), True, *net._param_list())
+                got = _FusedLosses.apply(net, tables, batch.soa, n_rows, spec, config.engine(), True,
+                                         len(net._param_list()), *net._param_list(), *tables.variables)
                 g_got = torch.autograd.grad(got.sum(), params, allow_unused=True)
             scale = float(ref.detach().abs().max().clamp_min(1e-30))
             bad = float((got.detach() - ref.detach()).abs().max()) > 1e-4 * scale or got.shape != ref.shape
@@ -473,7 +481,7 @@ class Model:
                 need_bwd = any(p.requires_grad for p in params)
                 outputs_ = None
                 losses = _FusedLosses.apply(self.net, tables, batch.soa, int(batch.aos.shape[0]), spec, config.engine(),
-                                            need_bwd, *params)
+                                            need_bwd, len(params), *params, *tables.variables)
             else:
                 x = batch.aos.detach().requires_grad_()
                 with self.net.jet_scope(spec, batch.soa, param_grad=param_grad):

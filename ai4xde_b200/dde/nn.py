@@ -99,11 +99,14 @@ class _FusedLosses(torch.autograd.Function):
     `tables`: _lib.ResidualTables of the traced loss code (ai4xde_b200/residual.py)."""
 
     @staticmethod
-    def forward(ctx, net, tables, x_soa, n, spec, engine, need_backward, *params):
+    def forward(ctx, net, tables, x_soa, n, spec, engine, need_backward, n_params, *tensors):
+        """tensors = the net's parameters, then the trainable variables the program reads (inverse problems)"""
+        params, variables = tensors[:n_params], tensors[n_params:]
         jets, stash, desc, pad, flat = _launch_forward(net, x_soa, n, spec, engine, need_backward)
         ctx.spec, ctx.engine, ctx.n, ctx.desc, ctx.pad = spec, engine, n, desc, pad
         ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = x_soa, stash, bool(need_backward), flat
         ctx.shapes = [p.shape for p in params]
+        ctx.var_shapes = [v.shape for v in variables]
         ctx.tables, ctx.jets = tables, (jets if need_backward else None)
         return _lib.residual_forward(tables, x_soa, jets, n)
 
@@ -112,9 +115,10 @@ class _FusedLosses(torch.autograd.Function):
     def backward(ctx, g_losses):
         if not ctx.kept:
             raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
-        jets_bar = _lib.residual_backward(ctx.tables, ctx.x_soa, ctx.jets, ctx.n, g_losses)
+        jets_bar, sgrad = _lib.residual_backward(ctx.tables, ctx.x_soa, ctx.jets, ctx.n, g_losses)
         ctx.jets = None
-        return (None, None, None, None, None, None, None) + _launch_backward(ctx, jets_bar)
+        var_grads = tuple(sgrad[k].reshape(shp) for k, shp in zip(ctx.tables.scalar_grad, ctx.var_shapes))
+        return (None, None, None, None, None, None, None, None) + _launch_backward(ctx, jets_bar) + var_grads
 
 
 class _TensorCorePad:

@@ -60,6 +60,7 @@ class Graph:
         self._diff = {}
         self.aux = []       # (tensor [rows, ncol] on the device, first row)
         self.scalars = []   # one-element device tensors read at run time (their value may change between steps)
+        self.scalar_grad = set()   # indices of scalars that are trainable variables: the reverse pass returns d/d(scalar)
 
     def _mk(self, op, args):
         key = (op,) + tuple(a.uid if isinstance(a, Node) else a for a in args)
@@ -224,6 +225,51 @@ class Graph:
         raise Unsupported(f"derivative of {op}")
 
 
+# ---- trainable scalars (dde.Variable of inverse problems) ----------------------------------------------------------
+_TRACE = {}       # "graph": the Graph being built while a trace runs
+
+
+class VariableTensor(torch.Tensor):
+    """What `dde.Variable(v)` returns: an ordinary trainable leaf tensor everywhere -- except while a residual
+    program is being traced, when any torch operation on it (`-self.v_e / self.e`, `1e-3 * self.D`, `torch.exp(C)`,
+    cases/InverseCases.py:314,505) is recorded as an expression of a run-time scalar instead of being evaluated:
+    the program reads the variable's CURRENT value from its storage at every step and returns its gradient."""
+
+    @staticmethod
+    def make(data):
+        return torch.Tensor._make_subclass(VariableTensor, data, True)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        g = _TRACE.get("graph")
+        if g is None:
+            return super().__torch_function__(func, types, args, kwargs or {})
+        name = _name_of(func)
+        if name in ("__get__", "__set__", "data_ptr", "numel", "dim", "size", "is_floating_point", "__repr__",
+                    "__len__", "__hash__", "__reduce_ex__", "__deepcopy__"):
+            return super().__torch_function__(func, types, args, kwargs or {})      # attribute reads are not algebra
+        return Sym.__torch_function__(func, types, args, kwargs)
+
+
+def _scalar_sym(g, var):
+    """scalar Sym over the storage of a dde.Variable (registered once per trace, by identity)"""
+    if g is None:
+        raise Unsupported("a dde.Variable used outside a trace")
+    with torch._C.DisableTorchFunctionSubclass():
+        if var.numel() != 1:
+            raise Unsupported("a trainable variable with more than one element")
+        if not var.is_leaf:
+            raise Unsupported("a derived tensor of a variable computed before the trace")
+    for k, t in enumerate(g.scalars):
+        if t is var:
+            break
+    else:
+        g.scalars.append(var)
+        k = len(g.scalars) - 1
+    g.scalar_grad.add(k)
+    return Sym(g, [g.scalar(k)], None)
+
+
 # ---- symbolic tensors ---------------------------------------------------------------------------------------------
 class Term:
     """One loss term: scale * sum over the rows of `win` of `expr` (what torch.mean / torch.sum of a Sym returns)."""
@@ -256,8 +302,14 @@ class Sym:
     dtype = torch.float32
     is_input = False
 
+    scalar = False      # True: one value for every point (an expression of trainable variables); no row range
+
     def __init__(self, graph, cols, win, vec=False):
-        self.g, self.cols, self.win, self.vec = graph, list(cols), (int(win[0]), int(win[1])), vec
+        self.g, self.cols, self.vec = graph, list(cols), vec
+        if win is None:
+            self.win, self.scalar = (0, 1), True
+        else:
+            self.win = (int(win[0]), int(win[1]))
 
     # -- tensor-like surface --------------------------------------------------------------------------------------
     @property
@@ -283,9 +335,11 @@ class Sym:
         return int(np.prod(self.shape))
 
     def _like(self, cols, vec=None):
-        return Sym(self.g, cols, self.win, self.vec if vec is None else vec)
+        return Sym(self.g, cols, None if self.scalar else self.win, self.vec if vec is None else vec)
 
     def __getitem__(self, idx):
+        if self.scalar:
+            raise Unsupported("indexing a variable expression")
         rows, colspec = (idx if isinstance(idx, tuple) else (idx, slice(None)))
         if isinstance(idx, tuple) and len(idx) != 2:
             raise Unsupported("index with more than two axes")
@@ -312,9 +366,15 @@ class Sym:
     def _operand(self, o):
         """-> list of column expressions broadcast against self (len 1 or len(self.cols))"""
         g = self.g
+        if isinstance(o, VariableTensor):
+            o = _scalar_sym(g, o)
         if isinstance(o, Sym):
             if o.g is not g:
                 raise Unsupported("operands of two traces")
+            if o.scalar:
+                return o.cols          # a variable expression: the same value at every point
+            if self.scalar:
+                raise Unsupported("internal: scalar operand order")
             if o.win != self.win:
                 raise Unsupported(f"operands cover different rows {o.win} / {self.win}")
             if o.vec != self.vec:
@@ -330,7 +390,9 @@ class Sym:
             o = torch.as_tensor(o)
         if torch.is_tensor(o):
             if o.requires_grad:
-                raise Unsupported("a trainable tensor inside the residual (inverse problems stay on autograd)")
+                raise Unsupported("a trainable tensor that is not a dde.Variable inside the residual")
+            if self.scalar:
+                raise Unsupported("a variable expression combined with an array outside the point-wise algebra")
             if o.numel() == 1:
                 if not (o.is_cuda and o.dtype == torch.float32):
                     return [g.const(float(o))]       # a host number: frozen like any Python constant
@@ -350,6 +412,8 @@ class Sym:
         raise Unsupported(f"operand of type {type(o).__name__}")
 
     def _binary(self, o, fn, swap=False):
+        if self.scalar and isinstance(o, Sym) and not o.scalar:
+            return o._binary(self, fn, swap=not swap)      # the point-wise operand decides rows and columns
         oc = self._operand(o)
         mine = self.cols
         n = max(len(mine), len(oc))
@@ -448,6 +512,8 @@ class Sym:
         return Sym(self.g, [tot], self.win, not keepdim)
 
     def _reduce(self, scale):
+        if self.scalar:
+            raise Unsupported("a loss term made of variables only")
         if len(self) == 0:
             raise Unsupported("reduction over an empty slice")
         tot = self.cols[0]
@@ -462,6 +528,9 @@ class Sym:
         name = _name_of(func).strip("_")
         if name.startswith("r") and name[1:] in ("add", "sub", "mul", "truediv", "div", "pow"):
             name = name[1:]            # Tensor.__rsub__(t, sym) arrives with its operands already in order
+        if any(isinstance(a, VariableTensor) for a in args):
+            g0 = next((a.g for a in args if isinstance(a, Sym)), None) or _TRACE.get("graph")
+            args = tuple(_scalar_sym(g0, a) if isinstance(a, VariableTensor) else a for a in args)
         first = next((a for a in args if isinstance(a, Sym)), None)
         if first is None:
             for a in args:
@@ -590,6 +659,7 @@ class Program:
         self.S, self.C, self.d_in = spec.S, graph.n_out, graph.n_in
         self.scale = np.array([t.scale for t in terms], dtype=np.float64)   # uploaded as float32
         self.aux, self.scalars = graph.aux, graph.scalars
+        self.scalar_grad = sorted(graph.scalar_grad)     # scalars whose gradient the reverse pass accumulates
         consts, cindex = [], {}
         by_win = {}
         for t, term in enumerate(terms):
@@ -671,16 +741,19 @@ def trace(losses_fn, spec, n_rows, n_in, n_out, output_transform=None):
     x = Sym(g, [g.x(d) for d in range(n_in)], (0, n_rows))
     x.is_input = True
     y = Sym(g, [g.net(c) for c in range(n_out)], (0, n_rows))
-    if output_transform is not None:
-        y = output_transform(x, y)
-        if not isinstance(y, Sym) or y.vec or y.win != (0, n_rows):
-            raise Unsupported("output transform does not return one row per point")
+    _TRACE["graph"] = g
     try:
+        if output_transform is not None:
+            y = output_transform(x, y)
+            if not isinstance(y, Sym) or y.vec or y.scalar or y.win != (0, n_rows):
+                raise Unsupported("output transform does not return one row per point")
         terms = losses_fn(x, y)
     except Unsupported:
         raise
     except (TypeError, AttributeError, ValueError, IndexError, RuntimeError, NotImplementedError) as e:
         raise Unsupported(f"{type(e).__name__}: {e}") from e
+    finally:
+        _TRACE.pop("graph", None)
     if not isinstance(terms, (list, tuple)):
         terms = [terms]
     for t in terms:
@@ -697,21 +770,24 @@ def trace_operator(operator_fn, spec, n_rows, n_in, n_out, output_transform=None
     x = Sym(g, [g.x(d) for d in range(n_in)], (0, n_rows))
     x.is_input = True
     y = Sym(g, [g.net(c) for c in range(n_out)], (0, n_rows))
-    if output_transform is not None:
-        y = output_transform(x, y)
-        if not isinstance(y, Sym) or y.vec or y.win != (0, n_rows):
-            raise Unsupported("output transform does not return one row per point")
+    _TRACE["graph"] = g
     try:
+        if output_transform is not None:
+            y = output_transform(x, y)
+            if not isinstance(y, Sym) or y.vec or y.scalar or y.win != (0, n_rows):
+                raise Unsupported("output transform does not return one row per point")
         outs = operator_fn(x, y)
     except Unsupported:
         raise
     except (TypeError, AttributeError, ValueError, IndexError, RuntimeError, NotImplementedError) as e:
         raise Unsupported(f"{type(e).__name__}: {e}") from e
+    finally:
+        _TRACE.pop("graph", None)
     as_list = isinstance(outs, (list, tuple))
     outs = list(outs) if as_list else [outs]
     cols, widths = [], []
     for o in outs:
-        if not isinstance(o, Sym) or o.vec or o.win != (0, n_rows):
+        if not isinstance(o, Sym) or o.vec or o.scalar or o.win != (0, n_rows):
             raise Unsupported("operator output is not one row per point")
         cols += o.cols
         widths.append(len(o.cols))

@@ -266,14 +266,17 @@ typedef struct ax_residual_program {
   const int32_t *aux_meta;
   const void *const *scalars;
   const float *term_scale;
-  int32_t n_instr, n_seg, n_reg, n_terms, n_streams, n_const;
+  int32_t n_instr, n_seg, n_reg, n_terms, n_streams, n_const, n_scalars;
 } ax_residual_program;
 
 size_t ax_residual_ws_bytes(const ax_residual_program *prog, int64_t n);
 int ax_residual_forward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
                         float *losses, void *ws, size_t ws_bytes, void *stream);
+/* scalar_grads (may be NULL): [n_scalars] d(sum_t term_grads[t] losses[t]) / d(scalar k) -- the trainable coefficients
+ * of inverse problems (dde.Variable, cases/InverseCases.py:61-63, :288-289, :368); needs ws of ax_residual_ws_bytes. */
 int ax_residual_backward(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,
-                         const float *term_grads, float *jets_bar, void *stream);
+                         const float *term_grads, float *jets_bar, float *scalar_grads, void *ws, size_t ws_bytes,
+                         void *stream);
 /* the same interpreter for `model.predict(x, operator=pde)` (the residual probe of algorithm/RAD.py:26, RAR_D.py:24,
  * R3Sampling.py:78): opcode 20 STORE dst=column, a=register writes out[column][p]; out is [columns][ldn]. */
 int ax_residual_eval(const ax_residual_program *prog, const float *x_soa, const float *jets, int64_t n, int64_t ldn,

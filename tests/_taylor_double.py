@@ -112,6 +112,7 @@ class ResidualTables:
     def __init__(self, program, device=None):
         self.program = program
         self.n_terms, self.n_streams = program.n_terms, program.S * program.C
+        self.n_scalars, self.scalar_grad = len(program.scalars), list(program.scalar_grad)
 
 
 def _run_program(program, x_soa, jets, n):
@@ -134,7 +135,7 @@ def _run_program(program, x_soa, jets, n):
                 ten, first = program.aux[a]
                 reg[dst] = ten.to(jets.dtype)[beg - first : end - first, b]
             elif op == R.OP_LOADS:
-                reg[dst] = program.scalars[a].to(jets.dtype).reshape(()).expand(end - beg)
+                reg[dst] = torch.Tensor.as_subclass(program.scalars[a], torch.Tensor).to(device=jets.device, dtype=jets.dtype).reshape(()).expand(end - beg)
             elif op == R.OP_CONST:
                 reg[dst] = torch.full((end - beg,), float(program.consts[a]), dtype=jets.dtype)
             elif op == R.OP_ADD:
@@ -176,7 +177,7 @@ def residual_eval(tables, x_soa, jets, n, n_cols):
                 ten, first = program.aux[a]
                 reg[dst] = ten.double()[beg - first : end - first, b]
             elif op == R.OP_LOADS:
-                reg[dst] = program.scalars[a].double().reshape(()).expand(end - beg)
+                reg[dst] = torch.Tensor.as_subclass(program.scalars[a], torch.Tensor).to(device=jets.device).double().reshape(()).expand(end - beg)
             elif op == R.OP_CONST:
                 reg[dst] = torch.full((end - beg,), float(program.consts[a]), dtype=torch.float64)
             elif op == R.OP_ADD:
@@ -206,10 +207,21 @@ def residual_forward(tables, x_soa, jets, n):
 def residual_backward(tables, x_soa, jets, n, term_grads):
     """reverse pass by torch.autograd over the interpreter (the kernel's hand-written adjoint rules are held to it)"""
     j = jets.detach().clone().requires_grad_()
-    with torch.enable_grad():
-        tot = (_run_program(tables.program, x_soa, j, n) * term_grads.to(j.dtype)).sum()
-        (g,) = torch.autograd.grad(tot, j, allow_unused=True)
-    return torch.zeros_like(jets) if g is None else g
+    prog = tables.program
+    live = prog.scalars
+    stand_ins = [torch.Tensor.as_subclass(t.detach(), torch.Tensor).to(jets.device).clone().requires_grad_() for t in live]
+    prog.scalars = stand_ins          # plain leaves for the duration: d/d(scalar) by autograd
+    try:
+        with torch.enable_grad():
+            tot = (_run_program(prog, x_soa, j, n) * term_grads.to(j.dtype)).sum()
+            grads = torch.autograd.grad(tot, [j] + stand_ins, allow_unused=True)
+    finally:
+        prog.scalars = live
+    g = torch.zeros_like(jets) if grads[0] is None else grads[0]
+    if not tables.scalar_grad:
+        return g, None
+    sg = torch.stack([torch.zeros((), dtype=jets.dtype) if s is None else s.reshape(()) for s in grads[1:]])
+    return g, sg.to(torch.float32)
 
 
 def torch_lbfgs(params, **kw):

@@ -15,13 +15,18 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+_VARS = {}
+
+
 def _all_ops_code(x, y):
     import ai4xde_b200.dde as dde
+
+    c1, c2 = _VARS["c1"], _VARS["c2"]       # trainable scalars (dde.Variable): read at run time, gradients returned
 
     u = torch.sin(x[:, 0:1]) * y[:, 0:1] + torch.exp(-x[:, 1:2]) * torch.tanh(y[:, 1:2]) / (1.5 + torch.cos(x[:, 0:1] * x[:, 1:2]))
     u = u + torch.sqrt(2.0 + (y[:, 0:1] * y[:, 1:2]) ** 2) - abs(y[:, 0:1]) ** 3 + torch.log(3.0 + u ** 2) + 2.0 ** x[:, 1:2]
     r = dde.grad.jacobian(u, x, i=0, j=1) - 0.3 * dde.grad.hessian(u, x, i=0, j=0) + dde.grad.hessian(u, x, i=0, j=1) * u
-    v = dde.grad.hessian(y, x, component=1, i=1, j=1) / (1.0 + y[:, 0:1] ** 2)
+    v = dde.grad.hessian(y, x, component=1, i=1, j=1) / (1.0 + y[:, 0:1] ** 2) * torch.exp(-c1) + 1e-3 * c2 * u - c1 / 3.0
     return [torch.mean(torch.square(r)), torch.mean(abs(u[5:200])), torch.mean(torch.square(v[100:])), torch.sum(v * u)]
 
 
@@ -32,8 +37,11 @@ def test_interpreter_kernels_match_the_float64_interpreter(n):
     from ai4xde_b200 import _lib, residual as R
     from ai4xde_b200.jet import JetSpec
 
+    import ai4xde_b200.dde as dde
+
     dev = torch.device("cuda:0")
     spec = JetSpec.full(2)
+    _VARS["c1"], _VARS["c2"] = dde.Variable(0.7), dde.Variable(-1.3)
     code = _all_ops_code if n >= 256 else (lambda x, y: [torch.mean(torch.square(
         torch.sin(x[:, 0:1]) * y[:, 0:1] - y[:, 1:2] ** 2 / (2.0 + torch.exp(x[:, 1:2]))))])
     prog = R.trace(code, spec, n, 2, 2)
@@ -45,16 +53,21 @@ def test_interpreter_kernels_match_the_float64_interpreter(n):
     jets[..., :n] = torch.randn((1, spec.S, 2, n), generator=gen, dtype=torch.float64)
     tg = torch.randn(prog.n_terms, generator=gen, dtype=torch.float64)
     want = td._run_program(prog, x, jets, n)
-    want_bar = td.residual_backward(td.ResidualTables(prog), x, jets, n, tg)
+    want_bar, want_sg = td.residual_backward(td.ResidualTables(prog), x, jets, n, tg)
     tables = _lib.ResidualTables(prog, dev)
     xs, js = x.float().to(dev), jets.float().to(dev)
     got = _lib.residual_forward(tables, xs, js, n)
-    got_bar = _lib.residual_backward(tables, xs, js, n, tg.float().to(dev))
+    got_bar, got_sg = _lib.residual_backward(tables, xs, js, n, tg.float().to(dev))
     assert _rel(got.double().cpu(), want) < 1e-5, (got, want)
     assert _rel(got_bar.double().cpu(), want_bar) < 1e-5
     assert bool((got_bar[..., n:] == 0).all())
+    if n >= 256:
+        assert prog.scalar_grad == [0, 1] and _rel(got_sg.double().cpu(), want_sg.double()) < 1e-5, (got_sg, want_sg)
+    else:
+        assert got_sg is None
     assert torch.equal(got, _lib.residual_forward(tables, xs, js, n))
-    assert torch.equal(got_bar, _lib.residual_backward(tables, xs, js, n, tg.float().to(dev)))
+    again_bar, again_sg = _lib.residual_backward(tables, xs, js, n, tg.float().to(dev))
+    assert torch.equal(got_bar, again_bar) and (got_sg is None or torch.equal(got_sg, again_sg))
     print(f"n={n}: {prog.describe()}; losses rel {_rel(got.double().cpu(), want):.2e}, jets_bar rel {_rel(got_bar.double().cpu(), want_bar):.2e}")
 
 
@@ -152,3 +165,43 @@ def test_training_with_programs_follows_the_autograd_trajectory():
             dde.config.set_residual_programs(True)
     print(hist)
     assert np.allclose(hist[True], hist[False], rtol=2e-3)
+
+
+def test_inverse_problem_variables_get_their_gradient_from_the_program():
+    """dde.Variable coefficients (cases/InverseCases.py:368, :392-400: Diffusion_Inverse `dy_t - C dy_xx + ...`, and the
+    derived forms `-v_e / e`, `1e-3 * D` of :314, :505): the program reads their current value at every step and returns
+    d loss / d variable; compared with autograd, then trained for 50 steps both ways."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    dde.config.set_default_float("float32")
+    out = {}
+    for fused in (False, True):
+        np.random.seed(5)
+        torch.manual_seed(5)
+        case = pc.Burgers(NumDomain=4000, layer_size=[2] + [20] * 3 + [1], soft_constraints=True)
+        C, D = dde.Variable(2.0), dde.Variable(0.5)
+        base = case.data.pde
+
+        def make_pde(base, C, D):
+            def pde(x, y):          # two arguments: deepxde counts them to decide how to call it
+                return base(x, y) * torch.exp(-D) - 1e-2 * C * dde.grad.hessian(y, x, i=0, j=0) + (-C / 7.0) * y
+            return pde
+
+        case.data.pde = make_pde(base, C, D)
+        model = dde.Model(case.data, case.net)
+        model.compile("adam", lr=1e-3, external_trainable_variables=[C, D])
+        dde.config.set_residual_programs(fused)
+        try:
+            l, g = _closure_loss_and_grad(model, fused)
+            gv = torch.stack([C.grad.reshape(()), D.grad.reshape(())]).clone()
+            dde.config.set_residual_programs(fused)
+            model.train(iterations=50, display_every=50)
+            out[fused] = (l, g, gv, float(C), float(D), model.residual_program_note())
+        finally:
+            dde.config.set_residual_programs(True)
+    (l0, g0, v0, c0, d0, _), (l1, g1, v1, c1, d1, note) = out[False], out[True]
+    print(note, "variable gradients", v0.tolist(), v1.tolist(), "after 50 steps", (c0, d0), (c1, d1))
+    assert "2 trainable variables" in note
+    assert abs(float(l1) - float(l0)) <= 1e-5 * abs(float(l0)) and _rel(g1, g0) < 1e-5 and _rel(v1, v0) < 1e-5
+    assert abs(c1 - c0) < 1e-4 and abs(d1 - d0) < 1e-4 and abs(c1 - 2.0) > 1e-3

@@ -197,3 +197,47 @@ def test_operator_programs_reproduce_predict(name):
     got2 = model.predict(X[:50], operator=case.pde)
     got2 = got2 if isinstance(got2, list) else [got2]
     assert np.abs(got2[0] - ref[0][:50]).max() <= 2e-5 * np.abs(ref[0]).max()
+
+
+def test_trainable_variables_are_traced_as_run_time_scalars():
+    """dde.Variable (inverse problems): expressions of variables formed before they meet a point-wise tensor
+    (`-v / e`, `1e-3 * D`, exp(-D)) are traced too; the program returns their gradients; a step changes them."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    np.random.seed(5)
+    torch.manual_seed(5)
+    case = pc.Burgers(NumDomain=200, layer_size=[2, 10, 10, 1], soft_constraints=True)
+    C, D = dde.Variable(2.0), dde.Variable(0.5)
+    base = case.data.pde
+
+    def pde(x, y):
+        return base(x, y) * torch.exp(-D) - 1e-2 * C * dde.grad.hessian(y, x, i=0, j=0) + (-C / 7.0) * y
+
+    case.data.pde = pde
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-2, external_trainable_variables=[C, D])
+    res = {}
+    for fused in (False, True):
+        C.grad = D.grad = None
+        l, g = _losses_and_grad(model, fused=fused)
+        res[fused] = (l, g, float(C.grad), float(D.grad))
+    note = model.residual_program_note()
+    assert "2 trainable variables" in note, note
+    assert abs(res[True][0] - res[False][0]) <= 2e-5 * abs(res[False][0])
+    assert float((res[True][1] - res[False][1]).abs().max()) <= 2e-4 * float(res[False][1].abs().max())
+    assert abs(res[True][2] - res[False][2]) <= 2e-4 * abs(res[False][2]) and abs(res[True][3] - res[False][3]) <= 2e-4 * abs(res[False][3])
+    import ai4xde_b200.dde as dde2
+
+    dde2.config.set_residual_programs(True)
+    before = (float(C), float(D))
+    model.train_step(case.data.train_x, None, None)          # the program of the NEXT step reads the moved values
+    l_after, _ = _losses_and_grad(model, fused=True)
+    l_ref, _ = _losses_and_grad(model, fused=False)
+    assert (float(C), float(D)) != before and abs(l_after - l_ref) <= 2e-5 * abs(l_ref)
+    # a variable the model does not optimise is refused
+    E = dde.Variable(1.0)
+    case.data.pde = lambda x, y: base(x, y) * E
+    model.compile("adam", lr=1e-2, external_trainable_variables=[C, D])
+    _losses_and_grad(model, fused=True)
+    assert model.residual_program_note().startswith("autograd path")
