@@ -12,7 +12,7 @@ namespace ax {
 
 enum {
   R_LOADX = 0, R_LOADJ, R_LOADA, R_LOADS, R_CONST, R_ADD, R_SUB, R_MUL, R_DIV, R_NEG, R_SIN, R_COS, R_EXP, R_TANH,
-  R_LOG, R_SQRT, R_ABS, R_SIGN, R_POW, R_SUMT, R_STORE
+  R_LOG, R_SQRT, R_ABS, R_SIGN, R_POW, R_SUMT, R_STORE, R_SUMT_ADJ
 };
 enum { RES_SUM = 0, RES_ADJ = 1, RES_EVAL = 2 };   // what a forward sweep is for
 
@@ -40,8 +40,8 @@ __device__ __forceinline__ void res_forward(const int4 *code, int cb, int ce, co
     const int4 in = code[pc];
     float v;
     switch (in.x) {
-      case R_LOADX: v = __ldg(x + (long long)in.z * ldn + p); break;
-      case R_LOADJ: v = __ldg(jets + (long long)in.z * ldn + p); break;
+      case R_LOADX: v = __ldg(x + (long long)in.z * ldn + p + in.w); break;     // in.w: row offset (PeriodicBC pairs)
+      case R_LOADJ: v = __ldg(jets + (long long)in.z * ldn + p + in.w); break;
       case R_LOADA: {
         const int2 m = pv.aux_meta[in.z];
         v = __ldg(pv.aux[in.z] + (p - m.x) * m.y + in.w);
@@ -65,6 +65,8 @@ __device__ __forceinline__ void res_forward(const int4 *code, int cb, int ce, co
       case R_POW: v = powf(R[in.z * T], consts[in.w]); break;
       case R_STORE:
         if (MODE == RES_EVAL) sink[(long long)in.y * ldn + p] = R[in.z * T];
+        continue;
+      case R_SUMT_ADJ:   // mirror segment of a term that reads other rows: adjoints only, the sum is taken elsewhere
         continue;
       default:   // R_SUMT: term in.y += register in.z
         if (MODE == RES_SUM) sink[in.y * T] += R[in.z * T];
@@ -184,7 +186,7 @@ k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict_
         res_forward<RES_ADJ>(code, sg.z, sg.w, consts, pv, x, jets, p, ldn, R, A, nullptr, T);
         for (int pc = sg.w - 1; pc >= sg.z; --pc) {
           const int4 in = code[pc];
-          if (in.x == R_SUMT) {
+          if (in.x == R_SUMT || in.x == R_SUMT_ADJ) {
             A[in.z * T] += tg[in.y];
             continue;
           }
@@ -192,7 +194,7 @@ k_residual_bwd(ResView pv, const float *__restrict__ x, const float *__restrict_
           const float d = A[in.y * T];
           if (d == 0.0f) continue;          // nothing flows through this value (also keeps 0 * inf out)
           switch (in.x) {
-            case R_LOADJ: J[in.z * T] += d; break;
+            case R_LOADJ: if (in.w == 0) J[in.z * T] += d; break;   // another row's streams: its mirror segment's job
             case R_LOADS: if (want_scalars) sacc[in.z * T + tid] += d; break;
             case R_ADD: A[in.z * T] += d; A[in.w * T] += d; break;
             case R_SUB: A[in.z * T] += d; A[in.w * T] -= d; break;

@@ -31,7 +31,7 @@ class Unsupported(Exception):
 OP_LOADX, OP_LOADJ, OP_LOADA, OP_LOADS, OP_CONST = 0, 1, 2, 3, 4
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG = 5, 6, 7, 8, 9
 OP_SIN, OP_COS, OP_EXP, OP_TANH, OP_LOG, OP_SQRT, OP_ABS, OP_SIGN, OP_POW = 10, 11, 12, 13, 14, 15, 16, 17, 18
-OP_SUMT, OP_STORE = 19, 20
+OP_SUMT, OP_STORE, OP_SUMT_ADJ = 19, 20, 21
 _UNARY = {"sin": OP_SIN, "cos": OP_COS, "exp": OP_EXP, "tanh": OP_TANH, "log": OP_LOG, "sqrt": OP_SQRT,
           "abs": OP_ABS, "sign": OP_SIGN, "neg": OP_NEG}
 _BINARY = {"add": OP_ADD, "sub": OP_SUB, "mul": OP_MUL, "div": OP_DIV}
@@ -58,6 +58,7 @@ class Graph:
         self.n_in, self.n_out = n_in, n_out
         self._nodes = {}
         self._diff = {}
+        self._shift = {}
         self.aux = []       # (tensor [rows, ncol] on the device, first row)
         self.scalars = []   # one-element device tensors read at run time (their value may change between steps)
         self.scalar_grad = set()   # indices of scalars that are trainable variables: the reverse pass returns d/d(scalar)
@@ -70,18 +71,48 @@ class Graph:
         return hit
 
     # leaves
-    def x(self, d):
-        return self._mk("x", (int(d),))
+    def x(self, d, delta=0):
+        return self._mk("x", (int(d), int(delta)))
 
-    def net(self, c, dims=()):
-        return self._mk("net", (int(c), tuple(sorted(int(d) for d in dims))))
+    def net(self, c, dims=(), delta=0):
+        """stream of network output c differentiated along `dims`, read `delta` rows away from the point"""
+        return self._mk("net", (int(c), tuple(sorted(int(d) for d in dims)), int(delta)))
 
     def const(self, v):
         v = float(v)
         return self._mk("const", (v if v == v else "nan",))
 
-    def aux_col(self, k, col):
-        return self._mk("aux", (int(k), int(col)))
+    def aux_col(self, k, col, delta=0):
+        return self._mk("aux", (int(k), int(col), int(delta)))
+
+    def shift(self, e, delta, _memo=None):
+        """The same expression evaluated `delta` rows further down the batch (PeriodicBC pairs row p of the left
+        boundary with row p + m of the right one, deepxde icbc PeriodicBC.error)."""
+        if delta == 0:
+            return e
+        memo = self._shift.setdefault(delta, {})
+        hit = memo.get(e.uid)
+        if hit is not None:
+            return hit
+        op, a = e.op, e.args
+        if op == "x":
+            out = self.x(a[0], a[1] + delta)
+        elif op == "net":
+            out = self.net(a[0], a[1], a[2] + delta)
+        elif op == "aux":
+            out = self.aux_col(a[0], a[1], a[2] + delta)
+        elif op in ("const", "scal"):
+            out = e
+        elif op == "pow":
+            out = self.pow(self.shift(a[0], delta), a[1])
+        elif op in ("add", "sub", "mul", "div"):
+            out = getattr(self, op)(self.shift(a[0], delta), self.shift(a[1], delta))
+        elif op == "neg":
+            out = self.neg(self.shift(a[0], delta))
+        else:
+            out = self.unary(op, self.shift(a[0], delta))
+        memo[e.uid] = out
+        return out
 
     def scalar(self, k):
         return self._mk("scal", (int(k),))
@@ -185,6 +216,8 @@ class Graph:
     def _diff_new(self, e, j):
         op, a = e.op, e.args
         D = self.diff
+        if op in ("x", "net") and a[-1] != 0:
+            raise Unsupported("derivative of a row-shifted expression")
         if op == "x":
             return self.const(1.0 if a[0] == j else 0.0)
         if op == "net":
@@ -376,7 +409,11 @@ class Sym:
             if self.scalar:
                 raise Unsupported("internal: scalar operand order")
             if o.win != self.win:
-                raise Unsupported(f"operands cover different rows {o.win} / {self.win}")
+                if o.win[1] - o.win[0] != self.win[1] - self.win[0] or o.vec != self.vec:
+                    raise Unsupported(f"operands cover different rows {o.win} / {self.win}")
+                # row i of one slice against row i of another (PeriodicBC: left boundary rows vs their periodic
+                # images): the other operand is read (o.win[0] - self.win[0]) rows away
+                return [g.shift(c, o.win[0] - self.win[0]) for c in o.cols]
             if o.vec != self.vec:
                 raise Unsupported("one-axis with two-axis operand")
             return o.cols
@@ -613,6 +650,20 @@ def hessian(y, xs, component=None, i=0, j=0, grad_y=None):
 
 
 # ---- lowering -------------------------------------------------------------------------------------------------------
+def _row_offsets(expr):
+    """the set of row offsets an expression's loads use"""
+    seen, out, stack = set(), set(), [expr]
+    while stack:
+        e = stack.pop()
+        if e.uid in seen:
+            continue
+        seen.add(e.uid)
+        if e.op in ("x", "net", "aux"):
+            out.add(e.args[-1])
+        stack.extend(a for a in e.args if isinstance(a, Node))
+    return out
+
+
 def _stream_of(spec, dims):
     """index of the kernel stream that carries d^|dims| / dx_dims of the network, None for a structural zero"""
     if not dims:
@@ -658,12 +709,19 @@ class Program:
         self.n_terms, self.n_rows = len(terms), int(n_rows)
         self.S, self.C, self.d_in = spec.S, graph.n_out, graph.n_in
         self.scale = np.array([t.scale for t in terms], dtype=np.float64)   # uploaded as float32
-        self.aux, self.scalars = graph.aux, graph.scalars
+        self.aux, self.scalars = list(graph.aux), graph.scalars
         self.scalar_grad = sorted(graph.scalar_grad)     # scalars whose gradient the reverse pass accumulates
         consts, cindex = [], {}
         by_win = {}
+        aux_shifted = {}
         for t, term in enumerate(terms):
             by_win.setdefault(term.win, []).append((OP_SUMT, t, term.expr))
+            # a term that reads other rows (PeriodicBC: row p against row p + m): the thread of row p cannot write the
+            # adjoint of row p + m's streams, so row p + m gets a MIRROR segment -- the same expression re-centred on
+            # it, contributing adjoints only (OP_SUMT_ADJ) -- and every thread keeps only the adjoints of its own row
+            for delta in sorted(_row_offsets(term.expr) - {0}):
+                mirror = (term.win[0] + delta, term.win[1] + delta)
+                by_win.setdefault(mirror, []).append((OP_SUMT_ADJ, t, graph.shift(term.expr, -delta)))
         for c, expr in enumerate(outputs or ()):
             by_win.setdefault((0, int(n_rows)), []).append((OP_STORE, c, expr))
         self.segments, n_reg = [], 0
@@ -680,22 +738,31 @@ class Program:
                         emit(a)
                 r = len(reg)
                 op, a = node.op, node.args
+                if op in ("x", "net", "aux") and a[-1] != 0 and (win[0] + a[-1] < 0 or win[1] + a[-1] > n_rows):
+                    raise Unsupported("row offset leaves the batch")
                 if op == "x":
-                    code.append((OP_LOADX, r, a[0], 0))
+                    code.append((OP_LOADX, r, a[0], a[1]))
                 elif op == "net":
                     s = _stream_of(spec, a[1])
                     if s is None:
                         code.append((OP_CONST, r, cindex.setdefault(0.0, len(cindex)), 0))
                     else:
-                        code.append((OP_LOADJ, r, s * self.C + a[0], 0))
+                        code.append((OP_LOADJ, r, s * self.C + a[0], a[2]))
                 elif op == "const":
                     v = float("nan") if a[0] == "nan" else a[0]
                     code.append((OP_CONST, r, cindex.setdefault(v, len(cindex)), 0))
                 elif op == "aux":
-                    ten, first = self.aux[a[0]]
+                    k = a[0]
+                    if a[2] != 0:            # the same array read a[2] rows away = an entry whose first row moved
+                        key = (a[0], a[2])
+                        if key not in aux_shifted:
+                            self.aux.append((self.aux[a[0]][0], self.aux[a[0]][1] - a[2]))
+                            aux_shifted[key] = len(self.aux) - 1
+                        k = aux_shifted[key]
+                    ten, first = self.aux[k]
                     if first > win[0] or first + ten.shape[0] < win[1]:
                         raise Unsupported("array does not cover the rows of the term it feeds")
-                    code.append((OP_LOADA, r, a[0], a[1]))
+                    code.append((OP_LOADA, r, k, a[1]))
                 elif op == "scal":
                     code.append((OP_LOADS, r, a[0], 0))
                 elif op in _BINARY:

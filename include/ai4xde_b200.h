@@ -246,10 +246,12 @@ int ax_adam_step(float *params, const float *grad, float *exp_avg, float *exp_av
  * solver/PDESolver.py:79-85 through model.train) -- as ONE interpreted program per collocation point instead of a few
  * hundred tensor kernels.  The host traces the case's own Python code once (ai4xde_b200/residual.py) and hands over:
  *   code      [n_instr][4] int32  = opcode, destination register, operand a, operand b
- *             0 LOADX a=input dim | 1 LOADJ a=stream*d_out+component | 2 LOADA a=array, b=column | 3 LOADS a=scalar |
+ *             0 LOADX a=input dim, b=row offset | 1 LOADJ a=stream*d_out+component, b=row offset | 2 LOADA a=array,
+ *             b=column | 3 LOADS a=scalar |
  *             4 CONST a=index | 5 ADD 6 SUB 7 MUL 8 DIV (registers a, b) | 9 NEG 10 SIN 11 COS 12 EXP 13 TANH 14 LOG
  *             15 SQRT 16 ABS 17 SIGN (register a) | 18 POW a=register, b=index of the constant exponent |
- *             19 SUMT dst=term, a=register: term += register | 20 STORE (ax_residual_eval only)
+ *             19 SUMT dst=term, a=register: term += register | 20 STORE (ax_residual_eval only) | 21 SUMT_ADJ: seeds
+ *             the adjoint like SUMT without adding to the sum (mirror segment of a term that pairs rows: PeriodicBC)
  *   segments  [n_seg][4] int32    = first row, end row, first instruction, end instruction: a point runs the segments
  *             whose row range holds it (BC rows come first in train_x, then the residual rows)
  *   aux       [n_aux] device pointers to row-major float arrays (BC target values, normals ...), aux_meta [n_aux][2]

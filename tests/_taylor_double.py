@@ -128,9 +128,9 @@ def _run_program(program, x_soa, jets, n):
         reg = {}
         for op, dst, a, b in code.tolist():
             if op == R.OP_LOADX:
-                reg[dst] = x_soa[a, beg:end].to(jets.dtype)
+                reg[dst] = x_soa[a, beg + b : end + b].to(jets.dtype)
             elif op == R.OP_LOADJ:
-                reg[dst] = flat[a, beg:end]
+                reg[dst] = flat[a, beg + b : end + b]
             elif op == R.OP_LOADA:
                 ten, first = program.aux[a]
                 reg[dst] = ten.to(jets.dtype)[beg - first : end - first, b]
@@ -150,8 +150,8 @@ def _run_program(program, x_soa, jets, n):
                 reg[dst] = reg[a] ** float(program.consts[b])
             elif op == R.OP_SUMT:
                 sums[dst] = sums[dst] + reg[a].sum()
-            elif op == R.OP_STORE:
-                pass
+            elif op in (R.OP_STORE, R.OP_SUMT_ADJ):
+                pass          # mirror segments only exist for the kernel's adjoint bookkeeping: autograd needs none
             else:
                 reg[dst] = un[op](reg[a])
     return torch.stack(sums) * torch.as_tensor(program.scale, dtype=jets.dtype)
@@ -170,9 +170,9 @@ def residual_eval(tables, x_soa, jets, n, n_cols):
         reg = {}
         for op, dst, a, b in code.tolist():
             if op == R.OP_LOADX:
-                reg[dst] = x_soa[a, beg:end].double()
+                reg[dst] = x_soa[a, beg + b : end + b].double()
             elif op == R.OP_LOADJ:
-                reg[dst] = flat[a, beg:end]
+                reg[dst] = flat[a, beg + b : end + b]
             elif op == R.OP_LOADA:
                 ten, first = program.aux[a]
                 reg[dst] = ten.double()[beg - first : end - first, b]
@@ -192,7 +192,7 @@ def residual_eval(tables, x_soa, jets, n, n_cols):
                 reg[dst] = reg[a] ** float(program.consts[b])
             elif op == R.OP_STORE:
                 out[dst, beg:end] = reg[a].to(torch.float32)
-            elif op == R.OP_SUMT:
+            elif op in (R.OP_SUMT, R.OP_SUMT_ADJ):
                 pass
             else:
                 reg[dst] = un[op](reg[a])

@@ -27,13 +27,16 @@ def _all_ops_code(x, y):
     u = u + torch.sqrt(2.0 + (y[:, 0:1] * y[:, 1:2]) ** 2) - abs(y[:, 0:1]) ** 3 + torch.log(3.0 + u ** 2) + 2.0 ** x[:, 1:2]
     r = dde.grad.jacobian(u, x, i=0, j=1) - 0.3 * dde.grad.hessian(u, x, i=0, j=0) + dde.grad.hessian(u, x, i=0, j=1) * u
     v = dde.grad.hessian(y, x, component=1, i=1, j=1) / (1.0 + y[:, 0:1] ** 2) * torch.exp(-c1) + 1e-3 * c2 * u - c1 / 3.0
-    return [torch.mean(torch.square(r)), torch.mean(abs(u[5:200])), torch.mean(torch.square(v[100:])), torch.sum(v * u)]
+    # a term that pairs rows (PeriodicBC: left boundary rows against their periodic images further down the batch)
+    per = (u[10:60] - u[110:160]) * x[10:60, 0:1] + dde.grad.jacobian(y, x, i=1, j=0)[10:60] - dde.grad.jacobian(y, x, i=1, j=0)[110:160]
+    return [torch.mean(torch.square(r)), torch.mean(abs(u[5:200])), torch.mean(torch.square(v[100:])), torch.sum(v * u),
+            torch.mean(torch.square(per))]
 
 
 @pytest.mark.parametrize("n", [1, 37, 1000, 300001])
 def test_interpreter_kernels_match_the_float64_interpreter(n):
-    """Every opcode, four terms over three row ranges, two network outputs, S = 6 streams; ragged sizes; repeated
-    launches bit-identical (fixed-order reductions)."""
+    """Every opcode, five terms over four row ranges (one of them pairing rows 50 apart: mirror segment), two trainable
+    scalars, two network outputs, S = 6 streams; ragged sizes; repeated launches bit-identical (fixed-order reductions)."""
     from ai4xde_b200 import _lib, residual as R
     from ai4xde_b200.jet import JetSpec
 
@@ -205,3 +208,30 @@ def test_inverse_problem_variables_get_their_gradient_from_the_program():
     assert "2 trainable variables" in note
     assert abs(float(l1) - float(l0)) <= 1e-5 * abs(float(l0)) and _rel(g1, g0) < 1e-5 and _rel(v1, v0) < 1e-5
     assert abs(c1 - c0) < 1e-4 and abs(d1 - d0) < 1e-4 and abs(c1 - 2.0) > 1e-3
+
+
+def test_periodic_bc_pairs_rows_through_mirror_segments():
+    """PeriodicBC (value and first derivative: reference cases Schrodinger, Poisson_1D_Dirichlet_Periodic) -- the loss
+    term subtracts row p + m from row p; the thread of row p + m gets a mirror segment for its share of the adjoint.
+    Train closure with the program against autograd over the jet leaves."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    dde.config.set_default_float("float32")
+    np.random.seed(2)
+    torch.manual_seed(2)
+    case = pc.Burgers(NumDomain=3000, layer_size=[2] + [20] * 3 + [1], soft_constraints=True)
+    gt = case.geomtime
+    on_x = lambda x, on_boundary: on_boundary and (np.isclose(x[0], -1) or np.isclose(x[0], 1))
+    bcs = list(case.data.bcs) + [dde.icbc.PeriodicBC(gt, 0, on_x, derivative_order=0),
+                                 dde.icbc.PeriodicBC(gt, 0, on_x, derivative_order=1)]
+    data = dde.data.TimePDE(gt, case.data.pde, bcs, num_domain=3000, num_boundary=200, num_initial=100,
+                            train_distribution="pseudo")
+    model = dde.Model(data, case.net)
+    model.compile("adam", lr=1e-3)
+    l_ref, g_ref = _closure_loss_and_grad(model, fused=False)
+    l_fus, g_fus = _closure_loss_and_grad(model, fused=True)
+    note = model.residual_program_note()
+    print(note, f"loss rel {abs(float(l_fus) - float(l_ref)) / abs(float(l_ref)):.2e}, grad rel {_rel(g_fus, g_ref):.2e}")
+    assert not note.startswith("autograd path"), note
+    assert abs(float(l_fus) - float(l_ref)) <= 1e-5 * abs(float(l_ref)) and _rel(g_fus, g_ref) < 1e-5

@@ -241,3 +241,30 @@ def test_trainable_variables_are_traced_as_run_time_scalars():
     model.compile("adam", lr=1e-2, external_trainable_variables=[C, D])
     _losses_and_grad(model, fused=True)
     assert model.residual_program_note().startswith("autograd path")
+
+
+def test_periodic_bc_is_traced_with_row_offsets():
+    """PeriodicBC subtracts two row ranges of equal length: the second operand becomes the same expression read m rows
+    further down; the lowered program carries a mirror segment for those rows (adjoints only)."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc, residual as R
+
+    np.random.seed(2)
+    torch.manual_seed(2)
+    case = pc.Burgers(NumDomain=200, layer_size=[2, 10, 10, 1], soft_constraints=True)
+    gt = case.geomtime
+    on_x = lambda x, on_boundary: on_boundary and (np.isclose(x[0], -1) or np.isclose(x[0], 1))
+    bcs = list(case.data.bcs) + [dde.icbc.PeriodicBC(gt, 0, on_x, derivative_order=0),
+                                 dde.icbc.PeriodicBC(gt, 0, on_x, derivative_order=1)]
+    data = dde.data.TimePDE(gt, case.data.pde, bcs, num_domain=200, num_boundary=40, num_initial=20,
+                            train_distribution="pseudo")
+    model = dde.Model(data, case.net)
+    model.compile("adam", lr=1e-3)
+    l_ref, g_ref = _losses_and_grad(model, fused=False)
+    l_fus, g_fus = _losses_and_grad(model, fused=True)
+    note = model.residual_program_note()
+    assert not note.startswith("autograd path"), note
+    prog = model._residual["train"][2].program
+    assert any(int(op) == R.OP_SUMT_ADJ for _, _, code in prog.segments for op in code[:, 0])
+    assert abs(l_fus - l_ref) <= 2e-5 * abs(l_ref)
+    assert float((g_fus - g_ref).abs().max()) <= 2e-4 * float(g_ref.abs().max())
