@@ -63,7 +63,7 @@ class _DeviceBatch:
     """Device-resident mirror of one host point array: AoS tensor for the case's `pde` code,
     SoA copy for the kernels."""
 
-    __slots__ = ("host", "aos", "soa", "version")
+    __slots__ = ("host", "aos", "soa", "version", "_feat")
 
     def __init__(self, host, version=None):
         self.host = host
@@ -75,6 +75,19 @@ class _DeviceBatch:
             t = torch.as_tensor(np.ascontiguousarray(host, dtype=np.float32)).to(dev, non_blocking=True)
         self.aos = t
         self.soa = jet.to_soa(t)
+
+    def soa_for(self, net):
+        """what the kernels evaluate `net` on: the points, or -- net.apply_feature_transform(f) -- f(points), computed
+        once per batch; with a transform the pair (points, features) for the residual-program path"""
+        f = getattr(net, "_input_transform", None)
+        if f is None:
+            return self.soa
+        hit = getattr(self, "_feat", None)
+        if hit is None or hit[0] is not f:
+            with torch.no_grad():
+                hit = (f, jet.to_soa(f(self.aos).to(torch.float32)))
+            self._feat = hit
+        return (self.soa, hit[1])
 
     @classmethod
     def on_device(cls, aos, soa=None, host=None, version=None):
@@ -232,11 +245,12 @@ class Model:
         net = self.net
         from .nn import FNN, _FusedLosses
 
-        if not config.residual_programs() or type(net) is not FNN or net._input_transform is not None \
+        if not config.residual_programs() or type(net) is not FNN \
                 or net.regularizer is not None or net.auxiliary_vars is not None:
             return None
         owners = (self.data, self.data.pde, losses_fn.__func__ if hasattr(losses_fn, "__func__") else losses_fn,
-                  net._output_transform, loss_fn if not isinstance(loss_fn, (list, tuple)) else tuple(loss_fn)) \
+                  net._output_transform, net._input_transform,
+                  loss_fn if not isinstance(loss_fn, (list, tuple)) else tuple(loss_fn)) \
             + tuple(getattr(self.data, "bcs", ()))
         n_rows = int(batch.aos.shape[0])
         key = (getattr(self.data, "version", None), n_rows, spec.key(), self._residual_epoch, batch.host is self.data.train_x)
@@ -250,8 +264,8 @@ class Model:
                 grad.clear()
                 return out
 
-            prog = residual.trace(fn, spec, n_rows, net.layer_sizes[0], net.layer_sizes[-1],
-                                  output_transform=net._output_transform)
+            prog = residual.trace(fn, spec, n_rows, int(batch.aos.shape[1]), net.layer_sizes[-1],
+                                  output_transform=net._output_transform, feature_transform=net._input_transform)
             tables = _lib.ResidualTables(prog, batch.aos.device)
             note = prog.describe()
             # the trainable scalars the program reads must be exactly variables this model optimises
@@ -271,7 +285,7 @@ class Model:
             with torch.enable_grad():
                 ref = autograd_losses()
                 g_ref = torch.autograd.grad(ref.sum(), params, allow_unused=True)
-                got = _FusedLosses.apply(net, tables, batch.soa, n_rows, spec, config.engine(), True,
+                got = _FusedLosses.apply(net, tables, batch.soa_for(net), n_rows, spec, config.engine(), True,
                                          len(net._param_list()), *net._param_list(), *tables.variables)
                 g_got = torch.autograd.grad(got.sum(), params, allow_unused=True)
             scale = float(ref.detach().abs().max().clamp_min(1e-30))
@@ -295,12 +309,12 @@ class Model:
         net = self.net
         from .nn import FNN
 
-        if not config.residual_programs() or type(net) is not FNN or net._input_transform is not None \
+        if not config.residual_programs() or type(net) is not FNN \
                 or net.auxiliary_vars is not None or utils.get_num_args(operator) != 2:
             return None
         n_rows = int(batch.aos.shape[0])
         use = ("operator", id(operator), n_rows)
-        owners = (operator, net._output_transform)
+        owners = (operator, net._output_transform, net._input_transform)
         key = (spec.key(), self._residual_epoch)
         hit = self._residual.get(use)
         if hit is not None and hit[1] == key and all(a is b for a, b in zip(hit[0], owners)):
@@ -308,8 +322,8 @@ class Model:
         entry, note = None, ""
         try:
             prog, widths, as_list = residual.trace_operator(
-                lambda xs, ys: operator(xs, ys), spec, n_rows, net.layer_sizes[0], net.layer_sizes[-1],
-                output_transform=net._output_transform)
+                lambda xs, ys: operator(xs, ys), spec, n_rows, int(batch.aos.shape[1]), net.layer_sizes[-1],
+                output_transform=net._output_transform, feature_transform=net._input_transform)
             entry = (_lib.ResidualTables(prog, batch.aos.device), widths, as_list)
             note = prog.describe()
         except residual.Unsupported as e:
@@ -340,7 +354,8 @@ class Model:
         tables, widths, as_list = entry
         n = int(batch.aos.shape[0])
         with torch.no_grad():
-            jets = _launch_forward(self.net, batch.soa, n, spec, config.engine(), False)[0]
+            soa = batch.soa_for(self.net)
+            jets = _launch_forward(self.net, soa[1] if isinstance(soa, tuple) else soa, n, spec, config.engine(), False)[0]
             out = _lib.residual_eval(tables, batch.soa, jets, n, sum(widths))
         cols, res = 0, []
         for w in widths:
@@ -480,8 +495,8 @@ class Model:
                 params = self.net._param_list()
                 need_bwd = any(p.requires_grad for p in params)
                 outputs_ = None
-                losses = _FusedLosses.apply(self.net, tables, batch.soa, int(batch.aos.shape[0]), spec, config.engine(),
-                                            need_bwd, len(params), *params, *tables.variables)
+                losses = _FusedLosses.apply(self.net, tables, batch.soa_for(self.net), int(batch.aos.shape[0]), spec,
+                                            config.engine(), need_bwd, len(params), *params, *tables.variables)
             else:
                 x = batch.aos.detach().requires_grad_()
                 with self.net.jet_scope(spec, batch.soa, param_grad=param_grad):

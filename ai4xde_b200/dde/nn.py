@@ -100,11 +100,15 @@ class _FusedLosses(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, net, tables, x_soa, n, spec, engine, need_backward, n_params, *tensors):
-        """tensors = the net's parameters, then the trainable variables the program reads (inverse problems)"""
+        """tensors = the net's parameters, then the trainable variables the program reads (inverse problems).
+        x_soa: the batch's points, or (points, features) when the net has a feature transform -- the kernels
+        evaluate the net on the features, the program reads the raw points."""
         params, variables = tensors[:n_params], tensors[n_params:]
-        jets, stash, desc, pad, flat = _launch_forward(net, x_soa, n, spec, engine, need_backward)
+        x_soa, net_soa = x_soa if isinstance(x_soa, tuple) else (x_soa, x_soa)
+        jets, stash, desc, pad, flat = _launch_forward(net, net_soa, n, spec, engine, need_backward)
         ctx.spec, ctx.engine, ctx.n, ctx.desc, ctx.pad = spec, engine, n, desc, pad
-        ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = x_soa, stash, bool(need_backward), flat
+        ctx.x_soa, ctx.stash, ctx.kept, ctx.flat = net_soa, stash, bool(need_backward), flat
+        ctx.raw_soa = x_soa
         ctx.shapes = [p.shape for p in params]
         ctx.var_shapes = [v.shape for v in variables]
         ctx.tables, ctx.jets = tables, (jets if need_backward else None)
@@ -115,7 +119,7 @@ class _FusedLosses(torch.autograd.Function):
     def backward(ctx, g_losses):
         if not ctx.kept:
             raise RuntimeError("fused forward ran without a stash; parameter gradients unavailable")
-        jets_bar, sgrad = _lib.residual_backward(ctx.tables, ctx.x_soa, ctx.jets, ctx.n, g_losses)
+        jets_bar, sgrad = _lib.residual_backward(ctx.tables, ctx.raw_soa, ctx.jets, ctx.n, g_losses)
         ctx.jets = None
         var_grads = tuple(sgrad[k].reshape(shp) for k, shp in zip(ctx.tables.scalar_grad, ctx.var_shapes))
         return (None, None, None, None, None, None, None, None) + _launch_backward(ctx, jets_bar) + var_grads

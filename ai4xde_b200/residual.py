@@ -59,6 +59,7 @@ class Graph:
         self._nodes = {}
         self._diff = {}
         self._shift = {}
+        self.features = None    # net.apply_feature_transform(f): the columns of f(x); the network's streams are d/dfeature
         self.aux = []       # (tensor [rows, ncol] on the device, first row)
         self.scalars = []   # one-element device tensors read at run time (their value may change between steps)
         self.scalar_grad = set()   # indices of scalars that are trainable variables: the reverse pass returns d/d(scalar)
@@ -223,6 +224,14 @@ class Graph:
         if op == "net":
             if len(a[1]) >= 4:
                 raise Unsupported("fifth-order derivative of the network")
+            if self.features is not None:
+                # the kernels differentiate w.r.t. the FEATURES phi = f(x): chain rule through f, symbolically
+                tot = self.const(0.0)
+                for m, phi in enumerate(self.features):
+                    dphi = D(phi, j)
+                    if self.cval(dphi) != 0.0:
+                        tot = self.add(tot, self.mul(self.net(a[0], a[1] + (m,)), dphi))
+                return tot
             return self.net(a[0], a[1] + (j,))
         if op in ("const", "aux", "scal", "sign"):
             return self.const(0.0)
@@ -801,7 +810,7 @@ class Program:
                 f"{self.n_reg} registers, {len(self.aux)} arrays")
 
 
-def trace(losses_fn, spec, n_rows, n_in, n_out, output_transform=None):
+def trace(losses_fn, spec, n_rows, n_in, n_out, output_transform=None, feature_transform=None):
     """Run `losses_fn(x, y)` -- the model's own loss code -- on symbolic columns and lower what it did.
     `losses_fn` must return the list of per-term losses (each the torch.mean / torch.sum of point-wise algebra)."""
     g = Graph(n_in, n_out)
@@ -810,6 +819,11 @@ def trace(losses_fn, spec, n_rows, n_in, n_out, output_transform=None):
     y = Sym(g, [g.net(c) for c in range(n_out)], (0, n_rows))
     _TRACE["graph"] = g
     try:
+        if feature_transform is not None:
+            phi = feature_transform(x)
+            if not isinstance(phi, Sym) or phi.vec or phi.scalar or phi.win != (0, n_rows):
+                raise Unsupported("feature transform does not return one row per point")
+            g.features = list(phi.cols)
         if output_transform is not None:
             y = output_transform(x, y)
             if not isinstance(y, Sym) or y.vec or y.scalar or y.win != (0, n_rows):
@@ -829,7 +843,7 @@ def trace(losses_fn, spec, n_rows, n_in, n_out, output_transform=None):
     return Program(g, spec, list(terms), n_rows)
 
 
-def trace_operator(operator_fn, spec, n_rows, n_in, n_out, output_transform=None):
+def trace_operator(operator_fn, spec, n_rows, n_in, n_out, output_transform=None, feature_transform=None):
     """`operator_fn(x, y)` -- the operator of model.predict(x, operator=...), usually the case's pde -- on symbolic
     columns.  Returns (program that stores every output column, column counts of the tensors it returned, whether
     it returned a list)."""
@@ -839,6 +853,11 @@ def trace_operator(operator_fn, spec, n_rows, n_in, n_out, output_transform=None
     y = Sym(g, [g.net(c) for c in range(n_out)], (0, n_rows))
     _TRACE["graph"] = g
     try:
+        if feature_transform is not None:
+            phi = feature_transform(x)
+            if not isinstance(phi, Sym) or phi.vec or phi.scalar or phi.win != (0, n_rows):
+                raise Unsupported("feature transform does not return one row per point")
+            g.features = list(phi.cols)
         if output_transform is not None:
             y = output_transform(x, y)
             if not isinstance(y, Sym) or y.vec or y.scalar or y.win != (0, n_rows):

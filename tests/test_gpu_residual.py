@@ -235,3 +235,33 @@ def test_periodic_bc_pairs_rows_through_mirror_segments():
     print(note, f"loss rel {abs(float(l_fus) - float(l_ref)) / abs(float(l_ref)):.2e}, grad rel {_rel(g_fus, g_ref):.2e}")
     assert not note.startswith("autograd path"), note
     assert abs(float(l_fus) - float(l_ref)) <= 1e-5 * abs(float(l_ref)) and _rel(g_fus, g_ref) < 1e-5
+
+
+def test_feature_transform_is_chained_symbolically():
+    """net.apply_feature_transform(f) (reference: Laplace_disk in polar coordinates, LotkaVolterra's Fourier features,
+    cases/PDECases.py:212,405): the kernels differentiate w.r.t. the features, the program applies the chain rule through
+    f symbolically; the kernels are fed f(points), the program reads the raw points."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    dde.config.set_default_float("float32")
+    np.random.seed(4)
+    torch.manual_seed(4)
+    case = pc.Burgers(NumDomain=3000, layer_size=[2] + [20] * 3 + [1], soft_constraints=True)
+    case.net.apply_feature_transform(
+        lambda x: torch.cat([x[:, 0:1] * torch.sin(x[:, 1:2]), torch.exp(-x[:, 1:2]) + x[:, 0:1] ** 2], dim=1))
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3)
+    l_ref, g_ref = _closure_loss_and_grad(model, fused=False)
+    l_fus, g_fus = _closure_loss_and_grad(model, fused=True)
+    note = model.residual_program_note()
+    assert not note.startswith("autograd path"), note
+    assert abs(float(l_fus) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
+    assert float((g_fus - g_ref).abs().max()) <= 1e-5 * float(g_ref.abs().max()), note
+    X = case.geomtime.random_points(500)
+    dde.config.set_residual_programs(False)
+    r0 = model.predict(X, operator=case.pde)
+    dde.config.set_residual_programs(True)
+    r1 = model.predict(X, operator=case.pde)
+    assert not model.residual_program_note("operator").startswith("autograd path")
+    assert np.abs(r1 - r0).max() <= 2e-5 * np.abs(r0).max()
