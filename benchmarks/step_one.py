@@ -20,12 +20,14 @@ def main():
     ap.add_argument("--case", default="burgers20")
     ap.add_argument("--n", type=int, default=2 ** 20)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--engine", default="auto")
     args = ap.parse_args()
     import ai4xde_b200.dde as dde
     from ai4xde_b200 import cases
 
     dde.config.set_default_float("float32")
     dde.config.set_cuda_graphs(False)
+    dde.config.set_engine(args.engine)
     np.random.seed(0)
     torch.manual_seed(0)
     lw = None
