@@ -86,6 +86,20 @@ def test_product_host_path_matches_reference_goldens(name):
     assert rel(np.stack([r.numpy() for r in res]), g["residuals"]) < 5e-5
     assert rel(losses.detach().numpy(), g["losses"]) < 2e-5
     assert rel(grad, g["grad"]) < 1e-4
+    # the operator above and the train closure below run as traced residual programs (ai4xde_b200/residual.py): the
+    # program path is held to the UNMODIFIED reference's golden numbers directly, not only to the autograd path
+    assert not model.residual_program_note("operator").startswith("autograd path")
+    case.net.zero_grad()
+    seen, step = {}, model.opt.step
+    model.opt.step = lambda closure: seen.__setitem__("loss", closure())
+    try:
+        model.train_step(case.data.train_x, None, None)
+    finally:
+        model.opt.step = step
+    assert not model.residual_program_note().startswith("autograd path"), model.residual_program_note()
+    grad_c = torch.cat([p.grad.reshape(-1) for p in case.net.parameters()]).numpy()
+    assert abs(float(seen["loss"]) - float(np.sum(g["losses"]))) < 2e-5 * abs(float(np.sum(g["losses"])))
+    assert rel(grad_c, g["grad"]) < 1e-4
 
 
 @pytest.mark.parametrize("cfg,n", [("cfg1", 400), ("cfg2", 300), ("cfg3", 256), ("cfg4", 200), ("cfg5", 300)])

@@ -92,6 +92,17 @@ CASES = [
 ]
 
 
+# reference case classes whose loss side runs as a traced residual program on the fused path (the others stay on
+# autograd over the jet leaves: non-FNN nets, IDE quadrature rows, auxiliary variables, 1-D BC target arrays)
+TRACED = {"Burgers", "AllenCahn", "Heat", "Helmholtz", "Helmholtz_Sound_hard_Absorbing", "NS_Flow_in_LidDriven_Cavity",
+          "Klein_Gordon", "Schrodinger", "Poisson_1D_Dirichlet_Robin", "Poisson_1D_Dirichlet_PointSetOperator",
+          "Bimodal_2D", "Beltrami_flow", "Diffusion_Reaction_Inverse", "Laplace_disk", "LotkaVolterra",
+          "Poisson_2D_L_Shaped", "Euler_Beam", "A_Simple_ODE", "SecondOrderODE", "Diffusion", "Diffusion_reaction",
+          "Harmonic_Oscillator_1D", "Helmholtz_Hole", "Poisson_1D_Dirichlet", "Poisson_1D_Dirichlet_Neumann",
+          "Poisson_1D_Dirichlet_Periodic", "Poisson_1D_Hard_Boundary", "Poisson_2D_Peak", "Wave_1D_Hard_Boundary",
+          "Brinkman_Forchheimer_Inverse", "Diffusion_Inverse", "Lorenz_Inverse"}
+
+
 def _evaluate(dde, case):
     model = dde.Model(case.data, case.net)
     case.compile(model, "adam", lr=1e-3)
@@ -103,7 +114,20 @@ def _evaluate(dde, case):
     # gradient is taken of the finite terms, the NaN term must be NaN on both sides
     losses[torch.isfinite(losses)].sum().backward()
     g = torch.cat([p.grad.reshape(-1).double().cpu() for p in case.net.parameters()]).numpy()
-    return losses.detach().double().cpu().numpy(), g
+    extra = {}
+    if hasattr(model, "residual_program_note") and not torch.isnan(losses).any():
+        # the train closure as model.train runs it: on the fused path its loss side is a traced residual program for
+        # most cases (benchmarks/residual_program_sweep.py); total loss and gradient go to the oracle comparison too
+        case.net.zero_grad()
+        seen, step = {}, model.opt.step
+        model.opt.step = lambda closure: seen.__setitem__("loss", closure())
+        try:
+            model.train_step(case.data.train_x, case.data.train_y, aux)
+        finally:
+            model.opt.step = step
+        extra = dict(note=model.residual_program_note(), loss=float(seen["loss"]),
+                     grad=torch.cat([p.grad.reshape(-1).double().cpu() for p in case.net.parameters()]).numpy())
+    return losses.detach().double().cpu().numpy(), g, extra
 
 
 @pytest.mark.parametrize("name,kwargs", CASES)
@@ -114,7 +138,7 @@ def test_unmodified_reference_case_runs_on_the_fused_path(name, kwargs, monkeypa
         np.random.seed(0)
         torch.manual_seed(0)
         case_o = getattr(A.cases, name)(**kwargs)
-        ref_losses, ref_grad = _evaluate(dde_o, case_o)
+        ref_losses, ref_grad, _ = _evaluate(dde_o, case_o)
         state = {k: v.detach().float() for k, v in case_o.net.state_dict().items()}
         X_all = case_o.data.train_x_all.copy()
         dde_o.config.set_default_float("float32")
@@ -138,7 +162,7 @@ def test_unmodified_reference_case_runs_on_the_fused_path(name, kwargs, monkeypa
         for nm in ("b_x", "b_t"):         # STMsFFN: likewise
             if hasattr(case_o.net, nm):
                 setattr(case_f.net, nm, [t.detach().float().clone() for t in getattr(case_o.net, nm)])
-        losses, g = _evaluate(dde_f, case_f)
+        losses, g, closure = _evaluate(dde_f, case_f)
     finally:
         _purge()
         from oracle import ddelite
@@ -148,6 +172,12 @@ def test_unmodified_reference_case_runs_on_the_fused_path(name, kwargs, monkeypa
     assert losses.shape == ref_losses.shape
     np.testing.assert_allclose(losses, ref_losses, rtol=2e-3, atol=1e-6 * np.nanmax(np.abs(ref_losses)))
     assert np.abs(g - ref_grad).max() / max(np.abs(ref_grad).max(), 1e-30) < 2e-3
+    if closure:
+        # total loss and gradient of the train closure against the ORACLE (both sides carry the case's loss weights)
+        assert abs(closure["loss"] - ref_losses.sum()) <= 2e-3 * abs(ref_losses.sum()), closure["note"]
+        assert np.abs(closure["grad"] - ref_grad).max() / max(np.abs(ref_grad).max(), 1e-30) < 2e-3, closure["note"]
+        if name in TRACED:
+            assert closure["note"] is not None and not closure["note"].startswith("autograd path"), closure["note"]
 
 
 # ---- the reference's ALGORITHM classes, unmodified ---------------------------------------------------------------
