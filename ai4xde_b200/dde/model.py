@@ -386,7 +386,9 @@ class Model:
             and self.train_step.__qualname__.startswith("Model.compile")
             and self.outputs_losses_train.__qualname__.startswith("Model.compile")
         )
-        key = (id(inputs), getattr(self.data, "version", None), id(self.opt), id(self.data.pde))
+        # a captured step bakes in the device tables of the traced loss program: a new trace (every compile / train
+        # call, every new point set) must never replay an old capture
+        key = (id(inputs), getattr(self.data, "version", None), id(self.opt), id(self.data.pde), self._residual_epoch)
         eligible = eligible and self._owns(inputs)   # foreign arrays are re-uploaded per call: nothing stable to capture
         if not eligible:
             st.update(key=None, seen=0, graph=None, batch=None)
@@ -414,6 +416,7 @@ class Model:
             with torch.cuda.graph(g):         # records the next steps; nothing executes here
                 self.opt.step(closure)
             st["graph"] = g
+            st["program"] = self._residual.get("train")     # the tables the captured kernels point at stay alive
             return True
         except Exception as e:                # capture is an optimisation: stay on the eager fused path
             import warnings
@@ -551,7 +554,8 @@ class Model:
             if targets is None and auxiliary_vars is None and hasattr(inputs, "__len__"):
                 # lets DeviceLBFGS decide whether its per-iteration sequence may be replayed from a CUDA graph
                 closure.graph_rows = len(inputs) if self._owns(inputs) else None
-                closure.graph_key = (id(inputs), getattr(self.data, "version", None), id(self.data.pde))
+                closure.graph_key = (id(inputs), getattr(self.data, "version", None), id(self.data.pde),
+                                     self._residual_epoch)
                 closure.graph_batch = self.device_batch(inputs)   # kept alive by the optimiser's graph
             scope = None
             if optimizers.is_external_optimizer(self.opt_name) and config.engine() == "auto":

@@ -265,3 +265,48 @@ def test_feature_transform_is_chained_symbolically():
     r1 = model.predict(X, operator=case.pde)
     assert not model.residual_program_note("operator").startswith("autograd path")
     assert np.abs(r1 - r0).max() <= 2e-5 * np.abs(r0).max()
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "L-BFGS"])
+def test_repeated_train_calls_never_replay_a_stale_capture(optimizer):
+    """model.train() called again on the same compiled model re-traces the loss code (its Python constants may have
+    moved); a CUDA graph captured for the previous trace points at that trace's device tables and must not be
+    replayed.  Three train() calls with programs == the same three calls on autograd."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    dde.config.set_default_float("float32")
+    hist = {}
+    for fused in (False, True):
+        np.random.seed(1)
+        torch.manual_seed(1)
+        dde.config.set_residual_programs(fused)
+        try:
+            case = pc.Heat(NumDomain=1000, layer_size=[2] + [20] * 3 + [1])
+            model = dde.Model(case.data, case.net)
+            if optimizer == "adam":
+                model.compile("adam", lr=1e-3)
+                out = []
+                for _ in range(3):
+                    lh, _ = model.train(iterations=40, display_every=40)
+                    out.append(float(np.sum(lh.loss_train[-1])))
+                    torch.cuda.empty_cache()      # a dangling table pointer would now read recycled memory
+                    junk = torch.full((1 << 22,), float("nan"), device="cuda")
+                    del junk
+            else:
+                model.compile("adam", lr=1e-3)
+                model.train(iterations=200, display_every=200)
+                dde.optimizers.set_LBFGS_options(maxiter=60)
+                model.compile("L-BFGS")
+                out = []
+                for _ in range(3):
+                    lh, _ = model.train(display_every=1000)
+                    out.append(float(np.sum(lh.loss_train[-1])))
+                    junk = torch.full((1 << 22,), float("nan"), device="cuda")
+                    del junk
+            hist[fused] = out
+        finally:
+            dde.config.set_residual_programs(True)
+            dde.optimizers.set_LBFGS_options()
+    print(optimizer, hist)
+    assert np.all(np.isfinite(hist[True])) and np.allclose(hist[True], hist[False], rtol=5e-3)
