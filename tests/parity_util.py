@@ -91,12 +91,24 @@ def product_vs_oracle(cfg, n_domain, engine="fp32", seed=0, oracle_dtype="float6
     def rel(a, b):
         return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
+    def elementwise(a, b):
+        """(median, 99th percentile) of |a - b| / |b| over the entries that are not tiny (|b| >= 1e-3 max|b|): the
+        max-normalised figures above say nothing about small entries; these do"""
+        a, b = np.asarray(a, dtype=np.float64).reshape(-1), np.asarray(b, dtype=np.float64).reshape(-1)
+        keep = np.abs(b) >= 1e-3 * max(np.abs(b).max(), 1e-300)
+        e = np.abs(a[keep] - b[keep]) / np.abs(b[keep])
+        return (float(np.median(e)), float(np.percentile(e, 99))) if e.size else (0.0, 0.0)
+
     res_rel = max(rel(r.double().cpu().numpy(), rr) for r, rr in zip(res, ref["residuals"]))
     return {
         "loss_rel": rel(losses.detach().double().cpu().numpy(), ref["losses"]),
         "grad_rel": rel(g, ref["grad"]),
         "res_rel": res_rel,
         "out_rel": rel(outs.detach().double().cpu().numpy(), ref["outputs"]),
+        "elementwise": {"out": elementwise(outs.detach().double().cpu().numpy(), ref["outputs"]),
+                        "grad": elementwise(g, ref["grad"]),
+                        "res": elementwise(np.concatenate([r.double().cpu().numpy().reshape(-1) for r in res]),
+                                           np.concatenate([np.asarray(rr).reshape(-1) for rr in ref["residuals"]]))},
         "closure_loss_rel": abs(l_closure - float(np.sum(ref["losses"]))) / abs(float(np.sum(ref["losses"]))),
         "closure_grad_rel": rel(g_closure, ref["grad"]),
         "program": model.residual_program_note(),

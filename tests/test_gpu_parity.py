@@ -27,11 +27,17 @@ def test_fp32_engine_matches_oracle(cfg, n):
     full 2^20 + 80 rows of cfg4 are covered by tests/test_gpu_tc.py::test_cfg4_full_size_properties (tile independence, shard
     additivity, exact linearity, a 2048-point subset against the double)."""
     r = product_vs_oracle(cfg, n, engine="fp32")
-    print(cfg, n, {k: f"{v:.2e}" for k, v in r.items() if k.endswith("_rel")})
+    print(cfg, n, {k: f"{v:.2e}" for k, v in r.items() if k.endswith("_rel")},
+          "elementwise (median, p99):", {k: (f"{v[0]:.1e}", f"{v[1]:.1e}") for k, v in r["elementwise"].items()})
     tol = FP32_TOL[cfg]
     assert r["loss_rel"] < tol["loss"], r
     assert r["grad_rel"] < tol["grad"], r
     assert r["res_rel"] < tol["res"], r
+    # ELEMENTWISE relative error over the entries above 1e-3 of the largest one (the gates above are normalised by the
+    # largest entry): median below 1e-5, 99th percentile below 4e-4 -- within 3x of the measured worst (cfg5's residual,
+    # whose (50 pi)^2 forcing is evaluated in float32 by the case's own code: p99 1.3e-4; everything else <= 5.4e-5)
+    for what, (med, p99) in r["elementwise"].items():
+        assert med < 1e-5 and p99 < 4e-4, (cfg, what, med, p99)
     # the same step through the train closure, its loss side running as a traced residual program
     assert r["program"] is not None and not r["program"].startswith("autograd path"), r["program"]
     assert r["closure_loss_rel"] < tol["loss"] and r["closure_grad_rel"] < tol["grad"], r

@@ -229,8 +229,12 @@ TF32_CFG_TOL = {
 @pytest.mark.parametrize("cfg,n", [("cfg2", 10000), ("cfg3", 4096), ("cfg4", 4096), ("cfg5", 4096)])
 def test_tf32_engine_matches_oracle(cfg, n):
     r = product_vs_oracle(cfg, n, engine="tf32")
-    print(cfg, {k: v for k, v in r.items() if k.endswith("_rel")})
+    print(cfg, {k: v for k, v in r.items() if k.endswith("_rel")},
+          "elementwise (median, p99):", {k: (f"{v[0]:.1e}", f"{v[1]:.1e}") for k, v in r["elementwise"].items()})
     tol = TF32_CFG_TOL[cfg]
+    # elementwise, over the entries above 1e-3 of the largest: TF32 medians 7e-5 .. 4.7e-3, 99th percentiles up to 5.9e-2
+    for what, (med, p99) in r["elementwise"].items():
+        assert med < 1.5e-2 and p99 < 0.18, (cfg, what, med, p99)
     assert r["loss_rel"] < tol["loss"], r
     assert r["grad_rel"] < tol["grad"], r
     assert r["res_rel"] < tol["res"], r
