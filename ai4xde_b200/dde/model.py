@@ -253,7 +253,8 @@ class Model:
                   loss_fn if not isinstance(loss_fn, (list, tuple)) else tuple(loss_fn)) \
             + tuple(getattr(self.data, "bcs", ()))
         n_rows = int(batch.aos.shape[0])
-        key = (getattr(self.data, "version", None), n_rows, spec.key(), self._residual_epoch, batch.host is self.data.train_x)
+        key = (getattr(self.data, "version", None), n_rows, spec.key(), self._residual_epoch, batch.host is self.data.train_x,
+               residual.fingerprint(self.data.pde, net._output_transform, net._input_transform))
         hit = self._residual.get(use)
         if hit is not None and hit[1] == key and len(hit[0]) == len(owners) and all(a is b for a, b in zip(hit[0], owners)):
             return hit[2]
@@ -315,7 +316,7 @@ class Model:
         n_rows = int(batch.aos.shape[0])
         use = ("operator", id(operator), n_rows)
         owners = (operator, net._output_transform, net._input_transform)
-        key = (spec.key(), self._residual_epoch)
+        key = (spec.key(), self._residual_epoch, residual.fingerprint(operator, net._output_transform, net._input_transform))
         hit = self._residual.get(use)
         if hit is not None and hit[1] == key and all(a is b for a, b in zip(hit[0], owners)):
             return hit[2]

@@ -17,6 +17,7 @@ reproduce that path on the live batch (dde/model.py).
 """
 import math
 import numbers
+import numbers as numbers_mod
 import sys
 
 import numpy as np
@@ -878,3 +879,37 @@ def trace_operator(operator_fn, spec, n_rows, n_in, n_out, output_transform=None
         cols += o.cols
         widths.append(len(o.cols))
     return Program(g, spec, [], n_rows, outputs=cols), widths, as_list
+
+
+def fingerprint(*functions):
+    """The Python-level numbers a traced function can see without being re-run: closure cells, defaults, and the
+    numeric attributes of the objects they hold (a case instance's `self.nu`, `self.k0` ...), one level deep.  A program
+    freezes such numbers at trace time; the model re-traces when this tuple changes (a callback that anneals a PDE
+    coefficient), which costs a few microseconds per step to check."""
+    out = []
+
+    def numbers(obj, depth):
+        if isinstance(obj, (bool, numbers_mod.Number, np.generic)):
+            out.append(float(obj) if not isinstance(obj, complex) else obj)
+        elif isinstance(obj, (list, tuple)) and len(obj) <= 64:
+            for v in obj:
+                if isinstance(v, (numbers_mod.Number, np.generic)):
+                    out.append(float(v) if not isinstance(v, complex) else v)
+        elif depth > 0 and hasattr(obj, "__dict__") and not callable(obj) and not isinstance(obj, (torch.nn.Module, type)):
+            for k in sorted(vars(obj)):
+                numbers(vars(obj)[k], depth - 1)
+
+    for fn in functions:
+        if fn is None:
+            continue
+        target = getattr(fn, "__func__", fn)
+        if getattr(fn, "__self__", None) is not None:
+            numbers(fn.__self__, 1)
+        for cell in getattr(target, "__closure__", None) or ():
+            try:
+                numbers(cell.cell_contents, 1)
+            except ValueError:       # empty cell
+                pass
+        for v in getattr(target, "__defaults__", None) or ():
+            numbers(v, 0)
+    return tuple(out)

@@ -298,3 +298,35 @@ def test_feature_transform_is_chained_symbolically():
     r1 = model.predict(X, operator=case.pde)
     assert not model.residual_program_note("operator").startswith("autograd path")
     assert np.abs(r1 - r0).max() <= 2e-5 * np.abs(r0).max()
+
+
+def test_a_coefficient_changed_between_steps_is_picked_up():
+    """A program freezes the Python numbers its code reads; the model watches the ones it can see (closure cells and the
+    numeric attributes of the objects in them) and re-traces when one moves -- a callback annealing `case.nu`."""
+    import ai4xde_b200.dde as dde
+    from ai4xde_b200 import cases as pc
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    case = pc.Burgers(NumDomain=100, layer_size=[2, 8, 8, 1], soft_constraints=True)
+
+    class Coef:
+        nu = 0.01
+
+    coef = Coef()
+    base = case.data.pde
+
+    def pde(x, y):
+        return base(x, y) + coef.nu * dde.grad.hessian(y, x, i=0, j=0)
+
+    case.data.pde = pde
+    model = dde.Model(case.data, case.net)
+    model.compile("adam", lr=1e-3)
+    l0, _ = _losses_and_grad(model, fused=True)
+    first = model._residual["train"][2]
+    coef.nu = 0.5
+    l1, g1 = _losses_and_grad(model, fused=True)
+    assert model._residual["train"][2] is not first
+    l_ref, g_ref = _losses_and_grad(model, fused=False)
+    assert abs(l1 - l0) > 1e-6 * abs(l0) and abs(l1 - l_ref) <= 2e-5 * abs(l_ref)
+    assert float((g1 - g_ref).abs().max()) <= 2e-4 * float(g_ref.abs().max())
