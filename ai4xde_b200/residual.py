@@ -574,7 +574,8 @@ class Sym:
         kwargs = kwargs or {}
         name = _name_of(func).strip("_")
         if name.startswith("r") and name[1:] in ("add", "sub", "mul", "truediv", "div", "pow"):
-            name = name[1:]            # Tensor.__rsub__(t, sym) arrives with its operands already in order
+            name = name[1:]            # Tensor.__rsub__(self, other) means other - self (`1.0 - C` with C a dde.Variable)
+            args = (args[1], args[0]) + tuple(args[2:])
         if any(isinstance(a, VariableTensor) for a in args):
             g0 = next((a.g for a in args if isinstance(a, Sym)), None) or _TRACE.get("graph")
             args = tuple(_scalar_sym(g0, a) if isinstance(a, VariableTensor) else a for a in args)

@@ -212,7 +212,9 @@ def test_trainable_variables_are_traced_as_run_time_scalars():
     base = case.data.pde
 
     def pde(x, y):
-        return base(x, y) * torch.exp(-D) - 1e-2 * C * dde.grad.hessian(y, x, i=0, j=0) + (-C / 7.0) * y
+        # reflected forms with the variable on the right: 1.0 - D, 3.0 / C, 2.0 ** D
+        return base(x, y) * torch.exp(-D) - 1e-2 * C * dde.grad.hessian(y, x, i=0, j=0) + (-C / 7.0) * y \
+            + (1.0 - D) * (3.0 / C) * y * 1e-2 + (2.0 ** D) * 1e-3 * y
 
     case.data.pde = pde
     model = dde.Model(case.data, case.net)
