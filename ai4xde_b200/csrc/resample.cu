@@ -88,11 +88,41 @@ __global__ void k_pw_leaves(const T *__restrict__ a, int64_t n, int depth, T *__
   }
 }
 
-// single block: combine level by level (children of an internal node always exist)
+// does node `p` of `level` exist as an INTERNAL node (more than 128 elements below it)?
+__device__ __forceinline__ bool pw_internal(int64_t n, int level, int64_t p) {
+  int64_t m = n;
+  for (int l = 0; l < level; ++l) {
+    if (m <= 128) return false;
+    const int64_t nl = pw_left(m);
+    m = ((p >> (level - l - 1)) & 1) ? (m - nl) : nl;
+  }
+  return m > 128;
+}
+
+// many blocks: block r combines the subtree rooted at node (top, r), bottom-up, level by level.  The tree above
+// `top` is left to k_pw_combine (one block).  Same additions in the same order as the single-block version: the
+// rounding order NumPy's pairwise sum fixes depends on the tree only.
 template <typename T>
-__global__ void k_pw_combine(int64_t n, int depth, T *__restrict__ heap, T *__restrict__ out,
+__global__ void __launch_bounds__(256) k_pw_combine_sub(int64_t n, int depth, int top, T *__restrict__ heap) {
+  const int64_t r = blockIdx.x;
+  for (int level = depth - 1; level >= top; --level) {
+    const int64_t sub = (int64_t)1 << (level - top);
+    for (int64_t q = threadIdx.x; q < sub; q += blockDim.x) {
+      const int64_t p = (r << (level - top)) + q;
+      if (pw_internal(n, level, p)) {
+        const int64_t idx = ((int64_t)1 << level) + p;
+        heap[idx] = add_rn(heap[2 * idx], heap[2 * idx + 1]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// single block: combine level by level from `start` up (children of an internal node always exist)
+template <typename T>
+__global__ void k_pw_combine(int64_t n, int start, T *__restrict__ heap, T *__restrict__ out,
                              T scale_div) {
-  for (int level = depth - 1; level >= 0; --level) {
+  for (int level = start - 1; level >= 0; --level) {
     const int64_t cnt = (int64_t)1 << level;
     for (int64_t p = threadIdx.x; p < cnt; p += blockDim.x) {
       int64_t m = n;
@@ -137,7 +167,13 @@ static int pairwise_sum_impl(const T *a, int64_t n, T *out, T scale_div, void *w
   const int bs = 128;
   k_pw_leaves<T><<<(unsigned)((threads + bs - 1) / bs), bs, 0, stream>>>(a, n, depth, heap);
   AX_LAUNCH_OK();
-  k_pw_combine<T><<<1, 1024, 0, stream>>>(n, depth, heap, out, scale_div);
+  int top = depth;       // levels [top, depth) are combined by 2^top blocks in parallel, the rest by one block
+  if (depth > 10) {
+    top = 8;
+    k_pw_combine_sub<T><<<1u << top, 256, 0, stream>>>(n, depth, top, heap);
+    AX_LAUNCH_OK();
+  }
+  k_pw_combine<T><<<1, 1024, 0, stream>>>(n, top, heap, out, scale_div);
   AX_LAUNCH_OK();
   return 0;
 }
