@@ -59,6 +59,16 @@ class LossHistory:
         self.metrics_test.append(self.metrics_test[-1] if metrics_test is None else metrics_test)
 
 
+_UPLOAD_STREAM = {}
+
+
+def _upload_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _UPLOAD_STREAM:
+        _UPLOAD_STREAM[dev] = torch.cuda.Stream(device=dev)
+    return _UPLOAD_STREAM[dev]
+
+
 class _DeviceBatch:
     """Device-resident mirror of one host point array: AoS tensor for the case's `pde` code,
     SoA copy for the kernels."""
@@ -69,6 +79,20 @@ class _DeviceBatch:
         self.host = host
         self.version = version
         dev = config.device()
+        pinned = torch.is_tensor(host) and host.device.type == "cpu" and host.is_pinned()
+        if pinned and dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+            # a pinned host buffer handed in per step (bench.py's end-to-end arm, a user's own input pipeline): copy
+            # and transpose on a side stream, so the upload of step k overlaps the kernels of step k - 1 that are
+            # still queued on the compute stream; the compute stream waits for the copy, not the other way round
+            main, side = torch.cuda.current_stream(), _upload_stream()
+            with torch.cuda.stream(side):
+                t = host.to(device=dev, dtype=torch.float32, non_blocking=True)
+                soa = jet.to_soa(t)
+            main.wait_stream(side)
+            t.record_stream(main)
+            soa.record_stream(main)
+            self.aos, self.soa = t, soa
+            return
         if torch.is_tensor(host):
             t = host.to(device=dev, dtype=torch.float32, non_blocking=True)
         else:
