@@ -1082,6 +1082,25 @@ static __global__ void k_tc_reduce(const float *__restrict__ partial, long long 
   for (int b = 0; b < nblocks; ++b) s += __ldg(partial + (long long)b * stride + sub + j);
   out[j] = s;
 }
+// the same sum with FOUR lanes per output (large outputs, many partials: the weight-gradient partials of the fused
+// backward, one per cluster): lane q sums the partials b = q, q + 4, ... in order, then ((s0 + s1) + (s2 + s3)) --
+// a fixed order, four times the loads in flight.  Consecutive outputs sit in consecutive lane QUADS, so a warp reads
+// 8 consecutive floats per partial; the grid is sized for whole warps.
+static __global__ void k_tc_reduce4(const float *__restrict__ partial, long long stride, long long sub, int nblocks,
+                             long long count, float *__restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long j = t >> 2;
+  const int q = (int)(t & 3);
+  float s = 0.0f;
+  if (j < count) {
+#pragma unroll 4
+    for (int b = q; b < nblocks; b += 4) s += __ldg(partial + (long long)b * stride + sub + j);
+  }
+  const float s1 = __shfl_xor_sync(0xffffffffu, s, 1);
+  const float pair = (q & 1) ? s1 + s : s + s1;          // (s0 + s1) on lanes 0, 1; (s2 + s3) on lanes 2, 3
+  const float other = __shfl_xor_sync(0xffffffffu, pair, 2);
+  if (q == 0 && j < count) out[j] = pair + other;
+}
 
 // =========================================================================================
 // host side
@@ -1227,9 +1246,32 @@ static int launch_gemm_pair(const float *wop, const float *in, const GemmArgs &g
 }
 
 
+// few outputs, hundreds of partials (the per-block partials of the output-layer backward): one WARP per output, lane q
+// sums b = q, q + 32, ... in order, then a fixed butterfly
+static __global__ void k_tc_reduce32(const float *__restrict__ partial, long long stride, long long sub, int nblocks,
+                              long long count, float *__restrict__ out) {
+  const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int q = threadIdx.x & 31;
+  if (j >= count) return;       // whole warps leave together
+  float s = 0.0f;
+#pragma unroll 4
+  for (int b = q; b < nblocks; b += 32) s += __ldg(partial + (long long)b * stride + sub + j);
+#pragma unroll
+  for (int step = 1; step < 32; step <<= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, s, step);
+    s = (q & step) ? o + s : s + o;          // both lanes of a pair form (lower + upper): identical bits
+  }
+  if (q == 0) out[j] = s;
+}
+
 static int reduce_to(const float *partial, long long stride, long long sub, int nblocks, long long count,
                      float *out, cudaStream_t st) {
-  k_tc_reduce<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partial, stride, sub, nblocks, count, out);
+  if (nblocks >= 16 && count >= 4096)
+    k_tc_reduce4<<<(unsigned)((4 * count + 255) / 256), 256, 0, st>>>(partial, stride, sub, nblocks, count, out);
+  else if (nblocks >= 64)
+    k_tc_reduce32<<<(unsigned)((32 * count + 255) / 256), 256, 0, st>>>(partial, stride, sub, nblocks, count, out);
+  else
+    k_tc_reduce<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partial, stride, sub, nblocks, count, out);
   AX_LAUNCH_OK();
   return 0;
 }
