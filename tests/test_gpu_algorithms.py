@@ -448,7 +448,10 @@ def test_end_to_end_training_reaches_the_reference_solutions():
     X, y = case.get_testdata()
     err = dde.metrics.l2_relative_error(y, s.model.predict(X))
     print("Helmholtz (reference-default sin net) L2 relative error", err)
-    assert err < 0.02
+    # a snapshot in mid-convergence (L-BFGS capped at 3000 of its 15 000 iterations): 1.5-2.1 % over builds that differ
+    # only in the summation order of the gradient partials; 4.0 % when the L-BFGS phase runs on TF32 gradients, which
+    # is what this bound still tells apart (dde.config.set_lbfgs_engine)
+    assert err < 0.03
 
 
 def test_causal_pinn_round_on_device():
