@@ -29,6 +29,21 @@ struct ResView {
 
 __device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.0f) - (v < 0.0f)); }
 
+// a load / constant instruction's value
+__device__ __forceinline__ float res_load(const int4 in, const float *consts, const ResView &pv, const float *x,
+                                          const float *jets, long long p, long long ldn) {
+  switch (in.x) {
+    case R_LOADX: return __ldg(x + (long long)in.z * ldn + p + in.w);
+    case R_LOADJ: return __ldg(jets + (long long)in.z * ldn + p + in.w);
+    case R_LOADA: {
+      const int2 m = pv.aux_meta[in.z];
+      return __ldg(pv.aux[in.z] + (p - m.x) * m.y + in.w);
+    }
+    case R_LOADS: return __ldg(pv.scalars[in.z]);
+    default: return consts[in.z];
+  }
+}
+
 // one forward sweep of code [cb, ce) for point p; R = this thread's register column (stride T)
 // MODE RES_SUM: `sink` = this thread's term accumulators (stride T); RES_ADJ: adjoint registers A are zeroed as the
 // values are written; RES_EVAL: `sink` = output matrix [columns][ldn], R_STORE writes column in.y at point p
@@ -36,7 +51,32 @@ template <int MODE>
 __device__ __forceinline__ void res_forward(const int4 *code, int cb, int ce, const float *consts, const ResView &pv,
                                             const float *x, const float *jets, long long p, long long ldn, float *R,
                                             float *A, float *sink, int T) {
-  for (int pc = cb; pc < ce; ++pc) {
+  int pc = cb;
+  // the lowering puts every load / constant of a segment first: eight independent global loads in flight per
+  // batch instead of one dependent load per interpreted instruction
+  while (pc + 8 <= ce && code[pc + 7].x <= R_CONST) {
+    int4 in8[8];
+    float v8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) in8[k] = code[pc + k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v8[k] = res_load(in8[k], consts, pv, x, jets, p, ldn);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      R[in8[k].y * T] = v8[k];
+      if (MODE == RES_ADJ) A[in8[k].y * T] = 0.0f;
+    }
+    pc += 8;
+  }
+  while (pc + 2 <= ce && code[pc + 1].x <= R_CONST) {       // the tail of the load block, two at a time
+    const int4 ia = code[pc], ib = code[pc + 1];
+    const float va = res_load(ia, consts, pv, x, jets, p, ldn), vb = res_load(ib, consts, pv, x, jets, p, ldn);
+    R[ia.y * T] = va;
+    R[ib.y * T] = vb;
+    if (MODE == RES_ADJ) A[ia.y * T] = A[ib.y * T] = 0.0f;
+    pc += 2;
+  }
+  for (; pc < ce; ++pc) {
     const int4 in = code[pc];
     float v;
     switch (in.x) {

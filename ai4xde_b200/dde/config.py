@@ -100,6 +100,18 @@ def cuda_graphs():
     return _state["graphs"], _state["graph_max_rows"]
 
 
+def cuda_graph_max_bytes():
+    """'auto' also captures the Adam step of larger point sets when the layers the backward keeps (the stash) stay below
+    this many bytes -- narrow nets on millions of points are still launch-bound on the host side (a 2-[20]x3-1 step at
+    2^20 points is 1.3 ms of kernels and ~20 launches), wide ones are not and would only pin tens of GB in the graph's
+    private pool."""
+    return int(_state.get("graph_max_bytes", 2 << 30))
+
+
+def set_cuda_graph_max_bytes(nbytes):
+    _state["graph_max_bytes"] = int(nbytes)
+
+
 def set_residual_programs(on):
     """True (default): the loss side of a train step -- pde / BC algebra, per-term reductions, their reverse pass --
     runs as one traced program per point (ai4xde_b200/residual.py) whenever the case's code can be traced and the

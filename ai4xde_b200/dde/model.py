@@ -388,6 +388,19 @@ class Model:
             cols += w
         return res if as_list else res[0]
 
+    def _graph_fits(self, n_rows):
+        """larger point sets: is the stash of this net small enough to live in a captured graph's private pool?"""
+        hit, net = self._specs.get(("losses",)), self.net
+        if hit is None or not hasattr(net, "net_desc"):
+            return False
+        try:
+            descs = [net.net_desc] + [p.desc for p in (getattr(net, "_tc_pad", None), getattr(net, "_narrow_pad", None))
+                                      if p is not None]
+            worst = max(_lib.stash_bytes(d, hit[1].desc, _lib.pad32(n_rows), True, "fp32") for d in descs)
+        except Exception:      # noqa: BLE001 -- an estimate only: no estimate, no capture
+            return False
+        return 2 * worst <= config.cuda_graph_max_bytes()      # sin nets on the tensor cores keep two stashes
+
     # ---- CUDA-graph replay of the small-problem step -------------------------------------------
     def _graphed_step(self, inputs, targets, auxiliary_vars, closure):
         """Launch-bound regime (cfg1 is ~60 MFLOP per step): after three eager
@@ -401,7 +414,7 @@ class Model:
             return False
         n_rows = len(inputs) if hasattr(inputs, "__len__") else 0
         eligible = (
-            (mode is True or n_rows <= max_rows)
+            (mode is True or n_rows <= max_rows or self._graph_fits(n_rows))
             and not optimizers.is_external_optimizer(self.opt_name)
             and self.lr_scheduler is None
             and targets is None and auxiliary_vars is None

@@ -795,6 +795,9 @@ class Program:
             finally:
                 sys.setrecursionlimit(limit)
             n_reg = max(n_reg, len(reg))
+            # loads and constants first (they read no register; every value has a register of its own): the
+            # interpreter issues them eight at a time instead of one dependent global load after the other
+            code = [c for c in code if c[0] <= OP_CONST] + [c for c in code if c[0] > OP_CONST]
             self.segments.append((win[0], win[1], np.array(code, dtype=np.int32).reshape(-1, 4)))
         consts = [0.0] * len(cindex)
         for v, i in cindex.items():

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--n", type=int, default=2 ** 20)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--timing", action="store_true", help="per-kernel CUDA-event times of one more step")
     args = ap.parse_args()
     import ai4xde_b200.dde as dde
     from ai4xde_b200 import cases
@@ -46,6 +47,20 @@ def main():
         model.train_step(X, None, None)
     torch.cuda.synchronize()
     print(args.case, len(X), "rows;", model.residual_program_note())
+    if args.timing:
+        import json
+
+        from ai4xde_b200 import _lib
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.timing_enable(True)
+        e0.record()
+        model.train_step(X, None, None)
+        e1.record()
+        rep = _lib.timing_report()
+        _lib.timing_enable(False)
+        print("step", round(e0.elapsed_time(e1), 3), "ms; kernels",
+              json.dumps({k: [v["launches"], round(v["ms"], 3)] for k, v in sorted(rep.items())}))
 
 
 if __name__ == "__main__":
