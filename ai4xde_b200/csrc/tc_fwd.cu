@@ -516,7 +516,7 @@ __global__ void k_tc_jets_combine(const float *__restrict__ part, const float *_
 // =========================================================================================
 constexpr int kL2MaxG = 8;
 constexpr int kL2EpiWarps = 16;                        // four warps per TMEM lane quarter: the epilogue is latency-bound
-constexpr int kL2Threads = 32 * (2 + kL2EpiWarps);
+constexpr int kL2Threads = 32 * (3 + kL2EpiWarps);   // TMA producer, MMA issuer, 16 epilogue warps, release warp
 constexpr int kL2Subs = kL2EpiWarps / 4;
 
 struct L2ChainArgs {
@@ -527,6 +527,8 @@ struct L2ChainArgs {
   int L;                              // hidden layers: GEMM layers are 1 .. L-1
   int G;                              // tiles per group (<= kL2MaxG)
   int hints;                          // L2 eviction hints on the TMA loads (AX_TC_L2CHAIN_HINTS)
+  int defer;                          // who releases a finished tile to the producers (AX_TC_L2CHAIN_DEFER): 0 the epilogue
+                                      // warps at once, 1 the epilogue warps during the NEXT item, 2 the release warp
   long long n;
   int num_tiles;
   int act;
@@ -591,7 +593,7 @@ __device__ __forceinline__ void tma_load_3d_2sm_hint_p(const CUtensorMap *map, u
       : "memory");
 }
 
-template <class P>
+template <class P, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kL2Threads, 1)
 k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_act,
             const __grid_constant__ L2ChainArgs g) {
@@ -612,7 +614,8 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
   uint64_t *tmem_full = empty + NSTAGE;   // [2]
   uint64_t *tmem_empty = tmem_full + 2;   // [2]
   uint64_t *tile_done = tmem_empty + 2;   // [kL2MaxG]: tile j of the current group finished a layer (pair-wide)
-  uint32_t *tmem_slot = (uint32_t *)(tile_done + kL2MaxG);
+  uint64_t *rows_done = tile_done + kL2MaxG;   // [kL2MaxG]: this CTA's epilogue warps stored their rows of tile j
+  uint32_t *tmem_slot = (uint32_t *)(rows_done + kL2MaxG);
   float *jacc = reinterpret_cast<float *>(tmem_slot + 4);   // [2 items][G8][4 quarters][32] (fused output layer)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -630,7 +633,10 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 2 * kL2EpiWarps);
     }
-    for (int j = 0; j < kL2MaxG; ++j) mbar_init(&tile_done[j], 2 * kL2EpiWarps);
+    for (int j = 0; j < kL2MaxG; ++j) {
+      mbar_init(&tile_done[j], g.defer == 2 ? 2 : 2 * kL2EpiWarps);
+      mbar_init(&rows_done[j], kL2EpiWarps);
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -714,6 +720,29 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
         }
       }
     }
+  } else if (warp == 2 + kL2EpiWarps) {
+    // ------------------------------ release warp (both CTAs) ----
+    // The cluster-scope release fence of a hand-off waits until the stores before it are acknowledged by L2 -- about a
+    // microsecond.  Issued by the epilogue warps themselves that wait is idle issue time of the warps that bound the
+    // kernel (ERRBAR / MEMBAR: 17 % of the stall samples); here they only release at CTA scope on `rows_done` and go
+    // on, and THIS warp acquires their rows (cumulativity), fences and arrives on the pair-wide barrier.
+    if (g.defer == 2) {
+      uint32_t par = 0;
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+        for (int l = 1; l < L - 1; ++l) {
+          for (int j = 0; j < G; ++j) {
+            if (grp * G + j >= g.num_tiles) break;
+            mbar_wait(&rows_done[j], (par >> j) & 1u);
+            par ^= 1u << j;
+            if (lane == 0) {
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+              mbar_arrive_both_after_release(&tile_done[j]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------ epilogue (both CTAs, own 128 units) --------
     const int q = warp & 3;
@@ -724,16 +753,40 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
     const int o = (int)rank * 128 + q * 32 + lane;
     constexpr bool kCanFuseOut = (8 * S == 32);
     const float wout_o = (kCanFuseOut && g.wout != nullptr) ? __ldg(g.wout + o) : 0.0f;
+    // the activation is a compile-time constant for tanh / sin instantiations: the per-point code of a full tile is
+    // branch-free, so the eight points of a group are scheduled as one block (their SFU chains overlap)
+    const int act = (ACT >= 0) ? ACT : g.act;
+    // Release of a finished tile to the pair's TMA producers: the warp's rows are written (generic proxy, ordered
+    // before lane 0 by the warp barrier); lane 0 fences towards the async proxy and release-arrives, once per warp, on
+    // the barrier of BOTH CTAs.  (A per-lane `fence.proxy.async` over all state spaces here cost 13 % of the kernel's
+    // stall samples: MEMBAR + CCTL.IVALL + ERRBAR + FENCE.VIEW.ASYNC in every thread.)  The producer fences once more
+    // on its side after the acquire.  The release fence waits until the warp's stores are acknowledged by L2, about a
+    // microsecond in which the warp issues nothing; with g.defer the release of item i is therefore issued during
+    // item i + 1, after its first group has been computed and before that group's stores: by then the stores of item i
+    // have long landed and the fence returns at once.  (Item i + 1 never depends on the release of item i when the
+    // group holds two tiles or more; single-tile groups release at once.)
+    auto release = [&](int jj) {
+      __syncwarp();
+      if (lane == 0) {
+        if (g.defer == 2) {
+          asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rows_done[jj])) : "memory");
+        } else {
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          mbar_arrive_both_after_release(&tile_done[jj]);
+        }
+      }
+    };
+    int pending = -1;
     uint32_t it = 0;
     for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      const int gcount = (g.num_tiles - grp * G) < G ? (g.num_tiles - grp * G) : G;
       for (int l = 1; l < L; ++l) {
         const float bias = __ldg(g.bias[l] + o);
         float *const outl = g.out[l];
         float *const zoutl = g.zout[l];
         const bool fuse_out = kCanFuseOut && (g.wout != nullptr) && (l == L - 1);
-        for (int j = 0; j < G; ++j) {
+        for (int j = 0; j < gcount; ++j) {
           const int tile = grp * G + j;
-          if (tile >= g.num_tiles) break;
           const uint32_t b = it & 1, bphase = (it >> 1) & 1;
           const long long p0 = (long long)tile * PT;
           const bool full_tile = (p0 + PT <= g.n);
@@ -754,35 +807,81 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
               __syncwarp();
               if (lane == 0) mbar_arrive_cta(&tmem_empty[b], 0);
             }
-            const int valid = full_tile ? 8 : (int)((g.n - p0 - g8 * 8) < 8 ? (g.n - p0 - g8 * 8) : 8);
             float t[kCanFuseOut ? 32 : 1];
-#pragma unroll
-            for (int pp = 0; pp < 8; ++pp) {
-              if (full_tile || pp < valid) {
+            if (full_tile && zbase == nullptr) {
+              // full tile, post-activation streams only: branch-free per-point code, computed in place
+              auto point = [&](int pp) {
                 float z[S], w[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
                 z[0] += bias;
-                if (zbase != nullptr) {
-                  float *zp = zbase + g8 * GSTRIDE;
+                jet_forward_A<P>(act, z, w);
+                r[pp * S] = w[0];
 #pragma unroll
-                  for (int s = 0; s < S; ++s) zp[(pp * S + s) * H] = z[s];
+                for (int s = 1; s < S; ++s) r[pp * S + s] = to_tf32(w[s]);
+              };
+              float *op = obase != nullptr ? obase + g8 * GSTRIDE : nullptr;
+              if (g.defer == 1) {
+                // deferred release: the fence sits between the arithmetic and the stores of this group
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp) point(pp);
+                if (pending >= 0) {
+                  release(pending);
+                  pending = -1;
                 }
-                jet_forward_A<P>(g.act, z, w);
+                if (op != nullptr) {
 #pragma unroll
-                for (int s = 1; s < S; ++s) w[s] = to_tf32(w[s]);
-                if (obase != nullptr) {
-                  float *op = obase + g8 * GSTRIDE;
-#pragma unroll
-                  for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = w[s];
+                  for (int i = 0; i < 8 * S; ++i) op[i * H] = r[i];
                 }
-                if (kCanFuseOut && fuse_out) {
+              } else {
+                // stores follow their point (no 32-store burst per warp: the LSU queue throttled those)
 #pragma unroll
-                  for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = wout_o * w[s];
+                for (int pp = 0; pp < 8; ++pp) {
+                  point(pp);
+                  if (op != nullptr) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = r[pp * S + s];
+                  }
                 }
-              } else if (kCanFuseOut && fuse_out) {
+              }
+              if (kCanFuseOut && fuse_out) {
 #pragma unroll
-                for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = 0.0f;
+                for (int i = 0; i < 8 * S; ++i) t[i & 31] = wout_o * r[i];
+              }
+            } else {
+              if (pending >= 0) {
+                release(pending);
+                pending = -1;
+              }
+              const int valid = full_tile ? 8 : (int)((g.n - p0 - g8 * 8) < 8 ? (g.n - p0 - g8 * 8) : 8);
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp) {
+                if (full_tile || pp < valid) {
+                  float z[S], w[S];
+#pragma unroll
+                  for (int s = 0; s < S; ++s) z[s] = r[pp * S + s];
+                  z[0] += bias;
+                  if (zbase != nullptr) {
+                    float *zp = zbase + g8 * GSTRIDE;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) zp[(pp * S + s) * H] = z[s];
+                  }
+                  jet_forward_A<P>(act, z, w);
+#pragma unroll
+                  for (int s = 1; s < S; ++s) w[s] = to_tf32(w[s]);
+                  if (obase != nullptr) {
+                    float *op = obase + g8 * GSTRIDE;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) op[(pp * S + s) * H] = w[s];
+                  }
+                  if (kCanFuseOut && fuse_out) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = wout_o * w[s];
+                  }
+                } else if (kCanFuseOut && fuse_out) {
+#pragma unroll
+                  for (int s = 0; s < S; ++s) t[(pp * S + s) & 31] = 0.0f;
+                }
               }
             }
             if (kCanFuseOut && fuse_out) {
@@ -800,16 +899,10 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
             }
           }
           if (l < L - 1) {
-            // release the tile to the pair's TMA producers: the warp's rows are written (generic proxy, ordered before
-            // lane 0 by the warp barrier); lane 0 fences towards the async proxy and release-arrives, once per warp, on
-            // the barrier of BOTH CTAs.  (A per-lane `fence.proxy.async` over all state spaces here cost 13 % of the
-            // kernel's stall samples: MEMBAR + CCTL.IVALL + ERRBAR + FENCE.VIEW.ASYNC in every thread.)  The producer
-            // fences once more on its side after the acquire.
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("fence.proxy.async.global;" ::: "memory");
-              mbar_arrive_both_after_release(&tile_done[j]);
-            }
+            if (g.defer == 1 && gcount >= 2)
+              pending = j;
+            else
+              release(j);
           }
           if (kCanFuseOut && fuse_out) {
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kL2EpiWarps) : "memory");
@@ -826,6 +919,7 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
         }
       }
     }
+    if (pending >= 0) release(pending);
   }
   tc_fence_before();
   __syncthreads();
@@ -838,7 +932,7 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
 
 // AX_TC_L2CHAIN=0: layer-by-layer forward launches (k_tc_gemm2) instead of the L2-chained kernel; AX_TC_L2CHAIN_G:
 // tiles per group (default 3)
-static int g_l2chain = -1, g_l2chain_G = 0, g_l2chain_hints = -1;
+static int g_l2chain = -1, g_l2chain_G = 0, g_l2chain_hints = -1, g_l2chain_defer = -1;
 static bool l2chain_on() {
   if (g_l2chain < 0) {
     const char *e = getenv("AX_TC_L2CHAIN");
@@ -849,7 +943,7 @@ static bool l2chain_on() {
 static int l2chain_group() {
   if (!g_l2chain_G) {
     const char *e = getenv("AX_TC_L2CHAIN_G");
-    g_l2chain_G = e ? atoi(e) : 2;
+    g_l2chain_G = e ? atoi(e) : 3;
     if (g_l2chain_G < 1) g_l2chain_G = 1;
     if (g_l2chain_G > kL2MaxG) g_l2chain_G = kL2MaxG;
   }
@@ -862,14 +956,23 @@ static int l2chain_hints() {
   }
   return g_l2chain_hints;
 }
+static int l2chain_defer() {
+  if (g_l2chain_defer < 0) {
+    const char *e = getenv("AX_TC_L2CHAIN_DEFER");
+    g_l2chain_defer = e ? atoi(e) : 2;
+    if (g_l2chain_defer < 0 || g_l2chain_defer > 2) g_l2chain_defer = 2;
+  }
+  return g_l2chain_defer;
+}
 // run-time switches of the tensor-core forward (tests compare the chained kernel with the layer-by-layer one bit for bit)
 int tc_set_option(const char *name, int value) {
   const std::string n(name ? name : "");
   if (n == "l2chain") g_l2chain = value != 0;
   else if (n == "l2chain_group") g_l2chain_G = value < 1 ? 1 : (value > kL2MaxG ? kL2MaxG : value);
   else if (n == "l2chain_hints") g_l2chain_hints = value != 0;
+  else if (n == "l2chain_defer") g_l2chain_defer = value < 0 ? 0 : (value > 2 ? 2 : value);
   else {
-    set_error("unknown tensor-core option '%s' (l2chain, l2chain_group, l2chain_hints)", n.c_str());
+    set_error("unknown tensor-core option '%s' (l2chain, l2chain_group, l2chain_hints, l2chain_defer)", n.c_str());
     return 1;
   }
   return 0;
@@ -951,6 +1054,7 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       la.L = g.L;
       la.G = l2chain_group();
       la.hints = l2chain_hints();
+      la.defer = l2chain_defer();
       la.n = a.n;
       la.num_tiles = (int)((a.n + PT - 1) / PT);
       la.act = act;
@@ -966,10 +1070,14 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       CUtensorMap mw, ma;
       if (make_map(&mw, wr, (long long)(g.L - 1) * H, H, 128, 1)) return 1;
       if (make_map(&ma, stash, (long long)slots * slot_rows, H, NHALF_, 1)) return 1;
-      static bool attr = false;
-      if (!attr) {
-        AX_CUDA_OK(cudaFuncSetAttribute(k_tc_fwd_l2<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+      // tanh and sin (the reference's activations for wide nets) are compiled in; sigmoid reads the id at run time
+      auto *kern = act == AX_ACT_TANH ? k_tc_fwd_l2<P, AX_ACT_TANH>
+                   : act == AX_ACT_SIN ? k_tc_fwd_l2<P, AX_ACT_SIN> : k_tc_fwd_l2<P, -1>;
+      static bool attr[3] = {false, false, false};
+      const int ai = act == AX_ACT_TANH ? 0 : act == AX_ACT_SIN ? 1 : 2;
+      if (!attr[ai]) {
+        AX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[ai] = true;
       }
       int clusters = sm_count() / 2;
       const int groups = (la.num_tiles + la.G - 1) / la.G;
@@ -977,7 +1085,7 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
       {
         KernelTimer t("tc_fwd_l2chain", a.stream, 2.0 * S * H * (double)H * (double)a.n * (g.L - 1),
                       4.0 * S * H * (double)a.n * (a.keep_all ? g.L : 1.0));
-        k_tc_fwd_l2<P><<<2 * clusters, kL2Threads, smem, a.stream>>>(mw, ma, la);
+        kern<<<2 * clusters, kL2Threads, smem, a.stream>>>(mw, ma, la);
       }
       AX_LAUNCH_OK();
       if (fuse_out) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B of the forward of cfg4 (2-[256]x6-1 tanh, Laplacian pattern, layers kept) inside ONE process: one launch per
 hidden layer (k_tc_gemm2) vs the L2-chained kernel (k_tc_fwd_l2) at several group sizes, with and without the L2
-eviction hints; configurations interleaved round-robin so that clock / power-cap drift hits them alike.
+eviction hints, with the tile release issued at once or deferred into the next item; configurations interleaved round-robin so that clock / power-cap drift hits them alike.
 Usage: python benchmarks/l2chain_bench.py [n_points]"""
 import json
 import os
@@ -29,12 +29,14 @@ def main():
         chunks += [torch.randn((1, o * i), generator=gen) * (2.0 / (i + o)) ** 0.5, torch.zeros((1, o))]
     params = torch.cat(chunks, dim=1).to(dev)
     xs = to_soa(torch.rand((n, 2), generator=gen).to(dev))
-    configs = [("layer launches", 0, 2, 1), ("l2chain G=2 hints", 1, 2, 1), ("l2chain G=2", 1, 2, 0),
-               ("l2chain G=3 hints", 1, 3, 1), ("l2chain G=1 hints", 1, 1, 1)]
+    configs = [("layer launches", 0, 2, 1, 0), ("l2chain G=2 hints", 1, 2, 1, 0), ("l2chain G=3 hints", 1, 3, 1, 0),
+               ("l2chain G=3 hints defer", 1, 3, 1, 1), ("l2chain G=3 hints release-warp", 1, 3, 1, 2),
+               ("l2chain G=2 hints release-warp", 1, 2, 1, 2), ("l2chain G=4 hints release-warp", 1, 4, 1, 2)]
     times = {c[0]: [] for c in configs}
     for keep in (True, False):
         for rnd in range(6):
-            for name, on, G, hints in configs:
+            for name, on, G, hints, defer in configs:
+                _lib.tc_set_option("l2chain_defer", defer)
                 _lib.tc_set_option("l2chain", on)
                 _lib.tc_set_option("l2chain_group", G)
                 _lib.tc_set_option("l2chain_hints", hints)
@@ -53,8 +55,9 @@ def main():
                           "forward_ms_min": {k: round(min(v), 3) for k, v in times.items()}}))
         times = {c[0]: [] for c in configs}
     _lib.tc_set_option("l2chain", 1)
-    _lib.tc_set_option("l2chain_group", 2)
+    _lib.tc_set_option("l2chain_group", 3)
     _lib.tc_set_option("l2chain_hints", 1)
+    _lib.tc_set_option("l2chain_defer", 2)
 
 
 if __name__ == "__main__":

@@ -260,6 +260,9 @@ def test_reference_default_helmholtz_sin_net_on_the_tensor_cores():
     assert f["loss_rel"] < 1e-5 and f["grad_rel"] < 1e-5 and f["res_rel"] < 1e-5, f
 
 
+L2CHAIN_DEFAULT_GROUP = 3   # csrc/tc_fwd.cu l2chain_group()
+
+
 @pytest.mark.parametrize("widths,act,spec,n,keep", [
     ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((15, 15),)), 200003, True),      # cfg4 as trained: 5 chained layers
     ([2, 256] + [256] * 5 + [1], "tanh", ((0, 1), ((15, 15),)), 200003, False),     # residual probe: ping-pong slots
@@ -288,18 +291,20 @@ def test_l2_chained_forward_is_bit_identical_to_the_layer_launches(widths, act, 
         L = len(widths) - 2
         n_layers = L * (2 if act == "sin" else 1) if keep else 0
         s0 = stash0.view(torch.float32)
-        for G in (1, 2, 3, 5, 8):
+        for defer, G in [(d, G) for d in (2, 1, 0) for G in (1, 2, 3, 5, 8)]:
             _lib.tc_set_option("l2chain", 1)
             _lib.tc_set_option("l2chain_group", G)
-            for rep in range(5 if G == 2 else 2):
+            _lib.tc_set_option("l2chain_defer", defer)   # tile released by the release warp / during the next item / at once
+            for rep in range(5 if G in (2, 3) and defer == 2 else 2):
                 jets1, stash1 = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=keep, engine="tf32")
-                assert torch.equal(jets1[..., :n], jets0[..., :n]), (G, rep)
+                assert torch.equal(jets1[..., :n], jets0[..., :n]), (defer, G, rep)
                 s1 = stash1.view(torch.float32)
                 for l in range(n_layers):
-                    assert torch.equal(s1[l * layer : l * layer + rows], s0[l * layer : l * layer + rows]), (G, rep, l)
+                    assert torch.equal(s1[l * layer : l * layer + rows], s0[l * layer : l * layer + rows]), (defer, G, rep, l)
     finally:
         _lib.tc_set_option("l2chain", 1)
-        _lib.tc_set_option("l2chain_group", 2)
+        _lib.tc_set_option("l2chain_group", L2CHAIN_DEFAULT_GROUP)
+        _lib.tc_set_option("l2chain_defer", 2)
 
 
 def test_cfg4_full_size_properties():
