@@ -379,7 +379,7 @@ def residual_backward(tables, x_soa, jets, n, term_grads):
 
 
 def tc_set_option(name, value):
-    """run-time switch of the tcgen05 engine ("l2chain", "l2chain_group", "l2chain_hints", "l2chain_defer")"""
+    """run-time switch of the tcgen05 engine ("l2chain", "l2chain_group", "l2chain_hints", "l2chain_defer", "l2chain_wres")"""
     _check(load().ax_tc_set_option(name.encode(), int(value)), "ax_tc_set_option")
 
 

@@ -593,25 +593,46 @@ __device__ __forceinline__ void tma_load_3d_2sm_hint_p(const CUtensorMap *map, u
       : "memory");
 }
 
-template <class P, int ACT>
+// smem geometry of k_tc_fwd_l2.  WRES = false: a ring of stages, each one 32-wide K block of the CTA's 128 weight rows
+// plus the same K block of its row half of the tile (the layer kernel's ring).  WRES = true: the CTA's 128 rows of W_l
+// stay RESIDENT for a whole (group, layer) visit -- eight 16 KB K blocks, each reloaded for the next visit as soon as the
+// visit's last item has consumed it -- and the ring carries activations only: the weights come out of L2 once per G
+// items instead of once per item (a third less TMA / L2 traffic at G = 3).
+template <int S, bool WRES>
+struct L2Smem {
+  static constexpr int NHALF = TileOf<S>::N / 2;
+  static constexpr int W_BYTES = 128 * 128, IN_BYTES = NHALF * 128;
+  static constexpr int A_STAGE = ((IN_BYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = WRES ? A_STAGE : W_BYTES + A_STAGE;
+  static constexpr int RING_OFF = WRES ? 8 * W_BYTES : 0;
+  static constexpr int RING_BUDGET = WRES ? 84 * 1024 : 196 * 1024;
+  static constexpr int NSTAGE = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr size_t BYTES = (size_t)RING_OFF + (size_t)NSTAGE * STAGE_BYTES + 1024 + 512 + 2 * 8 * 4 * 32 * sizeof(float);
+};
+
+template <class P, int ACT, bool WRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kL2Threads, 1)
 k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_act,
             const __grid_constant__ L2ChainArgs g) {
   constexpr int S = P::S, H = 256;
   constexpr int PT = TileOf<S>::PT, N = TileOf<S>::N, NHALF = N / 2;
   constexpr int KB = H / 32;
-  constexpr int W_BYTES = 128 * 128, IN_BYTES = NHALF * 128;
-  constexpr int STAGE_BYTES = W_BYTES + ((IN_BYTES + 1023) / 1024) * 1024;
-  constexpr int NSTAGE = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
+  using SM = L2Smem<S, WRES>;
+  constexpr int W_BYTES = SM::W_BYTES, IN_BYTES = SM::IN_BYTES;
+  constexpr int STAGE_BYTES = SM::STAGE_BYTES, NSTAGE = SM::NSTAGE;
   constexpr uint32_t IDESC = make_idesc_m256(N);
   constexpr int G8 = PT / 8;
   static_assert(NHALF % 8 == 0, "row halves must be whole swizzle atoms");
+  static_assert(NSTAGE >= 3, "activation ring too short");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *full = (uint64_t *)(smem + NSTAGE * STAGE_BYTES);
+  uint8_t *ring = smem + SM::RING_OFF;
+  uint64_t *full = (uint64_t *)(ring + NSTAGE * STAGE_BYTES);
   uint64_t *empty = full + NSTAGE;
-  uint64_t *tmem_full = empty + NSTAGE;   // [2]
+  uint64_t *wfull = empty + NSTAGE;       // [KB] (WRES): K block kb of the resident weights landed (both CTAs)
+  uint64_t *wempty = wfull + KB;          // [KB] (WRES): K block kb consumed by the last item of the visit
+  uint64_t *tmem_full = wempty + KB;      // [2]
   uint64_t *tmem_empty = tmem_full + 2;   // [2]
   uint64_t *tile_done = tmem_empty + 2;   // [kL2MaxG]: tile j of the current group finished a layer (pair-wide)
   uint64_t *rows_done = tile_done + kL2MaxG;   // [kL2MaxG]: this CTA's epilogue warps stored their rows of tile j
@@ -633,6 +654,10 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 2 * kL2EpiWarps);
     }
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_init(&wfull[kb], 1);
+      mbar_init(&wempty[kb], 1);
+    }
     for (int j = 0; j < kL2MaxG; ++j) {
       mbar_init(&tile_done[j], g.defer == 2 ? 2 : 2 * kL2EpiWarps);
       mbar_init(&rows_done[j], kL2EpiWarps);
@@ -651,10 +676,16 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
     // ------------------------------ TMA producer (both CTAs; whole warp, one elected lane issues) ----
     const uint32_t issue = elect_one();
     const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, visit = 0;
     uint32_t done_par = 0;   // bit j: parity of tile_done[j] the next wait looks for (one toggle per completed wait)
+    auto load = [&](const CUtensorMap *m, uint32_t bar, void *dst, int c1, int c2, uint64_t pol) {
+      if (g.hints)
+        tma_load_3d_2sm_hint_p(m, bar, dst, 0, c1, c2, pol, issue);
+      else
+        tma_load_3d_2sm_p(m, bar, dst, 0, c1, c2, issue);
+    };
     for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
-      for (int l = 1; l < L; ++l) {
+      for (int l = 1; l < L; ++l, ++visit) {
         for (int j = 0; j < G; ++j) {
           const int tile = grp * G + j;
           if (tile >= g.num_tiles) break;
@@ -667,17 +698,18 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
           const int row0 = g.in_row[l] + tile * N + (int)rank * NHALF;
           const int wrow = (l - 1) * H + (int)rank * 128;
           for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t *sw = smem + stage * STAGE_BYTES;
-            mbar_expect_tx_p(&full[stage], 2 * (W_BYTES + IN_BYTES), rank == 0 ? issue : 0u);
-            const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
-            if (g.hints) {
-              tma_load_3d_2sm_hint_p(&map_w, leader_bar, sw, 0, wrow, kb, pol_w, issue);
-              tma_load_3d_2sm_hint_p(&map_act, leader_bar, sw + W_BYTES, 0, row0, kb, pol_a, issue);
-            } else {
-              tma_load_3d_2sm_p(&map_w, leader_bar, sw, 0, wrow, kb, issue);
-              tma_load_3d_2sm_p(&map_act, leader_bar, sw + W_BYTES, 0, row0, kb, issue);
+            if (WRES && j == 0) {
+              // next visit's K block kb follows the previous visit's last item through the resident weights
+              mbar_wait(&wempty[kb], (visit & 1u) ^ 1u);
+              mbar_expect_tx_p(&wfull[kb], 2 * W_BYTES, rank == 0 ? issue : 0u);
+              load(&map_w, smem_u32(&wfull[kb]) & 0xFEFFFFFFu, smem + kb * W_BYTES, wrow, kb, pol_w);
             }
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t *sw = ring + stage * STAGE_BYTES;
+            mbar_expect_tx_p(&full[stage], 2 * ((WRES ? 0 : W_BYTES) + IN_BYTES), rank == 0 ? issue : 0u);
+            const uint32_t leader_bar = smem_u32(&full[stage]) & 0xFEFFFFFFu;
+            if (!WRES) load(&map_w, leader_bar, sw, wrow, kb, pol_w);
+            load(&map_act, leader_bar, sw + (WRES ? 0 : W_BYTES), row0, kb, pol_a);
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1;
@@ -690,26 +722,29 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
     // ------------------------------ MMA issuer (leader CTA only; whole warp, one elected lane issues) ----
     if (rank == 0) {
       const uint32_t issue = elect_one();
-      uint32_t stage = 0, phase = 0, it = 0;
+      uint32_t stage = 0, phase = 0, it = 0, visit = 0;
       const uint64_t d_w = make_desc(smem_u32(smem), 16, 1024);
-      const uint64_t d_in = make_desc(smem_u32(smem) + W_BYTES, 16, 1024);
+      const uint64_t d_in = make_desc(smem_u32(ring) + (WRES ? 0 : W_BYTES), 16, 1024);
       for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
-        for (int l = 1; l < L; ++l) {
-          for (int j = 0; j < G; ++j) {
-            if (grp * G + j >= g.num_tiles) break;
+        const int gcount = (g.num_tiles - grp * G) < G ? (g.num_tiles - grp * G) : G;
+        for (int l = 1; l < L; ++l, ++visit) {
+          for (int j = 0; j < gcount; ++j) {
             const uint32_t b = it & 1, bphase = (it >> 1) & 1;
             ++it;
             mbar_wait(&tmem_empty[b], bphase ^ 1);
             tc_fence_after();
             for (int kb = 0; kb < KB; ++kb) {
+              if (WRES && j == 0) mbar_wait(&wfull[kb], visit & 1u);
               mbar_wait(&full[stage], phase);
               tc_fence_after();
               const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
+              const uint64_t wo = WRES ? (uint64_t)(kb * (W_BYTES >> 4)) : so;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_tf32_2sm_p(tmem_base + b * 256, d_w + so + ((ks * 32) >> 4), d_in + so + ((ks * 32) >> 4), IDESC,
+                umma_tf32_2sm_p(tmem_base + b * 256, d_w + wo + ((ks * 32) >> 4), d_in + so + ((ks * 32) >> 4), IDESC,
                                 (kb | ks) != 0 ? 1u : 0u, issue);
               umma_commit_2sm_p(&empty[stage], issue);
+              if (WRES && j == gcount - 1) umma_commit_2sm_p(&wempty[kb], issue);
               if (++stage == NSTAGE) {
                 stage = 0;
                 phase ^= 1;
@@ -932,7 +967,7 @@ k_tc_fwd_l2(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
 
 // AX_TC_L2CHAIN=0: layer-by-layer forward launches (k_tc_gemm2) instead of the L2-chained kernel; AX_TC_L2CHAIN_G:
 // tiles per group (default 3)
-static int g_l2chain = -1, g_l2chain_G = 0, g_l2chain_hints = -1, g_l2chain_defer = -1;
+static int g_l2chain = -1, g_l2chain_G = 0, g_l2chain_hints = -1, g_l2chain_defer = -1, g_l2chain_wres = -1;
 static bool l2chain_on() {
   if (g_l2chain < 0) {
     const char *e = getenv("AX_TC_L2CHAIN");
@@ -964,6 +999,13 @@ static int l2chain_defer() {
   }
   return g_l2chain_defer;
 }
+static int l2chain_wres() {
+  if (g_l2chain_wres < 0) {
+    const char *e = getenv("AX_TC_L2CHAIN_WRES");
+    g_l2chain_wres = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_l2chain_wres;
+}
 // run-time switches of the tensor-core forward (tests compare the chained kernel with the layer-by-layer one bit for bit)
 int tc_set_option(const char *name, int value) {
   const std::string n(name ? name : "");
@@ -971,8 +1013,9 @@ int tc_set_option(const char *name, int value) {
   else if (n == "l2chain_group") g_l2chain_G = value < 1 ? 1 : (value > kL2MaxG ? kL2MaxG : value);
   else if (n == "l2chain_hints") g_l2chain_hints = value != 0;
   else if (n == "l2chain_defer") g_l2chain_defer = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (n == "l2chain_wres") g_l2chain_wres = value != 0;
   else {
-    set_error("unknown tensor-core option '%s' (l2chain, l2chain_group, l2chain_hints, l2chain_defer)", n.c_str());
+    set_error("unknown tensor-core option '%s' (l2chain, l2chain_group, l2chain_hints, l2chain_defer, l2chain_wres)", n.c_str());
     return 1;
   }
   return 0;
@@ -1063,21 +1106,23 @@ static int tc_forward_impl(const NetGeom &g, const FwdArgs &a) {
         la.wout = prm + g.w_off[g.L];
         la.jets_part = jets_part;
       }
-      constexpr int N_ = TileOf<S>::N, NHALF_ = N_ / 2;
-      constexpr int STAGE_BYTES_ = 128 * 128 + ((NHALF_ * 128 + 1023) / 1024) * 1024;
-      constexpr int NSTAGE_ = (196 * 1024 / STAGE_BYTES_) > 8 ? 8 : (196 * 1024 / STAGE_BYTES_);
-      const size_t smem = (size_t)NSTAGE_ * STAGE_BYTES_ + 1024 + 512 + 2 * 8 * 4 * 32 * sizeof(float);
+      constexpr int NHALF_ = TileOf<S>::N / 2;
+      const bool wres = l2chain_wres() != 0;
+      const size_t smem = wres ? L2Smem<S, true>::BYTES : L2Smem<S, false>::BYTES;
       CUtensorMap mw, ma;
       if (make_map(&mw, wr, (long long)(g.L - 1) * H, H, 128, 1)) return 1;
       if (make_map(&ma, stash, (long long)slots * slot_rows, H, NHALF_, 1)) return 1;
       // tanh and sin (the reference's activations for wide nets) are compiled in; sigmoid reads the id at run time
-      auto *kern = act == AX_ACT_TANH ? k_tc_fwd_l2<P, AX_ACT_TANH>
-                   : act == AX_ACT_SIN ? k_tc_fwd_l2<P, AX_ACT_SIN> : k_tc_fwd_l2<P, -1>;
-      static bool attr[3] = {false, false, false};
       const int ai = act == AX_ACT_TANH ? 0 : act == AX_ACT_SIN ? 1 : 2;
-      if (!attr[ai]) {
+      using KernT = void (*)(const CUtensorMap, const CUtensorMap, const L2ChainArgs);
+      static const KernT kerns[2][3] = {
+          {k_tc_fwd_l2<P, AX_ACT_TANH, false>, k_tc_fwd_l2<P, AX_ACT_SIN, false>, k_tc_fwd_l2<P, -1, false>},
+          {k_tc_fwd_l2<P, AX_ACT_TANH, true>, k_tc_fwd_l2<P, AX_ACT_SIN, true>, k_tc_fwd_l2<P, -1, true>}};
+      const KernT kern = kerns[wres ? 1 : 0][ai];
+      static bool attr[2][3] = {{false, false, false}, {false, false, false}};
+      if (!attr[wres ? 1 : 0][ai]) {
         AX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr[ai] = true;
+        attr[wres ? 1 : 0][ai] = true;
       }
       int clusters = sm_count() / 2;
       const int groups = (la.num_tiles + la.G - 1) / la.G;

@@ -291,20 +291,22 @@ def test_l2_chained_forward_is_bit_identical_to_the_layer_launches(widths, act, 
         L = len(widths) - 2
         n_layers = L * (2 if act == "sin" else 1) if keep else 0
         s0 = stash0.view(torch.float32)
-        for defer, G in [(d, G) for d in (2, 1, 0) for G in (1, 2, 3, 5, 8)]:
+        for wres, defer, G in [(w, d, G) for w in (1, 0) for d in (2, 1, 0) for G in (1, 2, 3, 5, 8)]:
             _lib.tc_set_option("l2chain", 1)
+            _lib.tc_set_option("l2chain_wres", wres)     # weights resident per (group, layer) visit / streamed per item
             _lib.tc_set_option("l2chain_group", G)
             _lib.tc_set_option("l2chain_defer", defer)   # tile released by the release warp / during the next item / at once
-            for rep in range(5 if G in (2, 3) and defer == 2 else 2):
+            for rep in range(5 if G in (2, 3) and defer == 2 and wres else 2):
                 jets1, stash1 = _lib.jet_forward(net, js.desc, params, xs, n, keep_all=keep, engine="tf32")
-                assert torch.equal(jets1[..., :n], jets0[..., :n]), (defer, G, rep)
+                assert torch.equal(jets1[..., :n], jets0[..., :n]), (wres, defer, G, rep)
                 s1 = stash1.view(torch.float32)
                 for l in range(n_layers):
-                    assert torch.equal(s1[l * layer : l * layer + rows], s0[l * layer : l * layer + rows]), (defer, G, rep, l)
+                    assert torch.equal(s1[l * layer : l * layer + rows], s0[l * layer : l * layer + rows]), (wres, defer, G, rep, l)
     finally:
         _lib.tc_set_option("l2chain", 1)
         _lib.tc_set_option("l2chain_group", L2CHAIN_DEFAULT_GROUP)
         _lib.tc_set_option("l2chain_defer", 2)
+        _lib.tc_set_option("l2chain_wres", 1)
 
 
 def test_cfg4_full_size_properties():
