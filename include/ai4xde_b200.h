@@ -285,7 +285,10 @@ int ax_residual_eval(const ax_residual_program *prog, const float *x_soa, const 
                      float *out, void *stream);
 
 /* run-time switches of the tcgen05 engine, e.g. ("l2chain", 0) = one launch per hidden layer instead of the L2-chained
- * forward kernel; results are bit-identical either way.  Returns non-zero for an unknown name. */
+ * forward kernel; results are bit-identical either way.  Names: "l2chain" (0 / 1), "l2chain_group"
+ * (tiles per group, 1..8, default 3), "l2chain_hints" (L2 eviction hints, 0 / 1), "l2chain_defer" (who releases a
+ * finished tile: 0 the epilogue warps at once, 1 the epilogue warps one item later, 2 the release warp -- default),
+ * "l2chain_wres" (weights resident per visit, 0 / 1).  Returns non-zero for an unknown name. */
 int ax_tc_set_option(const char *name, int32_t value);
 
 /* gather columns: x_out[:, j] = x[:, idx[j]]  (X[ids], algorithm/RAD.py:39) */
