@@ -316,6 +316,133 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// weight gradient, pipelined: the same 64 x 64 tile, 4 x 4 accumulators per thread and the same summation order as
+// k_wgrad (chunks in ascending order, four points per float4 step), but the tiles of chunk c + 1 travel global ->
+// shared as 16-byte cp.async copies while chunk c is multiplied (two buffers, two barriers per chunk), and the raw
+// stash streams are turned into post-activation streams IN PLACE in shared memory (one pass, S reads + S writes per
+// element) instead of between a scalar load and a scalar store.  k_wgrad spent 40 % of its issue slots on the tile
+// loads (scalar __ldg, div / mod index arithmetic per element) with nothing else in flight.
+// Needs ldn % 4 == 0 and 16-byte aligned bases (the launcher checks); a partial last chunk is staged by plain loads.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(float *dst_smem, const float *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class P, int PC>
+__global__ void __launch_bounds__(256) k_wgrad_pipe(WgradArgs a) {
+  constexpr int S = P::S, LD = PC + 4, Q = PC / 4;
+  constexpr int TILE = S * 64 * LD;        // floats of one operand tile
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tk = tid & 15;
+  const int net = blockIdx.z / a.nsplit, split = blockIdx.z % a.nsplit;
+  const int i0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const float *zb = a.zb + net * a.zb_net_stride;
+  const float *asrc = a.asrc + net * a.a_net_stride;
+  const int64_t pbeg = (int64_t)split * a.pts_per_split;
+  int64_t pend = pbeg + a.pts_per_split;
+  if (pend > a.n) pend = a.n;
+
+  float acc[4][4];
+  float dbacc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    dbacc[u] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0f;
+  }
+
+  // stage chunk [pc, pc + PC) into buffer b: Z tile, then the RAW stash tile
+  auto stage = [&](int64_t pc, int b) {
+    float *Zs = smem + b * 2 * TILE, *As = Zs + TILE;
+    if (pc + PC <= pend) {
+      for (int e = tid; e < S * 64 * Q; e += 256) {
+        const int q4 = e % Q, row = (e / Q) % 64, s = e / (Q * 64);
+        const bool okz = i0 + row < a.Hout, oka = k0 + row < a.Hin;
+        cp_async16_zfill(Zs + (s * 64 + row) * LD + 4 * q4,
+                         zb + ((int64_t)s * a.Hout + (okz ? i0 + row : 0)) * a.ldn + pc + 4 * q4, okz);
+        cp_async16_zfill(As + (s * 64 + row) * LD + 4 * q4,
+                         asrc + ((int64_t)s * a.Hin + (oka ? k0 + row : 0)) * a.ldn + pc + 4 * q4, oka);
+      }
+    } else {
+      for (int e = tid; e < S * 64 * PC; e += 256) {
+        const int pl = e % PC, row = (e / PC) % 64, s = e / (PC * 64);
+        const bool inp = pc + pl < pend;
+        Zs[(s * 64 + row) * LD + pl] =
+            (inp && i0 + row < a.Hout) ? __ldg(zb + ((int64_t)s * a.Hout + i0 + row) * a.ldn + pc + pl) : 0.0f;
+        As[(s * 64 + row) * LD + pl] =
+            (inp && k0 + row < a.Hin) ? __ldg(asrc + ((int64_t)s * a.Hin + k0 + row) * a.ldn + pc + pl) : 0.0f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  int b = 0;
+  if (pbeg < pend) stage(pbeg, 0);
+  for (int64_t pc = pbeg; pc < pend; pc += PC, b ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();   // chunk pc is in buffer b for everyone; everyone has finished multiplying buffer b ^ 1
+    if (pc + PC < pend) stage(pc + PC, b ^ 1);
+    float *Zs = smem + b * 2 * TILE, *As = Zs + TILE;
+    // raw stash streams -> post-activation streams, in place
+    for (int e = tid; e < 64 * PC; e += 256) {
+      const int pl = e % PC, row = e / PC;
+      float v[S], A[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) v[s] = As[(s * 64 + row) * LD + pl];
+      jet_reconstruct<P>(a.act, v, A);
+      const bool ok = (k0 + row < a.Hin) && (pc + pl < pend);
+#pragma unroll
+      for (int s = 0; s < S; ++s) As[(s * 64 + row) * LD + pl] = ok ? A[s] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int pp = 0; pp < PC; pp += 4) {
+        float4 zv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          zv[u] = *reinterpret_cast<const float4 *>(&Zs[(s * 64 + ti + 16 * u) * LD + pp]);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          av[v] = *reinterpret_cast<const float4 *>(&As[(s * 64 + tk + 16 * v) * LD + pp]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            acc[u][v] = fmaf(zv[u].x, av[v].x, acc[u][v]);
+            acc[u][v] = fmaf(zv[u].y, av[v].y, acc[u][v]);
+            acc[u][v] = fmaf(zv[u].z, av[v].z, acc[u][v]);
+            acc[u][v] = fmaf(zv[u].w, av[v].w, acc[u][v]);
+          }
+        if (s == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dbacc[u] += (zv[u].x + zv[u].y) + (zv[u].z + zv[u].w);
+        }
+      }
+    }
+  }
+
+  float *part = a.partial + net * a.partial_net_stride + split * a.partial_split_stride;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ti + 16 * u;
+    if (i >= a.Hout) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int k = k0 + tk + 16 * v;
+      if (k < a.Hin) part[(int64_t)i * a.Hin + k] = acc[u][v];
+    }
+    if (blockIdx.y == 0 && tk == 0) part[(int64_t)a.Hout * a.Hin + i] = dbacc[u];
+  }
+}
+
 // grad[net][off + j] = sum_split partial[net][split][j]   (fixed order -> deterministic)
 __global__ void k_reduce_partials(const float *__restrict__ partial, int64_t partial_net_stride,
                                   int64_t partial_split_stride, int nsplit, int64_t count,
@@ -458,10 +585,27 @@ static int launch_wgrad(WgradArgs wa, int n_nets, float *grad, int64_t p_stride,
   wa.partial_net_stride = count * pl.nsplit;
   dim3 grid((unsigned)((wa.Hout + 63) / 64), (unsigned)((wa.Hin + 63) / 64),
             (unsigned)(pl.nsplit * n_nets));
+  // pipelined kernel (cp.async double buffering, in-place reconstruction): hidden layers whose rows are 16-byte aligned
+  constexpr int PCP = 16;
+  const size_t smem_pipe = (size_t)2 * 2 * P::S * 64 * (PCP + 4) * sizeof(float);
+  static int use_pipe = -1;
+  if (use_pipe < 0) {
+    const char *e = getenv("AX_SIMT_WGRAD_PIPE");
+    use_pipe = (e && e[0] == '0') ? 0 : 1;
+    if (smem_pipe > 227 * 1024) use_pipe = 0;   // patterns with twelve streams or more keep the single-buffer kernel
+    if (use_pipe)
+      AX_CUDA_OK(cudaFuncSetAttribute(k_wgrad_pipe<P, PCP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe));
+  }
+  const bool pipe = use_pipe && !wa.from_input && wa.ldn % 4 == 0 && pl.pts_per_split % PCP == 0 &&
+                    ((uintptr_t)wa.zb % 16 == 0) && ((uintptr_t)wa.asrc % 16 == 0) && wa.zb_net_stride % 4 == 0 &&
+                    wa.a_net_stride % 4 == 0;
   {
     KernelTimer timer("simt_wgrad", stream, 2.0 * P::S * wa.Hout * wa.Hin * (double)wa.n * n_nets,
                       4.0 * P::S * ((double)wa.Hout + wa.Hin) * (double)wa.n * n_nets);
-    k_wgrad<P, PC><<<grid, 256, smem, stream>>>(wa);
+    if (pipe)
+      k_wgrad_pipe<P, PCP><<<grid, 256, smem_pipe, stream>>>(wa);
+    else
+      k_wgrad<P, PC><<<grid, 256, smem, stream>>>(wa);
   }
   AX_LAUNCH_OK();
   dim3 rg((unsigned)((count + 255) / 256), (unsigned)n_nets);
