@@ -10,6 +10,7 @@
 // (/root/reference/AI4XDE/cases/PDECases.py:38-42, :1087-1094) and the network part of
 // total_loss.backward() (/root/reference/AI4XDE/algorithm/FBPINN.py:178-184).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace ax {
@@ -218,7 +219,10 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
   float *Zs = smem;                // [S][64][LD]
   float *As = smem + S * 64 * LD;  // [S][64][LD]
   const int tid = threadIdx.x;
-  const int ti = tid >> 4, tk = tid & 15;
+  // a warp covers 4 rows of the Z tile x 8 rows of the A tile: its four zv loads are one shared-memory wavefront each
+  // (broadcast within 8 lanes) and so are its four av loads (8 rows x 16 bytes, conflict-free at LD = PC + 4) -- 8
+  // wavefronts per 64 FMA instructions; the 2 x 16 arrangement (tid >> 4, tid & 15) needed 12
+  const int ti = (tid >> 6) * 4 + ((tid & 31) >> 3), tk = ((tid >> 5) & 1) * 8 + (tid & 7);
   const int net = blockIdx.z / a.nsplit, split = blockIdx.z % a.nsplit;
   const int i0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   const float *zb = a.zb + net * a.zb_net_stride;
@@ -334,12 +338,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <class P, int PC>
-__global__ void __launch_bounds__(256) k_wgrad_pipe(WgradArgs a) {
+__global__ void __launch_bounds__(256, (P::S <= 5) ? 2 : 1) k_wgrad_pipe(WgradArgs a) {
   constexpr int S = P::S, LD = PC + 4, Q = PC / 4;
   constexpr int TILE = S * 64 * LD;        // floats of one operand tile
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
-  const int ti = tid >> 4, tk = tid & 15;
+  // a warp covers 4 rows of the Z tile x 8 rows of the A tile: its four zv loads are one shared-memory wavefront each
+  // (broadcast within 8 lanes) and so are its four av loads (8 rows x 16 bytes, conflict-free at LD = PC + 4) -- 8
+  // wavefronts per 64 FMA instructions; the 2 x 16 arrangement (tid >> 4, tid & 15) needed 12
+  const int ti = (tid >> 6) * 4 + ((tid & 31) >> 3), tk = ((tid >> 5) & 1) * 8 + (tid & 7);
   const int net = blockIdx.z / a.nsplit, split = blockIdx.z % a.nsplit;
   const int i0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   const float *zb = a.zb + net * a.zb_net_stride;
@@ -347,6 +354,9 @@ __global__ void __launch_bounds__(256) k_wgrad_pipe(WgradArgs a) {
   const int64_t pbeg = (int64_t)split * a.pts_per_split;
   int64_t pend = pbeg + a.pts_per_split;
   if (pend > a.n) pend = a.n;
+  // 16-row blocks of this tile that hold real units (uniform over the CTA)
+  const int nu = (a.Hout - i0 >= 64) ? 4 : (a.Hout - i0 + 15) / 16;
+  const int nv = (a.Hin - k0 >= 64) ? 4 : (a.Hin - k0 + 15) / 16;
 
   float acc[4][4];
   float dbacc[4];
@@ -366,8 +376,11 @@ __global__ void __launch_bounds__(256) k_wgrad_pipe(WgradArgs a) {
         const bool okz = i0 + row < a.Hout, oka = k0 + row < a.Hin;
         cp_async16_zfill(Zs + (s * 64 + row) * LD + 4 * q4,
                          zb + ((int64_t)s * a.Hout + (okz ? i0 + row : 0)) * a.ldn + pc + 4 * q4, okz);
-        cp_async16_zfill(As + (s * 64 + row) * LD + 4 * q4,
-                         asrc + ((int64_t)s * a.Hin + (oka ? k0 + row : 0)) * a.ldn + pc + 4 * q4, oka);
+        if (!a.from_input)
+          cp_async16_zfill(As + (s * 64 + row) * LD + 4 * q4,
+                           asrc + ((int64_t)s * a.Hin + (oka ? k0 + row : 0)) * a.ldn + pc + 4 * q4, oka);
+        else if (s == 0)   // x [d_in][ldn]: the value stream; the derivative streams are indicators (below)
+          cp_async16_zfill(As + row * LD + 4 * q4, asrc + (int64_t)(oka ? k0 + row : 0) * a.ldn + pc + 4 * q4, oka);
       }
     } else {
       for (int e = tid; e < S * 64 * PC; e += 256) {
@@ -375,8 +388,9 @@ __global__ void __launch_bounds__(256) k_wgrad_pipe(WgradArgs a) {
         const bool inp = pc + pl < pend;
         Zs[(s * 64 + row) * LD + pl] =
             (inp && i0 + row < a.Hout) ? __ldg(zb + ((int64_t)s * a.Hout + i0 + row) * a.ldn + pc + pl) : 0.0f;
-        As[(s * 64 + row) * LD + pl] =
-            (inp && k0 + row < a.Hin) ? __ldg(asrc + ((int64_t)s * a.Hin + k0 + row) * a.ldn + pc + pl) : 0.0f;
+        if (!a.from_input || s == 0)
+          As[(s * 64 + row) * LD + pl] =
+              (inp && k0 + row < a.Hin) ? __ldg(asrc + ((int64_t)s * a.Hin + k0 + row) * a.ldn + pc + pl) : 0.0f;
       }
     }
     cp_async_commit();
@@ -393,40 +407,65 @@ __global__ void __launch_bounds__(256) k_wgrad_pipe(WgradArgs a) {
     for (int e = tid; e < 64 * PC; e += 256) {
       const int pl = e % PC, row = e / PC;
       float v[S], A[S];
+      if (a.from_input) {
+        // input jets: value = x_k, first-order stream j = [direction j is input k], higher orders vanish
+        A[0] = As[row * LD + pl];
 #pragma unroll
-      for (int s = 0; s < S; ++s) v[s] = As[(s * 64 + row) * LD + pl];
-      jet_reconstruct<P>(a.act, v, A);
+        for (int j = 0; j < P::N1; ++j) A[1 + j] = (a.dirs.d[j] == k0 + row) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int q = 0; q < P::N2; ++q) A[1 + P::N1 + q] = 0.0f;
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) v[s] = As[(s * 64 + row) * LD + pl];
+        jet_reconstruct<P>(a.act, v, A);
+      }
       const bool ok = (k0 + row < a.Hin) && (pc + pl < pend);
 #pragma unroll
       for (int s = 0; s < S; ++s) As[(s * 64 + row) * LD + pl] = ok ? A[s] : 0.0f;
     }
     __syncthreads();
+    // register fragments double-buffered by hand: the loads of step it + 1 are issued before the FMAs of step it.
+    // Edge tiles (150 = 64 + 64 + 22 units) multiply only the 16-row blocks that hold real units: NU x NV of the 4 x 4
+    // accumulator blocks (uniform over the CTA), e.g. 160^2 instead of 192^2 products for a 150 x 150 layer.
+    auto multiply = [&](auto nu_tag, auto nv_tag) {
+      constexpr int NU = decltype(nu_tag)::value, NV = decltype(nv_tag)::value;
+      constexpr int STEPS = S * Q;   // fully unrolled (a rolled stream loop was measured 15-20 % slower)
+      float4 zv[2][NU], av[2][NV];
+      auto frag = [&](int it, int fb) {
+        const int s = it / Q, pp = (it % Q) * 4;
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
+        for (int u = 0; u < NU; ++u)
+          zv[fb][u] = *reinterpret_cast<const float4 *>(&Zs[(s * 64 + ti + 16 * u) * LD + pp]);
 #pragma unroll
-      for (int pp = 0; pp < PC; pp += 4) {
-        float4 zv[4], av[4];
+        for (int v = 0; v < NV; ++v)
+          av[fb][v] = *reinterpret_cast<const float4 *>(&As[(s * 64 + tk + 16 * v) * LD + pp]);
+      };
+      frag(0, 0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          zv[u] = *reinterpret_cast<const float4 *>(&Zs[(s * 64 + ti + 16 * u) * LD + pp]);
+      for (int it = 0; it < STEPS; ++it) {
+        const int fb = it & 1;
+        if (it + 1 < STEPS) frag(it + 1, fb ^ 1);
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          av[v] = *reinterpret_cast<const float4 *>(&As[(s * 64 + tk + 16 * v) * LD + pp]);
+        for (int u = 0; u < NU; ++u) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            acc[u][v] = fmaf(zv[u].x, av[v].x, acc[u][v]);
-            acc[u][v] = fmaf(zv[u].y, av[v].y, acc[u][v]);
-            acc[u][v] = fmaf(zv[u].z, av[v].z, acc[u][v]);
-            acc[u][v] = fmaf(zv[u].w, av[v].w, acc[u][v]);
+          for (int v = 0; v < NV; ++v) {
+            acc[u][v] = fmaf(zv[fb][u].x, av[fb][v].x, acc[u][v]);
+            acc[u][v] = fmaf(zv[fb][u].y, av[fb][v].y, acc[u][v]);
+            acc[u][v] = fmaf(zv[fb][u].z, av[fb][v].z, acc[u][v]);
+            acc[u][v] = fmaf(zv[fb][u].w, av[fb][v].w, acc[u][v]);
           }
-        if (s == 0) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dbacc[u] += (zv[u].x + zv[u].y) + (zv[u].z + zv[u].w);
+          if (it < Q) dbacc[u] += (zv[fb][u].x + zv[fb][u].y) + (zv[fb][u].z + zv[fb][u].w);   // stream 0: bias gradient
         }
       }
-    }
+    };
+    using I1 = std::integral_constant<int, 1>;
+    using I4 = std::integral_constant<int, 4>;
+    // output layers (<= 16 output units) and input layers (<= 16 inputs) multiply one 16-row block instead of four:
+    // a 64 -> 1 layer cost as much as a 64 x 64 one.  (Compile-time variants for the edge tiles of widths 100 / 150 --
+    // 3 x 3, 2 x 2 blocks -- were measured: no gain, the smaller blocks have the worse FMA : load ratio.)
+    if (nu == 1 && nv > 1) multiply(I1{}, I4{});
+    else if (nv == 1 && nu > 1) multiply(I4{}, I1{});
+    else multiply(I4{}, I4{});
   }
 
   float *part = a.partial + net * a.partial_net_stride + split * a.partial_split_stride;
@@ -596,7 +635,7 @@ static int launch_wgrad(WgradArgs wa, int n_nets, float *grad, int64_t p_stride,
     if (use_pipe)
       AX_CUDA_OK(cudaFuncSetAttribute(k_wgrad_pipe<P, PCP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe));
   }
-  const bool pipe = use_pipe && !wa.from_input && wa.ldn % 4 == 0 && pl.pts_per_split % PCP == 0 &&
+  const bool pipe = use_pipe && wa.ldn % 4 == 0 && pl.pts_per_split % PCP == 0 &&
                     ((uintptr_t)wa.zb % 16 == 0) && ((uintptr_t)wa.asrc % 16 == 0) && wa.zb_net_stride % 4 == 0 &&
                     wa.a_net_stride % 4 == 0;
   {
