@@ -191,6 +191,51 @@ __global__ void __launch_bounds__(NW * 32) k_layer(LayerArgs a) {
   }
 }
 
+// The multiply phase of both weight-gradient kernels: 4 x 4 accumulator blocks of 16 rows each (NU x NV of them hold real
+// units), streams outermost, four points per float4 step, register fragments of step it + 1 loaded before the FMAs of
+// step it (double-buffered by hand; fully unrolled -- a rolled stream loop was measured 15-20 % slower).  The order of
+// additions into every accumulator is: chunk by chunk, stream by stream, point by point.
+template <int S, int PC, int NU, int NV>
+__device__ __forceinline__ void wgrad_multiply(const float *__restrict__ Zs, const float *__restrict__ As, int ti, int tk,
+                                               float (&acc)[4][4], float (&dbacc)[4]) {
+  constexpr int LD = PC + 4, Q = PC / 4, STEPS = S * Q;
+  float4 zv[2][NU], av[2][NV];
+  auto frag = [&](int it, int fb) {
+    const int s = it / Q, pp = (it % Q) * 4;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) zv[fb][u] = *reinterpret_cast<const float4 *>(&Zs[(s * 64 + ti + 16 * u) * LD + pp]);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) av[fb][v] = *reinterpret_cast<const float4 *>(&As[(s * 64 + tk + 16 * v) * LD + pp]);
+  };
+  frag(0, 0);
+#pragma unroll
+  for (int it = 0; it < STEPS; ++it) {
+    const int fb = it & 1;
+    if (it + 1 < STEPS) frag(it + 1, fb ^ 1);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        acc[u][v] = fmaf(zv[fb][u].x, av[fb][v].x, acc[u][v]);
+        acc[u][v] = fmaf(zv[fb][u].y, av[fb][v].y, acc[u][v]);
+        acc[u][v] = fmaf(zv[fb][u].z, av[fb][v].z, acc[u][v]);
+        acc[u][v] = fmaf(zv[fb][u].w, av[fb][v].w, acc[u][v]);
+      }
+      if (it < Q) dbacc[u] += (zv[fb][u].x + zv[fb][u].y) + (zv[fb][u].z + zv[fb][u].w);   // stream 0: bias gradient
+    }
+  }
+}
+// output layers (<= 16 output units) and input layers (<= 16 inputs) multiply one 16-row block instead of four: a 64 -> 1
+// layer cost as much as a 64 x 64 one.  (Compile-time 3 x 3 / 2 x 2 variants for the edge tiles of widths 100 / 150 were
+// measured: no gain, the smaller blocks have the worse FMA : load ratio; their run-time predicated form: -25 %.)
+template <int S, int PC>
+__device__ __forceinline__ void wgrad_multiply_tile(const float *Zs, const float *As, int ti, int tk, int nu, int nv,
+                                                    float (&acc)[4][4], float (&dbacc)[4]) {
+  if (nu == 1 && nv > 1) wgrad_multiply<S, PC, 1, 4>(Zs, As, ti, tk, acc, dbacc);
+  else if (nv == 1 && nu > 1) wgrad_multiply<S, PC, 4, 1>(Zs, As, ti, tk, acc, dbacc);
+  else wgrad_multiply<S, PC, 4, 4>(Zs, As, ti, tk, acc, dbacc);
+}
+
 // ---------------------------------------------------------------------------------------
 // weight gradient: dW[i][k] = sum_{s,p} zb_s[i][p] * A_s[k][p],  db[i] = sum_p zb_0[i][p]
 // split over point ranges; partial[net][split][Hout*Hin + Hout]
@@ -230,7 +275,6 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
   const int64_t pbeg = (int64_t)split * a.pts_per_split;
   int64_t pend = pbeg + a.pts_per_split;
   if (pend > a.n) pend = a.n;
-
   float acc[4][4];
   float dbacc[4];
 #pragma unroll
@@ -321,12 +365,12 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// weight gradient, pipelined: the same 64 x 64 tile, 4 x 4 accumulators per thread and the same summation order as
-// k_wgrad (chunks in ascending order, four points per float4 step), but the tiles of chunk c + 1 travel global ->
-// shared as 16-byte cp.async copies while chunk c is multiplied (two buffers, two barriers per chunk), and the raw
-// stash streams are turned into post-activation streams IN PLACE in shared memory (one pass, S reads + S writes per
-// element) instead of between a scalar load and a scalar store.  k_wgrad spent 40 % of its issue slots on the tile
-// loads (scalar __ldg, div / mod index arithmetic per element) with nothing else in flight.
+// weight gradient, pipelined: the same 64 x 64 tile, 4 x 4 accumulators per thread, the same chunk length and therefore
+// the same order of additions as k_wgrad (bit-identical results), but the tiles of chunk c + 1 travel global -> shared
+// as 16-byte cp.async copies while chunk c is multiplied (two buffers, two barriers per chunk), and the raw stash
+// streams are turned into post-activation streams IN PLACE in shared memory (one pass, S reads + S writes per element)
+// instead of between a scalar load and a scalar store.  k_wgrad spends 40 % of its issue slots on the tile loads
+// (scalar __ldg, div / mod index arithmetic per element) with nothing else in flight.
 // Needs ldn % 4 == 0 and 16-byte aligned bases (the launcher checks); a partial last chunk is staged by plain loads.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16_zfill(float *dst_smem, const float *src, bool valid) {
@@ -338,7 +382,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <class P, int PC>
-__global__ void __launch_bounds__(256, (P::S <= 5) ? 2 : 1) k_wgrad_pipe(WgradArgs a) {
+__global__ void __launch_bounds__(256, (2 * 2 * P::S * 64 * (PC + 4) * 4 <= 100 * 1024) ? 2 : 1) k_wgrad_pipe(WgradArgs a) {
   constexpr int S = P::S, LD = PC + 4, Q = PC / 4;
   constexpr int TILE = S * 64 * LD;        // floats of one operand tile
   extern __shared__ __align__(16) float smem[];
@@ -424,48 +468,7 @@ __global__ void __launch_bounds__(256, (P::S <= 5) ? 2 : 1) k_wgrad_pipe(WgradAr
       for (int s = 0; s < S; ++s) As[(s * 64 + row) * LD + pl] = ok ? A[s] : 0.0f;
     }
     __syncthreads();
-    // register fragments double-buffered by hand: the loads of step it + 1 are issued before the FMAs of step it.
-    // Edge tiles (150 = 64 + 64 + 22 units) multiply only the 16-row blocks that hold real units: NU x NV of the 4 x 4
-    // accumulator blocks (uniform over the CTA), e.g. 160^2 instead of 192^2 products for a 150 x 150 layer.
-    auto multiply = [&](auto nu_tag, auto nv_tag) {
-      constexpr int NU = decltype(nu_tag)::value, NV = decltype(nv_tag)::value;
-      constexpr int STEPS = S * Q;   // fully unrolled (a rolled stream loop was measured 15-20 % slower)
-      float4 zv[2][NU], av[2][NV];
-      auto frag = [&](int it, int fb) {
-        const int s = it / Q, pp = (it % Q) * 4;
-#pragma unroll
-        for (int u = 0; u < NU; ++u)
-          zv[fb][u] = *reinterpret_cast<const float4 *>(&Zs[(s * 64 + ti + 16 * u) * LD + pp]);
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-          av[fb][v] = *reinterpret_cast<const float4 *>(&As[(s * 64 + tk + 16 * v) * LD + pp]);
-      };
-      frag(0, 0);
-#pragma unroll
-      for (int it = 0; it < STEPS; ++it) {
-        const int fb = it & 1;
-        if (it + 1 < STEPS) frag(it + 1, fb ^ 1);
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            acc[u][v] = fmaf(zv[fb][u].x, av[fb][v].x, acc[u][v]);
-            acc[u][v] = fmaf(zv[fb][u].y, av[fb][v].y, acc[u][v]);
-            acc[u][v] = fmaf(zv[fb][u].z, av[fb][v].z, acc[u][v]);
-            acc[u][v] = fmaf(zv[fb][u].w, av[fb][v].w, acc[u][v]);
-          }
-          if (it < Q) dbacc[u] += (zv[fb][u].x + zv[fb][u].y) + (zv[fb][u].z + zv[fb][u].w);   // stream 0: bias gradient
-        }
-      }
-    };
-    using I1 = std::integral_constant<int, 1>;
-    using I4 = std::integral_constant<int, 4>;
-    // output layers (<= 16 output units) and input layers (<= 16 inputs) multiply one 16-row block instead of four:
-    // a 64 -> 1 layer cost as much as a 64 x 64 one.  (Compile-time variants for the edge tiles of widths 100 / 150 --
-    // 3 x 3, 2 x 2 blocks -- were measured: no gain, the smaller blocks have the worse FMA : load ratio.)
-    if (nu == 1 && nv > 1) multiply(I1{}, I4{});
-    else if (nv == 1 && nu > 1) multiply(I4{}, I1{});
-    else multiply(I4{}, I4{});
+    wgrad_multiply_tile<S, PC>(Zs, As, ti, tk, nu, nv, acc, dbacc);
   }
 
   float *part = a.partial + net * a.partial_net_stride + split * a.partial_split_stride;
@@ -625,13 +628,15 @@ static int launch_wgrad(WgradArgs wa, int n_nets, float *grad, int64_t p_stride,
   dim3 grid((unsigned)((wa.Hout + 63) / 64), (unsigned)((wa.Hin + 63) / 64),
             (unsigned)(pl.nsplit * n_nets));
   // pipelined kernel (cp.async double buffering, in-place reconstruction): hidden layers whose rows are 16-byte aligned
-  constexpr int PCP = 16;
+  // the same chunk as k_wgrad: every accumulator receives its products in the same order, results are bit-identical
+  // (AX_SIMT_WGRAD_PIPE=16: 16-point chunks, two CTAs per SM at S <= 5, another order of additions)
+  constexpr int PCP = PC;
   const size_t smem_pipe = (size_t)2 * 2 * P::S * 64 * (PCP + 4) * sizeof(float);
   static int use_pipe = -1;
   if (use_pipe < 0) {
     const char *e = getenv("AX_SIMT_WGRAD_PIPE");
     use_pipe = (e && e[0] == '0') ? 0 : 1;
-    if (smem_pipe > 227 * 1024) use_pipe = 0;   // patterns with twelve streams or more keep the single-buffer kernel
+    if (smem_pipe > 227 * 1024) use_pipe = 0;   // patterns whose two buffers do not fit keep the single-buffer kernel
     if (use_pipe)
       AX_CUDA_OK(cudaFuncSetAttribute(k_wgrad_pipe<P, PCP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe));
   }

@@ -60,6 +60,17 @@ def test_descriptor_queries_work_without_a_gpu():
         _lib.make_net_desc([2, 8, 1], "relu")
 
 
+def test_tensor_core_switches_are_named_and_refused_when_unknown():
+    """include/ai4xde_b200.h ax_tc_set_option: the documented switches of the L2-chained forward are accepted (they only
+    set host-side state: no GPU needed), an unknown name fails loudly with the list of names."""
+    from ai4xde_b200 import _lib
+
+    for name, value in (("l2chain", 1), ("l2chain_group", 3), ("l2chain_hints", 1), ("l2chain_defer", 2), ("l2chain_wres", 1)):
+        _lib.tc_set_option(name, value)
+    with pytest.raises(_lib.NativeLibraryError, match="l2chain_defer"):
+        _lib.tc_set_option("l2chain_nonsense", 1)
+
+
 def test_no_cpu_fallback():
     from ai4xde_b200 import _lib
     from ai4xde_b200.jet import JetSpec
