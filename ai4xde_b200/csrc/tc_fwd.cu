@@ -507,10 +507,14 @@ __global__ void k_tc_jets_combine(const float *__restrict__ part, const float *_
 // streams a tile wrote for layer l are read back for layer l + 1 a few items later, out of L2: HBM sees the stash
 // writes (which the backward needs anyway) and the first layer's read, nothing else.  Inside an item the kernel IS
 // k_tc_gemm2<fwd> (TMA ring -> tcgen05.mma cta_group::2 -> epilogue out of two TMEM accumulators); what is new is the
-// hand-off: the 16 epilogue warps of the pair release a finished tile to both TMA producers through a cluster-scope
-// mbarrier (generic-proxy stores -> fence.proxy.async -> arrive.release.cluster; the producer acquires, fences, and
-// only then lets the async proxy read those rows).  With G >= 3 the producer's wait is always already satisfied:
-// it runs at most ~1.75 items ahead of the epilogue (6-stage ring + double-buffered accumulator).
+// hand-off: a finished tile is released to both TMA producers through a cluster-scope mbarrier (generic-proxy stores ->
+// fence.proxy.async -> fence.acq_rel.cluster -> arrive; the producer acquires, fences, and only then lets the async
+// proxy read those rows).  By default (defer = 2) the 16 epilogue warps only release at CTA scope on rows_done[j] and
+// a 19th warp performs the cluster-scope release on their behalf (cumulativity), so the microsecond the fence waits
+// for the stores to be acknowledged is not idle time of the warps that bound the kernel; defer = 0 / 1 keep the
+// release in the epilogue warps (at once / one item later).  With WRES the CTA's 128 weight rows stay resident for
+// the G items of a (group, layer) visit and the ring carries activations only (see L2Smem).  With G >= 3 the
+// producer's wait is normally already satisfied.
 // Unlike the smem-mediated chain above, two to three tiles are in flight per cluster, so the tensor pipe, the TMA ring
 // and the epilogue overlap exactly as in the layer-by-layer kernel.
 // =========================================================================================
