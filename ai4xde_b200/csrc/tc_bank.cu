@@ -92,11 +92,110 @@ __device__ __forceinline__ float sigmoid_acc(float t) { return 1.0f / (1.0f + ex
 // hardware does anyway) -- one integer add instead of two instructions per operand value.
 __device__ __forceinline__ float tf32_round_for_mma(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+// ---- packed FP32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE operations per issued instruction).  The bank's epilogue
+// is bound by issue slots (61 % busy, FMA pipe 36 %, profiles/r02_bank_v4_ncu_full.md) and half of its instructions
+// are FP32 multiplies / adds on values that sit in ADJACENT registers -- TMEM column = (stream, unit), so v[s][i] and
+// v[s][i + 1] are two units of one stream -- the activation jets of two units are therefore evaluated as one packed
+// instruction stream; the two special-function calls per unit and the TF32 rounding stay scalar.
+struct F2 {
+  uint64_t v;
+};
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_splat(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+// jet_forward_fast on two units at once (same operations per element; tanh_fast / sigmoid_fast of tc_common.cuh)
+template <class P, int ACT>
+__device__ __forceinline__ void jet_forward_fast2(F2 (&z)[P::S], F2 (&A)[P::S]) {
+  const F2 one = f2_splat(1.0f);
+  F2 a, s1, s2;
+  float t0, t1;
+  if (ACT == AX_ACT_TANH) {
+    f2_unpack(f2_mul(z[0], f2_splat(2.8853900817779268f)), t0, t1);
+    f2_unpack(f2_add(f2_pack(ex2_approx(t0), ex2_approx(t1)), one), t0, t1);
+    a = f2_fma(f2_splat(-2.0f), f2_pack(rcp_approx(t0), rcp_approx(t1)), one);
+    const F2 na = f2_mul(a, f2_splat(-1.0f));
+    s1 = f2_fma(na, a, one);
+    s2 = f2_mul(f2_add(na, na), s1);
+  } else {
+    f2_unpack(f2_mul(z[0], f2_splat(-1.4426950408889634f)), t0, t1);
+    f2_unpack(f2_add(one, f2_pack(ex2_approx(t0), ex2_approx(t1))), t0, t1);
+    a = f2_pack(rcp_approx(t0), rcp_approx(t1));
+    s1 = f2_mul(a, f2_fma(a, f2_splat(-1.0f), one));
+    s2 = f2_mul(s1, f2_fma(a, f2_splat(-2.0f), one));
+  }
+  A[0] = a;
+#pragma unroll
+  for (int j = 0; j < P::N1; ++j) A[1 + j] = f2_mul(s1, z[1 + j]);
+#pragma unroll
+  for (int q = 0; q < P::N2; ++q) {
+    if (P::pa(q) == kTracePair) {
+      F2 sq = f2_mul(z[1], z[1]);
+#pragma unroll
+      for (int j = 1; j < P::N1; ++j) sq = f2_fma(z[1 + j], z[1 + j], sq);
+      A[1 + P::N1 + q] = f2_fma(s2, sq, f2_mul(s1, z[1 + P::N1 + q]));
+    } else {
+      A[1 + P::N1 + q] = f2_fma(f2_mul(s2, z[1 + (P::pa(q) & 3)]), z[1 + (P::pb(q) & 3)], f2_mul(s1, z[1 + P::N1 + q]));
+    }
+  }
+}
+// activation jets of 16 units held as v[s][0..15] (in place: post-activation streams, optionally rounded for the MMA)
+template <class P, int ACT, bool PK, bool ROUND>
+__device__ __forceinline__ void bank_activate16(float (&v)[P::S][16], const float *__restrict__ bias) {
+  constexpr int S = P::S;
+  if (PK) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      F2 z[S], A[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) z[s] = f2_pack(v[s][i], v[s][i + 1]);
+      if (bias != nullptr) z[0] = f2_add(z[0], f2_pack(bias[i], bias[i + 1]));
+      jet_forward_fast2<P, ACT>(z, A);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float x0, x1;
+        f2_unpack(A[s], x0, x1);
+        v[s][i] = ROUND ? tf32_round_for_mma(x0) : x0;
+        v[s][i + 1] = ROUND ? tf32_round_for_mma(x1) : x1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float z[S], A[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) z[s] = v[s][i];
+      if (bias != nullptr) z[0] += bias[i];
+      jet_forward_fast<P, ACT>(z, A);
+#pragma unroll
+      for (int s = 0; s < S; ++s) v[s][i] = ROUND ? tf32_round_for_mma(A[s]) : A[s];
+    }
+  }
+}
+
 // 18 warps put 5 on one scheduler partition: 16 K registers / (5 x 32) caps a thread at 96 registers (a launch with
 // 112 is refused).  ncu of the first version attributed 26 % of its stall samples to LDL -- a select chain over a
 // register copy of the W0 row that the compiler had turned into a local-memory array, not spills; with that gone the
 // kernel fits 96 registers with a handful of spilled bytes (profiles/r02_bank_v2_ncu_full.md).
-template <class P, int ACT, int NT, bool WINDOW>
+template <class P, int ACT, int NT, bool WINDOW, bool PK>
 __global__ void __launch_bounds__(kBankThreads, 1)
 k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
   constexpr int S = P::S;
@@ -281,18 +380,15 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 w = *reinterpret_cast<const float4 *>(sw0 + (u0 + i) * 4);
-            float z[S], A[S];
-            z[0] = fmaf(w.w, xv[3], fmaf(w.z, xv[2], fmaf(w.y, xv[1], fmaf(w.x, xv[0], sb[u0 + i]))));
+            v[0][i] = fmaf(w.w, xv[3], fmaf(w.z, xv[2], fmaf(w.y, xv[1], fmaf(w.x, xv[0], sb[u0 + i]))));
             // d z / d x_dir = W0[unit][dir]: an indexed shared-memory read (a select chain over a register copy of the
             // row is turned into a local-memory array by the compiler)
 #pragma unroll
-            for (int j = 0; j < P::N1; ++j) z[1 + j] = sw0[(u0 + i) * 4 + g.dirs.d[j]];
+            for (int j = 0; j < P::N1; ++j) v[1 + j][i] = sw0[(u0 + i) * 4 + g.dirs.d[j]];
 #pragma unroll
-            for (int qq = 0; qq < P::N2; ++qq) z[1 + P::N1 + qq] = 0.0f;
-            jet_forward_fast<P, ACT>(z, A);
-#pragma unroll
-            for (int s = 0; s < S; ++s) v[s][i] = tf32_round_for_mma(A[s]);
+            for (int qq = 0; qq < P::N2; ++qq) v[1 + P::N1 + qq][i] = 0.0f;
           }
+          bank_activate16<P, ACT, PK, true>(v, nullptr);
           store_image(t, v);
           signal_image(t);
         }
@@ -308,16 +404,7 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
             for (int s = 0; s < S; ++s) tmem_ld16(taddr + (t * S + s) * 64, v[s]);
             tmem_ld_wait();
             if (!last) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float z[S], A[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) z[s] = v[s][i];
-                z[0] += bl[i];
-                jet_forward_fast<P, ACT>(z, A);
-#pragma unroll
-                for (int s = 0; s < S; ++s) v[s][i] = tf32_round_for_mma(A[s]);
-              }
+              bank_activate16<P, ACT, PK, true>(v, bl);
               store_image(t, v);
               signal_image(t);
             } else {
@@ -327,19 +414,15 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
               for (int s = 0; s < S; ++s)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) part[s][c] = 0.0f;
+              bank_activate16<P, ACT, PK, false>(v, bl);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                float z[S], A[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) z[s] = v[s][i];
-                z[0] += bl[i];
-                jet_forward_fast<P, ACT>(z, A);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   if (c < g.C) {
                     const float w = swo[c * 64 + u0 + i];
 #pragma unroll
-                    for (int s = 0; s < S; ++s) part[s][c] = fmaf(w, A[s], part[s][c]);
+                    for (int s = 0; s < S; ++s) part[s][c] = fmaf(w, v[s][i], part[s][c]);
                   }
                 }
               }
@@ -487,11 +570,17 @@ static int tc_bank_launch(const NetGeom &g, const FwdArgs &a, const BankWindow *
   ba.nets_per_chunk = (ba.n_list + chunks - 1) / chunks;
   chunks = (ba.n_list + ba.nets_per_chunk - 1) / ba.nets_per_chunk;
   ba.out = WINDOW ? (chunks > 1 ? part : win->out) : a.jets;
-  auto kern = act == AX_ACT_TANH ? k_tc_bank_fwd<P, AX_ACT_TANH, NT, WINDOW> : k_tc_bank_fwd<P, AX_ACT_SIGMOID, NT, WINDOW>;
-  static bool attr[2] = {false, false};
-  if (!attr[act == AX_ACT_TANH]) {
+  static int packed = -1;   // AX_TC_BANK_PACKED=0: scalar activation jets (A/B)
+  if (packed < 0) {
+    const char *e = getenv("AX_TC_BANK_PACKED");
+    packed = (e && e[0] == '0') ? 0 : 1;
+  }
+  auto kern = packed ? (act == AX_ACT_TANH ? k_tc_bank_fwd<P, AX_ACT_TANH, NT, WINDOW, true> : k_tc_bank_fwd<P, AX_ACT_SIGMOID, NT, WINDOW, true>)
+                     : (act == AX_ACT_TANH ? k_tc_bank_fwd<P, AX_ACT_TANH, NT, WINDOW, false> : k_tc_bank_fwd<P, AX_ACT_SIGMOID, NT, WINDOW, false>);
+  static bool attr[2][2] = {{false, false}, {false, false}};
+  if (!attr[packed][act == AX_ACT_TANH]) {
     AX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-    attr[act == AX_ACT_TANH] = true;
+    attr[packed][act == AX_ACT_TANH] = true;
   }
   {
     const double pts = (double)a.n * ba.n_list;
