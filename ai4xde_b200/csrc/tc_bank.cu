@@ -48,12 +48,15 @@ struct BankArgs {
   JetDirs dirs;
   long long n, ldn;
   int groups;            // ceil(tiles / NT)
+  int onebar;            // window mode: one block barrier per net (partials in their own scratch), AX_TC_BANK_ONEBAR
 };
 
 template <int S, int NT>
 struct BankGeom {
   static constexpr int IMG_BYTES = S * 2 * 128 * 128;   // [stream][K block][128 points][32 floats], per tile
-  static constexpr int FIXED = 1024 + 2 * kBankParamFloats * 4 + 256;
+  // window mode: the three partial sums per (tile, stream, point) that are not the combining thread's own
+  static constexpr int WSCR_BYTES = NT * 3 * (S <= 3 ? S : 0) * 128 * 4;
+  static constexpr int FIXED = 1024 + 2 * kBankParamFloats * 4 + 256 + WSCR_BYTES;
   static constexpr int NW_RAW = (227 * 1024 - FIXED - NT * IMG_BYTES) / kBankWBytes;
   static constexpr int NW = NW_RAW > 4 ? 4 : NW_RAW;
   static constexpr size_t SMEM = (size_t)FIXED + (size_t)NT * IMG_BYTES + (size_t)(NW > 0 ? NW : 0) * kBankWBytes;
@@ -217,6 +220,7 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
   uint64_t *tmem_full = w_empty + NW;     // [NT]
   uint64_t *opnd_full = tmem_full + NT;   // [NT]
   uint32_t *tmem_slot = (uint32_t *)(opnd_full + NT);
+  float *wscr = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(w_full) + 256);   // [NT][3][S][128] (window mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = g.L;
@@ -371,6 +375,9 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
         const float *blk = prm + pbuf * kBankParamFloats;
         const float *sb = blk, *sw0 = blk + kBankMaxL * 64, *swo = sw0 + 64 * 4, *sbo = swo + 4 * 64;
         float v[S][16];
+        float mine[S];   // window mode, one barrier: this thread's own partial sums of the tile it combines
+#pragma unroll
+        for (int s = 0; s < S; ++s) mine[s] = 0.0f;
         // ---- layer 0 from x (FP32 FMA), both tiles ----
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -426,15 +433,37 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
                   }
                 }
               }
-              // partial sums into the (now idle) operand image of this tile
-              float *scr = reinterpret_cast<float *>(img + t * G::IMG_BYTES);
+              if (WINDOW && g.onebar) {
+                // the thread that will combine tile t (sub == t) keeps its own partial sums; the other three unit
+                // groups hand theirs over through a scratch of their own, so the operand images are free for the next
+                // net's first layer as soon as this net's last MMA has been read
+                if (sub == t) {
 #pragma unroll
-              for (int s = 0; s < S; ++s)
+                  for (int s = 0; s < S; ++s) mine[s] = part[s][0];
+                } else {
+                  float *ws = wscr + ((t * 3 + (sub < t ? sub : sub - 1)) * S) * 128 + row;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  if (c < g.C) scr[(sub * NV + s * g.C + c) * 128 + row] = part[s][c];
+                  for (int s = 0; s < S; ++s) ws[s * 128] = part[s][0];
+                }
+              } else {
+                // partial sums into the (now idle) operand image of this tile
+                float *scr = reinterpret_cast<float *>(img + t * G::IMG_BYTES);
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    if (c < g.C) scr[(sub * NV + s * g.C + c) * 128 + row] = part[s][c];
+              }
             }
           }
+        }
+        const bool onebar = WINDOW && g.onebar;
+        if (onebar) {
+          // parameters of the next net into the other block BEFORE the only barrier of this net (nobody reads that
+          // block any more: its net's combine lies before every thread's first hand-off of the current net)
+          int nli = li + 1;
+          if (nli >= li_end) nli = li_beg;
+          load_params(net_of(nli), prm + (pbuf ^ 1) * kBankParamFloats);
         }
         tc_fence_before();
         asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -443,10 +472,21 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
           if (sub < NT) {
             const float *scr = reinterpret_cast<const float *>(img + sub * G::IMG_BYTES);
             float N[3] = {0.0f, 0.0f, 0.0f};
+            if (onebar) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                float pv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  pv[j] = (j == sub) ? mine[s] : wscr[((sub * 3 + (j < sub ? j : j - 1)) * S + s) * 128 + row];
+                N[s] = (pv[0] + pv[1]) + (pv[2] + pv[3]) + (s == 0 ? sbo[0] : 0.0f);
+              }
+            } else {
 #pragma unroll
             for (int s = 0; s < S; ++s)
               N[s] = (scr[(0 * NV + s) * 128 + row] + scr[(1 * NV + s) * 128 + row]) +
                      (scr[(2 * NV + s) * 128 + row] + scr[(3 * NV + s) * 128 + row]) + (s == 0 ? sbo[0] : 0.0f);
+            }
             // w = sigmoid(x - lo) sigmoid(hi - x) and its first two derivatives (FBPINN.py:45-50)
             const float a = sigmoid_acc(xw - __ldg(g.win_lo + net)), b = sigmoid_acc(__ldg(g.win_hi + net) - xw);
             const float a1 = a * (1.0f - a), b1 = -b * (1.0f - b);
@@ -469,12 +509,12 @@ k_tc_bank_fwd(const __grid_constant__ CUtensorMap map_w, const BankArgs g) {
           }
         }
         // parameters of the next net this CTA evaluates into the other block
-        {
+        if (!onebar) {
           int nli = li + 1;
           if (nli >= li_end) nli = li_beg;   // first net of the next group
           load_params(net_of(nli), prm + (pbuf ^ 1) * kBankParamFloats);
+          asm volatile("bar.sync 1, 512;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
       if (WINDOW && sub < NT) {
         const long long pw = ((long long)grp * NT + sub) * 128 + row;
@@ -570,6 +610,12 @@ static int tc_bank_launch(const NetGeom &g, const FwdArgs &a, const BankWindow *
   ba.nets_per_chunk = (ba.n_list + chunks - 1) / chunks;
   chunks = (ba.n_list + ba.nets_per_chunk - 1) / ba.nets_per_chunk;
   ba.out = WINDOW ? (chunks > 1 ? part : win->out) : a.jets;
+  static int onebar = -1;   // AX_TC_BANK_ONEBAR=0: two block barriers per net (A/B)
+  if (onebar < 0) {
+    const char *e = getenv("AX_TC_BANK_ONEBAR");
+    onebar = (e && e[0] == '0') ? 0 : 1;
+  }
+  ba.onebar = (WINDOW && ba.C == 1) ? onebar : 0;
   static int packed = -1;   // AX_TC_BANK_PACKED=0: scalar activation jets (A/B)
   if (packed < 0) {
     const char *e = getenv("AX_TC_BANK_PACKED");

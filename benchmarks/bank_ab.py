@@ -1,6 +1,7 @@
-"""A/B of the FBPINN windowed bank forward (K = 64 nets 1-[64]x3-1, tanh, u / u_x / u_xx) with the activation jets
-evaluated on packed FP32 pairs (default) or scalars (AX_TC_BANK_PACKED=0): time per launch at 2^17 and 2^20 points and
-the largest difference between the two outputs.  Each variant runs in its own process (the switch is read once)."""
+"""A/B of the FBPINN windowed bank forward (K = 64 nets 1-[64]x3-1, tanh, u / u_x / u_xx): activation jets on packed FP32
+pairs (default) or scalars (AX_TC_BANK_PACKED=0), one block barrier per net (default) or two (AX_TC_BANK_ONEBAR=0): time
+per launch at 2^17 and 2^20 points and the largest difference between the outputs of the variants.  Each variant runs in
+its own process (the switches are read once)."""
 import json
 import os
 import subprocess
@@ -39,7 +40,7 @@ def child():
         e1.record()
         torch.cuda.synchronize()
         rec[str(n)] = {"ms": e0.elapsed_time(e1) / 5, "checksum": [float(v) for v in out[..., :n].double().abs().sum(dim=-1).reshape(-1)]}
-        torch.save(out[..., :n].cpu(), f"/tmp/bank_ab_{os.environ.get('AX_TC_BANK_PACKED', '1')}_{n}.pt")
+        torch.save(out[..., :n].cpu(), f"/tmp/bank_ab_{os.environ.get('AX_BANK_AB_TAG', 'x')}_{n}.pt")
     print(json.dumps(rec))
 
 
@@ -49,19 +50,23 @@ def main():
     import torch
 
     res = {}
-    for packed in ("0", "1", "0", "1"):
-        env = dict(os.environ, AX_TC_BANK_PACKED=packed)
-        out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
-        if not line:
-            print(out.stdout[-2000:], out.stderr[-2000:])
-            sys.exit(1)
-        res.setdefault("packed" if packed == "1" else "scalar", []).append({k: v["ms"] for k, v in json.loads(line[-1]).items()})
+    variants = [("scalar_two_barriers", "0", "0"), ("packed_two_barriers", "1", "0"), ("packed_one_barrier", "1", "1")]
+    for rnd in range(2):
+        for tag, packed, onebar in variants:
+            env = dict(os.environ, AX_TC_BANK_PACKED=packed, AX_TC_BANK_ONEBAR=onebar, AX_BANK_AB_TAG=tag)
+            out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
+            line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+            if not line:
+                print(out.stdout[-2000:], out.stderr[-2000:])
+                sys.exit(1)
+            res.setdefault(tag, []).append({k: v["ms"] for k, v in json.loads(line[-1]).items()})
     diff = {}
     for n in (1 << 17, 1 << 20):
-        a, b = torch.load(f"/tmp/bank_ab_0_{n}.pt").double(), torch.load(f"/tmp/bank_ab_1_{n}.pt").double()
-        diff[str(n)] = float((a - b).abs().max() / a.abs().max())
-    res["max_abs_difference_over_largest_entry"] = diff
+        a = torch.load(f"/tmp/bank_ab_scalar_two_barriers_{n}.pt").double()
+        for tag, _, _ in variants[1:]:
+            b = torch.load(f"/tmp/bank_ab_{tag}_{n}.pt").double()
+            diff[f"{tag}_{n}"] = float((a - b).abs().max() / a.abs().max())
+    res["max_abs_difference_from_scalar_over_largest_entry"] = diff
     print(json.dumps(res))
 
 
