@@ -297,3 +297,58 @@ def test_fnn_below_width_32_rides_the_narrow_kernels_padded(widths, act):
     assert _rel(y.detach().double().cpu(), yd.detach()) < 1e-5
     assert _rel(r.detach().double().cpu(), rd.detach()) < 1e-5
     assert _rel(g, gd) < 2e-5
+
+
+_VARIANT_CHILD = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from ai4xde_b200 import _lib
+from ai4xde_b200.jet import JetSpec, to_soa
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(11)
+# (a) FBPINN windowed bank forward: 8 nets 1-[64]x3-1, value / first / second derivative
+K, n = 8, 5000
+widths = [1, 64, 64, 64, 1]
+js = JetSpec((0,), ((0, 0),))
+net = _lib.make_net_desc(widths, "tanh", n_nets=K)
+params = (torch.randn((K, _lib.param_count(_lib.make_net_desc(widths, "tanh"))), generator=g) * 0.2).to(dev)
+xs = to_soa(torch.rand((n, 1), generator=g).to(dev))
+edges = torch.linspace(0, 1, K + 1)
+lst = torch.arange(K, dtype=torch.int32, device=dev)
+bank = _lib.fbpinn_window_forward(net, js.desc, params, xs, n, edges[:-1].contiguous().to(dev), edges[1:].contiguous().to(dev),
+                                  lst, engine="tf32")
+# (b) FP32 engine gradient of a ragged-width net (edge tiles, input layer, two-unit output layer)
+widths = [2, 100, 100, 100, 2]
+js2 = JetSpec((0, 1), ((0, 0), (1, 1)))
+net2 = _lib.make_net_desc(widths, "tanh")
+p2 = (torch.randn((1, _lib.param_count(net2)), generator=g) * 0.3).to(dev)
+m = 3001
+x2 = to_soa((torch.rand((m, 2), generator=g) * 2 - 1).to(dev))
+jets, stash = _lib.jet_forward(net2, js2.desc, p2, x2, m, keep_all=True, engine="fp32")
+jb = torch.randn(jets.shape, generator=g).to(dev)
+jb[..., m:] = 0
+grad = _lib.jet_backward(net2, js2.desc, p2, x2, m, jb, stash, engine="fp32")
+torch.save({"bank": bank[..., :n].cpu(), "grad": grad.cpu()}, sys.argv[2])
+"""
+
+
+def test_measurement_switches_do_not_change_a_bit(tmp_path):
+    """The A/B switches of the round-2 kernels are read once per process: packed FP32 pairs
+    vs scalar activation jets and one vs two block barriers per net in the FBPINN bank kernel (csrc/tc_bank.cu), the
+    pipelined vs the single-buffer FP32 weight-gradient kernel (csrc/simt_kernels.cuh).  Every variant must return the
+    default build's bits: same operations per element, same order of additions."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("default", {}), ("plain", {"AX_TC_BANK_PACKED": "0", "AX_TC_BANK_ONEBAR": "0", "AX_SIMT_WGRAD_PIPE": "0"})):
+        path = str(tmp_path / f"{tag}.pt")
+        r = subprocess.run([sys.executable, "-c", _VARIANT_CHILD, root, path], env=dict(os.environ, **env),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = torch.load(path)
+    assert torch.equal(outs["default"]["bank"], outs["plain"]["bank"])
+    assert torch.equal(outs["default"]["grad"], outs["plain"]["grad"])
+    assert float(outs["default"]["bank"].abs().sum()) > 0 and float(outs["default"]["grad"].abs().sum()) > 0
